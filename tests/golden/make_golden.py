@@ -1,0 +1,128 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference solver
+(/root/reference/lib/ode.py) on the torch-backed JAX stand-in (oracle/jax_shim.py).
+
+Run in the build container only (``python tests/golden/make_golden.py``); the
+GPU box has no /root/reference and only reads the committed .npz files.
+
+What the vectors pin: the reference's own control flow and arithmetic for the
+dopri5 loop, the eight other tableaux loops, NFE accounting, dense output, and
+the adjoint (_odeint_rev via jax.vjp -> torch.func.vjp) including the split
+wrapper odeint_aux_one.  The dynamics closures (MLP, Taylor-mode regulariser)
+come from oracle/dynamics_oracle.py because the reference builds them with
+Haiku + jax.experimental.jet, which cannot be imported here.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.jax_shim import load_reference_ode, ravel_pytree  # noqa: E402
+from oracle import dynamics_oracle as do  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+TABLEAUX = ["heun", "fehlberg", "bosh", "rk_fehlberg", "cash_karp", "owrenzen", "owrenzen5", "tanyam"]
+
+
+def flat_params(p):
+    return ravel_pytree(p)[0].numpy()
+
+
+def mlp_case(B, D, H, seed, scale):
+    g = torch.Generator().manual_seed(1000 + seed)
+    params = do.init_mlp_params(D, H, seed=seed, scale=scale)
+    x0 = torch.rand((B, D), generator=g)
+    eps = torch.randint(0, 2, (B, D), generator=g).float() * 2 - 1
+    gy = torch.randn((B, D), generator=g)
+    return params, x0, eps, gy
+
+
+def main():
+    ref = load_reference_ode()
+    torch.set_num_threads(8)
+
+    # ---- KAT: y' = a + (y - (a t + b))^5, exact y = a t + b (lib/ode.py:1782-1797)
+    a, b = 0.2, 3.0
+    f = lambda y, t: a + (y - (a * t + b)) ** 5
+    ts = torch.tensor([1., 8.])
+    y0 = torch.tensor([a * 1. + b])
+    rec = {}
+    ys, nfe = ref.odeint(f, y0, ts, rtol=1e-5, atol=1e-5)
+    rec["dopri5_y"], rec["dopri5_nfe"] = ys.numpy(), float(nfe)
+    for name in TABLEAUX:
+        ys, nfe = getattr(ref, f"_{name}_odeint")(f, 1e-5, 1e-5, math.inf, y0, ts)
+        rec[f"{name}_y"], rec[f"{name}_nfe"] = ys.numpy(), float(nfe)
+    np.savez(os.path.join(OUT, "kat_const.npz"), **rec)
+
+    # ---- forward, MLP dynamics, several tolerances and output grids
+    B, D, H = 6, 16, 8
+    params, x0, eps, gy = mlp_case(B, D, H, seed=0, scale=2.0)
+    cl = do.make_mnist_closures("r3")
+    rec = dict(B=B, D=D, H=H, x0=x0.numpy(), params=flat_params(params), scale=2.0, seed=0)
+    for tag, tol in [("d", 1.4e-8), ("5", 1e-5), ("3", 1e-3)]:
+        ts = torch.tensor([0., 1.])
+        ys, nfe = ref.odeint(cl["dynamics_wrap"], x0, ts, params, rtol=tol, atol=tol)
+        rec[f"fwd_{tag}_y"], rec[f"fwd_{tag}_nfe"], rec[f"fwd_{tag}_tol"] = ys.numpy(), float(nfe), tol
+    ts = torch.tensor([0., 0.1, 0.15, 0.7, 1.0, 2.5])
+    ys, nfe = ref.odeint(cl["dynamics_wrap"], x0, ts, params, rtol=1e-6, atol=1e-6)
+    rec["fwd_multi_ts"], rec["fwd_multi_y"], rec["fwd_multi_nfe"] = ts.numpy(), ys.numpy(), float(nfe)
+    # mxstep exhaustion: silent early exit (lib/ode.py:829-831)
+    ts = torch.tensor([0., 1.])
+    ys, nfe = ref.odeint(cl["dynamics_wrap"], x0, ts, params, rtol=1e-7, atol=1e-7, mxstep=2)
+    rec["fwd_mx2_y"], rec["fwd_mx2_nfe"] = ys.numpy(), float(nfe)
+    fun = lambda y, t: cl["dynamics_wrap"](y, t, params).reshape(-1)
+    for name in TABLEAUX:
+        for tag, tol in [("3", 1e-3), ("5", 1e-5)]:
+            if name == "tanyam" and tag == "5":
+                continue  # tens of thousands of iterations; tol 1e-3 already pins it
+            ys, nfe = getattr(ref, f"_{name}_odeint")(fun, tol, tol, math.inf, x0.reshape(-1), ts)
+            rec[f"{name}_{tag}_y"], rec[f"{name}_{tag}_nfe"] = ys.numpy(), float(nfe)
+    np.savez(os.path.join(OUT, "mlp_forward.npz"), **rec)
+
+    # ---- odeint_aux_one forward + adjoint, R2 and R3, two tolerances
+    rec = dict(B=B, D=D, H=H, x0=x0.numpy(), params=flat_params(params), eps=eps.numpy(), gy=gy.numpy(),
+               g_r=0.01)
+    ts = torch.tensor([0., 1.])
+    y0 = (x0, torch.zeros(B))
+    for reg in ["r2", "r3"]:
+        cl = do.make_mnist_closures(reg)
+        fwd_w = ref.ravel_first_arg(cl["fwd"], ravel_pytree(y0[0])[1])
+        rev_w = ref.ravel_first_arg(cl["aug_dynamics"], ravel_pytree(y0)[1])
+        for tag, tol in [("5", 1e-5), ("d", 1.4e-8)]:
+            (res, nfe), saved = ref._odeint_aux_one_fwd(fwd_w, rev_w, tol, tol, math.inf, y0, ts, eps, params)
+            g = (torch.zeros_like(res[0]), torch.zeros_like(res[1]))
+            g[0][-1] = gy
+            g[1][-1] = 0.01
+            out = ref._odeint_aux_one_rev(fwd_w, rev_w, tol, tol, math.inf, saved, (g, None))
+            k = f"{reg}_{tag}"
+            rec[f"{k}_y1"], rec[f"{k}_nfe"] = res[0][-1].numpy(), float(nfe)
+            rec[f"{k}_x0_bar"], rec[f"{k}_r0_bar"] = out[0][0].numpy(), out[0][1].numpy()
+            rec[f"{k}_ts_bar"], rec[f"{k}_eps_bar"] = out[1].numpy(), out[2].numpy()
+            rec[f"{k}_params_bar"] = flat_params(out[3])
+    # augmented FORWARD (evaluation path, mnist.py:333-334): regulariser value
+    cl = do.make_mnist_closures("r3")
+    y0_all = (x0, torch.zeros(B), torch.zeros(B), torch.zeros(B))
+    (ya, ra, fro, kin), nfe = ref.odeint(cl["all_aug_dynamics"], y0_all, ts, eps, params, rtol=1e-5, atol=1e-5)
+    rec["all_y1"], rec["all_r"], rec["all_fro"], rec["all_kin"], rec["all_nfe"] = (
+        ya[-1].numpy(), ra[-1].numpy(), fro[-1].numpy(), kin[-1].numpy(), float(nfe))
+    np.savez(os.path.join(OUT, "mlp_adjoint.npz"), **rec)
+
+    # ---- plain adjoint on the pendulum (lib/ode.py:1720-1722, 1765-1774), multi-output
+    def pend(y, t, m, g):
+        return torch.stack([y[1], -m * y[1] - g * torch.sin(y[0])])
+    y0 = torch.tensor([math.pi - 0.1, 0.0])
+    ts = torch.linspace(0., 2., 5)
+    args = (torch.tensor(0.25), torch.tensor(9.8))
+    (ys, nfe), res = ref._odeint_fwd(pend, 1e-6, 1e-6, math.inf, y0, ts, *args)
+    g = torch.ones_like(ys)
+    out = ref._odeint_rev(pend, 1e-6, 1e-6, math.inf, res, (g, None))
+    np.savez(os.path.join(OUT, "pendulum.npz"), ts=ts.numpy(), ys=ys.numpy(), nfe=float(nfe),
+             y0_bar=out[0].numpy(), ts_bar=out[1].numpy(), m_bar=float(out[2]), g_bar=float(out[3]))
+    print("golden vectors written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
