@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Headline benchmark: MNIST Neural-ODE train step, dopri5 + Taylor R3 (mnist.py --reg r3 --lam 6e-5,
+batch 100 synthetic 28x28 inputs, rtol = atol = 1.4e-8 script default).
+
+    python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torch.distributed.run)
+    python bench.py --impl reference ...                   (CPU arm: the oracle port on all host cores)
+
+One "step" = one full update(): PreODE, forward solve, loss head, adjoint solve, momentum update.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what every field means.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train_steps_per_s"
+UNIT = "steps/s"
+B, D, H, LAM, TOL = 100, 784, 100, 6e-5, 1.4e-8
+WORKLOAD = "mnist.py Neural ODE classifier, dopri5, --reg r3 --lam 6e-5, batch 100 synthetic 28x28 (configs[0])"
+
+
+def synth_batch(rank, step, pin=False):
+    """Synthetic MNIST-shaped batch, a different one per (rank, step % 8)."""
+    import torch
+    g = torch.Generator().manual_seed(1234 + 97 * rank + (step % 8))
+    images = torch.randint(0, 256, (B, 28, 28, 1), generator=g, dtype=torch.uint8)
+    labels = torch.randint(0, 10, (B,), generator=g)
+    eps = torch.randint(0, 2, (B, D), generator=g).float() * 2 - 1
+    if pin:
+        images, labels, eps = images.pin_memory(), labels.pin_memory(), eps.pin_memory()
+    return images, labels, eps
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in list(self.lines):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_train_steps(n_steps, warmup, threads):
+    """The oracle port of one update() on host cores; returns (seconds per step, info)."""
+    import torch
+    from oracle import dynamics_oracle as do
+    torch.set_num_threads(threads)
+    p_ode = do.init_mlp_params(D, H, seed=0)
+    p_post = do.init_post_params(D, seed=1)
+    vel = None
+    times, info = [], {}
+    for s in range(warmup + n_steps):
+        images, labels, eps = synth_batch(0, s)
+        t0 = time.perf_counter()
+        out = do.train_step_grads(p_ode, p_post, do.pre_ode(images), labels, eps, LAM, reg="r3", rtol=TOL, atol=TOL)
+        if vel is None:
+            vel = {k: {kk: torch.zeros_like(vv) for kk, vv in v.items()} for k, v in p_ode.items()}
+        p_ode, vel = do.momentum_update(p_ode, vel, out["grads"]["ode"], 1e-1)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+        info = dict(nfe=float(out["nfe"]), fwd_iters=out["fwd_stats"]["n_iters"],
+                    bwd_iters=out["bwd_stats"][0]["n_iters"])
+    return sum(times) / len(times), info
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's algorithm on the box's host cores.  The reference itself (JAX,
+    Haiku, mid-2020 API) cannot be installed in this image, so this is the oracle PORT (kind 'port')."""
+    if rank != 0:
+        return
+    threads = len(os.sched_getaffinity(0))
+    steps = max(1, min(args.steps, 40))
+    sec, info = cpu_train_steps(steps, min(args.warmup, 1), threads)
+    val = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B, "rtol": TOL, "atol": TOL},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{steps} full train steps (forward solve + adjoint + momentum) after "
+                                   f"{min(args.warmup, 1)} warm-up, torch CPU fp32, {threads} threads; "
+                                   f"nfe {info['nfe']}, adjoint iterations {info['bwd_iters']}"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "nfe_per_s": info["nfe"] * B * val,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    global B
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=B, help="per-GPU batch (development sweeps only)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    import easy_neural_ode_b200 as eno
+    from easy_neural_ode_b200 import mnist_step, _cabi
+
+    B = args.batch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model = mnist_step.MnistNode(reg="r3", lam=LAM, rtol=TOL, atol=TOL, device=dev, dim=D, hidden=H)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    dev_batches = [tuple(t.to(dev) for t in synth_batch(rank, s)) for s in range(8)]
+    host_batches = [synth_batch(rank, s, pin=True) for s in range(8)]
+
+    def step(s, batch=None):
+        images, labels, eps = batch if batch is not None else dev_batches[s % 8]
+        if world == 1:
+            return model.update(images, labels, eps)
+        out = model.loss_and_grads(images, labels, eps)
+        g = out["grads"]
+        flat = torch.cat([g["ode"], g["post_w"].reshape(-1), g["post_b"]])
+        dist.all_reduce(flat)                      # NCCL over NVLink: data-parallel gradient sum
+        flat /= world
+        n1 = g["ode"].numel(); n2 = g["post_w"].numel()
+        model.apply_grads(flat[:n1], flat[n1:n1 + n2].reshape(g["post_w"].shape), flat[n1 + n2:])
+        return out
+
+    for s in range(max(args.warmup, 3)):
+        out = step(s)
+    torch.cuda.synchronize()
+
+    # ---- timed region: device-resident inputs, L2 flushed between steps, CUDA events, max over ranks
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    nfe_total = 0.0
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        evs[s][0].record()
+        out = step(s)
+        evs[s][1].record()
+        launches += out["fwd_stats"]["n_launches"] + sum(b["n_launches"] for b in out["bwd_stats"])
+        nfe_total += float(out["fwd_stats"]["nfe"])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    value = world * 1e3 / ms_per_step            # batch-100 train steps per second, all ranks
+
+    # ---- e2e: host (pinned) buffers through the public API, H2D + D2H inside the timed region
+    def step_e2e(s):
+        images, labels, eps = host_batches[s % 8]
+        di, dl, de = images.to(dev, non_blocking=True), labels.to(dev, non_blocking=True), eps.to(dev, non_blocking=True)
+        o = step(s, (di, dl, de))
+        return float(o["loss"].item())             # device -> host read of the step's result
+    for s in range(3):
+        step_e2e(s)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_e2e(s)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / float(t.item())
+    h2d = sum(x.numel() * x.element_size() for x in host_batches[0])
+
+    # ---- roofline of the dominant kernel (adjoint per-sample step kernel), separate profiled pass
+    L = _cabi.lib()
+    h = _cabi.ctx(dev.index)
+    L.eno_profile_enable(h, 1)
+    for s in range(min(args.steps, 10)):
+        step(s)
+    torch.cuda.synchronize()
+    L.eno_profile_enable(h, 0)
+    ms = (C.c_double * 4)()
+    cnt = (C.c_int64 * 4)()
+    L.eno_profile_read(h, ms, cnt)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = float(peaks.get("bf16_tflops", 1590.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback 1.59 PFLOP/s"
+    ffma = C.c_double()
+    L.eno_ffma_peak(h, C.byref(ffma), None)
+    rows_ms = ms[1] / max(cnt[1], 1)
+    flop_rows = 6.0 * B * 12 * 2 * D * H + 70.0 * 2 * B * D   # DESIGN.md "Algorithmic work"
+    achieved = flop_rows / (rows_ms * 1e-3) / 1e12 if rows_ms > 0 else 0.0
+    roofline = {"kernel": "k_adj_rows<STEP> (adjoint dopri5 iteration, per-sample blocks)", "bound": "tensor",
+                "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": rows_ms, "launches_timed": int(cnt[1]),
+                "fp32_ffma_peak_tflops": ffma.value, "frac_of_fp32_ffma": achieved / ffma.value if ffma.value else None,
+                "other_kernels_ms": {"k_fwd_step": ms[0] / max(cnt[0], 1), "k_adj_pgrad<STEP>": ms[2] / max(cnt[2], 1)},
+                "note": "fp32 FFMA kernel; the tensor pipe is the contract's denominator, the fp32 pipe is the one it uses"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "rtol": TOL, "atol": TOL,
+                   "parallelism": f"dp{world} (batch shards, local step control, NCCL gradient all-reduce)" if world > 1 else "single GPU",
+                   "l2": "flushed between steps (256 MiB device write, outside the per-step events)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "nfe_per_s": nfe_total * B * world / (dev_ms * 1e-3),
+        "solver": {"fwd": out["fwd_stats"], "bwd": out["bwd_stats"][0]},
+        "roofline": roofline,
+        "wall_s": wall,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        sec, info = cpu_train_steps(5, 1, threads)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "5 full train steps after 1 warm-up, oracle port (torch CPU fp32), "
+                                          f"nfe {info['nfe']}, adjoint iterations {info['bwd_iters']}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

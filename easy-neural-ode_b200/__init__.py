@@ -1,0 +1,12 @@
+"""B200-native adaptive ODE-solve path of easy-neural-ode (odeint + adjoint + Taylor regulariser).
+
+Import name: ``easy_neural_ode_b200`` (a one-file shim next to this directory maps it here,
+because the directory name the project layout prescribes contains a hyphen).
+"""
+from . import _cabi
+from .dynamics import MLPDynamics, EnoFunc, REGS
+from .ode import (odeint, odeint_aux_one, _dopri5_odeint, _heun_odeint, _fehlberg_odeint, _bosh_odeint,
+                  _rk_fehlberg_odeint, _cash_karp_odeint, _owrenzen_odeint, _owrenzen5_odeint, _tanyam_odeint,
+                  solve_with_trace, rhs, last_stats)
+
+__all__ = ["MLPDynamics", "EnoFunc", "REGS", "odeint", "odeint_aux_one", "solve_with_trace", "rhs", "last_stats"]

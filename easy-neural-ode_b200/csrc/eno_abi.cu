@@ -1,0 +1,346 @@
+// C ABI (include/eno.h) and host-side launch logic of libeno.so.
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "adj_kernels.cuh"
+#include "fwd_kernels.cuh"
+#include "tableaux.cuh"
+
+using namespace eno;
+
+struct eno_ctx {
+  int device = 0;
+  Ctrl* mailbox = nullptr;  // pinned host copy of the device controller
+  std::string err;
+  int hint_fwd = 8;         // launches to enqueue before the first poll
+  int hint_bwd = 8;
+  int sm_count = 148;
+  Profiler prof;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(eno_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  g_err = msg;
+  return code;
+}
+
+#define ENO_CUDA(ctx, expr)                                                                         \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      return fail(ctx, ENO_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t n) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += align_up(n * sizeof(T));
+    return p;
+  }
+};
+
+bool desc_ok(const eno_dynamics_desc* d) {
+  return d && d->arch == ENO_ARCH_MLP_SIGMOID && d->D > 0 && d->H > 0 && d->D % 4 == 0 && d->H % 4 == 0 &&
+         d->D / 4 <= kThreads && d->H / 4 <= kThreads;
+}
+
+int pick_rows_fwd(int B, int D, int H, int s, int sms) {
+  int R = 1;
+  if (B > sms) R = 2;
+  if (B > 2 * sms) R = 4;
+  while (R > 1 && fwd_smem_bytes(R, D, H, s) > 220 * 1024) R >>= 1;
+  return R;
+}
+
+__global__ void k_ctrl_reset(Ctrl* c, float rtol, float atol, int T, int mxstep, int trace_cap, float n_state) {
+  memset(c, 0, sizeof(Ctrl));
+  c->rtol = rtol;
+  c->atol = atol;
+  c->T = T;
+  c->mxstep = mxstep;
+  c->trace_cap = trace_cap;
+  c->n_state = n_state;
+}
+
+// 16 independent FMA chains per thread: the non-tensor fp32 peak this chip actually reaches.
+__global__ void k_ffma_peak(float* sink, int iters, float m) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, 0.5f);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456f) *sink = s;
+}
+
+size_t fwd_ws_bytes(int B, int D) {
+  const size_t N = (size_t)B * D;
+  return align_up(sizeof(Ctrl)) + align_up(3 * N * 4) * 2 + align_up(2 * N * 4) + 2 * align_up((size_t)B * 8) + 1024;
+}
+
+template <typename KernelT>
+cudaError_t set_smem(KernelT k, size_t bytes) {
+  return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+void fill_stats(eno_stats* st, const Ctrl& c, int launches, int n_rhs) {
+  if (!st) return;
+  st->nfe = (float)c.nfe;
+  st->n_iters = c.n_iters;
+  st->n_accepted = c.n_accepted;
+  st->status = c.status;
+  st->last_dt = c.dt;
+  st->last_t = c.t;
+  st->n_launches = launches;
+  st->n_rhs = n_rhs;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t eno_abi_version(void) { return ENO_ABI_VERSION; }
+
+const char* eno_last_error_string(const eno_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int32_t eno_create(eno_ctx** out, int32_t device) {
+  if (!out) return fail(nullptr, ENO_E_ARG, "eno_create: out is null");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(nullptr, ENO_E_CUDA, std::string("eno_create: no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(nullptr, ENO_E_ARG, "eno_create: bad device index");
+  eno_ctx* c = new eno_ctx();
+  c->device = device;
+  ENO_CUDA(c, cudaSetDevice(device));
+  ENO_CUDA(c, cudaMallocHost(&c->mailbox, sizeof(Ctrl)));
+  cudaDeviceProp prop;
+  ENO_CUDA(c, cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    std::string m = "eno_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                    ", this library is built for sm_100a only";
+    cudaFreeHost(c->mailbox);
+    delete c;
+    return fail(nullptr, ENO_E_UNSUPPORTED, m);
+  }
+  *out = c;
+  return ENO_OK;
+}
+
+void eno_destroy(eno_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+  delete ctx;
+}
+
+int64_t eno_param_count(const eno_dynamics_desc* d) {
+  if (!d) return -1;
+  return (int64_t)(d->D + 1) * d->H + d->H + (int64_t)(d->H + 1) * d->D + d->D;
+}
+
+int64_t eno_adjoint_state_size(const eno_dynamics_desc* d, int32_t B) {
+  if (!d) return -1;
+  const int64_t n_aux = (d->aug == ENO_AUG_NONE) ? 0 : 1;
+  return 2 * ((int64_t)B * d->D + n_aux * B) + 1 + (d->eps_in_args ? (int64_t)B * d->D : 0) + eno_param_count(d);
+}
+
+size_t eno_workspace_bytes(const eno_dynamics_desc* d, int32_t B, int32_t T, int32_t tableau, int32_t mode) {
+  (void)T;
+  (void)tableau;
+  if (!desc_ok(d) || B <= 0) return 0;
+  if (mode == 0) return fwd_ws_bytes(B, d->D);
+  return adj_ws_bytes(B, d->D, d->H);
+}
+
+int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tableau, int32_t B, const float* y0,
+                       const float* ts, int32_t T, const float* params, const float* eps, float rtol, float atol,
+                       int32_t mxstep, void* workspace, size_t workspace_bytes, float* ys_out, float* aux_out,
+                       eno_stats* stats_host, eno_trace_row* trace_out, int32_t trace_cap, void* stream_) {
+  (void)eps;
+  (void)aux_out;
+  if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_odeint_fwd: ctx is null");
+  if (!desc_ok(desc)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd: unsupported dynamics desc (MLP sigmoid, D%4==0, H%4==0)");
+  if (desc->aug != ENO_AUG_NONE) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd: augmented forward not built yet");
+  if (B <= 0 || T < 1 || !y0 || !ts || !params || !ys_out || !workspace)
+    return fail(ctx, ENO_E_ARG, "eno_odeint_fwd: null pointer or empty batch");
+  if (((uintptr_t)params | (uintptr_t)y0 | (uintptr_t)ys_out | (uintptr_t)workspace) & 15)
+    return fail(ctx, ENO_E_ARG, "eno_odeint_fwd: buffers must be 16-byte aligned");
+  if (workspace_bytes < fwd_ws_bytes(B, desc->D)) return fail(ctx, ENO_E_WORKSPACE, "eno_odeint_fwd: workspace too small");
+  Tableau tab;
+  if (!fill_tableau(tableau, &tab)) return fail(ctx, ENO_E_ARG, "eno_odeint_fwd: unknown tableau id");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  const int D = desc->D, H = desc->H;
+  const size_t N = (size_t)B * D;
+  Carver cv(workspace);
+  FwdArgs a;
+  a.ctrl = cv.take<Ctrl>(1);
+  a.Y = cv.take<float>(3 * N);
+  a.F = cv.take<float>(3 * N);
+  a.MID = cv.take<float>(2 * N);
+  a.rowpart0 = cv.take<double>(B);
+  a.rowpart1 = cv.take<double>(B);
+  a.w = mlp_weights_from_flat(params, D, H, nullptr, nullptr);
+  a.B = B;
+  a.N = N;
+  a.y0 = y0;
+  a.ts = ts;
+  a.ys_out = ys_out;
+  a.trace = trace_out;
+
+  const int R = pick_rows_fwd(B, D, H, tab.s, ctx->sm_count);
+  const size_t smem = fwd_smem_bytes(R, D, H, tab.s < 2 ? 2 : tab.s);
+  const int grid = (B + R - 1) / R;
+  int launches = 0;
+
+  ENO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tab, &tab, sizeof(Tableau), 0, cudaMemcpyHostToDevice, stream));
+  k_ctrl_reset<<<1, 1, 0, stream>>>(a.ctrl, rtol, atol, T, mxstep <= 0 ? INT_MAX : mxstep, trace_out ? trace_cap : 0,
+                                    (float)N);
+  ++launches;
+
+#define ENO_FWD_DISPATCH(RR)                                                        \
+  {                                                                                 \
+    ENO_CUDA(ctx, set_smem(k_fwd_init<RR, 0>, smem));                               \
+    ENO_CUDA(ctx, set_smem(k_fwd_init<RR, 1>, smem));                               \
+    ENO_CUDA(ctx, set_smem(k_fwd_step<RR>, smem));                                  \
+    k_fwd_init<RR, 0><<<grid, kThreads, smem, stream>>>(a);                         \
+    k_fwd_init<RR, 1><<<grid, kThreads, smem, stream>>>(a);                         \
+    launches += 2;                                                                  \
+    int chunk = ctx->hint_fwd;                                                      \
+    const int out_grid = (int)((N + 1023) / 1024) < 4 * ctx->sm_count ? (int)((N + 1023) / 1024) : 4 * ctx->sm_count; \
+    for (;;) {                                                                      \
+      for (int i = 0; i < chunk; ++i) {                                             \
+        const int ps_ = ctx->prof.begin(PROF_FWD_STEP, stream);                     \
+        k_fwd_step<RR><<<grid, kThreads, smem, stream>>>(a);                        \
+        ctx->prof.end(ps_, stream);                                                 \
+        k_fwd_out<<<out_grid, 256, 0, stream>>>(a);                                 \
+        launches += 2;                                                              \
+      }                                                                             \
+      ENO_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, a.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream)); \
+      ENO_CUDA(ctx, cudaStreamSynchronize(stream));                                 \
+      if (ctx->mailbox->done) break;                                                \
+      chunk = 4;                                                                    \
+    }                                                                               \
+  }
+  if (R == 1) ENO_FWD_DISPATCH(1)
+  else if (R == 2) ENO_FWD_DISPATCH(2)
+  else ENO_FWD_DISPATCH(4)
+#undef ENO_FWD_DISPATCH
+
+  ENO_CUDA(ctx, cudaGetLastError());
+  const Ctrl& c = *ctx->mailbox;
+  {
+    int valid[PROF_KINDS] = {c.n_iters, 0, 0, 0};
+    ctx->prof.resolve(valid);
+  }
+  ctx->hint_fwd = c.n_iters + 1 > 64 ? 64 : c.n_iters + 1;
+  const int per_iter = tab.clip ? 2 * (tab.s - 1) : (tab.s - 1);
+  fill_stats(stats_host, c, launches, 2 + per_iter * c.n_iters);
+  return c.status;
+}
+
+int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32_t B, const float* y, float t,
+                const float* params, const float* eps, const float* y_bar, const float* r_bar, void* workspace,
+                size_t workspace_bytes, float* dy_out, float* aux_out, float* ybar_dot_out, float* tbar_out,
+                float* params_bar_out, void* stream_) {
+  (void)eps;
+  if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_rhs: ctx is null");
+  if (!desc_ok(desc)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_rhs: unsupported dynamics desc");
+  if (B <= 0 || !y || !params || !dy_out) return fail(ctx, ENO_E_ARG, "eno_rhs: null pointer or empty batch");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int D = desc->D, H = desc->H;
+  if (mode == 0) {
+    const size_t smem = fwd_smem_bytes(1, D, H, 2);
+    ENO_CUDA(ctx, set_smem(k_rhs_plain<1>, smem));
+    k_rhs_plain<1><<<B, kThreads, smem, stream>>>(mlp_weights_from_flat(params, D, H, nullptr, nullptr), B, y, t, dy_out);
+    ENO_CUDA(ctx, cudaGetLastError());
+    ENO_CUDA(ctx, cudaStreamSynchronize(stream));
+    return ENO_OK;
+  }
+  return adj_rhs(ctx ? &ctx->err : nullptr, ctx->sm_count, desc, mode, B, y, t, params, y_bar, r_bar, workspace,
+                 workspace_bytes, dy_out, aux_out, ybar_dot_out, tbar_out, params_bar_out, stream);
+}
+
+int32_t eno_odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, const float* ys, const float* ts,
+                       int32_t T, const float* params, const float* g_y, const float* g_r, float rtol, float atol,
+                       int32_t mxstep, void* workspace, size_t workspace_bytes, float* y0_bar_out,
+                       float* r0_bar_out, float* ts_bar_out, float* params_bar_out, eno_stats* stats_host,
+                       eno_trace_row* trace_out, int32_t trace_cap, void* stream_) {
+  if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_odeint_bwd: ctx is null");
+  if (!desc_ok(desc)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: unsupported dynamics desc");
+  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (desc->aug != ENO_AUG_NONE && desc->aug != ENO_AUG_REG)
+    return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: aug must be ENO_AUG_NONE or ENO_AUG_REG");
+  return adj_solve(&ctx->prof, &ctx->err, ctx->mailbox, &ctx->hint_bwd, ctx->sm_count, desc, B, ys, ts, T, params, g_y, g_r, rtol,
+                   atol, mxstep, workspace, workspace_bytes, y0_bar_out, r0_bar_out, ts_bar_out, params_bar_out,
+                   stats_host, trace_out, trace_cap, static_cast<cudaStream_t>(stream_));
+}
+
+// ---- measurement hooks (bench.py) ------------------------------------------------------------
+int32_t eno_profile_enable(eno_ctx* ctx, int32_t on) {
+  if (!ctx) return ENO_E_ARG;
+  ctx->prof.enabled = on != 0;
+  return ENO_OK;
+}
+
+int32_t eno_profile_read(eno_ctx* ctx, double* ms_out, int64_t* count_out) {
+  if (!ctx || !ms_out || !count_out) return ENO_E_ARG;
+  for (int k = 0; k < PROF_KINDS; ++k) {
+    ms_out[k] = ctx->prof.ms[k];
+    count_out[k] = ctx->prof.count[k];
+    ctx->prof.ms[k] = 0;
+    ctx->prof.count[k] = 0;
+  }
+  return ENO_OK;
+}
+
+int32_t eno_ffma_peak(eno_ctx* ctx, double* tflops_out, void* stream_) {
+  if (!ctx || !tflops_out) return ENO_E_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+  float* sink = nullptr;
+  ENO_CUDA(ctx, cudaMalloc(&sink, 4));
+  const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, st);
+    k_ffma_peak<<<blocks, threads, 0, st>>>(sink, iters, 1.0001f);
+    cudaEventRecord(e1, st);
+    ENO_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 16 * iters * (double)blocks * threads;
+    if (ms > 0 && fl / ms * 1e-9 > best) best = fl / ms * 1e-9;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  *tflops_out = best;
+  return ENO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+"""Thin driver reproducing one ``update()`` of mnist.py (553-559) around the ODE path:
+PreODE (173-192) -> odeint_aux_one (330-341) -> PostODE (225-238) -> CE + lam*mean(r) (462-471)
+-> jax.grad (528) -> momentum SGD (530-540).
+
+Only what is needed to drive the hot path and to report the headline metric (train steps/s);
+the head (sigmoid + Linear(10) on [B, 784]) is a handful of tiny torch ops, everything inside the
+ODE block is libeno.so.
+"""
+import torch
+
+from .dynamics import MLPDynamics
+from . import ode
+
+
+class MnistNode:
+    def __init__(self, reg="r3", lam=6e-5, rtol=1.4e-8, atol=1.4e-8, device="cuda", dim=784, hidden=100,
+                 lr=1e-1, mass=0.9, n_cls=10):
+        self.spec = MLPDynamics(dim, hidden, reg=reg)
+        self.lam, self.rtol, self.atol = lam, rtol, atol
+        self.device = torch.device(device)
+        self.lr, self.mass = lr, mass
+        self.dim, self.n_cls = dim, n_cls
+        self.ts = torch.tensor([0., 1.], device=self.device)
+        self.init_params(0)
+
+    def init_params(self, seed=0, scale=1.0):
+        p = self.spec.init_params(seed=seed, device=self.device, scale=scale)
+        self.p_ode = self.spec.flatten_params(p).clone()
+        g = torch.Generator().manual_seed(seed + 1)
+        w = torch.empty((self.dim, self.n_cls), dtype=torch.float64)
+        torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=g)
+        self.post_w = (w / self.dim ** 0.5).float().to(self.device)
+        self.post_b = torch.zeros(self.n_cls, device=self.device)
+        self._reset_velocity()
+
+    def load_params(self, p_ode, p_post):
+        self.p_ode = self.spec.flatten_params({k: {kk: vv.to(self.device) for kk, vv in v.items()}
+                                               for k, v in p_ode.items()}).clone()
+        self.post_w = p_post["w"].to(self.device).clone()
+        self.post_b = p_post["b"].to(self.device).clone()
+        self._reset_velocity()
+
+    def _reset_velocity(self):
+        self.v_ode = torch.zeros_like(self.p_ode)
+        self.v_w = torch.zeros_like(self.post_w)
+        self.v_b = torch.zeros_like(self.post_b)
+
+    def loss_and_grads(self, images_u8, labels, eps):
+        """images [B,28,28,1] uint8, labels [B] int64, eps [B,784] Rademacher; all on self.device."""
+        B = images_u8.shape[0]
+        x0 = (images_u8.to(torch.float32) / 255.).reshape(B, -1)
+        p_ode = self.p_ode.detach().requires_grad_(True)
+        w = self.post_w.detach().requires_grad_(True)
+        b = self.post_b.detach().requires_grad_(True)
+        y0 = (x0, torch.zeros(B, device=self.device))
+        (ys, rs), nfe = ode.odeint_aux_one(self.spec.fwd, self.spec.aug_dynamics, y0, self.ts, eps, p_ode,
+                                           rtol=self.rtol, atol=self.atol)
+        y1, r1 = ys[-1], rs[-1]
+        logits = torch.sigmoid(y1) @ w + b
+        ce = torch.nn.functional.cross_entropy(logits, labels)
+        loss = ce + self.lam * r1.mean()
+        g_ode, g_w, g_b = torch.autograd.grad(loss, (p_ode, w, b))
+        return dict(loss=ce.detach(), y1=y1.detach(), nfe=nfe, grads={"ode": g_ode, "post_w": g_w, "post_b": g_b},
+                    fwd_stats=ode.last_stats["fwd"], bwd_stats=ode.last_stats["bwd"])
+
+    def update(self, images_u8, labels, eps):
+        """One training step; returns the (device) loss tensor."""
+        out = self.loss_and_grads(images_u8, labels, eps)
+        g = out["grads"]
+        self.apply_grads(g["ode"], g["post_w"], g["post_b"])
+        return out
+
+    def apply_grads(self, g_ode, g_w, g_b):
+        """jax.experimental.optimizers.momentum: v <- mass*v + g ; x <- x - lr*v."""
+        self.v_ode.mul_(self.mass).add_(g_ode); self.p_ode.sub_(self.lr * self.v_ode)
+        self.v_w.mul_(self.mass).add_(g_w); self.post_w.sub_(self.lr * self.v_w)
+        self.v_b.mul_(self.mass).add_(g_b); self.post_b.sub_(self.lr * self.v_b)

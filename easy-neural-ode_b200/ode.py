@@ -1,0 +1,260 @@
+"""Host-side mirror of the reference's solver surface (lib/ode.py), over libeno.so.
+
+Same names, argument order and return tuples as the reference:
+
+    odeint(func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=inf) -> (ys, nfe)       lib/ode.py:540-559
+    odeint_aux_one(fwd_func, rev_func, y0, t, *args, rtol, atol, mxstep)                 lib/ode.py:657-676
+    _heun_odeint / _bosh_odeint / ... (func, rtol, atol, mxstep, y0, ts, *args)          lib/ode.py:1048-1390
+
+``func`` must be a dynamics-spec closure (dynamics.EnoFunc); an arbitrary Python
+callable raises TypeError - the product path has no eager fallback.  The reference's
+custom_vjp (lib/ode.py:1708, 1713) is a torch.autograd.Function whose backward is the
+adjoint kernel path (eno_odeint_bwd).
+
+Inputs may live on the host: they are copied to the current CUDA device for the call
+and the results are returned on the input's device.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _cabi
+from .dynamics import EnoFunc
+
+last_stats = {"fwd": None, "bwd": None}   # controller statistics of the most recent solves
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    key = (device.index, )
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _dev(t):
+    if t.device.type == "cuda":
+        return t.device
+    if not torch.cuda.is_available():
+        raise _cabi.EnoLibraryError("the ODE path needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _mx(mxstep):
+    return 0 if (mxstep is None or math.isinf(mxstep)) else int(mxstep)
+
+
+def _f32c(t, device):
+    return t.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+def _fwd_call(spec, solver, y0, ts, pflat, rtol, atol, mxstep, trace_cap=0):
+    """eno_odeint_fwd on device tensors. -> (ys [T,B,D], stats dict, trace or None)."""
+    L = _cabi.lib()
+    device = y0.device
+    h = _cabi.ctx(device.index)
+    B, D = y0.shape
+    T = ts.numel()
+    desc = spec.desc(_cabi.AUG_NONE)
+    nbytes = L.eno_workspace_bytes(C.byref(desc), B, T, _cabi.TABLEAUX[solver], 0)
+    ws = _workspace(device, nbytes)
+    ys = torch.empty((T, B, D), dtype=torch.float32, device=device)
+    trace = torch.zeros((trace_cap, 4), dtype=torch.float32, device=device) if trace_cap else None
+    st = _cabi.Stats()
+    stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    with torch.cuda.device(device):
+        rc = L.eno_odeint_fwd(h, C.byref(desc), _cabi.TABLEAUX[solver], B, _ptr(y0), _ptr(ts), T, _ptr(pflat), None,
+                              float(rtol), float(atol), _mx(mxstep), _ptr(ws), ws.numel(), _ptr(ys), None,
+                              C.byref(st), _ptr(trace), trace_cap, stream)
+    _cabi.check(rc, h, "eno_odeint_fwd")
+    return ys, st.as_dict(), trace
+
+
+def _bwd_call(spec, aug, eps_in_args, ys, ts, pflat, g_y, g_r, rtol, atol, mxstep, trace_cap=0):
+    L = _cabi.lib()
+    device = ys.device
+    h = _cabi.ctx(device.index)
+    T, B, D = ys.shape
+    desc = spec.desc(aug, eps_in_args, reg_order=spec.reg_order if aug == _cabi.AUG_REG else 0)
+    nbytes = L.eno_workspace_bytes(C.byref(desc), B, T, 0, 1)
+    ws = _workspace(device, nbytes)
+    y0_bar = torch.empty((B, D), dtype=torch.float32, device=device)
+    r0_bar = torch.empty((B,), dtype=torch.float32, device=device)
+    ts_bar = torch.empty((T,), dtype=torch.float32, device=device)
+    p_bar = torch.empty((spec.n_params,), dtype=torch.float32, device=device)
+    trace = torch.zeros((trace_cap, 4), dtype=torch.float32, device=device) if trace_cap else None
+    st = (_cabi.Stats * max(T - 1, 1))()
+    stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    with torch.cuda.device(device):
+        rc = L.eno_odeint_bwd(h, C.byref(desc), B, _ptr(ys), _ptr(ts), T, _ptr(pflat), _ptr(g_y), _ptr(g_r),
+                              float(rtol), float(atol), _mx(mxstep), _ptr(ws), ws.numel(), _ptr(y0_bar), _ptr(r0_bar),
+                              _ptr(ts_bar), _ptr(p_bar), st, _ptr(trace), trace_cap, stream)
+    _cabi.check(rc, h, "eno_odeint_bwd")
+    return y0_bar, r0_bar, ts_bar, p_bar, [s.as_dict() for s in st][:max(T - 1, 0)], trace
+
+
+class _OdeintFn(torch.autograd.Function):
+    """custom_vjp pair (_odeint_fwd/_odeint_rev, lib/ode.py:1442-1444, 1494-1529) and the split
+    variant (_odeint_aux_one_fwd/_rev, 1478-1480, 1677-1684) when ``aug`` is AUG_REG."""
+
+    @staticmethod
+    def forward(ctx, spec, aug, eps_in_args, rtol, atol, mxstep, y0, r0, ts, pflat):
+        ys, st, _ = _fwd_call(spec, "dopri5", y0, ts, pflat, rtol, atol, mxstep)
+        last_stats["fwd"] = st
+        ctx.spec, ctx.aug, ctx.eps_in_args = spec, aug, eps_in_args
+        ctx.tols = (rtol, atol, mxstep)
+        ctx.save_for_backward(ys, ts, pflat)
+        T, B, _ = ys.shape
+        # aux outputs of the split wrappers are zeros of shape [T, B, 1] (lib/ode.py:998-1004)
+        rs = torch.zeros((T, B, 1), dtype=ys.dtype, device=ys.device)
+        nfe = torch.tensor(st["nfe"], dtype=torch.float32, device=ys.device)
+        ctx.mark_non_differentiable(nfe)
+        return ys, rs, nfe
+
+    @staticmethod
+    def backward(ctx, g_ys, g_rs, _g_nfe):
+        ys, ts, pflat = ctx.saved_tensors
+        rtol, atol, mxstep = ctx.tols
+        T, B, D = ys.shape
+        g_y = g_ys.contiguous().float()
+        g_r = g_rs.reshape(T, B).contiguous().float()
+        y0_bar, r0_bar, ts_bar, p_bar, st, _ = _bwd_call(ctx.spec, ctx.aug, ctx.eps_in_args, ys, ts, pflat, g_y, g_r,
+                                                        rtol, atol, mxstep)
+        last_stats["bwd"] = st
+        return None, None, None, None, None, None, y0_bar, r0_bar, ts_bar, p_bar
+
+
+def _split_args(func, args):
+    if len(args) != len(func.arg_names):
+        raise TypeError(f"{func!r} expects args {func.arg_names}, got {len(args)}")
+    named = dict(zip(func.arg_names, args))
+    return named.get("eps"), named["params"]
+
+
+def _require_spec(func, what):
+    if not isinstance(func, EnoFunc):
+        raise TypeError(f"{what}: func must be a dynamics-spec closure (e.g. MLPDynamics(...).dynamics_wrap); "
+                        "arbitrary Python callables cannot run inside the CUDA step kernel and there is no fallback")
+
+
+def odeint(func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=math.inf):
+    """Adaptive dopri5 solve; mirrors lib/ode.py:540-559.  -> (ys [T, B, D], nfe)."""
+    _require_spec(func, "odeint")
+    if func.kind != "plain":
+        raise NotImplementedError("odeint on the augmented closures (evaluation path, mnist.py:333-334) is not built yet; "
+                                  "training uses odeint_aux_one")
+    spec = func.spec
+    eps, params = _split_args(func, args)
+    out_dev = y0.device
+    dev = _dev(params if isinstance(params, torch.Tensor) else y0)
+    y = _f32c(y0.reshape(-1, spec.dim), dev)
+    ts = _f32c(torch.as_tensor(t), dev)
+    pflat = _f32c(spec.flatten_params(params), dev)
+    r0 = torch.zeros(y.shape[0], device=dev)
+    ys, _, nfe = _OdeintFn.apply(spec, _cabi.AUG_NONE, eps is not None, rtol, atol, mxstep, y, r0, ts, pflat)
+    ys = ys.reshape((ts.numel(),) + tuple(y0.shape))
+    if out_dev != ys.device:
+        ys, nfe = ys.to(out_dev), nfe.to(out_dev)
+    return ys, nfe
+
+
+def odeint_aux_one(fwd_func, rev_func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=math.inf):
+    """Split solve of lib/ode.py:657-676: forward integrates ``y0[0]`` with ``fwd_func`` and
+    returns zeros for the auxiliary state; backward runs the adjoint with ``rev_func`` on the
+    augmented state.  -> ((ys [T,B,D], rs [T,B,1]), nfe)."""
+    _require_spec(fwd_func, "odeint_aux_one")
+    _require_spec(rev_func, "odeint_aux_one")
+    if fwd_func.kind != "plain" or rev_func.kind != "aug" or fwd_func.spec is not rev_func.spec:
+        raise TypeError("odeint_aux_one expects (spec.fwd, spec.aug_dynamics) of the same dynamics spec")
+    spec = fwd_func.spec
+    eps, params = _split_args(rev_func, args)
+    y_in, r_in = y0
+    out_dev = y_in.device
+    dev = _dev(y_in)
+    y = _f32c(y_in.reshape(-1, spec.dim), dev)
+    r0 = _f32c(r_in.reshape(-1), dev)
+    ts = _f32c(torch.as_tensor(t), dev)
+    pflat = _f32c(spec.flatten_params(params), dev)
+    ys, rs, nfe = _OdeintFn.apply(spec, _cabi.AUG_REG, eps is not None, rtol, atol, mxstep, y, r0, ts, pflat)
+    if out_dev != ys.device:
+        ys, rs, nfe = ys.to(out_dev), rs.to(out_dev), nfe.to(out_dev)
+    return (ys, rs), nfe
+
+
+def _tableau_odeint(solver):
+    def run(func, rtol, atol, mxstep, y0, ts, *args):
+        _require_spec(func, f"_{solver}_odeint")
+        spec = func.spec
+        _, params = _split_args(func, args)
+        out_dev = y0.device
+        dev = _dev(y0)
+        y = _f32c(y0.reshape(-1, spec.dim), dev)
+        tsd = _f32c(torch.as_tensor(ts), dev)
+        pflat = _f32c(spec.flatten_params(params).detach(), dev)
+        ys, st, _ = _fwd_call(spec, solver, y.detach(), tsd, pflat, rtol, atol, mxstep)
+        last_stats["fwd"] = st
+        ys = ys.reshape((tsd.numel(),) + tuple(y0.shape))
+        nfe = torch.tensor(st["nfe"], dtype=torch.float32, device=out_dev)
+        return ys.to(out_dev), nfe
+    run.__name__ = f"_{solver}_odeint"
+    run.__doc__ = (f"Forward-only adaptive solve with the {solver} tableau on a flat or [B, D] state; mirrors "
+                   f"lib/ode.py's _{solver}_odeint(func, rtol, atol, mxstep, y0, ts, *args) -> (ys, nfe).")
+    return run
+
+
+_dopri5_odeint = _tableau_odeint("dopri5")
+_heun_odeint = _tableau_odeint("heun")
+_fehlberg_odeint = _tableau_odeint("fehlberg")
+_bosh_odeint = _tableau_odeint("bosh")
+_rk_fehlberg_odeint = _tableau_odeint("rk_fehlberg")
+_cash_karp_odeint = _tableau_odeint("cash_karp")
+_owrenzen_odeint = _tableau_odeint("owrenzen")
+_owrenzen5_odeint = _tableau_odeint("owrenzen5")
+_tanyam_odeint = _tableau_odeint("tanyam")
+
+
+def solve_with_trace(spec, solver, y0, ts, params, rtol, atol, mxstep=math.inf, trace_cap=4096):
+    """Forward solve that also returns the controller trace [(t, dt, ratio, accepted)]."""
+    dev = _dev(y0)
+    y = _f32c(y0.reshape(-1, spec.dim), dev)
+    tsd = _f32c(torch.as_tensor(ts), dev)
+    pflat = _f32c(spec.flatten_params(params).detach(), dev)
+    ys, st, trace = _fwd_call(spec, solver, y, tsd, pflat, rtol, atol, mxstep, trace_cap)
+    return ys, st, trace[: st["n_iters"]].cpu()
+
+
+def rhs(spec, mode, y, t, params, y_bar=None, r_bar=None):
+    """One evaluation of the integrated function (eno_rhs): mode 0 f, 1 (f, r_K), 2 the VJP."""
+    L = _cabi.lib()
+    dev = _dev(y)
+    h = _cabi.ctx(dev.index)
+    yd = _f32c(y.reshape(-1, spec.dim), dev)
+    B, D = yd.shape
+    pflat = _f32c(spec.flatten_params(params).detach(), dev)
+    desc = spec.desc(_cabi.AUG_REG if mode else _cabi.AUG_NONE, True)
+    nbytes = L.eno_workspace_bytes(C.byref(desc), B, 2, 0, 1)
+    ws = _workspace(dev, nbytes)
+    dy = torch.empty_like(yd)
+    r = torch.empty(B, device=dev)
+    zb = torch.empty_like(yd)
+    tbar = torch.empty(1, device=dev)
+    pbar = torch.empty(spec.n_params, device=dev)
+    yb = _f32c(y_bar.reshape(-1, D), dev) if y_bar is not None else None
+    rb = _f32c(r_bar.reshape(-1), dev) if r_bar is not None else None
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        rc = L.eno_rhs(h, C.byref(desc), mode, B, _ptr(yd), float(t), _ptr(pflat), None, _ptr(yb), _ptr(rb),
+                       _ptr(ws), ws.numel(), _ptr(dy), _ptr(r), _ptr(zb), _ptr(tbar), _ptr(pbar), stream)
+    _cabi.check(rc, h, "eno_rhs")
+    if mode == 0:
+        return dy
+    if mode == 1:
+        return dy, r
+    return dy, r, zb, tbar, pbar

@@ -1,0 +1,181 @@
+/*
+ * eno.h - C ABI of the B200-native adaptive ODE-solve path (libeno.so).
+ *
+ * Drop-in boundary for easy-neural-ode's lib/ode.py hot path.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference
+ * checkout).  Conventions:
+ *   - plain C, no torch / C++ types in any signature;
+ *   - every buffer pointer is a DEVICE pointer owned by the caller unless it is
+ *     called `*_host`; the library never allocates result buffers;
+ *   - arrays are row-major contiguous fp32: state [B, D], trajectories [T, B, D];
+ *   - the flat parameter vector of the MLP dynamics follows the reference's
+ *     ravel_pytree order of the Haiku dict (sorted keys: 'b' before 'w'):
+ *         [ b1 (H) | W1 ((D+1) x H) | b2 (D) | W2 ((H+1) x D) ]
+ *     with time being input row 0 of W1 and W2 (mnist.py:213-220);
+ *   - calls are asynchronous on `stream` until they have to read the device-side
+ *     controller state; they return after the solve has finished, with `stats`
+ *     filled in;
+ *   - return value: 0 ok, >0 solver condition (results still written, like the
+ *     reference which has no error channel, lib/ode.py:829-831), <0 usage error;
+ *   - thread-compatible: one in-flight call per eno_ctx.
+ */
+#ifndef ENO_H_
+#define ENO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ENO_ABI_VERSION 1
+
+/* status codes */
+#define ENO_OK 0
+#define ENO_MXSTEP 1        /* loop left because i >= mxstep (lib/ode.py:831) */
+#define ENO_DT_UNDERFLOW 2  /* loop left because !(dt > 0) (also NaN dt)      */
+#define ENO_NONFINITE 3     /* non-finite error ratio seen                     */
+#define ENO_E_ARG (-1)
+#define ENO_E_CUDA (-2)
+#define ENO_E_WORKSPACE (-3)
+#define ENO_E_UNSUPPORTED (-4)
+
+/* Butcher tableaux: odeint() is always dopri5 (lib/ode.py:746, 823-862); the others
+ * are the private forward-only loops lib/ode.py:1048-1390. */
+#define ENO_TABLEAU_DOPRI5 0
+#define ENO_TABLEAU_HEUN 1
+#define ENO_TABLEAU_FEHLBERG 2
+#define ENO_TABLEAU_BOSH 3
+#define ENO_TABLEAU_RK_FEHLBERG 4
+#define ENO_TABLEAU_CASH_KARP 5
+#define ENO_TABLEAU_OWRENZEN 6
+#define ENO_TABLEAU_OWRENZEN5 7
+#define ENO_TABLEAU_TANYAM 8
+#define ENO_NUM_TABLEAUX 9
+
+/* dynamics families (the reference's Python `func` cannot be called from a kernel;
+ * the spec names the closure instead) */
+#define ENO_ARCH_MLP_SIGMOID 0 /* MLPDynamics, mnist.py:195-222 */
+
+/* what the integrated function returns besides dy/dt (the reference's closures) */
+#define ENO_AUG_NONE 0 /* dynamics_wrap            mnist.py:285            */
+#define ENO_AUG_REG 1  /* aug_dynamics 'our'       mnist.py:302-308: (dy, r_K) */
+#define ENO_AUG_ALL 2  /* all_aug_dynamics         mnist.py:315-324: (dy, r_K, fro, kin) */
+
+typedef struct eno_ctx eno_ctx;
+
+typedef struct eno_dynamics_desc {
+  int32_t arch;      /* ENO_ARCH_*                                              */
+  int32_t D;         /* state width per sample (784 for MNIST); D % 4 == 0     */
+  int32_t H;         /* hidden width (100);                     H % 4 == 0     */
+  int32_t reg_order; /* K of the Taylor regulariser: 0 none, 2 (--reg r2), 3 (--reg r3),
+                        sol_recursive mnist.py:105-131 */
+  int32_t aug;       /* ENO_AUG_*                                               */
+  int32_t eps_in_args; /* 1 when the reference call passes eps among *args (mnist.py:330-332):
+                        its cotangent eps_bar (identically 0 for reg_type 'our') is then
+                        part of the adjoint state and dilutes the error mean            */
+} eno_dynamics_desc;
+
+typedef struct eno_stats {
+  float nfe;          /* the reference's counter: 2 + nfe_per_iter * iterations
+                         (lib/ode.py:845-847, 856)                              */
+  int32_t n_iters;    /* loop iterations, accepted + rejected                   */
+  int32_t n_accepted; /* accepted steps                                         */
+  int32_t status;     /* ENO_OK / ENO_MXSTEP / ENO_DT_UNDERFLOW / ENO_NONFINITE */
+  float last_dt;      /* controller's dt after the last iteration               */
+  float last_t;       /* solver time reached                                    */
+  int32_t n_launches; /* kernels launched by this call                          */
+  int32_t n_rhs;      /* dynamics evaluations actually performed per sample     */
+} eno_stats;
+
+/* One row per loop iteration when a trace buffer is supplied. */
+typedef struct eno_trace_row {
+  float t, dt, ratio, accepted;
+} eno_trace_row;
+
+int32_t eno_abi_version(void);
+const char* eno_last_error_string(const eno_ctx* ctx);
+
+/* Context = device id + pinned mailbox + cached kernel attributes. */
+int32_t eno_create(eno_ctx** out, int32_t device);
+void eno_destroy(eno_ctx* ctx);
+
+/* Number of parameters of a dynamics family: (D+1)*H + H + (H+1)*D + D. */
+int64_t eno_param_count(const eno_dynamics_desc* desc);
+/* Length of the flat adjoint ODE state, lib/ode.py:1516-1519:
+ * 2*(B*D + n_aux*B) + 1 + (eps_in_args ? B*D : 0) + P,  n_aux = 1 for ENO_AUG_REG, 0 for NONE. */
+int64_t eno_adjoint_state_size(const eno_dynamics_desc* desc, int32_t B);
+
+/* Scratch the solve needs (device bytes). mode: 0 forward, 1 backward. */
+size_t eno_workspace_bytes(const eno_dynamics_desc* desc, int32_t B, int32_t T, int32_t tableau, int32_t mode);
+
+/*
+ * Forward solve.  Replaces
+ *   odeint(func, y0, t, *args, rtol, atol, mxstep)            lib/ode.py:540-559, 742-747
+ *   -> _dopri5_odeint                                        lib/ode.py:823-862
+ *   and _X_odeint(func, rtol, atol, mxstep, y0, ts, *args)    lib/ode.py:1048-1390
+ * for func = desc (aug == ENO_AUG_NONE: y [B,D];  ENO_AUG_REG: (y, r[B]);
+ * ENO_AUG_ALL: (y, r, fro, kin)).  The forward half of odeint_aux_one /
+ * odeint_sepaux (lib/ode.py:993-1018) is this call with ENO_AUG_NONE: the aux
+ * outputs are zeros and are produced by the host wrapper.
+ *
+ *   y0      [B, D]            ts  [T] strictly increasing (device)
+ *   params  [P]               eps [B, D] or NULL (only ENO_AUG_ALL reads it)
+ *   ys_out  [T, B, D]         aux_out [T, n_aux, B] or NULL (n_aux = 1 REG, 3 ALL)
+ *   mxstep <= 0 means unbounded (np.inf).
+ *   trace_out: NULL or device array of trace_cap rows.
+ */
+int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tableau, int32_t B, const float* y0,
+                       const float* ts, int32_t T, const float* params, const float* eps, float rtol, float atol,
+                       int32_t mxstep, void* workspace, size_t workspace_bytes, float* ys_out, float* aux_out,
+                       eno_stats* stats_host, eno_trace_row* trace_out, int32_t trace_cap, void* stream);
+
+/*
+ * Backward (adjoint) solve.  Replaces
+ *   _odeint_rev(func, rtol, atol, mxstep, res, g)             lib/ode.py:1494-1529
+ *   as reached through _odeint_aux_one_rev                    lib/ode.py:1677-1684
+ * for rev_func = aug_dynamics(reg_type 'our') (mnist.py:302-308), i.e. the
+ * augmented state per sample is (y [D], r) and the adjoint ODE state is
+ * (y, r, y_bar, r_bar, t0_bar, eps_bar = 0, params_bar).
+ *
+ *   ys   [T, B, D]  forward trajectory (residuals, lib/ode.py:1444)
+ *   g_y  [T, B, D]  cotangent of ys;   g_r [T, B] cotangent of the aux output r
+ *   y0_bar_out [B, D], r0_bar_out [B], ts_bar_out [T], params_bar_out [P]
+ *   stats_host: array of T-1 entries, one per backward segment (i = T-1 .. 1).
+ */
+int32_t eno_odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, const float* ys, const float* ts,
+                       int32_t T, const float* params, const float* g_y, const float* g_r, float rtol, float atol,
+                       int32_t mxstep, void* workspace, size_t workspace_bytes, float* y0_bar_out,
+                       float* r0_bar_out, float* ts_bar_out, float* params_bar_out, eno_stats* stats_host,
+                       eno_trace_row* trace_out, int32_t trace_cap, void* stream);
+
+/*
+ * One evaluation of the integrated function (unit-test hook), the closures of
+ * mnist.py:285-324.
+ *   mode 0: dy = f(y, t)                                       -> dy_out [B,D]
+ *   mode 1: (dy, r_K [, fro, kin]) per desc->aug               -> dy_out, aux_out [n_aux, B]
+ *   mode 2: vjp of aug_dynamics('our') at (y, t) with cotangent (y_bar [B,D], r_bar [B])
+ *           -> dy_out, aux_out [1,B], ybar_dot_out [B,D], tbar_out [1], params_bar_out [P]
+ *              (lib/ode.py:1498-1504)
+ */
+int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32_t B, const float* y, float t,
+                const float* params, const float* eps, const float* y_bar, const float* r_bar, void* workspace,
+                size_t workspace_bytes, float* dy_out, float* aux_out, float* ybar_dot_out, float* tbar_out,
+                float* params_bar_out, void* stream);
+
+/*
+ * Measurement hooks used by bench.py (no reference counterpart; the reference only wall-clocks the
+ * whole jitted update, mnist.py:632-640).  With profiling on, the step kernels are bracketed by CUDA
+ * events on the launch stream; eno_profile_read returns and clears the accumulated milliseconds and
+ * launch counts per kernel kind: [0] forward step, [1] adjoint per-sample step, [2] adjoint
+ * parameter-gradient step, [3] unused.  eno_ffma_peak measures the non-tensor fp32 FMA peak (TFLOP/s).
+ */
+int32_t eno_profile_enable(eno_ctx* ctx, int32_t on);
+int32_t eno_profile_read(eno_ctx* ctx, double* ms_out /*[4]*/, int64_t* count_out /*[4]*/);
+int32_t eno_ffma_peak(eno_ctx* ctx, double* tflops_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENO_H_ */

@@ -1,0 +1,109 @@
+"""The oracle (oracle/ode_oracle.py) against the golden vectors that the UNMODIFIED reference solver
+produced (tests/golden/make_golden.py).  Same backend (torch CPU), so agreement is expected to the
+last bit for the solver core; a small tolerance is kept for library-version drift."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dynamics_oracle as do, ode_oracle as oo
+from tests.util import load, params_from_flat, flat_from_params
+
+TIGHT = dict(rtol=2e-6, atol=1e-7)
+TABLEAUX = ["heun", "fehlberg", "bosh", "rk_fehlberg", "cash_karp", "owrenzen", "owrenzen5", "tanyam"]
+
+
+def test_kat_const_problem():
+    g = load("kat_const.npz")
+    a, b = 0.2, 3.0
+    f = lambda y, t: a + (y - (a * t + b)) ** 5
+    ts = torch.tensor([1., 8.])
+    y0 = torch.tensor([a + b])
+    ys, nfe, _ = oo.solve(f, y0, ts, 1e-5, 1e-5)
+    assert nfe == float(g["dopri5_nfe"])
+    np.testing.assert_allclose(ys.numpy(), g["dopri5_y"], **TIGHT)
+    assert abs(float(ys[-1]) - (a * 8 + b)) < 1e-5            # exact solution y = a t + b
+    for name in TABLEAUX:
+        ys, nfe, _ = oo.solve(f, y0, ts, 1e-5, 1e-5, solver=name)
+        assert nfe == float(g[f"{name}_nfe"]), name
+        np.testing.assert_allclose(ys.numpy(), g[f"{name}_y"], **TIGHT)
+
+
+@pytest.fixture(scope="module")
+def fwd_case():
+    g = load("mlp_forward.npz")
+    B, D, H = int(g["B"]), int(g["D"]), int(g["H"])
+    return g, params_from_flat(g["params"], D, H), torch.as_tensor(g["x0"])
+
+
+@pytest.mark.parametrize("tag", ["d", "5", "3"])
+def test_dopri5_forward(fwd_case, tag):
+    g, params, x0 = fwd_case
+    tol = float(g[f"fwd_{tag}_tol"])
+    ys, nfe = oo.odeint(lambda y, t, p: do.mlp_dynamics(p, y, t), x0, torch.tensor([0., 1.]), params, rtol=tol, atol=tol)
+    assert nfe == float(g[f"fwd_{tag}_nfe"])
+    np.testing.assert_allclose(ys.numpy(), g[f"fwd_{tag}_y"], **TIGHT)
+
+
+def test_dopri5_multi_output_and_mxstep(fwd_case):
+    g, params, x0 = fwd_case
+    f = lambda y, t, p: do.mlp_dynamics(p, y, t)
+    ys, nfe = oo.odeint(f, x0, torch.as_tensor(g["fwd_multi_ts"]), params, rtol=1e-6, atol=1e-6)
+    assert nfe == float(g["fwd_multi_nfe"])
+    np.testing.assert_allclose(ys.numpy(), g["fwd_multi_y"], **TIGHT)
+    ys, nfe = oo.odeint(f, x0, torch.tensor([0., 0.07]), params, rtol=1e-7, atol=1e-7, mxstep=2)
+    assert nfe == float(g["fwd_mx2_nfe"])
+    np.testing.assert_allclose(ys.numpy(), g["fwd_mx2_y"], **TIGHT)
+
+
+@pytest.mark.parametrize("name", TABLEAUX)
+def test_tableau_sweep(fwd_case, name):
+    g, params, x0 = fwd_case
+    fun = lambda y, t: do.mlp_dynamics(params, y, t).reshape(-1)
+    for tag, tol in [("3", 1e-3), ("5", 1e-5)]:
+        if f"{name}_{tag}_y" not in g:
+            continue
+        ys, nfe, _ = oo.solve(fun, x0.reshape(-1), torch.tensor([0., 1.]), tol, tol, solver=name)
+        assert nfe == float(g[f"{name}_{tag}_nfe"]), (name, tag)
+        np.testing.assert_allclose(ys.numpy(), g[f"{name}_{tag}_y"], **TIGHT)
+
+
+@pytest.mark.parametrize("reg", ["r2", "r3"])
+def test_split_solve_and_adjoint(reg):
+    g = load("mlp_adjoint.npz")
+    B, D, H = int(g["B"]), int(g["D"]), int(g["H"])
+    params = params_from_flat(g["params"], D, H)
+    x0, eps, gy = (torch.as_tensor(g[k]) for k in ("x0", "eps", "gy"))
+    cl = do.make_mnist_closures(reg)
+    ts = torch.tensor([0., 1.])
+    tol = 1e-5
+    res, nfe = oo.odeint_split_fwd(cl["fwd"], (x0, torch.zeros(B)), ts, eps, params, n_aux=1, rtol=tol, atol=tol)
+    k = f"{reg}_5"
+    assert nfe == float(g[f"{k}_nfe"])
+    np.testing.assert_allclose(res[0][-1].numpy(), g[f"{k}_y1"], **TIGHT)
+    gg = (torch.zeros_like(res[0]), torch.zeros_like(res[1]))
+    gg[0][-1] = gy
+    gg[1][-1] = float(g["g_r"])
+    out = oo.odeint_split_rev(cl["aug_dynamics"], tol, tol, math.inf, res, ts, (eps, params), gg)
+    np.testing.assert_allclose(out[0][0].numpy(), g[f"{k}_x0_bar"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out[1].numpy(), g[f"{k}_ts_bar"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out[2].numpy(), g[f"{k}_eps_bar"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(flat_from_params(out[3]).numpy(), g[f"{k}_params_bar"], rtol=1e-5, atol=1e-6)
+
+
+def test_pendulum_adjoint_multi_segment():
+    g = load("pendulum.npz")
+
+    def pend(y, t, m, gr):
+        return torch.stack([y[1], -m * y[1] - gr * torch.sin(y[0])])
+    y0 = torch.tensor([math.pi - 0.1, 0.0])
+    ts = torch.as_tensor(g["ts"])
+    args = (torch.tensor(0.25), torch.tensor(9.8))
+    ys, nfe, _ = oo.solve(lambda y, t: pend(y, t, *args), y0, ts, 1e-6, 1e-6)
+    assert nfe == float(g["nfe"])
+    np.testing.assert_allclose(ys.numpy(), g["ys"], **TIGHT)
+    out = oo.odeint_rev(pend, 1e-6, 1e-6, math.inf, ys, ts, args, torch.ones_like(ys))
+    np.testing.assert_allclose(out[0].numpy(), g["y0_bar"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out[1].numpy(), g["ts_bar"], rtol=1e-5, atol=1e-6)
+    assert abs(float(out[2]) - float(g["m_bar"])) < 1e-4 and abs(float(out[3]) - float(g["g_bar"])) < 1e-4
