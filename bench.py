@@ -88,16 +88,17 @@ def cpu_train_steps(n_steps, warmup, threads):
     p_post = do.init_post_params(D, seed=1)
     vel = None
     times, info = [], {}
-    for s in range(warmup + n_steps):
-        images, labels, eps = synth_batch(0, s)
+    for s in range(-warmup, n_steps):
+        images, labels, eps = synth_batch(0, max(s, 0))
         t0 = time.perf_counter()
         out = do.train_step_grads(p_ode, p_post, do.pre_ode(images), labels, eps, LAM, reg="r3", rtol=TOL, atol=TOL)
-        if vel is None:
-            vel = {k: {kk: torch.zeros_like(vv) for kk, vv in v.items()} for k, v in p_ode.items()}
-        p_ode, vel = do.momentum_update(p_ode, vel, out["grads"]["ode"], 1e-1)
-        dt = time.perf_counter() - t0
-        if s >= warmup:
-            times.append(dt)
+        if s >= 0:   # warm-up evaluations (s < 0) do not move the parameters
+            params = {"ode": p_ode, "post": p_post}
+            if vel is None:
+                vel = do.ode_oracle_tree_zeros(params)
+            params, vel = do.momentum_update(params, vel, out["grads"], 1e-1)
+            p_ode, p_post = params["ode"], params["post"]
+            times.append(time.perf_counter() - t0)
         info = dict(nfe=float(out["nfe"]), fwd_iters=out["fwd_stats"]["n_iters"],
                     bwd_iters=out["bwd_stats"][0]["n_iters"])
     return sum(times) / len(times), info
@@ -110,7 +111,7 @@ def run_reference(args, rank, world):
         return
     threads = len(os.sched_getaffinity(0))
     steps = max(1, min(args.steps, 40))
-    sec, info = cpu_train_steps(steps, min(args.warmup, 1), threads)
+    sec, info = cpu_train_steps(steps, 1, threads)
     val = 1.0 / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -118,9 +119,9 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B, "rtol": TOL, "atol": TOL},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{steps} full train steps (forward solve + adjoint + momentum) after "
-                                   f"{min(args.warmup, 1)} warm-up, torch CPU fp32, {threads} threads; "
-                                   f"nfe {info['nfe']}, adjoint iterations {info['bwd_iters']}"},
+                         "sample": f"train steps 0..{steps - 1} from the initial parameters (forward solve + adjoint + "
+                                   f"momentum update each) after 1 untimed warm-up evaluation, torch CPU fp32, {threads} threads; "
+                                   f"last step nfe {info['nfe']}, adjoint iterations {info['bwd_iters']}"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "nfe_per_s": info["nfe"] * B * val,
     }
@@ -174,9 +175,14 @@ def main():
         model.apply_grads(flat[:n1], flat[n1:n1 + n2].reshape(g["post_w"].shape), flat[n1 + n2:])
         return out
 
+    # Every measured leg (device-timed, e2e, profiled, CPU) replays the SAME training trajectory:
+    # steps 0..K-1 from the initial parameters, so the arms do identical work (the solver takes
+    # more iterations as training stiffens the dynamics).
+    snap = model.snapshot()
     for s in range(max(args.warmup, 3)):
         out = step(s)
     torch.cuda.synchronize()
+    model.restore(snap)
 
     # ---- timed region: device-resident inputs, L2 flushed between steps, CUDA events, max over ranks
     sampler = ClockSampler(local_rank)
@@ -216,6 +222,7 @@ def main():
         return float(o["loss"].item())             # device -> host read of the step's result
     for s in range(3):
         step_e2e(s)
+    model.restore(snap)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -233,8 +240,9 @@ def main():
     # ---- roofline of the dominant kernel (adjoint per-sample step kernel), separate profiled pass
     L = _cabi.lib()
     h = _cabi.ctx(dev.index)
+    model.restore(snap)
     L.eno_profile_enable(h, 1)
-    for s in range(min(args.steps, 10)):
+    for s in range(args.steps):
         step(s)
     torch.cuda.synchronize()
     L.eno_profile_enable(h, 0)
@@ -277,10 +285,12 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))
-        sec, info = cpu_train_steps(5, 1, threads)
+        n_cpu = min(args.steps, 8)
+        sec, info = cpu_train_steps(n_cpu, 1, threads)
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "5 full train steps after 1 warm-up, oracle port (torch CPU fp32), "
-                                          f"nfe {info['nfe']}, adjoint iterations {info['bwd_iters']}"}
+                                "sample": f"train steps 0..{n_cpu - 1} of the same trajectory (the GPU legs time steps "
+                                          f"0..{args.steps - 1}), oracle port, torch CPU fp32, {threads} threads; "
+                                          f"last step nfe {info['nfe']}, adjoint iterations {info['bwd_iters']}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -40,6 +40,14 @@ class MnistNode:
         self.post_b = p_post["b"].to(self.device).clone()
         self._reset_velocity()
 
+    def snapshot(self):
+        """Copy of the trainable state (params + momentum)."""
+        return [t.clone() for t in (self.p_ode, self.post_w, self.post_b, self.v_ode, self.v_w, self.v_b)]
+
+    def restore(self, snap):
+        for dst, src in zip((self.p_ode, self.post_w, self.post_b, self.v_ode, self.v_w, self.v_b), snap):
+            dst.copy_(src)
+
     def _reset_velocity(self):
         self.v_ode = torch.zeros_like(self.p_ode)
         self.v_w = torch.zeros_like(self.post_w)

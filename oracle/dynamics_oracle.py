@@ -198,6 +198,10 @@ def train_step_grads(ode_params, post, x0, labels, eps, lam, reg="r3", rtol=1.4e
                 x0_bar=y0_bar[0], ts_bar=ts_bar, fwd_stats=fst, bwd_stats=bst)
 
 
+def ode_oracle_tree_zeros(tree):
+    return {k: (ode_oracle_tree_zeros(v) if isinstance(v, dict) else torch.zeros_like(v)) for k, v in tree.items()}
+
+
 def momentum_update(params, velocity, grads, lr, mass=0.9):
     """jax.experimental.optimizers.momentum: v <- mass*v + g ; x <- x - lr*v."""
     new_p, new_v = {}, {}
