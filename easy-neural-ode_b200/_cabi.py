@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeno.so")
+LIB_PATH = os.environ.get("ENO_LIB") or os.path.join(_HERE, "libeno.so")   # ENO_LIB: development variants only
 
 ENO_OK, ENO_MXSTEP, ENO_DT_UNDERFLOW, ENO_NONFINITE = 0, 1, 2, 3
 ARCH_MLP_SIGMOID = 0

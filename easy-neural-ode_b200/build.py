@@ -32,8 +32,17 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile if sources are newer than the library; returns the library path."""
+def build(force=False, verbose=False, phases=False):
+    """Compile if sources are newer than the library; returns the library path.
+    phases=True builds the development variant libeno_phases.so with in-kernel phase clocks."""
+    if phases:
+        out = os.path.join(HERE, "libeno_phases.so")
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-DENO_PHASES"] + SOURCES + ["-o", out]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed building libeno_phases.so")
+        return out
     if not force and not _stale():
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + SOURCES + ["-o", LIB]
@@ -47,4 +56,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, phases="--phases" in sys.argv))

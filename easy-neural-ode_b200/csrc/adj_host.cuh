@@ -1,0 +1,303 @@
+// Host-side driver of the adjoint solve: workspace carving, path selection (cluster-resident vs
+// streamed weights), launch sequence of lib/ode.py:1494-1529 per output segment.
+#pragma once
+#include <algorithm>
+#include <string>
+
+#include "adj_kernels.cuh"
+#include "cl_kernels.cuh"
+#include "tableaux.cuh"
+
+namespace eno {
+
+// ======================================================================================
+// host side
+// ======================================================================================
+inline size_t adj_align(size_t x) { return (x + 255) / 256 * 256; }
+
+inline size_t adj_ws_bytes(int B, int D, int H) {
+  const size_t N = (size_t)B * D, P = (size_t)(D + 1) * H + H + (size_t)(H + 1) * D + D;
+  const PgradGeom g = pgrad_geom(D, H);
+  size_t s = 0;
+  s += adj_align(sizeof(Ctrl)) + adj_align(sizeof(AdjScalars));
+  s += 4 * adj_align(3 * N * 4);                    // Z, ZB, FZ, FZB
+  s += 2 * adj_align(3 * (size_t)B * 4) + adj_align((size_t)B * 4);  // RS, FR, RB
+  s += adj_align(2 * N * 4);                        // MIDZB
+  s += 2 * adj_align(3 * P * 4) + adj_align(2 * P * 4);             // PB, FP, MIDP
+  s += kSlots * (2 * adj_align(3 * N * 4) + 2 * adj_align(3 * (size_t)B * H * 4) + adj_align((size_t)kC * B * 4));
+  s += 3 * adj_align((size_t)kC * B * 8) + 2 * adj_align((size_t)g.grid * 8);
+  s += adj_align(N * 4) + adj_align(P * 4);         // YBAR, POUT
+  s += 2 * adj_align((size_t)D * H * 4);            // transposes
+  return s + 4096;
+}
+
+struct AdjCarver {
+  char* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += adj_align(n * sizeof(T));
+    return p;
+  }
+};
+
+inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArgs* a) {
+  const size_t N = (size_t)B * D, P = (size_t)(D + 1) * H + H + (size_t)(H + 1) * D + D;
+  const PgradGeom g = pgrad_geom(D, H);
+  AdjCarver cv{static_cast<char*>(ws)};
+  a->ctrl = cv.take<Ctrl>(1);
+  a->sc = cv.take<AdjScalars>(1);
+  a->Z = cv.take<float>(3 * N); a->ZB = cv.take<float>(3 * N);
+  a->FZ = cv.take<float>(3 * N); a->FZB = cv.take<float>(3 * N);
+  a->RS = cv.take<float>(3 * (size_t)B); a->FR = cv.take<float>(3 * (size_t)B); a->RB = cv.take<float>(B);
+  a->MIDZB = cv.take<float>(2 * N);
+  a->PB = cv.take<float>(3 * P); a->FP = cv.take<float>(3 * P); a->MIDP = cv.take<float>(2 * P);
+  for (int j = 0; j < kSlots; ++j) {
+    a->slot[j].S = cv.take<float>(3 * N);
+    a->slot[j].G = cv.take<float>(3 * N);
+    a->slot[j].A = cv.take<float>(3 * (size_t)B * H);
+    a->slot[j].Hh = cv.take<float>(3 * (size_t)B * H);
+    a->slot[j].tbar = cv.take<float>((size_t)kC * B);
+  }
+  a->rowpart0 = cv.take<double>((size_t)kC * B); a->rowpart1 = cv.take<double>((size_t)kC * B);
+  a->rowpart2 = cv.take<double>((size_t)kC * B);
+  a->n_rp = B;
+  a->ppart0 = cv.take<double>(g.grid); a->ppart1 = cv.take<double>(g.grid);
+  a->YBAR = cv.take<float>(N);
+  a->POUT = cv.take<float>(P);
+  float* W1xT = cv.take<float>((size_t)D * H);
+  float* W2xT = cv.take<float>((size_t)D * H);
+  a->w = mlp_weights_from_flat(params, D, H, W1xT, W2xT);
+  a->B = B; a->P = (int)P; a->N = N;
+  a->n_state = (float)(2 * (N + (size_t)B) + 1 + N + P);
+}
+
+inline int adj_pick_rows(int B, int D, int H, int sms) {
+  int R = 1;
+  if (B > sms) R = 2;
+  while (R > 1 && adj_smem_bytes(R, D, H, kAdjStages) > 220 * 1024) R >>= 1;
+  return R;
+}
+
+#define ENO_ADJ_CHECK(expr)                                                                 \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      if (err) *err = std::string(#expr) + ": " + cudaGetErrorString(e_);                   \
+      return ENO_E_CUDA;                                                                    \
+    }                                                                                       \
+  } while (0)
+
+template <int R, int K>
+int adj_launch_rows(int mode, const AdjArgs& a, int grid, size_t smem, float rhs_tau, cudaStream_t st,
+                    std::string* err) {
+  switch (mode) {
+    case ADJ_STEP:
+      ENO_ADJ_CHECK(cudaFuncSetAttribute(k_adj_rows<R, K, ADJ_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_adj_rows<R, K, ADJ_STEP><<<grid, kThreads, smem, st>>>(a, rhs_tau);
+      break;
+    case ADJ_INIT0:
+      ENO_ADJ_CHECK(cudaFuncSetAttribute(k_adj_rows<R, K, ADJ_INIT0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_adj_rows<R, K, ADJ_INIT0><<<grid, kThreads, smem, st>>>(a, rhs_tau);
+      break;
+    case ADJ_INIT1:
+      ENO_ADJ_CHECK(cudaFuncSetAttribute(k_adj_rows<R, K, ADJ_INIT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_adj_rows<R, K, ADJ_INIT1><<<grid, kThreads, smem, st>>>(a, rhs_tau);
+      break;
+    default:
+      ENO_ADJ_CHECK(cudaFuncSetAttribute(k_adj_rows<R, K, ADJ_RHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_adj_rows<R, K, ADJ_RHS><<<grid, kThreads, smem, st>>>(a, rhs_tau);
+  }
+  return 0;
+}
+
+inline int adj_rows(int R, int K, int mode, const AdjArgs& a, int grid, size_t smem, float rhs_tau, cudaStream_t st,
+                    std::string* err) {
+#define ENO_RK(RR, KK) if (R == RR && K == KK) return adj_launch_rows<RR, KK>(mode, a, grid, smem, rhs_tau, st, err);
+  ENO_RK(1, 0) ENO_RK(1, 2) ENO_RK(1, 3) ENO_RK(2, 0) ENO_RK(2, 2) ENO_RK(2, 3)
+#undef ENO_RK
+  if (err) *err = "adjoint: unsupported (rows per CTA, reg_order) combination";
+  return ENO_E_UNSUPPORTED;
+}
+
+// One launch of the per-sample kernel on the chosen path.
+struct AdjPlan {
+  bool cluster;
+  int R, grid;
+  size_t smem;
+};
+
+inline AdjPlan adj_plan(int B, int D, int H, int sms, int path_mode, bool single_rhs) {
+  AdjPlan p;
+  p.cluster = path_mode != 1 && cl_supported(D, H, kClRows, kAdjStages, true);
+  if (p.cluster) {
+    p.R = kClRows;
+    p.grid = cl_grid(B);
+    p.smem = cl_smem_bytes(kClRows, D, H, kAdjStages, true);
+  } else {
+    p.R = single_rhs ? 1 : adj_pick_rows(B, D, H, sms);
+    p.grid = (B + p.R - 1) / p.R;
+    p.smem = adj_smem_bytes(p.R, D, H, single_rhs ? 2 : kAdjStages);
+  }
+  return p;
+}
+
+inline int adj_rows_any(const AdjPlan& p, int K, int mode, const AdjArgs& a, float rhs_tau, cudaStream_t st,
+                        std::string* err) {
+  if (p.cluster) {
+    cudaError_t e = cl_adj_rows(K, mode, a, p.grid, p.smem, rhs_tau, st);
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("cluster launch of k_cl_adj_rows: ") + cudaGetErrorString(e);
+      return ENO_E_CUDA;
+    }
+    return 0;
+  }
+  return adj_rows(p.R, K, mode, a, p.grid, p.smem, rhs_tau, st, err);
+}
+
+inline void adj_transposes(const AdjArgs& a, cudaStream_t st) {
+  const int D = a.w.D, H = a.w.H;
+  dim3 blk(32, 8);
+  k_transpose<<<dim3((H + 31) / 32, (D + 31) / 32), blk, 0, st>>>(a.w.W1x, const_cast<float*>(a.w.W1xT), D, H);
+  k_transpose<<<dim3((D + 31) / 32, (H + 31) / 32), blk, 0, st>>>(a.w.W2x, const_cast<float*>(a.w.W2xT), H, D);
+}
+
+inline int adj_solve(Profiler* prof, int path_mode, std::string* err, Ctrl* mailbox, int* hint, int sms, const eno_dynamics_desc* desc, int B,
+                     const float* ys, const float* ts, int T, const float* params, const float* g_y, const float* g_r,
+                     float rtol, float atol, int mxstep, void* ws, size_t ws_bytes, float* y0_bar_out,
+                     float* r0_bar_out, float* ts_bar_out, float* params_bar_out, eno_stats* stats,
+                     eno_trace_row* trace, int trace_cap, cudaStream_t st) {
+  const int D = desc->D, H = desc->H, K = desc->reg_order;
+  if (!(K == 0 || K == 2 || K == 3)) { if (err) *err = "eno_odeint_bwd: reg_order must be 0, 2 or 3"; return ENO_E_UNSUPPORTED; }
+  if (B <= 0 || T < 1 || !ys || !ts || !params || !g_y || !g_r || !ws || !y0_bar_out || !r0_bar_out || !ts_bar_out ||
+      !params_bar_out) { if (err) *err = "eno_odeint_bwd: null pointer or empty batch"; return ENO_E_ARG; }
+  if (ws_bytes < adj_ws_bytes(B, D, H)) { if (err) *err = "eno_odeint_bwd: workspace too small"; return ENO_E_WORKSPACE; }
+  const size_t N = (size_t)B * D;
+  AdjArgs a = {};
+  adj_carve(ws, B, D, H, params, &a);
+  a.np = (K == 0) ? 1 : K;
+  {
+    const size_t n_aux = (desc->aug == ENO_AUG_NONE) ? 0 : 1;
+    a.n_state = (float)(2 * (N + n_aux * (size_t)B) + 1 + (desc->eps_in_args ? N : 0) + (size_t)a.P);
+  }
+  a.trace = trace;
+  Tableau tab;
+  fill_tableau(ENO_TABLEAU_DOPRI5, &tab);
+  ENO_ADJ_CHECK(cudaMemcpyToSymbolAsync(c_tab, &tab, sizeof(Tableau), 0, cudaMemcpyHostToDevice, st));
+  const AdjPlan plan = adj_plan(B, D, H, sms, path_mode, false);
+  if (!plan.cluster) adj_transposes(a, st);
+  a.n_rp = plan.cluster ? kC * B : B;
+  const PgradGeom geo = pgrad_geom(D, H);
+  const int egrid = (int)std::min<size_t>((std::max(N, (size_t)a.P) + 255) / 256, (size_t)4 * sms);
+  const int mx = mxstep <= 0 ? INT_MAX : mxstep;
+  int worst = ENO_OK;
+  if (T == 1) {   // nothing to integrate: y0_bar = g[0], everything else zero (empty scan)
+    ENO_ADJ_CHECK(cudaMemcpyAsync(y0_bar_out, g_y, N * 4, cudaMemcpyDeviceToDevice, st));
+    ENO_ADJ_CHECK(cudaMemcpyAsync(r0_bar_out, g_r, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    ENO_ADJ_CHECK(cudaMemsetAsync(ts_bar_out, 0, 4, st));
+    ENO_ADJ_CHECK(cudaMemsetAsync(params_bar_out, 0, (size_t)a.P * 4, st));
+    ENO_ADJ_CHECK(cudaStreamSynchronize(st));
+    return ENO_OK;
+  }
+  for (int i = T - 1; i >= 1; --i) {
+    int launches = 0;
+    const int first = (i == T - 1);
+    a.g_y = g_y + (size_t)i * N;
+    a.g_r = g_r + (size_t)i * B;
+    a.g_y_prev = g_y + (size_t)(i - 1) * N;
+    a.tbar_out = ts_bar_out + i;
+    k_adj_seg_begin<<<egrid, 256, 0, st>>>(a, ys + (size_t)i * N, a.g_y, a.g_r, ts, i, first, rtol, atol, mx,
+                                           trace ? trace_cap : 0);
+    int rc;
+    if ((rc = adj_rows_any(plan, K, ADJ_INIT0, a, 0.f, st, err))) return rc;
+    k_adj_pgrad<ADJ_INIT0><<<geo.grid, kSlots * kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
+    if ((rc = adj_rows_any(plan, K, ADJ_INIT1, a, 0.f, st, err))) return rc;
+    k_adj_pgrad<ADJ_INIT1><<<geo.grid, kSlots * kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
+    launches += 5;
+    int chunk = *hint;
+    for (;;) {
+      for (int k = 0; k < chunk; ++k) {
+        int ps = prof->begin(PROF_ADJ_ROWS, st);
+        if ((rc = adj_rows_any(plan, K, ADJ_STEP, a, 0.f, st, err))) return rc;
+        prof->end(ps, st);
+        ps = prof->begin(PROF_ADJ_PGRAD, st);
+        k_adj_pgrad<ADJ_STEP><<<geo.grid, kSlots * kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
+        prof->end(ps, st);
+        launches += 2;
+      }
+      // A segment has one target, so a dense output can only become pending on the iteration that ends
+      // it; later launches exit at their first instruction and leave the rings intact.  One output
+      // launch per chunk (a no-op unless the segment finished) is therefore enough.
+      k_adj_out<<<egrid, 256, 0, st>>>(a);
+      ++launches;
+      ENO_ADJ_CHECK(cudaMemcpyAsync(mailbox, a.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+      ENO_ADJ_CHECK(cudaStreamSynchronize(st));
+      if (mailbox->done) break;
+      chunk = 4;
+    }
+    {
+      int valid[PROF_KINDS] = {0, mailbox->n_iters, mailbox->n_iters, 0};
+      prof->resolve(valid);
+    }
+    *hint = mailbox->n_iters + 1 > 64 ? 64 : mailbox->n_iters + 1;
+    if (stats) {
+      eno_stats* s = stats + (T - 1 - i);
+      s->nfe = (float)mailbox->nfe; s->n_iters = mailbox->n_iters; s->n_accepted = mailbox->n_accepted;
+      s->status = mailbox->status; s->last_dt = mailbox->dt; s->last_t = mailbox->t; s->n_launches = launches;
+      s->n_rhs = 2 + 6 * mailbox->n_iters;
+    }
+    if (mailbox->status != ENO_OK && worst == ENO_OK) worst = mailbox->status;
+    trace = nullptr;  // only the first segment is traced
+    a.trace = nullptr;
+  }
+  k_adj_finish<<<(B + 255) / 256, 256, 0, st>>>(a, g_r, r0_bar_out, ts_bar_out);
+  ENO_ADJ_CHECK(cudaMemcpyAsync(y0_bar_out, a.YBAR, N * 4, cudaMemcpyDeviceToDevice, st));
+  ENO_ADJ_CHECK(cudaMemcpyAsync(params_bar_out, a.POUT, (size_t)a.P * 4, cudaMemcpyDeviceToDevice, st));
+  ENO_ADJ_CHECK(cudaStreamSynchronize(st));
+  ENO_ADJ_CHECK(cudaGetLastError());
+  return worst;
+}
+
+inline int adj_rhs(int path_mode, std::string* err, int sms, const eno_dynamics_desc* desc, int mode, int B, const float* y, float t,
+                   const float* params, const float* y_bar, const float* r_bar, void* ws, size_t ws_bytes, float* dy_out,
+                   float* aux_out, float* ybar_dot_out, float* tbar_out, float* params_bar_out, cudaStream_t st) {
+  const int D = desc->D, H = desc->H, K = desc->reg_order;
+  if (!(K == 0 || K == 2 || K == 3)) { if (err) *err = "eno_rhs: reg_order must be 0, 2 or 3"; return ENO_E_UNSUPPORTED; }
+  if (!ws || ws_bytes < adj_ws_bytes(B, D, H)) { if (err) *err = "eno_rhs: workspace too small"; return ENO_E_WORKSPACE; }
+  if (mode == 2 && (!y_bar || !r_bar || !ybar_dot_out || !tbar_out || !params_bar_out || !aux_out)) {
+    if (err) *err = "eno_rhs: mode 2 needs y_bar, r_bar and all outputs"; return ENO_E_ARG;
+  }
+  const size_t N = (size_t)B * D;
+  AdjArgs a = {};
+  adj_carve(ws, B, D, H, params, &a);
+  a.np = (K == 0) ? 1 : K;
+  const AdjPlan plan = adj_plan(B, D, H, sms, path_mode, true);
+  if (!plan.cluster) adj_transposes(a, st);
+  a.n_rp = plan.cluster ? kC * B : B;
+  ENO_ADJ_CHECK(cudaMemcpyAsync(a.Z, y, N * 4, cudaMemcpyDeviceToDevice, st));
+  if (mode == 2) {
+    ENO_ADJ_CHECK(cudaMemcpyAsync(a.ZB, y_bar, N * 4, cudaMemcpyDeviceToDevice, st));
+    ENO_ADJ_CHECK(cudaMemcpyAsync(a.RB, r_bar, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    ENO_ADJ_CHECK(cudaMemsetAsync(a.ZB, 0, N * 4, st));
+    ENO_ADJ_CHECK(cudaMemsetAsync(a.RB, 0, (size_t)B * 4, st));
+  }
+  ENO_ADJ_CHECK(cudaMemsetAsync(a.RS, 0, (size_t)B * 4, st));
+  ENO_ADJ_CHECK(cudaMemsetAsync(a.ctrl, 0, sizeof(Ctrl), st));
+  a.rhs_dy = dy_out;
+  a.rhs_r = aux_out;
+  a.rhs_zb = ybar_dot_out;
+  int rc;
+  // solver time tau = -t, so that the kernel's t = -tau is the caller's t
+  if ((rc = adj_rows_any(plan, K, ADJ_RHS, a, -t, st, err))) return rc;
+  if (mode == 2) {
+    const PgradGeom geo = pgrad_geom(D, H);
+    k_adj_pgrad<ADJ_RHS><<<geo.grid, kSlots * kGroup, 0, st>>>(a, -t, params_bar_out, tbar_out);
+  }
+  ENO_ADJ_CHECK(cudaGetLastError());
+  ENO_ADJ_CHECK(cudaStreamSynchronize(st));
+  return ENO_OK;
+}
+
+}  // namespace eno

@@ -40,6 +40,7 @@ struct AdjArgs {
   AdjScalars* sc;
   MlpWeights w;
   int B, P, np;            // np = Taylor passes whose factors exist (1, 2 or 3)
+  int n_rp;                // entries of the per-sample partial-sum arrays: B (streamed) or kC*B (cluster)
   size_t N;                // B * D
   float n_state;
   // per-sample rings
@@ -381,7 +382,10 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
                                                                float* rhs_tbar) {
   Ctrl* c = a.ctrl;
   if (MODE == ADJ_STEP && c->done) return;
-  constexpr int NS = (MODE == ADJ_STEP) ? kSlots : 1;
+  // ADJ_STEP: thread group g contracts RHS slot g (stage g+1) over all rows.  Other modes have a single
+  // slot; the six groups then split its rows (K) between them and the tiles are summed.
+  constexpr bool SPLITK = (MODE != ADJ_STEP);
+  constexpr int NS = kSlots;
   __shared__ float tile[NS][kTile * kTile];
   __shared__ int pidx[kTile * kTile];   // flat parameter index of each tile element (-1 = padding)
   __shared__ double dred[kSlots * kGroup];
@@ -411,15 +415,17 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     if (grp < NS && mm < M && nn < N) {
-      const FactorSlot& sl = a.slot[grp];
+      const FactorSlot& sl = a.slot[SPLITK ? 0 : grp];
       const float* Am = first ? sl.S : sl.Hh;   // [KB][M]
       const float* Bm = first ? sl.A : sl.G;    // [KB][N]
       // factor rows live as [3][B][*]; only the first np*B rows are valid and contiguous
       const float4* Ap = reinterpret_cast<const float4*>(Am + mm);
       const float4* Bp = reinterpret_cast<const float4*>(Bm + nn);
       const size_t lda = (size_t)M / 4, ldb = (size_t)N / 4;
-      int k = 0;
-      for (; k + 4 <= KB; k += 4) {
+      const int kchunk = (KB + kSlots - 1) / kSlots;
+      int k = SPLITK ? grp * kchunk : 0;
+      const int kend = SPLITK ? min(KB, k + kchunk) : KB;
+      for (; k + 4 <= kend; k += 4) {
         float4 av[4], bv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -436,7 +442,7 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
             for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
         }
       }
-      for (; k < KB; ++k) {
+      for (; k < kend; ++k) {
         const float4 a4 = Ap[(size_t)k * lda], b4 = Bp[(size_t)k * ldb];
         const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
         const float br[4] = {b4.x, b4.y, b4.z, b4.w};
@@ -471,16 +477,18 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
     const int o = (first ? vb : vb - geo.nv1) * kGroup + tig;   // in [0, 2W)
     float acc = 0.f;
     if (grp < NS && o < 2 * W) {
-      const FactorSlot& sl = a.slot[grp];
+      const FactorSlot& sl = a.slot[SPLITK ? 0 : grp];
       const float* F0 = first ? sl.A : sl.G;             // pass-0 factor [B][W]
       const float* F1 = F0 + (size_t)B * W;              // pass-1 factor
       const float t_stage = -(tau + ((MODE == ADJ_STEP) ? dt * c_tab.alpha[grp] : (MODE == ADJ_INIT1 ? h0 : 0.f)));
+      const int rchunk = (B + kSlots - 1) / kSlots;
+      const int rb = SPLITK ? grp * rchunk : 0, re = SPLITK ? min(B, rb + rchunk) : B;
       if (o < W) {
-        for (int r = 0; r < B; ++r) acc += F0[(size_t)r * W + o];
+        for (int r = rb; r < re; ++r) acc += F0[(size_t)r * W + o];
       } else {
         const int n = o - W;
-        if (a.np >= 2) for (int r = 0; r < B; ++r) acc += fmaf(t_stage, F0[(size_t)r * W + n], F1[(size_t)r * W + n]);
-        else for (int r = 0; r < B; ++r) acc += t_stage * F0[(size_t)r * W + n];
+        if (a.np >= 2) for (int r = rb; r < re; ++r) acc += fmaf(t_stage, F0[(size_t)r * W + n], F1[(size_t)r * W + n]);
+        else for (int r = rb; r < re; ++r) acc += t_stage * F0[(size_t)r * W + n];
       }
     }
     if (grp < NS) tile[grp][tig] = acc;
@@ -528,7 +536,7 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
     for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
       const int p = pidx[e];
       if (p < 0) continue;
-      const float f0 = tile[0][e];
+      const float f0 = ((((tile[0][e] + tile[1][e]) + tile[2][e]) + tile[3][e]) + tile[4][e]) + tile[5][e];
       const float p0 = PBc[p];
       const float sc = atol + fabsf(p0) * rtol;
       const float q0 = p0 / sc, q1 = f0 / sc;
@@ -543,13 +551,14 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
       const int p = pidx[e];
       if (p < 0) continue;
       const float sc = atol + fabsf(PBc[p]) * rtol;
-      const float q = (tile[0][e] - FPc[p]) / sc;
+      const float f1 = ((((tile[0][e] + tile[1][e]) + tile[2][e]) + tile[3][e]) + tile[4][e]) + tile[5][e];
+      const float q = (f1 - FPc[p]) / sc;
       part0 += (double)(q * q);
     }
   } else {  // ADJ_RHS
     for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
       const int p = pidx[e];
-      if (p >= 0) rhs_pbar[p] = tile[0][e];
+      if (p >= 0) rhs_pbar[p] = ((((tile[0][e] + tile[1][e]) + tile[2][e]) + tile[3][e]) + tile[4][e]) + tile[5][e];
     }
   }
   // deterministic block reduction of the partial sums
@@ -577,18 +586,18 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
   __shared__ double fin[12];
   {
     double v;
-    v = block_sum_global(a.rowpart0, B, dred); if (threadIdx.x == 0) fin[0] = v; __syncthreads();
+    v = block_sum_global(a.rowpart0, a.n_rp, dred); if (threadIdx.x == 0) fin[0] = v; __syncthreads();
     v = block_sum_global(a.ppart0, geo.grid, dred); if (threadIdx.x == 0) fin[1] = v; __syncthreads();
     if (MODE == ADJ_INIT0) {
-      v = block_sum_global(a.rowpart1, B, dred); if (threadIdx.x == 0) fin[2] = v; __syncthreads();
+      v = block_sum_global(a.rowpart1, a.n_rp, dred); if (threadIdx.x == 0) fin[2] = v; __syncthreads();
       v = block_sum_global(a.ppart1, geo.grid, dred); if (threadIdx.x == 0) fin[3] = v; __syncthreads();
-      v = block_sum_global(a.rowpart2, B, dred); if (threadIdx.x == 0) fin[4] = v; __syncthreads();
+      v = block_sum_global(a.rowpart2, a.n_rp, dred); if (threadIdx.x == 0) fin[4] = v; __syncthreads();
     }
     // stage derivatives of t0_bar: sums of the per-sample t_bar contributions
-    for (int j = 0; j < NS; ++j) {
+    for (int j = 0; j < (SPLITK ? 1 : NS); ++j) {
       const float* tb = a.slot[j].tbar;
-      const int per = (B + blockDim.x - 1) / blockDim.x;
-      const int b0 = threadIdx.x * per, b1 = min(B, b0 + per);
+      const int per = (a.n_rp + blockDim.x - 1) / blockDim.x;
+      const int b0 = threadIdx.x * per, b1 = min(a.n_rp, b0 + per);
       double acc = 0.0;
       for (int i = b0; i < b1; ++i) acc += (double)tb[i];
       dred[threadIdx.x] = acc;
@@ -748,256 +757,6 @@ __global__ void k_transpose(const float* __restrict__ W, float* __restrict__ WT,
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y)
     if (n0 + j < N && k0 + threadIdx.x < K) WT[(size_t)(n0 + j) * K + k0 + threadIdx.x] = t[threadIdx.x][j];
-}
-
-// ======================================================================================
-// host side
-// ======================================================================================
-inline size_t adj_align(size_t x) { return (x + 255) / 256 * 256; }
-
-inline size_t adj_ws_bytes(int B, int D, int H) {
-  const size_t N = (size_t)B * D, P = (size_t)(D + 1) * H + H + (size_t)(H + 1) * D + D;
-  const PgradGeom g = pgrad_geom(D, H);
-  size_t s = 0;
-  s += adj_align(sizeof(Ctrl)) + adj_align(sizeof(AdjScalars));
-  s += 4 * adj_align(3 * N * 4);                    // Z, ZB, FZ, FZB
-  s += 2 * adj_align(3 * (size_t)B * 4) + adj_align((size_t)B * 4);  // RS, FR, RB
-  s += adj_align(2 * N * 4);                        // MIDZB
-  s += 2 * adj_align(3 * P * 4) + adj_align(2 * P * 4);             // PB, FP, MIDP
-  s += kSlots * (2 * adj_align(3 * N * 4) + 2 * adj_align(3 * (size_t)B * H * 4) + adj_align((size_t)B * 4));
-  s += 3 * adj_align((size_t)B * 8) + 2 * adj_align((size_t)g.grid * 8);
-  s += adj_align(N * 4) + adj_align(P * 4);         // YBAR, POUT
-  s += 2 * adj_align((size_t)D * H * 4);            // transposes
-  return s + 4096;
-}
-
-struct AdjCarver {
-  char* base;
-  size_t off = 0;
-  template <typename T>
-  T* take(size_t n) {
-    T* p = reinterpret_cast<T*>(base + off);
-    off += adj_align(n * sizeof(T));
-    return p;
-  }
-};
-
-inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArgs* a) {
-  const size_t N = (size_t)B * D, P = (size_t)(D + 1) * H + H + (size_t)(H + 1) * D + D;
-  const PgradGeom g = pgrad_geom(D, H);
-  AdjCarver cv{static_cast<char*>(ws)};
-  a->ctrl = cv.take<Ctrl>(1);
-  a->sc = cv.take<AdjScalars>(1);
-  a->Z = cv.take<float>(3 * N); a->ZB = cv.take<float>(3 * N);
-  a->FZ = cv.take<float>(3 * N); a->FZB = cv.take<float>(3 * N);
-  a->RS = cv.take<float>(3 * (size_t)B); a->FR = cv.take<float>(3 * (size_t)B); a->RB = cv.take<float>(B);
-  a->MIDZB = cv.take<float>(2 * N);
-  a->PB = cv.take<float>(3 * P); a->FP = cv.take<float>(3 * P); a->MIDP = cv.take<float>(2 * P);
-  for (int j = 0; j < kSlots; ++j) {
-    a->slot[j].S = cv.take<float>(3 * N);
-    a->slot[j].G = cv.take<float>(3 * N);
-    a->slot[j].A = cv.take<float>(3 * (size_t)B * H);
-    a->slot[j].Hh = cv.take<float>(3 * (size_t)B * H);
-    a->slot[j].tbar = cv.take<float>(B);
-  }
-  a->rowpart0 = cv.take<double>(B); a->rowpart1 = cv.take<double>(B); a->rowpart2 = cv.take<double>(B);
-  a->ppart0 = cv.take<double>(g.grid); a->ppart1 = cv.take<double>(g.grid);
-  a->YBAR = cv.take<float>(N);
-  a->POUT = cv.take<float>(P);
-  float* W1xT = cv.take<float>((size_t)D * H);
-  float* W2xT = cv.take<float>((size_t)D * H);
-  a->w = mlp_weights_from_flat(params, D, H, W1xT, W2xT);
-  a->B = B; a->P = (int)P; a->N = N;
-  a->n_state = (float)(2 * (N + (size_t)B) + 1 + N + P);
-}
-
-inline int adj_pick_rows(int B, int D, int H, int sms) {
-  int R = 1;
-  if (B > sms) R = 2;
-  while (R > 1 && adj_smem_bytes(R, D, H, kAdjStages) > 220 * 1024) R >>= 1;
-  return R;
-}
-
-#define ENO_ADJ_CHECK(expr)                                                                 \
-  do {                                                                                      \
-    cudaError_t e_ = (expr);                                                                \
-    if (e_ != cudaSuccess) {                                                                \
-      if (err) *err = std::string(#expr) + ": " + cudaGetErrorString(e_);                   \
-      return ENO_E_CUDA;                                                                    \
-    }                                                                                       \
-  } while (0)
-
-template <int R, int K>
-int adj_launch_rows(int mode, const AdjArgs& a, int grid, size_t smem, float rhs_tau, cudaStream_t st,
-                    std::string* err) {
-  switch (mode) {
-    case ADJ_STEP:
-      ENO_ADJ_CHECK(cudaFuncSetAttribute(k_adj_rows<R, K, ADJ_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_adj_rows<R, K, ADJ_STEP><<<grid, kThreads, smem, st>>>(a, rhs_tau);
-      break;
-    case ADJ_INIT0:
-      ENO_ADJ_CHECK(cudaFuncSetAttribute(k_adj_rows<R, K, ADJ_INIT0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_adj_rows<R, K, ADJ_INIT0><<<grid, kThreads, smem, st>>>(a, rhs_tau);
-      break;
-    case ADJ_INIT1:
-      ENO_ADJ_CHECK(cudaFuncSetAttribute(k_adj_rows<R, K, ADJ_INIT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_adj_rows<R, K, ADJ_INIT1><<<grid, kThreads, smem, st>>>(a, rhs_tau);
-      break;
-    default:
-      ENO_ADJ_CHECK(cudaFuncSetAttribute(k_adj_rows<R, K, ADJ_RHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_adj_rows<R, K, ADJ_RHS><<<grid, kThreads, smem, st>>>(a, rhs_tau);
-  }
-  return 0;
-}
-
-inline int adj_rows(int R, int K, int mode, const AdjArgs& a, int grid, size_t smem, float rhs_tau, cudaStream_t st,
-                    std::string* err) {
-#define ENO_RK(RR, KK) if (R == RR && K == KK) return adj_launch_rows<RR, KK>(mode, a, grid, smem, rhs_tau, st, err);
-  ENO_RK(1, 0) ENO_RK(1, 2) ENO_RK(1, 3) ENO_RK(2, 0) ENO_RK(2, 2) ENO_RK(2, 3)
-#undef ENO_RK
-  if (err) *err = "adjoint: unsupported (rows per CTA, reg_order) combination";
-  return ENO_E_UNSUPPORTED;
-}
-
-inline void adj_transposes(const AdjArgs& a, cudaStream_t st) {
-  const int D = a.w.D, H = a.w.H;
-  dim3 blk(32, 8);
-  k_transpose<<<dim3((H + 31) / 32, (D + 31) / 32), blk, 0, st>>>(a.w.W1x, const_cast<float*>(a.w.W1xT), D, H);
-  k_transpose<<<dim3((D + 31) / 32, (H + 31) / 32), blk, 0, st>>>(a.w.W2x, const_cast<float*>(a.w.W2xT), H, D);
-}
-
-inline int adj_solve(Profiler* prof, std::string* err, Ctrl* mailbox, int* hint, int sms, const eno_dynamics_desc* desc, int B,
-                     const float* ys, const float* ts, int T, const float* params, const float* g_y, const float* g_r,
-                     float rtol, float atol, int mxstep, void* ws, size_t ws_bytes, float* y0_bar_out,
-                     float* r0_bar_out, float* ts_bar_out, float* params_bar_out, eno_stats* stats,
-                     eno_trace_row* trace, int trace_cap, cudaStream_t st) {
-  const int D = desc->D, H = desc->H, K = desc->reg_order;
-  if (!(K == 0 || K == 2 || K == 3)) { if (err) *err = "eno_odeint_bwd: reg_order must be 0, 2 or 3"; return ENO_E_UNSUPPORTED; }
-  if (B <= 0 || T < 1 || !ys || !ts || !params || !g_y || !g_r || !ws || !y0_bar_out || !r0_bar_out || !ts_bar_out ||
-      !params_bar_out) { if (err) *err = "eno_odeint_bwd: null pointer or empty batch"; return ENO_E_ARG; }
-  if (ws_bytes < adj_ws_bytes(B, D, H)) { if (err) *err = "eno_odeint_bwd: workspace too small"; return ENO_E_WORKSPACE; }
-  const size_t N = (size_t)B * D;
-  AdjArgs a = {};
-  adj_carve(ws, B, D, H, params, &a);
-  a.np = (K == 0) ? 1 : K;
-  {
-    const size_t n_aux = (desc->aug == ENO_AUG_NONE) ? 0 : 1;
-    a.n_state = (float)(2 * (N + n_aux * (size_t)B) + 1 + (desc->eps_in_args ? N : 0) + (size_t)a.P);
-  }
-  a.trace = trace;
-  Tableau tab;
-  fill_tableau(ENO_TABLEAU_DOPRI5, &tab);
-  ENO_ADJ_CHECK(cudaMemcpyToSymbolAsync(c_tab, &tab, sizeof(Tableau), 0, cudaMemcpyHostToDevice, st));
-  adj_transposes(a, st);
-  const int R = adj_pick_rows(B, D, H, sms);
-  const size_t smem = adj_smem_bytes(R, D, H, kAdjStages);
-  const int grid = (B + R - 1) / R;
-  const PgradGeom geo = pgrad_geom(D, H);
-  const int egrid = (int)std::min<size_t>((std::max(N, (size_t)a.P) + 255) / 256, (size_t)4 * sms);
-  const int mx = mxstep <= 0 ? INT_MAX : mxstep;
-  int worst = ENO_OK;
-  if (T == 1) {   // nothing to integrate: y0_bar = g[0], everything else zero (empty scan)
-    ENO_ADJ_CHECK(cudaMemcpyAsync(y0_bar_out, g_y, N * 4, cudaMemcpyDeviceToDevice, st));
-    ENO_ADJ_CHECK(cudaMemcpyAsync(r0_bar_out, g_r, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
-    ENO_ADJ_CHECK(cudaMemsetAsync(ts_bar_out, 0, 4, st));
-    ENO_ADJ_CHECK(cudaMemsetAsync(params_bar_out, 0, (size_t)a.P * 4, st));
-    ENO_ADJ_CHECK(cudaStreamSynchronize(st));
-    return ENO_OK;
-  }
-  for (int i = T - 1; i >= 1; --i) {
-    int launches = 0;
-    const int first = (i == T - 1);
-    a.g_y = g_y + (size_t)i * N;
-    a.g_r = g_r + (size_t)i * B;
-    a.g_y_prev = g_y + (size_t)(i - 1) * N;
-    a.tbar_out = ts_bar_out + i;
-    k_adj_seg_begin<<<egrid, 256, 0, st>>>(a, ys + (size_t)i * N, a.g_y, a.g_r, ts, i, first, rtol, atol, mx,
-                                           trace ? trace_cap : 0);
-    int rc;
-    if ((rc = adj_rows(R, K, ADJ_INIT0, a, grid, smem, 0.f, st, err))) return rc;
-    k_adj_pgrad<ADJ_INIT0><<<geo.grid, kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
-    if ((rc = adj_rows(R, K, ADJ_INIT1, a, grid, smem, 0.f, st, err))) return rc;
-    k_adj_pgrad<ADJ_INIT1><<<geo.grid, kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
-    launches += 5;
-    int chunk = *hint;
-    for (;;) {
-      for (int k = 0; k < chunk; ++k) {
-        int ps = prof->begin(PROF_ADJ_ROWS, st);
-        if ((rc = adj_rows(R, K, ADJ_STEP, a, grid, smem, 0.f, st, err))) return rc;
-        prof->end(ps, st);
-        ps = prof->begin(PROF_ADJ_PGRAD, st);
-        k_adj_pgrad<ADJ_STEP><<<geo.grid, kSlots * kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
-        prof->end(ps, st);
-        k_adj_out<<<egrid, 256, 0, st>>>(a);
-        launches += 3;
-      }
-      ENO_ADJ_CHECK(cudaMemcpyAsync(mailbox, a.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-      ENO_ADJ_CHECK(cudaStreamSynchronize(st));
-      if (mailbox->done) break;
-      chunk = 4;
-    }
-    {
-      int valid[PROF_KINDS] = {0, mailbox->n_iters, mailbox->n_iters, 0};
-      prof->resolve(valid);
-    }
-    *hint = mailbox->n_iters + 1 > 64 ? 64 : mailbox->n_iters + 1;
-    if (stats) {
-      eno_stats* s = stats + (T - 1 - i);
-      s->nfe = (float)mailbox->nfe; s->n_iters = mailbox->n_iters; s->n_accepted = mailbox->n_accepted;
-      s->status = mailbox->status; s->last_dt = mailbox->dt; s->last_t = mailbox->t; s->n_launches = launches;
-      s->n_rhs = 2 + 6 * mailbox->n_iters;
-    }
-    if (mailbox->status != ENO_OK && worst == ENO_OK) worst = mailbox->status;
-    trace = nullptr;  // only the first segment is traced
-    a.trace = nullptr;
-  }
-  k_adj_finish<<<(B + 255) / 256, 256, 0, st>>>(a, g_r, r0_bar_out, ts_bar_out);
-  ENO_ADJ_CHECK(cudaMemcpyAsync(y0_bar_out, a.YBAR, N * 4, cudaMemcpyDeviceToDevice, st));
-  ENO_ADJ_CHECK(cudaMemcpyAsync(params_bar_out, a.POUT, (size_t)a.P * 4, cudaMemcpyDeviceToDevice, st));
-  ENO_ADJ_CHECK(cudaStreamSynchronize(st));
-  ENO_ADJ_CHECK(cudaGetLastError());
-  return worst;
-}
-
-inline int adj_rhs(std::string* err, int sms, const eno_dynamics_desc* desc, int mode, int B, const float* y, float t,
-                   const float* params, const float* y_bar, const float* r_bar, void* ws, size_t ws_bytes, float* dy_out,
-                   float* aux_out, float* ybar_dot_out, float* tbar_out, float* params_bar_out, cudaStream_t st) {
-  (void)sms;
-  const int D = desc->D, H = desc->H, K = desc->reg_order;
-  if (!(K == 0 || K == 2 || K == 3)) { if (err) *err = "eno_rhs: reg_order must be 0, 2 or 3"; return ENO_E_UNSUPPORTED; }
-  if (!ws || ws_bytes < adj_ws_bytes(B, D, H)) { if (err) *err = "eno_rhs: workspace too small"; return ENO_E_WORKSPACE; }
-  if (mode == 2 && (!y_bar || !r_bar || !ybar_dot_out || !tbar_out || !params_bar_out || !aux_out)) {
-    if (err) *err = "eno_rhs: mode 2 needs y_bar, r_bar and all outputs"; return ENO_E_ARG;
-  }
-  const size_t N = (size_t)B * D;
-  AdjArgs a = {};
-  adj_carve(ws, B, D, H, params, &a);
-  a.np = (K == 0) ? 1 : K;
-  adj_transposes(a, st);
-  ENO_ADJ_CHECK(cudaMemcpyAsync(a.Z, y, N * 4, cudaMemcpyDeviceToDevice, st));
-  if (mode == 2) {
-    ENO_ADJ_CHECK(cudaMemcpyAsync(a.ZB, y_bar, N * 4, cudaMemcpyDeviceToDevice, st));
-    ENO_ADJ_CHECK(cudaMemcpyAsync(a.RB, r_bar, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
-  } else {
-    ENO_ADJ_CHECK(cudaMemsetAsync(a.ZB, 0, N * 4, st));
-    ENO_ADJ_CHECK(cudaMemsetAsync(a.RB, 0, (size_t)B * 4, st));
-  }
-  ENO_ADJ_CHECK(cudaMemsetAsync(a.RS, 0, (size_t)B * 4, st));
-  ENO_ADJ_CHECK(cudaMemsetAsync(a.ctrl, 0, sizeof(Ctrl), st));
-  a.rhs_dy = dy_out;
-  a.rhs_r = aux_out;
-  a.rhs_zb = ybar_dot_out;
-  const size_t smem = adj_smem_bytes(1, D, H, 2);
-  int rc;
-  // solver time tau = -t, so that the kernel's t = -tau is the caller's t
-  if ((rc = adj_rows(1, K, ADJ_RHS, a, B, smem, -t, st, err))) return rc;
-  if (mode == 2) {
-    const PgradGeom geo = pgrad_geom(D, H);
-    k_adj_pgrad<ADJ_RHS><<<geo.grid, kGroup, 0, st>>>(a, -t, params_bar_out, tbar_out);
-  }
-  ENO_ADJ_CHECK(cudaGetLastError());
-  ENO_ADJ_CHECK(cudaStreamSynchronize(st));
-  return ENO_OK;
 }
 
 }  // namespace eno

@@ -1,0 +1,540 @@
+// "Cluster-resident" formulation of the MLP dynamics and its Taylor / adjoint sweeps.
+//
+// A thread-block cluster of kC = 4 CTAs owns a tile of R samples.  The state width D is split
+// into kC column slices; CTA `rank` keeps, for the whole launch, its slice of BOTH weight
+// matrices in shared memory:
+//     W1 rows  d0..d0+Dl  ([Dl][H])   - used as  a[n]  = sum_{d local} x[d] W1[d][n]   (partial over d)
+//                                       and      sb[d] = sum_n ab[n] W1[d][n]           (local d)
+//     W2 cols  d0..d0+Dl  ([H][Dl])   - used as  f[d]  = sum_n h[n] W2[n][d]            (local d)
+//                                       and      hb[n] = sum_{d local} g[d] W2[n][d]    (partial over d)
+// Every D-vector is distributed (each CTA holds its Dl columns), every H-vector is replicated;
+// the only cluster traffic is an all-reduce of R x H partial sums per layer-1 product, done with
+// distributed-shared-memory loads after one cluster barrier.  Compared with the streamed
+// formulation (mlp_device.cuh) no weight byte crosses L2 after the prologue.
+//
+// Reference arithmetic: mnist.py:195-222 (MLPDynamics), 105-131 (sol_recursive), lib/ode.py:1498-1504.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "adj_device.cuh"
+
+namespace eno {
+namespace cg = cooperative_groups;
+
+// Optional phase clocks (build with -DENO_PHASES): thread 0 of CTA 0 accumulates clock64() deltas by
+// phase kind.  Development aid only; compiled out of the product library.
+enum PhaseKind { PH_PROLOGUE = 0, PH_ELEM, PH_MV_DL, PH_MV_H, PH_ALLRED, PH_REDLOC, PH_STORE, PH_SCALAR, PH_COMBINE, PH_NKINDS };
+#ifdef ENO_PHASES
+__device__ long long g_phase_cycles[PH_NKINDS];
+__device__ long long g_phase_count[PH_NKINDS];
+__device__ long long g_phase_last;
+#define ENO_TICK(kind)                                                        \
+  do {                                                                        \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                \
+      const long long now_ = clock64();                                       \
+      g_phase_cycles[kind] += now_ - g_phase_last;                            \
+      g_phase_count[kind] += 1;                                               \
+      g_phase_last = now_;                                                    \
+    }                                                                         \
+  } while (0)
+#define ENO_TICK_START() do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_last = clock64(); } while (0)
+#else
+#define ENO_TICK(kind) do {} while (0)
+#define ENO_TICK_START() do {} while (0)
+#endif
+
+constexpr int kC = 4;          // CTAs per cluster
+constexpr int kKG = 7;         // k-groups of a product contracting over the local slice (K = Dl; 49 = 7 x 7 at D = 784)
+constexpr int kKGw = 5;        // k-groups of a product contracting over H (25 = 5 x 5 at H = 100)
+constexpr int kRG = 2;         // row groups (measured: 1 vs 2 makes no difference; the products are latency-bound)
+
+struct ClGeom {
+  int rank;   // CTA rank in cluster
+  int d0;     // first global column of this CTA's slice
+  int Dl;     // columns in the slice (multiple of 4)
+  int Dlp;    // padded slice width: stride of D-vectors and of W2 rows ((Dlp/4) odd -> conflict-free)
+  int ldw1;   // stride of W1 rows ((ldw1/4) odd)
+  int Hs;     // stride of the all-reduce staging rows (H + 4 scalar slots)
+};
+
+__host__ __device__ inline ClGeom cl_geom(int D, int H, int rank) {
+  ClGeom g;
+  const int c4 = D / 4, q = c4 / kC, rem = c4 % kC;
+  const int dl4 = q + (rank < rem ? 1 : 0);
+  const int d04 = rank * q + (rank < rem ? rank : rem);
+  int dmax4 = q + (rem > 0 ? 1 : 0);
+  if ((dmax4 & 1) == 0) dmax4 += 1;
+  int h4 = H / 4;
+  if ((h4 & 1) == 0) h4 += 1;
+  g.rank = rank;
+  g.d0 = 4 * d04;
+  g.Dl = 4 * dl4;
+  g.Dlp = 4 * dmax4;
+  g.ldw1 = 4 * h4;
+  g.Hs = H + 4;
+  return g;
+}
+
+struct ClWeights {
+  const float* W1;   // smem [Dl][ldw1]
+  const float* W2;   // smem [H][Dlp]
+  const float* b1;   // smem [H]
+  const float* w1t;  // smem [H]
+  const float* b2;   // smem [Dl]   this CTA's slice
+  const float* w2t;  // smem [Dl]
+  int D, H;
+};
+
+// cooperative copy of this CTA's weight slices into shared memory (once per launch)
+__device__ __forceinline__ void cl_load_weights(const MlpWeights& w, const ClGeom& g, float* W1s, float* W2s,
+                                                float* vec /*[2H + 2Dlp]: b1, w1t, b2 slice, w2t slice*/) {
+  const int H = w.H, D = w.D;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    vec[i] = __ldg(w.b1 + i);
+    vec[H + i] = __ldg(w.w1t + i);
+  }
+  for (int i = threadIdx.x; i < g.Dlp; i += blockDim.x) {
+    vec[2 * H + i] = (i < g.Dl) ? __ldg(w.b2 + g.d0 + i) : 0.f;
+    vec[2 * H + g.Dlp + i] = (i < g.Dl) ? __ldg(w.w2t + g.d0 + i) : 0.f;
+  }
+  const int h4 = H >> 2;
+  for (int i = threadIdx.x; i < g.Dl * h4; i += blockDim.x) {
+    const int d = i / h4, c = i - d * h4;
+    reinterpret_cast<float4*>(W1s + (size_t)d * g.ldw1)[c] =
+        __ldg(reinterpret_cast<const float4*>(w.W1x + (size_t)(g.d0 + d) * H) + c);
+  }
+  const int d4 = g.Dl >> 2;
+  for (int i = threadIdx.x; i < H * d4; i += blockDim.x) {
+    const int n = i / d4, c = i - n * d4;
+    reinterpret_cast<float4*>(W2s + (size_t)n * g.Dlp)[c] =
+        __ldg(reinterpret_cast<const float4*>(w.W2x + (size_t)n * D + g.d0) + c);
+  }
+}
+
+// partial[kg][r][n] = sum_{k in chunk kg} x[r][k] * W[k][n]      (outputs along W's contiguous dim)
+// R must be a multiple of kRG.  All sizes are compile-time constants in the specialised kernels, so the
+// k-loop unrolls completely and every address is an immediate offset.
+template <int R>
+__device__ __forceinline__ void mv_n(const float* __restrict__ W, int ldw, int K, int N, const float* __restrict__ x,
+                                     int ldx, float* __restrict__ red, int KG) {
+  constexpr int TR = R / kRG;
+  static_assert(R % kRG == 0, "rows per tile must be a multiple of the row groups");
+  const int NC4 = N >> 2;
+  const int per = NC4 * KG;
+  const int rg = threadIdx.x / per;
+  if (rg < kRG) {
+    const int rem = threadIdx.x - rg * per;
+    const int kg = rem / NC4, c4 = rem - kg * NC4;
+    const int K4 = K >> 2;
+    const int chunk = (K4 + KG - 1) / KG;
+    const bool exact = (chunk * KG == K4);   // folds to true in the specialised build: no tail predicate
+    const int k4b = kg * chunk;
+    const int r0 = rg * TR;
+    const int l4 = ldw >> 2;
+    float4 acc[TR];
+#pragma unroll
+    for (int t = 0; t < TR; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* Wp = reinterpret_cast<const float4*>(W) + (size_t)(4 * k4b) * l4 + c4;
+    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)r0 * ldx) + k4b;
+    const int lx4 = ldx >> 2;
+#pragma unroll
+    for (int i = 0; i < chunk; ++i) {
+      if (exact || k4b + i < K4) {
+        const float4 w0 = Wp[(4 * i) * l4], w1 = Wp[(4 * i + 1) * l4], w2 = Wp[(4 * i + 2) * l4], w3 = Wp[(4 * i + 3) * l4];
+#pragma unroll
+        for (int t = 0; t < TR; ++t) {
+          const float4 xv = xp[t * lx4 + i];
+          acc[t].x = fmaf(xv.x, w0.x, acc[t].x); acc[t].y = fmaf(xv.x, w0.y, acc[t].y);
+          acc[t].z = fmaf(xv.x, w0.z, acc[t].z); acc[t].w = fmaf(xv.x, w0.w, acc[t].w);
+          acc[t].x = fmaf(xv.y, w1.x, acc[t].x); acc[t].y = fmaf(xv.y, w1.y, acc[t].y);
+          acc[t].z = fmaf(xv.y, w1.z, acc[t].z); acc[t].w = fmaf(xv.y, w1.w, acc[t].w);
+          acc[t].x = fmaf(xv.z, w2.x, acc[t].x); acc[t].y = fmaf(xv.z, w2.y, acc[t].y);
+          acc[t].z = fmaf(xv.z, w2.z, acc[t].z); acc[t].w = fmaf(xv.z, w2.w, acc[t].w);
+          acc[t].x = fmaf(xv.w, w3.x, acc[t].x); acc[t].y = fmaf(xv.w, w3.y, acc[t].y);
+          acc[t].z = fmaf(xv.w, w3.z, acc[t].z); acc[t].w = fmaf(xv.w, w3.w, acc[t].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TR; ++t) reinterpret_cast<float4*>(red + (size_t)(kg * R + r0 + t) * N)[c4] = acc[t];
+  }
+}
+
+// partial[kg][r][n] = sum_{k in chunk kg} x[r][k] * W[n][k]      (contraction along W's contiguous dim)
+// thread q owns outputs n = q, q + N/4, q + 2N/4, q + 3N/4 (row stride with (ldw/4) odd: conflict-free)
+template <int R>
+__device__ __forceinline__ void mv_k(const float* __restrict__ W, int ldw, int N, int K, const float* __restrict__ x,
+                                     int ldx, float* __restrict__ red, int KG) {
+  constexpr int TR = R / kRG;
+  const int NQ = N >> 2;
+  const int per = NQ * KG;
+  const int rg = threadIdx.x / per;
+  if (rg < kRG) {
+    const int rem = threadIdx.x - rg * per;
+    const int kg = rem / NQ, q = rem - kg * NQ;
+    const int K4 = K >> 2;
+    const int chunk = (K4 + KG - 1) / KG;
+    const bool exact = (chunk * KG == K4);
+    const int k4b = kg * chunk;
+    const int r0 = rg * TR;
+    float acc[TR][4];
+#pragma unroll
+    for (int t = 0; t < TR; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
+    const int rs = NQ * (ldw >> 2);
+    const float4* W0 = reinterpret_cast<const float4*>(W + (size_t)q * ldw) + k4b;
+    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)r0 * ldx) + k4b;
+    const int lx4 = ldx >> 2;
+#pragma unroll
+    for (int j = 0; j < chunk; ++j) {
+      if (exact || k4b + j < K4) {
+        float4 wv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wv[i] = W0[i * rs + j];
+#pragma unroll
+        for (int t = 0; t < TR; ++t) {
+          const float4 xv = xp[t * lx4 + j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[t][i] = fmaf(xv.x, wv[i].x, acc[t][i]);
+            acc[t][i] = fmaf(xv.y, wv[i].y, acc[t][i]);
+            acc[t][i] = fmaf(xv.z, wv[i].z, acc[t][i]);
+            acc[t][i] = fmaf(xv.w, wv[i].w, acc[t][i]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TR; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) red[(size_t)(kg * R + r0 + t) * N + q + i * NQ] = acc[t][i];
+  }
+}
+
+// local (distributed-D) product: reduce the k-group partials and hand (r, n, sum) to the epilogue
+template <int R, typename Epi>
+__device__ __forceinline__ void reduce_local(const float* red, int KG, int N, Epi epi) {
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < R * N; idx += blockDim.x) {
+    const int r = idx / N, n = idx - r * N;
+    float s = 0.f;
+    for (int g = 0; g < KG; ++g) s += red[(size_t)(g * R + r) * N + n];
+    epi(r, n, s);
+  }
+  __syncthreads();
+  ENO_TICK(PH_REDLOC);
+}
+
+// Per-CTA staging area of the cluster all-reduce: two buffers used alternately so that a CTA can
+// start filling the next one while slower peers still read the previous one.
+struct ClComm {
+  float* part[2];   // [R][Hs]   columns [0,H): layer-1 partial sums; [H, H+4): per-sample scalars
+  int phase;
+};
+
+// All-reduce over the cluster of R x (H + nscal) partial sums.  `red` holds the k-group partials of
+// this CTA's layer-1 product; `scal[r*4 + j]` (may be null) holds up to 4 per-sample scalar partials.
+// Sum order over CTAs is fixed (rank 0..3), so every CTA obtains bit-identical results.
+template <int R, typename Epi, typename EpiS>
+__device__ __forceinline__ void allreduce_H(cg::cluster_group& cluster, ClComm& cm, const ClGeom& g, const float* red,
+                                            int KG, int H, const float* scal, int nscal, Epi epi, EpiS epis) {
+  float* mine = cm.part[cm.phase];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < R * H; idx += blockDim.x) {
+    const int r = idx / H, n = idx - r * H;
+    float s = 0.f;
+    for (int k = 0; k < KG; ++k) s += red[(size_t)(k * R + r) * H + n];
+    mine[r * g.Hs + n] = s;
+  }
+  if (scal && threadIdx.x < R * nscal) {
+    const int r = threadIdx.x / nscal, j = threadIdx.x - r * nscal;
+    mine[r * g.Hs + H + j] = scal[r * 4 + j];
+  }
+  cluster.sync();
+  const float* p0 = cluster.map_shared_rank(mine, 0);
+  const float* p1 = cluster.map_shared_rank(mine, 1);
+  const float* p2 = cluster.map_shared_rank(mine, 2);
+  const float* p3 = cluster.map_shared_rank(mine, 3);
+  for (int idx = threadIdx.x; idx < R * H; idx += blockDim.x) {
+    const int r = idx / H, n = idx - r * H;
+    const int o = r * g.Hs + n;
+    const float s = ((p0[o] + p1[o]) + p2[o]) + p3[o];
+    epi(r, n, s);
+  }
+  if (scal && threadIdx.x < R * nscal) {
+    const int r = threadIdx.x / nscal, j = threadIdx.x - r * nscal;
+    const int o = r * g.Hs + H + j;
+    epis(r, j, ((p0[o] + p1[o]) + p2[o]) + p3[o]);
+  }
+  cm.phase ^= 1;
+  __syncthreads();
+  ENO_TICK(PH_ALLRED);
+}
+
+// shared-memory working set (distributed D-vectors have stride Dlp, H-vectors stride H)
+struct ClScratch {
+  float *s, *u;                    // [R][Dlp]
+  float *f, *y1, *y2;              // [R][Dlp]
+  float *gf, *gy1, *zacc;          // [R][Dlp]
+  float *h, *a1, *h1, *a2, *h2;    // [R][H]
+  float *ga, *ga1, *ga2;           // [R][H]
+  float* red;
+  float* scal;                     // [R][4]
+  float* rdot;                     // [R]
+};
+
+// f = MLP(z, t) for the CTA's column slice; leaves s (local slice) and h (replicated).
+template <int R>
+__device__ __forceinline__ void cl_primal(cg::cluster_group& cluster, ClComm& cm, const ClGeom& g, const ClWeights& w,
+                                          float t, const float* z, float* f, const ClScratch& sc) {
+  const int H = w.H, Dl = g.Dl, Dlp = g.Dlp;
+  for (int i = threadIdx.x; i < R * Dlp; i += blockDim.x) {
+    const int d = i % Dlp;
+    sc.s[i] = (d < Dl) ? sigmoidf_(z[i]) : 0.f;
+  }
+  __syncthreads();
+  ENO_TICK(PH_ELEM);
+  mv_n<R>(w.W1, g.ldw1, Dl, H, sc.s, Dlp, sc.red, kKG);
+  ENO_TICK(PH_MV_DL);
+  allreduce_H<R>(cluster, cm, g, sc.red, kKG, H, nullptr, 0,
+                 [&](int r, int n, float sum) { sc.h[r * H + n] = sigmoidf_(sum + t * w.w1t[n] + w.b1[n]); },
+                 [&](int, int, float) {});
+  mv_n<R>(w.W2, Dlp, H, Dl, sc.h, H, sc.red, kKGw);
+  ENO_TICK(PH_MV_H);
+  reduce_local<R>(sc.red, kKGw, Dl, [&](int r, int d, float sum) {
+    f[r * Dlp + d] = sum + t * w.w2t[d] + w.b2[d];
+  });
+}
+
+}  // namespace eno
+
+namespace eno {
+
+// store this CTA's column slice of R distributed rows into a global [B][D] block
+template <int R>
+__device__ __forceinline__ void cl_store_D(float* dst, const float* src, const ClGeom& g, int D, int row0, int B) {
+  for (int i = threadIdx.x; i < R * g.Dlp; i += blockDim.x) {
+    const int r = i / g.Dlp, d = i - r * g.Dlp;
+    if (d < g.Dl && row0 + r < B) dst[(size_t)(row0 + r) * D + g.d0 + d] = src[i];
+  }
+}
+
+// store replicated H-rows (rank 0 only)
+template <int R>
+__device__ __forceinline__ void cl_store_H(float* dst, const float* src, const ClGeom& g, int H, int row0, int B) {
+  if (g.rank != 0) return;
+  for (int i = threadIdx.x; i < R * H; i += blockDim.x)
+    if (row0 + i / H < B) dst[(size_t)row0 * H + i] = src[i];
+}
+
+// per-sample partial of sum_d v[d]^2 over the local slice -> scal[r*4 + slot]
+template <int R>
+__device__ __forceinline__ void cl_sumsq_local(const float* v, const ClGeom& g, float* scal, int slot) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < R; r += nw) {
+    double acc = 0.0;
+    for (int d = lane; d < g.Dl; d += 32) {
+      const float x = v[r * g.Dlp + d];
+      acc += (double)(x * x);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) scal[r * 4 + slot] = (float)acc;
+  }
+}
+
+// Forward Taylor passes (aug_forward of adj_device.cuh, distributed).  On return: f, y1, y2 local slices,
+// h, a1, h1, a2, h2 replicated, scal[r*4+0] = local partial of sum_d yK^2 (K >= 2).
+template <int R, int K>
+__device__ __forceinline__ void cl_aug_forward(cg::cluster_group& cluster, ClComm& cm, const ClGeom& g,
+                                               const ClWeights& w, float t, const float* z, const ClScratch& m,
+                                               const FactorSlot* slot, int row0, int B) {
+  const int D = w.D, H = w.H, Dl = g.Dl, Dlp = g.Dlp;
+  const size_t BD = (size_t)B * D, BH = (size_t)B * H;
+  cl_primal<R>(cluster, cm, g, w, t, z, m.f, m);
+  if (slot) {
+    cl_store_D<R>(slot->S, m.s, g, D, row0, B);
+    ENO_TICK(PH_STORE);
+    cl_store_H<R>(slot->Hh, m.h, g, H, row0, B);
+    ENO_TICK(PH_STORE);
+  }
+  if (K >= 2) {
+    for (int i = threadIdx.x; i < R * Dlp; i += blockDim.x) {
+      const float s = m.s[i];
+      m.u[i] = ((i % Dlp) < Dl) ? s * (1.f - s) * m.f[i] : 0.f;
+    }
+    __syncthreads();
+    if (slot) cl_store_D<R>(slot->S + BD, m.u, g, D, row0, B);
+    ENO_TICK(PH_STORE);
+    mv_n<R>(w.W1, g.ldw1, Dl, H, m.u, Dlp, m.red, kKG);
+    ENO_TICK(PH_MV_DL);
+    allreduce_H<R>(cluster, cm, g, m.red, kKG, H, nullptr, 0,
+                   [&](int r, int n, float sum) {
+                     const float h = m.h[r * H + n];
+                     const float a1 = sum + w.w1t[n];
+                     m.a1[r * H + n] = a1;
+                     m.h1[r * H + n] = h * (1.f - h) * a1;
+                   },
+                   [&](int, int, float) {});
+    if (slot) cl_store_H<R>(slot->Hh + BH, m.h1, g, H, row0, B);
+    ENO_TICK(PH_STORE);
+    mv_n<R>(w.W2, Dlp, H, Dl, m.h1, H, m.red, kKGw);
+    ENO_TICK(PH_MV_H);
+    reduce_local<R>(m.red, kKGw, Dl, [&](int r, int d, float sum) { m.y1[r * Dlp + d] = sum + w.w2t[d]; });
+  }
+  if (K >= 3) {
+    for (int i = threadIdx.x; i < R * Dlp; i += blockDim.x) {
+      const float s = m.s[i];
+      const float sp = s * (1.f - s);
+      const float fi = m.f[i];
+      m.u[i] = ((i % Dlp) < Dl) ? sp * (1.f - 2.f * s) * fi * fi + sp * m.y1[i] : 0.f;
+    }
+    __syncthreads();
+    if (slot) cl_store_D<R>(slot->S + 2 * BD, m.u, g, D, row0, B);
+    ENO_TICK(PH_STORE);
+    mv_n<R>(w.W1, g.ldw1, Dl, H, m.u, Dlp, m.red, kKG);
+    ENO_TICK(PH_MV_DL);
+    allreduce_H<R>(cluster, cm, g, m.red, kKG, H, nullptr, 0,
+                   [&](int r, int n, float sum) {
+                     const float h = m.h[r * H + n];
+                     const float hp = h * (1.f - h);
+                     const float a1 = m.a1[r * H + n];
+                     m.a2[r * H + n] = sum;
+                     m.h2[r * H + n] = hp * (1.f - 2.f * h) * a1 * a1 + hp * sum;
+                   },
+                   [&](int, int, float) {});
+    if (slot) cl_store_H<R>(slot->Hh + 2 * BH, m.h2, g, H, row0, B);
+    ENO_TICK(PH_STORE);
+    mv_n<R>(w.W2, Dlp, H, Dl, m.h2, H, m.red, kKGw);
+    ENO_TICK(PH_MV_H);
+    reduce_local<R>(m.red, kKGw, Dl, [&](int r, int d, float sum) { m.y2[r * Dlp + d] = sum; });
+  }
+  if (K >= 2) {
+    cl_sumsq_local<R>((K >= 3) ? m.y2 : m.y1, g, m.scal, 0);
+    __syncthreads();
+  }
+}
+
+// Reverse sweep (aug_reverse, distributed).  zb: cotangent of f (local slice), rb[r]: cotangent of r_dot.
+// On return: zacc = vjp wrt z (local slice), rdot[r] = r_dot (all ranks), factors + per-CTA t_bar pieces stored.
+template <int R, int K>
+__device__ __forceinline__ void cl_aug_reverse(cg::cluster_group& cluster, ClComm& cm, const ClGeom& g,
+                                               const ClWeights& w, const float* zb, const float* rb,
+                                               const ClScratch& m, const FactorSlot& slot, int row0, int B) {
+  const int D = w.D, H = w.H, Dl = g.Dl, Dlp = g.Dlp;
+  const size_t BD = (size_t)B * D, BH = (size_t)B * H;
+  const float invD2 = 2.0f / (float)D;
+  const float invD = 1.0f / (float)D;
+  auto take_rdot = [&](int r, int, float v) { m.rdot[r] = v * invD; };
+
+  if (K >= 3) {
+    for (int i = threadIdx.x; i < R * Dlp; i += blockDim.x) m.u[i] = rb[i / Dlp] * invD2 * m.y2[i];
+    __syncthreads();
+    cl_store_D<R>(slot.G + 2 * BD, m.u, g, D, row0, B);
+    ENO_TICK(PH_STORE);
+    mv_k<R>(w.W2, Dlp, H, Dl, m.u, Dlp, m.red, kKG);
+    ENO_TICK(PH_MV_DL);
+    allreduce_H<R>(cluster, cm, g, m.red, kKG, H, m.scal, 1,
+                   [&](int r, int n, float hb2) {
+                     const float h = m.h[r * H + n];
+                     const float hp = h * (1.f - h);
+                     const float hpp = hp * (1.f - 2.f * h);
+                     const float hppp = hp * (1.f - 6.f * h + 6.f * h * h);
+                     const float a1 = m.a1[r * H + n], a2 = m.a2[r * H + n];
+                     m.ga2[r * H + n] = hb2 * hp;
+                     m.ga1[r * H + n] = hb2 * 2.f * hpp * a1;
+                     m.ga[r * H + n] = hb2 * (hppp * a1 * a1 + hpp * a2);
+                   },
+                   take_rdot);
+    cl_store_H<R>(slot.A + 2 * BH, m.ga2, g, H, row0, B);
+    ENO_TICK(PH_STORE);
+    mv_k<R>(w.W1, g.ldw1, Dl, H, m.ga2, H, m.red, kKGw);
+    ENO_TICK(PH_MV_H);
+    reduce_local<R>(m.red, kKGw, Dl, [&](int r, int d, float sb2) {
+      const int i = r * Dlp + d;
+      const float s = m.s[i];
+      const float sp = s * (1.f - s);
+      const float spp = sp * (1.f - 2.f * s);
+      const float sppp = sp * (1.f - 6.f * s + 6.f * s * s);
+      const float fi = m.f[i];
+      m.zacc[i] = sb2 * (sppp * fi * fi + spp * m.y1[i]);
+      m.gf[i] = sb2 * 2.f * spp * fi;
+      m.gy1[i] = sb2 * sp;
+    });
+  } else if (K == 2) {
+    for (int i = threadIdx.x; i < R * Dlp; i += blockDim.x) {
+      m.gy1[i] = rb[i / Dlp] * invD2 * m.y1[i];
+      m.gf[i] = 0.f;
+      m.zacc[i] = 0.f;
+    }
+    for (int i = threadIdx.x; i < R * H; i += blockDim.x) { m.ga[i] = 0.f; m.ga1[i] = 0.f; }
+    __syncthreads();
+  }
+  if (K >= 2) {
+    cl_store_D<R>(slot.G + BD, m.gy1, g, D, row0, B);
+    ENO_TICK(PH_STORE);
+    mv_k<R>(w.W2, Dlp, H, Dl, m.gy1, Dlp, m.red, kKG);
+    ENO_TICK(PH_MV_DL);
+    allreduce_H<R>(cluster, cm, g, m.red, kKG, H, (K == 2) ? m.scal : nullptr, 1,
+                   [&](int r, int n, float hb1) {
+                     const float h = m.h[r * H + n];
+                     const float hp = h * (1.f - h);
+                     const float hpp = hp * (1.f - 2.f * h);
+                     m.ga[r * H + n] += hb1 * hpp * m.a1[r * H + n];
+                     m.ga1[r * H + n] += hb1 * hp;
+                   },
+                   take_rdot);
+    cl_store_H<R>(slot.A + BH, m.ga1, g, H, row0, B);
+    ENO_TICK(PH_STORE);
+    mv_k<R>(w.W1, g.ldw1, Dl, H, m.ga1, H, m.red, kKGw);
+    ENO_TICK(PH_MV_H);
+    reduce_local<R>(m.red, kKGw, Dl, [&](int r, int d, float sb1) {
+      const int i = r * Dlp + d;
+      const float s = m.s[i];
+      const float sp = s * (1.f - s);
+      const float spp = sp * (1.f - 2.f * s);
+      m.zacc[i] += sb1 * spp * m.f[i];
+      m.gf[i] += sb1 * sp + zb[i];
+    });
+  } else {
+    for (int i = threadIdx.x; i < R * Dlp; i += blockDim.x) { m.gf[i] = zb[i]; m.zacc[i] = 0.f; }
+    for (int i = threadIdx.x; i < R * H; i += blockDim.x) m.ga[i] = 0.f;
+    if (threadIdx.x < R) m.rdot[threadIdx.x] = 0.f;
+    __syncthreads();
+  }
+  cl_store_D<R>(slot.G, m.gf, g, D, row0, B);
+    ENO_TICK(PH_STORE);
+  mv_k<R>(w.W2, Dlp, H, Dl, m.gf, Dlp, m.red, kKG);
+    ENO_TICK(PH_MV_DL);
+  allreduce_H<R>(cluster, cm, g, m.red, kKG, H, nullptr, 0,
+                 [&](int r, int n, float hb) {
+                   const float h = m.h[r * H + n];
+                   m.ga[r * H + n] += hb * h * (1.f - h);
+                 },
+                 [&](int, int, float) {});
+  cl_store_H<R>(slot.A, m.ga, g, H, row0, B);
+    ENO_TICK(PH_STORE);
+  mv_k<R>(w.W1, g.ldw1, Dl, H, m.ga, H, m.red, kKGw);
+    ENO_TICK(PH_MV_H);
+  reduce_local<R>(m.red, kKGw, Dl, [&](int r, int d, float sb) {
+    const int i = r * Dlp + d;
+    const float s = m.s[i];
+    m.zacc[i] += sb * s * (1.f - s);
+  });
+  // per-CTA piece of vjp wrt t: f_bar . w2t over the local slice (+ a_bar . w1t on rank 0)
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = warp; r < R; r += nw) {
+      double acc = 0.0;
+      for (int d = lane; d < Dl; d += 32) acc += (double)(m.gf[r * Dlp + d] * w.w2t[d]);
+      if (g.rank == 0)
+        for (int n = lane; n < H; n += 32) acc += (double)(m.ga[r * H + n] * w.w1t[n]);
+      acc = warp_sum(acc);
+      if (lane == 0 && row0 + r < B) slot.tbar[(size_t)g.rank * B + row0 + r] = (float)acc;
+    }
+  }
+  __syncthreads();
+  ENO_TICK(PH_SCALAR);
+}
+
+}  // namespace eno

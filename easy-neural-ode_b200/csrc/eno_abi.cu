@@ -6,7 +6,8 @@
 #include <cstring>
 #include <string>
 
-#include "adj_kernels.cuh"
+#include "adj_host.cuh"
+#include "cl_kernels.cuh"
 #include "fwd_kernels.cuh"
 #include "tableaux.cuh"
 
@@ -19,6 +20,7 @@ struct eno_ctx {
   int hint_fwd = 8;         // launches to enqueue before the first poll
   int hint_bwd = 8;
   int sm_count = 148;
+  int path_mode = 0;        // 0 auto, 1 force streamed weights, 2 force cluster-resident (ENO_PATH)
   Profiler prof;
 };
 
@@ -93,7 +95,7 @@ __global__ void k_ffma_peak(float* sink, int iters, float m) {
 
 size_t fwd_ws_bytes(int B, int D) {
   const size_t N = (size_t)B * D;
-  return align_up(sizeof(Ctrl)) + align_up(3 * N * 4) * 2 + align_up(2 * N * 4) + 2 * align_up((size_t)B * 8) + 1024;
+  return align_up(sizeof(Ctrl)) + align_up(3 * N * 4) * 2 + align_up(2 * N * 4) + 2 * align_up((size_t)kC * B * 8) + 1024;
 }
 
 template <typename KernelT>
@@ -141,6 +143,10 @@ int32_t eno_create(eno_ctx** out, int32_t device) {
     cudaFreeHost(c->mailbox);
     delete c;
     return fail(nullptr, ENO_E_UNSUPPORTED, m);
+  }
+  if (const char* pm = getenv("ENO_PATH")) {
+    if (!strcmp(pm, "stream")) c->path_mode = 1;
+    if (!strcmp(pm, "cluster")) c->path_mode = 2;
   }
   *out = c;
   return ENO_OK;
@@ -198,8 +204,8 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   a.Y = cv.take<float>(3 * N);
   a.F = cv.take<float>(3 * N);
   a.MID = cv.take<float>(2 * N);
-  a.rowpart0 = cv.take<double>(B);
-  a.rowpart1 = cv.take<double>(B);
+  a.rowpart0 = cv.take<double>((size_t)kC * B);
+  a.rowpart1 = cv.take<double>((size_t)kC * B);
   a.w = mlp_weights_from_flat(params, D, H, nullptr, nullptr);
   a.B = B;
   a.N = N;
@@ -233,16 +239,42 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
         const int ps_ = ctx->prof.begin(PROF_FWD_STEP, stream);                     \
         k_fwd_step<RR><<<grid, kThreads, smem, stream>>>(a);                        \
         ctx->prof.end(ps_, stream);                                                 \
-        k_fwd_out<<<out_grid, 256, 0, stream>>>(a);                                 \
-        launches += 2;                                                              \
+        ++launches;                                                                 \
+        if (T > 2) { k_fwd_out<<<out_grid, 256, 0, stream>>>(a); ++launches; }      \
       }                                                                             \
+      if (T <= 2) { k_fwd_out<<<out_grid, 256, 0, stream>>>(a); ++launches; }       \
       ENO_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, a.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream)); \
       ENO_CUDA(ctx, cudaStreamSynchronize(stream));                                 \
       if (ctx->mailbox->done) break;                                                \
       chunk = 4;                                                                    \
     }                                                                               \
   }
-  if (R == 1) ENO_FWD_DISPATCH(1)
+  const bool use_cluster = ctx->path_mode != 1 && cl_supported(D, H, kClRows, tab.s < 2 ? 2 : tab.s, false);
+  if (use_cluster) {
+    const size_t csm = cl_smem_bytes(kClRows, D, H, tab.s < 2 ? 2 : tab.s, false);
+    const int cgrid = cl_grid(B);
+    ENO_CUDA(ctx, cl_fwd_launch(1, a, cgrid, csm, stream));
+    ENO_CUDA(ctx, cl_fwd_launch(2, a, cgrid, csm, stream));
+    launches += 2;
+    int chunk = ctx->hint_fwd;
+    const int out_grid = (int)((N + 1023) / 1024) < 4 * ctx->sm_count ? (int)((N + 1023) / 1024) : 4 * ctx->sm_count;
+    for (;;) {
+      for (int i = 0; i < chunk; ++i) {
+        const int ps_ = ctx->prof.begin(PROF_FWD_STEP, stream);
+        ENO_CUDA(ctx, cl_fwd_launch(0, a, cgrid, csm, stream));
+        ctx->prof.end(ps_, stream);
+        ++launches;
+        // with several output times a step can leave targets behind mid-solve: evaluate them before
+        // the next step recycles the ring; with a single target one output launch per chunk suffices
+        if (T > 2) { k_fwd_out<<<out_grid, 256, 0, stream>>>(a); ++launches; }
+      }
+      if (T <= 2) { k_fwd_out<<<out_grid, 256, 0, stream>>>(a); ++launches; }
+      ENO_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, a.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+      ENO_CUDA(ctx, cudaStreamSynchronize(stream));
+      if (ctx->mailbox->done) break;
+      chunk = 4;
+    }
+  } else if (R == 1) ENO_FWD_DISPATCH(1)
   else if (R == 2) ENO_FWD_DISPATCH(2)
   else ENO_FWD_DISPATCH(4)
 #undef ENO_FWD_DISPATCH
@@ -278,7 +310,7 @@ int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32
     ENO_CUDA(ctx, cudaStreamSynchronize(stream));
     return ENO_OK;
   }
-  return adj_rhs(ctx ? &ctx->err : nullptr, ctx->sm_count, desc, mode, B, y, t, params, y_bar, r_bar, workspace,
+  return adj_rhs(ctx->path_mode, &ctx->err, ctx->sm_count, desc, mode, B, y, t, params, y_bar, r_bar, workspace,
                  workspace_bytes, dy_out, aux_out, ybar_dot_out, tbar_out, params_bar_out, stream);
 }
 
@@ -292,7 +324,7 @@ int32_t eno_odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, c
   ENO_CUDA(ctx, cudaSetDevice(ctx->device));
   if (desc->aug != ENO_AUG_NONE && desc->aug != ENO_AUG_REG)
     return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: aug must be ENO_AUG_NONE or ENO_AUG_REG");
-  return adj_solve(&ctx->prof, &ctx->err, ctx->mailbox, &ctx->hint_bwd, ctx->sm_count, desc, B, ys, ts, T, params, g_y, g_r, rtol,
+  return adj_solve(&ctx->prof, ctx->path_mode, &ctx->err, ctx->mailbox, &ctx->hint_bwd, ctx->sm_count, desc, B, ys, ts, T, params, g_y, g_r, rtol,
                    atol, mxstep, workspace, workspace_bytes, y0_bar_out, r0_bar_out, ts_bar_out, params_bar_out,
                    stats_host, trace_out, trace_cap, static_cast<cudaStream_t>(stream_));
 }
@@ -342,5 +374,18 @@ int32_t eno_ffma_peak(eno_ctx* ctx, double* tflops_out, void* stream_) {
   *tflops_out = best;
   return ENO_OK;
 }
+
+#ifdef ENO_PHASES
+// development aid: read and clear the phase clocks of the cluster kernels
+int32_t eno_debug_phases(long long* cycles, long long* counts) {
+  long long zero[PH_NKINDS] = {0};
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(cycles, g_phase_cycles, sizeof(long long) * PH_NKINDS);
+  cudaMemcpyFromSymbol(counts, g_phase_count, sizeof(long long) * PH_NKINDS);
+  cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero));
+  cudaMemcpyToSymbol(g_phase_count, zero, sizeof(zero));
+  return PH_NKINDS;
+}
+#endif
 
 }  // extern "C"

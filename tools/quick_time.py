@@ -33,3 +33,16 @@ for _ in range(n):
     eno.odeint(m.spec.dynamics_wrap, x0, m.ts, m.p_ode, rtol=tol, atol=tol)
 e1.record(); torch.cuda.synchronize()
 print(f"forward solve {e0.elapsed_time(e1)/n:.3f} ms")
+# per-kernel device times from the library's profiling hooks
+import ctypes as C
+from easy_neural_ode_b200 import _cabi
+L = _cabi.lib(); h = _cabi.ctx(0)
+L.eno_profile_enable(h, 1)
+for _ in range(5):
+    m.loss_and_grads(images, labels, eps)
+torch.cuda.synchronize()
+L.eno_profile_enable(h, 0)
+ms = (C.c_double * 4)(); cnt = (C.c_int64 * 4)()
+L.eno_profile_read(h, ms, cnt)
+for name, a, b in zip(["fwd_step", "adj_rows", "adj_pgrad"], ms, cnt):
+    print(f"{name}: {1e3*a/max(b,1):.1f} us avg over {b} launches")
