@@ -18,7 +18,8 @@ TABLEAUX = {"dopri5": 0, "heun": 1, "fehlberg": 2, "bosh": 3, "rk_fehlberg": 4, 
 # every symbol include/eno.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["eno_abi_version", "eno_last_error_string", "eno_create", "eno_destroy", "eno_param_count",
            "eno_adjoint_state_size", "eno_workspace_bytes", "eno_odeint_fwd", "eno_odeint_bwd", "eno_rhs",
-           "eno_profile_enable", "eno_profile_read", "eno_ffma_peak"]
+           "eno_profile_enable", "eno_profile_read", "eno_ffma_peak", "eno_comm_unique_id", "eno_comm_init",
+           "eno_comm_destroy"]
 
 
 class Desc(C.Structure):
@@ -79,6 +80,12 @@ def lib():
     L.eno_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.eno_ffma_peak.restype = i32
     L.eno_ffma_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
+    L.eno_comm_unique_id.restype = i32
+    L.eno_comm_unique_id.argtypes = [vp, vp, C.c_char_p]
+    L.eno_comm_init.restype = i32
+    L.eno_comm_init.argtypes = [vp, vp, i32, i32, C.c_char_p]
+    L.eno_comm_destroy.restype = i32
+    L.eno_comm_destroy.argtypes = [vp]
     _lib = L
     return L
 

@@ -6,6 +6,7 @@
 
 #include "adj_kernels.cuh"
 #include "cl_kernels.cuh"
+#include "dist.cuh"
 #include "tableaux.cuh"
 
 namespace eno {
@@ -15,7 +16,7 @@ namespace eno {
 // ======================================================================================
 inline size_t adj_align(size_t x) { return (x + 255) / 256 * 256; }
 
-inline size_t adj_ws_bytes(int B, int D, int H) {
+inline size_t adj_ws_bytes(int B, int D, int H, int world = 1) {
   const size_t N = (size_t)B * D, P = (size_t)(D + 1) * H + H + (size_t)(H + 1) * D + D;
   const PgradGeom g = pgrad_geom(D, H);
   size_t s = 0;
@@ -24,8 +25,10 @@ inline size_t adj_ws_bytes(int B, int D, int H) {
   s += 2 * adj_align(3 * (size_t)B * 4) + adj_align((size_t)B * 4);  // RS, FR, RB
   s += adj_align(2 * N * 4);                        // MIDZB
   s += 2 * adj_align(3 * P * 4) + adj_align(2 * P * 4);             // PB, FP, MIDP
-  s += kSlots * (2 * adj_align(3 * N * 4) + 2 * adj_align(3 * (size_t)B * H * 4) + adj_align((size_t)kC * B * 4));
-  s += 3 * adj_align((size_t)kC * B * 8) + 2 * adj_align((size_t)g.grid * 8);
+  const size_t npp = std::max((size_t)g.grid, (P + 255) / 256);
+  s += kSlots * (2 * adj_align(3 * N * 4) + 2 * adj_align(3 * (size_t)B * H * 4) + adj_align((size_t)kC * B * world * 4));
+  s += 3 * adj_align((size_t)kC * B * world * 8) + 2 * adj_align(npp * 8);
+  if (world > 1) s += adj_align(4 * P * 4);          // pcomb
   s += adj_align(N * 4) + adj_align(P * 4);         // YBAR, POUT
   s += 2 * adj_align((size_t)D * H * 4);            // transposes
   return s + 4096;
@@ -42,7 +45,7 @@ struct AdjCarver {
   }
 };
 
-inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArgs* a) {
+inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArgs* a, int world = 1) {
   const size_t N = (size_t)B * D, P = (size_t)(D + 1) * H + H + (size_t)(H + 1) * D + D;
   const PgradGeom g = pgrad_geom(D, H);
   AdjCarver cv{static_cast<char*>(ws)};
@@ -58,12 +61,15 @@ inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArg
     a->slot[j].G = cv.take<float>(3 * N);
     a->slot[j].A = cv.take<float>(3 * (size_t)B * H);
     a->slot[j].Hh = cv.take<float>(3 * (size_t)B * H);
-    a->slot[j].tbar = cv.take<float>((size_t)kC * B);
+    a->slot[j].tbar = cv.take<float>((size_t)kC * B * world);
   }
-  a->rowpart0 = cv.take<double>((size_t)kC * B); a->rowpart1 = cv.take<double>((size_t)kC * B);
-  a->rowpart2 = cv.take<double>((size_t)kC * B);
+  a->rowpart0 = cv.take<double>((size_t)kC * B * world); a->rowpart1 = cv.take<double>((size_t)kC * B * world);
+  a->rowpart2 = cv.take<double>((size_t)kC * B * world);
   a->n_rp = B;
-  a->ppart0 = cv.take<double>(g.grid); a->ppart1 = cv.take<double>(g.grid);
+  const size_t npp = std::max((size_t)g.grid, (P + 255) / 256);
+  a->ppart0 = cv.take<double>(npp); a->ppart1 = cv.take<double>(npp);
+  a->pcomb = (world > 1) ? cv.take<float>(4 * P) : nullptr;
+  a->dist = 0;
   a->YBAR = cv.take<float>(N);
   a->POUT = cv.take<float>(P);
   float* W1xT = cv.take<float>((size_t)D * H);
@@ -121,6 +127,18 @@ inline int adj_rows(int R, int K, int mode, const AdjArgs& a, int grid, size_t s
   return ENO_E_UNSUPPORTED;
 }
 
+// Point the kernels' write views at this rank's chunk of the gathered partial-sum arrays.
+inline void adj_set_views(AdjArgs* a, int stride, int rank, int world) {
+  const size_t n_loc = (size_t)stride * a->B;
+  a->n_rp = (int)(n_loc * world);
+  a->rp0_all = a->rowpart0; a->rp1_all = a->rowpart1; a->rp2_all = a->rowpart2;
+  a->rowpart0 += (size_t)rank * n_loc; a->rowpart1 += (size_t)rank * n_loc; a->rowpart2 += (size_t)rank * n_loc;
+  for (int j = 0; j < kSlots; ++j) {
+    a->tbar_all[j] = a->slot[j].tbar;
+    a->slot[j].tbar += (size_t)rank * n_loc;
+  }
+}
+
 // One launch of the per-sample kernel on the chosen path.
 struct AdjPlan {
   bool cluster;
@@ -163,7 +181,7 @@ inline void adj_transposes(const AdjArgs& a, cudaStream_t st) {
   k_transpose<<<dim3((D + 31) / 32, (H + 31) / 32), blk, 0, st>>>(a.w.W2x, const_cast<float*>(a.w.W2xT), H, D);
 }
 
-inline int adj_solve(Profiler* prof, int path_mode, std::string* err, Ctrl* mailbox, int* hint, int sms, const eno_dynamics_desc* desc, int B,
+inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, std::string* err, Ctrl* mailbox, int* hint, int sms, const eno_dynamics_desc* desc, int B,
                      const float* ys, const float* ts, int T, const float* params, const float* g_y, const float* g_r,
                      float rtol, float atol, int mxstep, void* ws, size_t ws_bytes, float* y0_bar_out,
                      float* r0_bar_out, float* ts_bar_out, float* params_bar_out, eno_stats* stats,
@@ -172,14 +190,18 @@ inline int adj_solve(Profiler* prof, int path_mode, std::string* err, Ctrl* mail
   if (!(K == 0 || K == 2 || K == 3)) { if (err) *err = "eno_odeint_bwd: reg_order must be 0, 2 or 3"; return ENO_E_UNSUPPORTED; }
   if (B <= 0 || T < 1 || !ys || !ts || !params || !g_y || !g_r || !ws || !y0_bar_out || !r0_bar_out || !ts_bar_out ||
       !params_bar_out) { if (err) *err = "eno_odeint_bwd: null pointer or empty batch"; return ENO_E_ARG; }
-  if (ws_bytes < adj_ws_bytes(B, D, H)) { if (err) *err = "eno_odeint_bwd: workspace too small"; return ENO_E_WORKSPACE; }
+  const bool dist = dc && dc->active();
+  const int world = dist ? dc->world : 1, rank = dist ? dc->rank : 0;
+  if (ws_bytes < adj_ws_bytes(B, D, H, world)) { if (err) *err = "eno_odeint_bwd: workspace too small"; return ENO_E_WORKSPACE; }
   const size_t N = (size_t)B * D;
   AdjArgs a = {};
-  adj_carve(ws, B, D, H, params, &a);
+  adj_carve(ws, B, D, H, params, &a, world);
+  a.dist = dist ? 1 : 0;
   a.np = (K == 0) ? 1 : K;
   {
     const size_t n_aux = (desc->aug == ENO_AUG_NONE) ? 0 : 1;
-    a.n_state = (float)(2 * (N + n_aux * (size_t)B) + 1 + (desc->eps_in_args ? N : 0) + (size_t)a.P);
+    const size_t Ng = N * world, Bg = (size_t)B * world;   // the ODE state spans the GLOBAL batch
+    a.n_state = (float)(2 * (Ng + n_aux * Bg) + 1 + (desc->eps_in_args ? Ng : 0) + (size_t)a.P);
   }
   a.trace = trace;
   Tableau tab;
@@ -187,8 +209,28 @@ inline int adj_solve(Profiler* prof, int path_mode, std::string* err, Ctrl* mail
   ENO_ADJ_CHECK(cudaMemcpyToSymbolAsync(c_tab, &tab, sizeof(Tableau), 0, cudaMemcpyHostToDevice, st));
   const AdjPlan plan = adj_plan(B, D, H, sms, path_mode, false);
   if (!plan.cluster) adj_transposes(a, st);
-  a.n_rp = plan.cluster ? kC * B : B;
+  adj_set_views(&a, plan.cluster ? kC : 1, rank, world);
   const PgradGeom geo = pgrad_geom(D, H);
+  const size_t n_loc = (size_t)(plan.cluster ? kC : 1) * B;
+  const int pf_grid = (a.P + 255) / 256;
+  // multi-GPU continuation of one pgrad launch: exchange, then the replicated finish kernel
+  auto exchange = [&](int mode) -> int {
+    if (!dist) return 0;
+    int rc = dc->api.GroupStart();
+    rc |= dc->allreduce(a.pcomb, (mode == ADJ_STEP ? 4 : 1) * (size_t)a.P, st);
+    rc |= dc->gather(const_cast<double*>(a.rp0_all), n_loc, st);
+    if (mode == ADJ_INIT0) {
+      rc |= dc->gather(const_cast<double*>(a.rp1_all), n_loc, st);
+      rc |= dc->gather(const_cast<double*>(a.rp2_all), n_loc, st);
+    }
+    for (int j = 0; j < (mode == ADJ_STEP ? kSlots : 1); ++j) rc |= dc->gather(const_cast<float*>(a.tbar_all[j]), n_loc, st);
+    rc |= dc->api.GroupEnd();
+    if (rc) { if (err) *err = "eno_odeint_bwd: NCCL exchange failed"; return ENO_E_CUDA; }
+    if (mode == ADJ_STEP) k_adj_pfinish<ADJ_STEP><<<pf_grid, 256, 0, st>>>(a);
+    else if (mode == ADJ_INIT0) k_adj_pfinish<ADJ_INIT0><<<pf_grid, 256, 0, st>>>(a);
+    else k_adj_pfinish<ADJ_INIT1><<<pf_grid, 256, 0, st>>>(a);
+    return 0;
+  };
   const int egrid = (int)std::min<size_t>((std::max(N, (size_t)a.P) + 255) / 256, (size_t)4 * sms);
   const int mx = mxstep <= 0 ? INT_MAX : mxstep;
   int worst = ENO_OK;
@@ -212,9 +254,11 @@ inline int adj_solve(Profiler* prof, int path_mode, std::string* err, Ctrl* mail
     int rc;
     if ((rc = adj_rows_any(plan, K, ADJ_INIT0, a, 0.f, st, err))) return rc;
     k_adj_pgrad<ADJ_INIT0><<<geo.grid, kSlots * kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
+    if ((rc = exchange(ADJ_INIT0))) return rc;
     if ((rc = adj_rows_any(plan, K, ADJ_INIT1, a, 0.f, st, err))) return rc;
     k_adj_pgrad<ADJ_INIT1><<<geo.grid, kSlots * kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
-    launches += 5;
+    if ((rc = exchange(ADJ_INIT1))) return rc;
+    launches += dist ? 7 : 5;
     int chunk = *hint;
     for (;;) {
       for (int k = 0; k < chunk; ++k) {
@@ -224,7 +268,8 @@ inline int adj_solve(Profiler* prof, int path_mode, std::string* err, Ctrl* mail
         ps = prof->begin(PROF_ADJ_PGRAD, st);
         k_adj_pgrad<ADJ_STEP><<<geo.grid, kSlots * kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
         prof->end(ps, st);
-        launches += 2;
+        if ((rc = exchange(ADJ_STEP))) return rc;
+        launches += dist ? 3 : 2;
       }
       // A segment has one target, so a dense output can only become pending on the iteration that ends
       // it; later launches exit at their first instruction and leave the rings intact.  One output
@@ -274,7 +319,7 @@ inline int adj_rhs(int path_mode, std::string* err, int sms, const eno_dynamics_
   a.np = (K == 0) ? 1 : K;
   const AdjPlan plan = adj_plan(B, D, H, sms, path_mode, true);
   if (!plan.cluster) adj_transposes(a, st);
-  a.n_rp = plan.cluster ? kC * B : B;
+  adj_set_views(&a, plan.cluster ? kC : 1, 0, 1);
   ENO_ADJ_CHECK(cudaMemcpyAsync(a.Z, y, N * 4, cudaMemcpyDeviceToDevice, st));
   if (mode == 2) {
     ENO_ADJ_CHECK(cudaMemcpyAsync(a.ZB, y_bar, N * 4, cudaMemcpyDeviceToDevice, st));

@@ -55,8 +55,12 @@ struct AdjArgs {
   // factors
   FactorSlot slot[kSlots];
   // partial sums
-  double *rowpart0, *rowpart1, *rowpart2;  // [B]
+  double *rowpart0, *rowpart1, *rowpart2;  // per-sample partials of THIS rank's rows (views into rp*_all)
+  const double *rp0_all, *rp1_all, *rp2_all;   // all ranks, canonical global row order, n_rp entries
+  const float* tbar_all[kSlots];           // same for the per-sample t_bar pieces of every slot
   double *ppart0, *ppart1;                 // [pgrad grid]
+  float* pcomb;                            // [4][P] multi-GPU: this rank's share of the stage combinations
+  int dist;                                // 1: multi-GPU split (local contraction | NCCL | finish)
   // segment inputs / outputs
   const float* g_y;        // [N]   g[i] (for t_bar)
   const float* g_r;        // [B]
@@ -355,6 +359,115 @@ __global__ void __launch_bounds__(kThreads, 1) k_adj_rows(AdjArgs a, float rhs_t
   }
 }
 
+// Norm over ALL blocks of the adjoint state, the t0_bar element, and the controller
+// (lib/ode.py:86-104 for the init modes, 836-847 for an iteration).  Runs in one CTA; `n_pp` is the
+// number of parameter-block partial sums in ppart0/ppart1.  Inputs are the per-sample partials
+// (rowpart*, slot[].tbar: n_rp entries each, already gathered from every rank in the multi-GPU case).
+template <int MODE>
+__device__ __forceinline__ void adj_finalize(AdjArgs& a, Ctrl* c, double* dred, int n_pp, float dt,
+                                             float* rhs_tbar) {
+  constexpr bool SPLITK = (MODE != ADJ_STEP);
+  constexpr int NS = kSlots;
+  const int B = a.B;
+  (void)B;
+  const float rtol = c->rtol, atol = c->atol;
+  const float h0 = c->h0;
+  __shared__ double fin[12];
+  {
+    double v;
+    v = block_sum_global(a.rp0_all, a.n_rp, dred); if (threadIdx.x == 0) fin[0] = v; __syncthreads();
+    v = block_sum_global(a.ppart0, n_pp, dred); if (threadIdx.x == 0) fin[1] = v; __syncthreads();
+    if (MODE == ADJ_INIT0) {
+      v = block_sum_global(a.rp1_all, a.n_rp, dred); if (threadIdx.x == 0) fin[2] = v; __syncthreads();
+      v = block_sum_global(a.ppart1, n_pp, dred); if (threadIdx.x == 0) fin[3] = v; __syncthreads();
+      v = block_sum_global(a.rp2_all, a.n_rp, dred); if (threadIdx.x == 0) fin[4] = v; __syncthreads();
+    }
+    // stage derivatives of t0_bar: sums of the per-sample t_bar contributions
+    for (int j = 0; j < (SPLITK ? 1 : NS); ++j) {
+      const float* tb = a.tbar_all[j];
+      const int per = (a.n_rp + blockDim.x - 1) / blockDim.x;
+      const int b0 = threadIdx.x * per, b1 = min(a.n_rp, b0 + per);
+      double acc = 0.0;
+      for (int i = b0; i < b1; ++i) acc += (double)tb[i];
+      dred[threadIdx.x] = acc;
+      __syncthreads();
+      for (int o = 256; o > 0; o >>= 1) {
+        if (threadIdx.x < o && threadIdx.x + o < blockDim.x) dred[threadIdx.x] += dred[threadIdx.x + o];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) fin[5 + j] = dred[0];
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x != 0) return;
+  c->ticket = 0;
+  AdjScalars* sc = a.sc;
+  if (MODE == ADJ_RHS) {
+    if (rhs_tbar) *rhs_tbar = (float)fin[5];
+    return;
+  }
+  if (MODE == ADJ_INIT0) {
+    // t_bar of this output time, then the state's t0_bar element (lib/ode.py:1513-1514)
+    const float t_bar = (float)fin[4];
+    *a.tbar_out = t_bar;
+    const float t0b = sc->t0[0] - t_bar;
+    sc->t0[0] = t0b;
+    const float f0 = (float)fin[5];
+    sc->ft0[0] = f0;
+    const float s = atol + fabsf(t0b) * rtol;
+    const double q0 = (double)(t0b / s) * (double)(t0b / s), q1 = (double)(f0 / s) * (double)(f0 / s);
+    const float d0 = sqrtf((float)(fin[0] + fin[1] + q0));
+    const float d1 = sqrtf((float)(fin[2] + fin[3] + q1));
+    c->d0 = d0; c->d1 = d1;
+    c->h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+    return;
+  }
+  if (MODE == ADJ_INIT1) {
+    const float s = atol + fabsf(sc->t0[0]) * rtol;
+    const float qt = ((float)fin[5] - sc->ft0[0]) / s;
+    const float d1 = c->d1;
+    const float d2 = sqrtf((float)(fin[0] + fin[1] + (double)(qt * qt))) / h0;
+    float h1;
+    if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
+    else h1 = powf(0.01f / (d1 + d2), 1.0f / ((float)c_tab.init_order + 1.0f));
+    c->dt = fminf(100.f * h0, h1);
+    if (isnan(h0) || isnan(h1)) c->dt = nanf("");
+    c->t = sc->seg_ts[0];
+    c->last_t = c->t;
+    c->step_dt = 0.f;
+    c->cur = 0; c->prev = 2; c->cand = 1; c->mid_acc = 0;
+    c->iters_tgt = 0; c->tgt = 1;
+    c->n_iters = 0; c->n_accepted = 0; c->nfe = 2;
+    c->out_begin = 1; c->out_end = 1;
+    c->done = 0; c->status = ENO_OK;
+    advance_targets(c, sc->seg_ts);
+    return;
+  }
+  // ADJ_STEP
+  {
+    const int cur = c->cur, cand = c->cand, midw = c->mid_acc ^ 1;
+    const float k0 = sc->ft0[cur];
+    float s = c_tab.c_sol[0] * k0, er = c_tab.c_err[0] * k0, md = c_tab.c_mid[0] * k0, k6 = 0.f;
+    for (int j = 0; j < kSlots; ++j) {
+      const float kj = (float)fin[5 + j];
+      s = fmaf(c_tab.c_sol[j + 1], kj, s);
+      er = fmaf(c_tab.c_err[j + 1], kj, er);
+      md = fmaf(c_tab.c_mid[j + 1], kj, md);
+      k6 = kj;
+    }
+    const float p0 = sc->t0[cur];
+    const float p1 = fmaf(dt, s, p0);
+    const float tol = atol + rtol * fmaxf(fabsf(p0), fabsf(p1));
+    const float q = dt * er / tol;
+    sc->t0[cand] = p1;
+    sc->ft0[cand] = k6;
+    sc->midt0[midw] = fmaf(dt, md, p0);
+    const double total = fin[0] + fin[1] + (double)(q * q);
+    const float ratio = (float)(total / (double)a.n_state);
+    finish_iteration(c, sc->seg_ts, ratio, dt, c_tab, a.trace);
+  }
+}
+
 // --------------------------------------------------------------------------------------
 // Parameter-gradient contraction.  Block kinds by blockIdx.x:
 //   [0, nt1)            : 32x32 tiles of dW1x  (M = D rows, N = H cols),  A = S,  Bm = A-factors
@@ -497,6 +610,34 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
   }
   __syncthreads();
 
+  if (a.dist) {
+    // multi-GPU: this rank only holds the sums over ITS rows.  Everything downstream is linear in the
+    // stage derivatives, so ship the four stage combinations (without the replicated k0 term) and let
+    // k_adj_pfinish continue after the all-reduce.
+    const size_t P = (size_t)a.P;
+    for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
+      const int p = pidx[e];
+      if (p < 0) continue;
+      if (MODE == ADJ_STEP) {
+        float s = 0.f, er = 0.f, md = 0.f;
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) {
+          const float kj = tile[j][e];
+          s = fmaf(c_tab.c_sol[j + 1], kj, s);
+          er = fmaf(c_tab.c_err[j + 1], kj, er);
+          md = fmaf(c_tab.c_mid[j + 1], kj, md);
+        }
+        a.pcomb[p] = s;
+        a.pcomb[P + p] = er;
+        a.pcomb[2 * P + p] = md;
+        a.pcomb[3 * P + p] = tile[kSlots - 1][e];
+      } else {
+        a.pcomb[p] = ((((tile[0][e] + tile[1][e]) + tile[2][e]) + tile[3][e]) + tile[4][e]) + tile[5][e];
+      }
+    }
+    return;
+  }
+
   // ---- combine the stage derivatives of this tile ----------------------------------------
   const float rtol = c->rtol, atol = c->atol;
   double part0 = 0.0, part1 = 0.0;
@@ -583,100 +724,72 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
 
   // ---- last CTA: norm over all blocks, t0_bar element, controller -----------------------
   if (!elect_last_block(&c->ticket)) return;
-  __shared__ double fin[12];
-  {
-    double v;
-    v = block_sum_global(a.rowpart0, a.n_rp, dred); if (threadIdx.x == 0) fin[0] = v; __syncthreads();
-    v = block_sum_global(a.ppart0, geo.grid, dred); if (threadIdx.x == 0) fin[1] = v; __syncthreads();
-    if (MODE == ADJ_INIT0) {
-      v = block_sum_global(a.rowpart1, a.n_rp, dred); if (threadIdx.x == 0) fin[2] = v; __syncthreads();
-      v = block_sum_global(a.ppart1, geo.grid, dred); if (threadIdx.x == 0) fin[3] = v; __syncthreads();
-      v = block_sum_global(a.rowpart2, a.n_rp, dred); if (threadIdx.x == 0) fin[4] = v; __syncthreads();
-    }
-    // stage derivatives of t0_bar: sums of the per-sample t_bar contributions
-    for (int j = 0; j < (SPLITK ? 1 : NS); ++j) {
-      const float* tb = a.slot[j].tbar;
-      const int per = (a.n_rp + blockDim.x - 1) / blockDim.x;
-      const int b0 = threadIdx.x * per, b1 = min(a.n_rp, b0 + per);
-      double acc = 0.0;
-      for (int i = b0; i < b1; ++i) acc += (double)tb[i];
-      dred[threadIdx.x] = acc;
-      __syncthreads();
-      for (int o = 256; o > 0; o >>= 1) {
-        if (threadIdx.x < o && threadIdx.x + o < blockDim.x) dred[threadIdx.x] += dred[threadIdx.x + o];
-        __syncthreads();
-      }
-      if (threadIdx.x == 0) fin[5 + j] = dred[0];
-      __syncthreads();
+  adj_finalize<MODE>(a, c, dred, geo.grid, dt, rhs_tbar);
+}
+
+// Multi-GPU continuation of k_adj_pgrad: pcomb now holds the all-reduced stage combinations of the
+// params_bar block.  One thread per parameter forms candidate / error / mid-point (STEP) or the
+// initial-step partial norms (INIT*), the last CTA runs the same finaliser as the single-GPU kernel.
+// Every rank executes it on identical inputs.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_adj_pfinish(AdjArgs a) {
+  Ctrl* c = a.ctrl;
+  if (MODE == ADJ_STEP && c->done) return;
+  __shared__ double dred[256];
+  const size_t P = (size_t)a.P;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const float rtol = c->rtol, atol = c->atol;
+  const float dt = (MODE == ADJ_STEP) ? c->dt : 0.f;
+  double part0 = 0.0, part1 = 0.0;
+  if (p < a.P) {
+    if (MODE == ADJ_STEP) {
+      const int cur = c->cur, cand = c->cand, midw = c->mid_acc ^ 1;
+      const float k0 = a.FP[(size_t)cur * P + p];
+      const float s = fmaf(c_tab.c_sol[0], k0, a.pcomb[p]);
+      const float er = fmaf(c_tab.c_err[0], k0, a.pcomb[P + p]);
+      const float md = fmaf(c_tab.c_mid[0], k0, a.pcomb[2 * P + p]);
+      const float p0 = a.PB[(size_t)cur * P + p];
+      const float p1 = fmaf(dt, s, p0);
+      const float tol = atol + rtol * fmaxf(fabsf(p0), fabsf(p1));
+      const float q = dt * er / tol;
+      part0 = (double)(q * q);
+      a.PB[(size_t)cand * P + p] = p1;
+      a.FP[(size_t)cand * P + p] = a.pcomb[3 * P + p];
+      a.MIDP[(size_t)midw * P + p] = fmaf(dt, md, p0);
+    } else if (MODE == ADJ_INIT0) {
+      const float f0 = a.pcomb[p];
+      const float p0 = a.PB[p];
+      const float sc = atol + fabsf(p0) * rtol;
+      const float q0 = p0 / sc, q1 = f0 / sc;
+      part0 = (double)(q0 * q0);
+      part1 = (double)(q1 * q1);
+      a.FP[p] = f0;
+    } else if (MODE == ADJ_INIT1) {
+      const float sc = atol + fabsf(a.PB[p]) * rtol;
+      const float q = (a.pcomb[p] - a.FP[p]) / sc;
+      part0 = (double)(q * q);
     }
   }
-  if (threadIdx.x != 0) return;
-  c->ticket = 0;
-  AdjScalars* sc = a.sc;
-  if (MODE == ADJ_RHS) {
-    if (rhs_tbar) *rhs_tbar = (float)fin[5];
-    return;
+  dred[threadIdx.x] = part0;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
+    __syncthreads();
   }
+  if (threadIdx.x == 0) a.ppart0[blockIdx.x] = dred[0];
+  __syncthreads();
   if (MODE == ADJ_INIT0) {
-    // t_bar of this output time, then the state's t0_bar element (lib/ode.py:1513-1514)
-    const float t_bar = (float)fin[4];
-    *a.tbar_out = t_bar;
-    const float t0b = sc->t0[0] - t_bar;
-    sc->t0[0] = t0b;
-    const float f0 = (float)fin[5];
-    sc->ft0[0] = f0;
-    const float s = atol + fabsf(t0b) * rtol;
-    const double q0 = (double)(t0b / s) * (double)(t0b / s), q1 = (double)(f0 / s) * (double)(f0 / s);
-    const float d0 = sqrtf((float)(fin[0] + fin[1] + q0));
-    const float d1 = sqrtf((float)(fin[2] + fin[3] + q1));
-    c->d0 = d0; c->d1 = d1;
-    c->h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
-    return;
-  }
-  if (MODE == ADJ_INIT1) {
-    const float s = atol + fabsf(sc->t0[0]) * rtol;
-    const float qt = ((float)fin[5] - sc->ft0[0]) / s;
-    const float d1 = c->d1;
-    const float d2 = sqrtf((float)(fin[0] + fin[1] + (double)(qt * qt))) / h0;
-    float h1;
-    if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
-    else h1 = powf(0.01f / (d1 + d2), 1.0f / ((float)c_tab.init_order + 1.0f));
-    c->dt = fminf(100.f * h0, h1);
-    if (isnan(h0) || isnan(h1)) c->dt = nanf("");
-    c->t = sc->seg_ts[0];
-    c->last_t = c->t;
-    c->step_dt = 0.f;
-    c->cur = 0; c->prev = 2; c->cand = 1; c->mid_acc = 0;
-    c->iters_tgt = 0; c->tgt = 1;
-    c->n_iters = 0; c->n_accepted = 0; c->nfe = 2;
-    c->out_begin = 1; c->out_end = 1;
-    c->done = 0; c->status = ENO_OK;
-    advance_targets(c, sc->seg_ts);
-    return;
-  }
-  // ADJ_STEP
-  {
-    const int cur = c->cur, cand = c->cand, midw = c->mid_acc ^ 1;
-    const float k0 = sc->ft0[cur];
-    float s = c_tab.c_sol[0] * k0, er = c_tab.c_err[0] * k0, md = c_tab.c_mid[0] * k0, k6 = 0.f;
-    for (int j = 0; j < kSlots; ++j) {
-      const float kj = (float)fin[5 + j];
-      s = fmaf(c_tab.c_sol[j + 1], kj, s);
-      er = fmaf(c_tab.c_err[j + 1], kj, er);
-      md = fmaf(c_tab.c_mid[j + 1], kj, md);
-      k6 = kj;
+    dred[threadIdx.x] = part1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
+      __syncthreads();
     }
-    const float p0 = sc->t0[cur];
-    const float p1 = fmaf(dt, s, p0);
-    const float tol = atol + rtol * fmaxf(fabsf(p0), fabsf(p1));
-    const float q = dt * er / tol;
-    sc->t0[cand] = p1;
-    sc->ft0[cand] = k6;
-    sc->midt0[midw] = fmaf(dt, md, p0);
-    const double total = fin[0] + fin[1] + (double)(q * q);
-    const float ratio = (float)(total / (double)a.n_state);
-    finish_iteration(c, sc->seg_ts, ratio, dt, c_tab, a.trace);
+    if (threadIdx.x == 0) a.ppart1[blockIdx.x] = dred[0];
+    __syncthreads();
   }
+  if (!elect_last_block(&c->ticket)) return;
+  adj_finalize<MODE>(a, c, dred, (int)gridDim.x, dt, nullptr);
 }
 
 // ---- segment set-up: state rings at index 0 (lib/ode.py:1516-1518) -------------------------

@@ -530,7 +530,7 @@ __device__ __forceinline__ void cl_aug_reverse(cg::cluster_group& cluster, ClCom
       if (g.rank == 0)
         for (int n = lane; n < H; n += 32) acc += (double)(m.ga[r * H + n] * w.w1t[n]);
       acc = warp_sum(acc);
-      if (lane == 0 && row0 + r < B) slot.tbar[(size_t)g.rank * B + row0 + r] = (float)acc;
+      if (lane == 0 && row0 + r < B) slot.tbar[(size_t)(row0 + r) * kC + g.rank] = (float)acc;
     }
   }
   __syncthreads();

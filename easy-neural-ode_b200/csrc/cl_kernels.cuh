@@ -94,7 +94,7 @@ __device__ __forceinline__ void cl_row_sums(const float* q, const ClGeom& g, int
     double acc = 0.0;
     for (int d = lane; d < g.Dl; d += 32) acc += (double)q[r * g.Dlp + d];
     acc = warp_sum(acc);
-    if (lane == 0 && row0 + r < B) out[(size_t)g.rank * B + row0 + r] = acc + ((extra && g.rank == 0) ? (double)extra[r] : 0.0);
+    if (lane == 0 && row0 + r < B) out[(size_t)(row0 + r) * kC + g.rank] = acc + ((extra && g.rank == 0) ? (double)extra[r] : 0.0);
   }
 }
 
@@ -239,12 +239,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_fwd(FwdArgs a) {
   }
   cluster.sync();   // no CTA may exit while a peer can still read its shared memory
 
+  if (a.dist) return;
   if (!elect_last_block(&c->ticket)) return;
-  const int nrp = kC * a.B;
-  const double s0 = block_sum_global(a.rowpart0, nrp, S.dred);
+  const int nrp = a.n_rp;
+  const double s0 = block_sum_global(a.rp0_all, nrp, S.dred);
   __syncthreads();
   double s1 = 0.0;
-  if (MODE == 1) s1 = block_sum_global(a.rowpart1, nrp, S.dred);
+  if (MODE == 1) s1 = block_sum_global(a.rp1_all, nrp, S.dred);
   if (threadIdx.x != 0) return;
   c->ticket = 0;
   if (MODE == 1) {
@@ -435,9 +436,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
           s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
           if (lane == 0 && row0 + r < a.B) {
             const bool lead = g.rank == 0;
-            a.rowpart0[(size_t)g.rank * B + row0 + r] = s0 + (lead ? (double)S.m.scal[r * 4 + 0] : 0.0);
-            a.rowpart1[(size_t)g.rank * B + row0 + r] = s1 + (lead ? (double)S.m.scal[r * 4 + 1] : 0.0);
-            a.rowpart2[(size_t)g.rank * B + row0 + r] = s2 + (lead ? (double)S.m.scal[r * 4 + 2] : 0.0);
+            a.rowpart0[(size_t)(row0 + r) * kC + g.rank] = s0 + (lead ? (double)S.m.scal[r * 4 + 0] : 0.0);
+            a.rowpart1[(size_t)(row0 + r) * kC + g.rank] = s1 + (lead ? (double)S.m.scal[r * 4 + 1] : 0.0);
+            a.rowpart2[(size_t)(row0 + r) * kC + g.rank] = s2 + (lead ? (double)S.m.scal[r * 4 + 2] : 0.0);
           }
         }
       }
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
         for (int d = lane; d < Dl; d += 32) s0 += (double)S.m.u[r * Dlp + d];
         s0 = warp_sum(s0);
         if (lane == 0 && row0 + r < a.B)
-          a.rowpart0[(size_t)g.rank * B + row0 + r] = s0 + (g.rank == 0 ? (double)S.m.scal[r * 4 + 0] : 0.0);
+          a.rowpart0[(size_t)(row0 + r) * kC + g.rank] = s0 + (g.rank == 0 ? (double)S.m.scal[r * 4 + 0] : 0.0);
       }
     }
     __syncthreads();

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 
+#include "dist.cuh"
 #include "adj_host.cuh"
 #include "cl_kernels.cuh"
 #include "fwd_kernels.cuh"
@@ -22,6 +23,7 @@ struct eno_ctx {
   int sm_count = 148;
   int path_mode = 0;        // 0 auto, 1 force streamed weights, 2 force cluster-resident (ENO_PATH)
   Profiler prof;
+  DistCtx dist;             // world 1 unless eno_comm_init was called
 };
 
 namespace {
@@ -93,15 +95,35 @@ __global__ void k_ffma_peak(float* sink, int iters, float m) {
   if (s == 123.456f) *sink = s;
 }
 
-size_t fwd_ws_bytes(int B, int D) {
-  const size_t N = (size_t)B * D;
-  return align_up(sizeof(Ctrl)) + align_up(3 * N * 4) * 2 + align_up(2 * N * 4) + 2 * align_up((size_t)kC * B * 8) + 1024;
-}
-
 template <typename KernelT>
 cudaError_t set_smem(KernelT k, size_t bytes) {
   return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
+
+int g_world = 1;   // ranks of this process group (set by eno_comm_init); sizes the gathered partial-sum arrays
+
+size_t fwd_ws_bytes(int B, int D) {
+  const size_t N = (size_t)B * D;
+  return align_up(sizeof(Ctrl)) + align_up(3 * N * 4) * 2 + align_up(2 * N * 4) +
+         2 * align_up((size_t)kC * B * g_world * 8) + 1024;
+}
+
+template <int R>
+cudaError_t fwd_stream_launch(int mode, const FwdArgs& a, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e;
+  if (mode == 1) {
+    if ((e = set_smem(k_fwd_init<R, 0>, smem)) != cudaSuccess) return e;
+    k_fwd_init<R, 0><<<grid, kThreads, smem, st>>>(a);
+  } else if (mode == 2) {
+    if ((e = set_smem(k_fwd_init<R, 1>, smem)) != cudaSuccess) return e;
+    k_fwd_init<R, 1><<<grid, kThreads, smem, st>>>(a);
+  } else {
+    if ((e = set_smem(k_fwd_step<R>, smem)) != cudaSuccess) return e;
+    k_fwd_step<R><<<grid, kThreads, smem, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+
 
 void fill_stats(eno_stats* st, const Ctrl& c, int launches, int n_rhs) {
   if (!st) return;
@@ -174,7 +196,7 @@ size_t eno_workspace_bytes(const eno_dynamics_desc* d, int32_t B, int32_t T, int
   (void)tableau;
   if (!desc_ok(d) || B <= 0) return 0;
   if (mode == 0) return fwd_ws_bytes(B, d->D);
-  return adj_ws_bytes(B, d->D, d->H);
+  return adj_ws_bytes(B, d->D, d->H, g_world);
 }
 
 int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tableau, int32_t B, const float* y0,
@@ -204,8 +226,8 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   a.Y = cv.take<float>(3 * N);
   a.F = cv.take<float>(3 * N);
   a.MID = cv.take<float>(2 * N);
-  a.rowpart0 = cv.take<double>((size_t)kC * B);
-  a.rowpart1 = cv.take<double>((size_t)kC * B);
+  a.rowpart0 = cv.take<double>((size_t)kC * B * g_world);
+  a.rowpart1 = cv.take<double>((size_t)kC * B * g_world);
   a.w = mlp_weights_from_flat(params, D, H, nullptr, nullptr);
   a.B = B;
   a.N = N;
@@ -214,56 +236,64 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   a.ys_out = ys_out;
   a.trace = trace_out;
 
+  const DistCtx& dc = ctx->dist;
+  const bool dist = dc.active();
+  const int world = dist ? dc.world : 1;
+  const bool use_cluster = ctx->path_mode != 1 && cl_supported(D, H, kClRows, tab.s < 2 ? 2 : tab.s, false);
+  const int stride = use_cluster ? kC : 1;           // partial sums per sample
+  const size_t n_loc = (size_t)stride * B;           // this rank's partial sums
+  a.n_rp = (int)(n_loc * world);
+  a.dist = dist ? 1 : 0;
+  a.rp0_all = a.rowpart0;
+  a.rp1_all = a.rowpart1;
+  a.rowpart0 += (size_t)(dist ? dc.rank : 0) * n_loc;
+  a.rowpart1 += (size_t)(dist ? dc.rank : 0) * n_loc;
+  double* rp0 = const_cast<double*>(a.rp0_all);
+  double* rp1 = const_cast<double*>(a.rp1_all);
+
   const int R = pick_rows_fwd(B, D, H, tab.s, ctx->sm_count);
-  const size_t smem = fwd_smem_bytes(R, D, H, tab.s < 2 ? 2 : tab.s);
-  const int grid = (B + R - 1) / R;
+  const size_t smem = use_cluster ? cl_smem_bytes(kClRows, D, H, tab.s < 2 ? 2 : tab.s, false)
+                                  : fwd_smem_bytes(R, D, H, tab.s < 2 ? 2 : tab.s);
+  const int grid = use_cluster ? cl_grid(B) : (B + R - 1) / R;
   int launches = 0;
 
   ENO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tab, &tab, sizeof(Tableau), 0, cudaMemcpyHostToDevice, stream));
   k_ctrl_reset<<<1, 1, 0, stream>>>(a.ctrl, rtol, atol, T, mxstep <= 0 ? INT_MAX : mxstep, trace_out ? trace_cap : 0,
-                                    (float)N);
+                                    (float)(N * world));
   ++launches;
 
-#define ENO_FWD_DISPATCH(RR)                                                        \
-  {                                                                                 \
-    ENO_CUDA(ctx, set_smem(k_fwd_init<RR, 0>, smem));                               \
-    ENO_CUDA(ctx, set_smem(k_fwd_init<RR, 1>, smem));                               \
-    ENO_CUDA(ctx, set_smem(k_fwd_step<RR>, smem));                                  \
-    k_fwd_init<RR, 0><<<grid, kThreads, smem, stream>>>(a);                         \
-    k_fwd_init<RR, 1><<<grid, kThreads, smem, stream>>>(a);                         \
-    launches += 2;                                                                  \
-    int chunk = ctx->hint_fwd;                                                      \
-    const int out_grid = (int)((N + 1023) / 1024) < 4 * ctx->sm_count ? (int)((N + 1023) / 1024) : 4 * ctx->sm_count; \
-    for (;;) {                                                                      \
-      for (int i = 0; i < chunk; ++i) {                                             \
-        const int ps_ = ctx->prof.begin(PROF_FWD_STEP, stream);                     \
-        k_fwd_step<RR><<<grid, kThreads, smem, stream>>>(a);                        \
-        ctx->prof.end(ps_, stream);                                                 \
-        ++launches;                                                                 \
-        if (T > 2) { k_fwd_out<<<out_grid, 256, 0, stream>>>(a); ++launches; }      \
-      }                                                                             \
-      if (T <= 2) { k_fwd_out<<<out_grid, 256, 0, stream>>>(a); ++launches; }       \
-      ENO_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, a.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream)); \
-      ENO_CUDA(ctx, cudaStreamSynchronize(stream));                                 \
-      if (ctx->mailbox->done) break;                                                \
-      chunk = 4;                                                                    \
-    }                                                                               \
-  }
-  const bool use_cluster = ctx->path_mode != 1 && cl_supported(D, H, kClRows, tab.s < 2 ? 2 : tab.s, false);
-  if (use_cluster) {
-    const size_t csm = cl_smem_bytes(kClRows, D, H, tab.s < 2 ? 2 : tab.s, false);
-    const int cgrid = cl_grid(B);
-    ENO_CUDA(ctx, cl_fwd_launch(1, a, cgrid, csm, stream));
-    ENO_CUDA(ctx, cl_fwd_launch(2, a, cgrid, csm, stream));
-    launches += 2;
+  auto launch = [&](int mode) -> cudaError_t {
+    ++launches;
+    if (use_cluster) return cl_fwd_launch(mode, a, grid, smem, stream);
+    if (R == 1) return fwd_stream_launch<1>(mode, a, grid, smem, stream);
+    if (R == 2) return fwd_stream_launch<2>(mode, a, grid, smem, stream);
+    return fwd_stream_launch<4>(mode, a, grid, smem, stream);
+  };
+  // multi-GPU: gather every rank's per-sample partials, then one CTA per rank runs the controller
+  auto finish = [&](int mode) -> int {
+    if (!dist) return 0;
+    if (dc.api.GroupStart()) return 1;
+    int rc = dc.gather(rp0, n_loc, stream);
+    if (mode == 1) rc |= dc.gather(rp1, n_loc, stream);
+    rc |= dc.api.GroupEnd();
+    if (rc) return rc;
+    k_fwd_finish<<<1, kThreads, 0, stream>>>(a, mode);
+    ++launches;
+    return 0;
+  };
+  ENO_CUDA(ctx, launch(1));
+  if (finish(1)) return fail(ctx, ENO_E_CUDA, "eno_odeint_fwd: NCCL all-gather failed");
+  ENO_CUDA(ctx, launch(2));
+  if (finish(2)) return fail(ctx, ENO_E_CUDA, "eno_odeint_fwd: NCCL all-gather failed");
+  {
     int chunk = ctx->hint_fwd;
     const int out_grid = (int)((N + 1023) / 1024) < 4 * ctx->sm_count ? (int)((N + 1023) / 1024) : 4 * ctx->sm_count;
     for (;;) {
       for (int i = 0; i < chunk; ++i) {
         const int ps_ = ctx->prof.begin(PROF_FWD_STEP, stream);
-        ENO_CUDA(ctx, cl_fwd_launch(0, a, cgrid, csm, stream));
+        ENO_CUDA(ctx, launch(0));
         ctx->prof.end(ps_, stream);
-        ++launches;
+        if (finish(0)) return fail(ctx, ENO_E_CUDA, "eno_odeint_fwd: NCCL all-gather failed");
         // with several output times a step can leave targets behind mid-solve: evaluate them before
         // the next step recycles the ring; with a single target one output launch per chunk suffices
         if (T > 2) { k_fwd_out<<<out_grid, 256, 0, stream>>>(a); ++launches; }
@@ -274,10 +304,7 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
       if (ctx->mailbox->done) break;
       chunk = 4;
     }
-  } else if (R == 1) ENO_FWD_DISPATCH(1)
-  else if (R == 2) ENO_FWD_DISPATCH(2)
-  else ENO_FWD_DISPATCH(4)
-#undef ENO_FWD_DISPATCH
+  }
 
   ENO_CUDA(ctx, cudaGetLastError());
   const Ctrl& c = *ctx->mailbox;
@@ -324,9 +351,45 @@ int32_t eno_odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, c
   ENO_CUDA(ctx, cudaSetDevice(ctx->device));
   if (desc->aug != ENO_AUG_NONE && desc->aug != ENO_AUG_REG)
     return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: aug must be ENO_AUG_NONE or ENO_AUG_REG");
-  return adj_solve(&ctx->prof, ctx->path_mode, &ctx->err, ctx->mailbox, &ctx->hint_bwd, ctx->sm_count, desc, B, ys, ts, T, params, g_y, g_r, rtol,
+  return adj_solve(&ctx->prof, ctx->path_mode, &ctx->dist, &ctx->err, ctx->mailbox, &ctx->hint_bwd, ctx->sm_count, desc, B, ys, ts, T, params, g_y, g_r, rtol,
                    atol, mxstep, workspace, workspace_bytes, y0_bar_out, r0_bar_out, ts_bar_out, params_bar_out,
                    stats_host, trace_out, trace_cap, static_cast<cudaStream_t>(stream_));
+}
+
+// ---- multi-GPU (one process per GPU) -----------------------------------------------------------
+int32_t eno_comm_unique_id(eno_ctx* ctx, uint8_t* id_out, const char* nccl_path) {
+  if (!ctx || !id_out) return fail(ctx, ENO_E_ARG, "eno_comm_unique_id: null argument");
+  if (!ctx->dist.api.load(nccl_path, &ctx->err)) return ENO_E_UNSUPPORTED;
+  NcclUniqueId id;
+  if (int rc = ctx->dist.api.GetUniqueId(&id))
+    return fail(ctx, ENO_E_CUDA, std::string("ncclGetUniqueId: ") + ctx->dist.api.GetErrorString(rc));
+  memcpy(id_out, id.internal, 128);
+  return ENO_OK;
+}
+
+int32_t eno_comm_init(eno_ctx* ctx, const uint8_t* id, int32_t rank, int32_t world, const char* nccl_path) {
+  if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return fail(ctx, ENO_E_ARG, "eno_comm_init: bad arguments");
+  if (world == 1) { ctx->dist.world = 1; ctx->dist.rank = 0; return ENO_OK; }
+  if (!ctx->dist.api.load(nccl_path, &ctx->err)) return ENO_E_UNSUPPORTED;
+  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+  NcclUniqueId uid;
+  memcpy(uid.internal, id, 128);
+  if (int rc = ctx->dist.api.CommInitRank(&ctx->dist.comm, world, uid, rank))
+    return fail(ctx, ENO_E_CUDA, std::string("ncclCommInitRank: ") + ctx->dist.api.GetErrorString(rc));
+  ctx->dist.world = world;
+  ctx->dist.rank = rank;
+  g_world = world;
+  return ENO_OK;
+}
+
+int32_t eno_comm_destroy(eno_ctx* ctx) {
+  if (!ctx) return ENO_E_ARG;
+  if (ctx->dist.comm) ctx->dist.api.CommDestroy(ctx->dist.comm);
+  ctx->dist.comm = nullptr;
+  ctx->dist.world = 1;
+  ctx->dist.rank = 0;
+  g_world = 1;
+  return ENO_OK;
 }
 
 // ---- measurement hooks (bench.py) ------------------------------------------------------------

@@ -26,8 +26,12 @@ struct FwdArgs {
   float* Y;             // [3][N] ring of states
   float* F;             // [3][N] ring of derivatives at those states
   float* MID;           // [2][N] mid-point of candidate / accepted step
-  double* rowpart0;     // [B]
-  double* rowpart1;     // [B]
+  double* rowpart0;     // per-sample partial sums, THIS rank's rows (view into rp0_all)
+  double* rowpart1;
+  const double* rp0_all;  // all ranks' partials in canonical global row order, n_rp entries
+  const double* rp1_all;
+  int n_rp;             // entries summed by the finaliser: stride * global batch
+  int dist;             // 1: multi-GPU - the step kernel leaves the reduction + controller to k_fwd_finish
   float* ys_out;        // [T][N]
   eno_trace_row* trace; // or nullptr
 };
@@ -139,11 +143,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_fwd_init(FwdArgs a) {
     __syncthreads();
     row_sums_to_global<R>(m.q, D, row0, a.B, a.rowpart0);
   }
+  if (a.dist) return;
   if (!elect_last_block(&c->ticket)) return;
-  const double s0 = block_sum_global(a.rowpart0, a.B, m.dred);
+  const double s0 = block_sum_global(a.rp0_all, a.n_rp, m.dred);
   __syncthreads();
   double s1 = 0.0;
-  if (PHASE == 0) s1 = block_sum_global(a.rowpart1, a.B, m.dred);
+  if (PHASE == 0) s1 = block_sum_global(a.rp1_all, a.n_rp, m.dred);
   if (threadIdx.x == 0) {
     c->ticket = 0;
     if (PHASE == 0) {
@@ -257,11 +262,55 @@ __global__ void __launch_bounds__(kThreads, 1) k_fwd_step(FwdArgs a) {
     }
   }
 
+  if (a.dist) return;
   if (!elect_last_block(&c->ticket)) return;
-  const double sum = block_sum_global(a.rowpart0, a.B, m.dred);
+  const double sum = block_sum_global(a.rp0_all, a.n_rp, m.dred);
   if (threadIdx.x == 0) {
     c->ticket = 0;
     const float ratio = (float)(sum / (double)c->n_state);
+    finish_iteration(c, a.ts, ratio, dt, c_tab, a.trace);
+  }
+}
+
+// Multi-GPU: reduction + controller as a separate one-CTA launch, after the per-sample partials of
+// every rank have been all-gathered.  mode 0 iteration, 1 / 2 initial-step phases.  Every rank runs it on
+// identical inputs and therefore takes identical decisions.
+__global__ void __launch_bounds__(kThreads) k_fwd_finish(FwdArgs a, int mode) {
+  __shared__ double dred[kThreads];
+  Ctrl* c = a.ctrl;
+  if (mode == 0 && c->done) return;
+  const double s0 = block_sum_global(a.rp0_all, a.n_rp, dred);
+  __syncthreads();
+  double s1 = 0.0;
+  if (mode == 1) s1 = block_sum_global(a.rp1_all, a.n_rp, dred);
+  if (threadIdx.x != 0) return;
+  if (mode == 1) {
+    const float d0 = sqrtf((float)s0), d1 = sqrtf((float)s1);
+    c->d0 = d0;
+    c->d1 = d1;
+    c->h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+  } else if (mode == 2) {
+    const float h0 = c->h0, d1 = c->d1;
+    const float d2 = sqrtf((float)s0) / h0;
+    float h1;
+    if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
+    else h1 = powf(0.01f / (d1 + d2), 1.0f / ((float)c_tab.init_order + 1.0f));
+    c->dt = fminf(100.f * h0, h1);
+    if (isnan(h0) || isnan(h1)) c->dt = nanf("");
+    c->t = a.ts[0];
+    c->last_t = c->t;
+    c->step_dt = 0.f;
+    c->cur = 0; c->prev = 2; c->cand = 1; c->mid_acc = 0;
+    c->iters_tgt = 0; c->tgt = 1;
+    c->n_iters = 0; c->n_accepted = 0; c->nfe = 2;
+    c->out_begin = 1; c->out_end = 1;
+    c->done = 0; c->status = ENO_OK;
+    advance_targets(c, a.ts);
+  } else {
+    float dt = c->dt;
+    const float target = a.ts[c->tgt];
+    if (c_tab.clip && (c->t + dt > target)) dt = target - c->t;
+    const float ratio = (float)(s0 / (double)c->n_state);
     finish_iteration(c, a.ts, ratio, dt, c_tab, a.trace);
   }
 }

@@ -14,12 +14,13 @@ from . import ode
 
 class MnistNode:
     def __init__(self, reg="r3", lam=6e-5, rtol=1.4e-8, atol=1.4e-8, device="cuda", dim=784, hidden=100,
-                 lr=1e-1, mass=0.9, n_cls=10):
+                 lr=1e-1, mass=0.9, n_cls=10, world=1):
         self.spec = MLPDynamics(dim, hidden, reg=reg)
         self.lam, self.rtol, self.atol = lam, rtol, atol
         self.device = torch.device(device)
         self.lr, self.mass = lr, mass
         self.dim, self.n_cls = dim, n_cls
+        self.world = world   # data-parallel ranks: the loss is the mean over the GLOBAL batch
         self.ts = torch.tensor([0., 1.], device=self.device)
         self.init_params(0)
 
@@ -66,8 +67,16 @@ class MnistNode:
         y1, r1 = ys[-1], rs[-1]
         logits = torch.sigmoid(y1) @ w + b
         ce = torch.nn.functional.cross_entropy(logits, labels)
-        loss = ce + self.lam * r1.mean()
+        # this rank's share of loss_fn (mnist.py:462-471) over the global batch of world * B samples
+        loss = (ce + self.lam * r1.mean()) / self.world
         g_ode, g_w, g_b = torch.autograd.grad(loss, (p_ode, w, b))
+        if self.world > 1:
+            # the adjoint's params_bar is already the global sum (exchanged per iteration inside the
+            # solve); the tiny head gradients are summed here
+            import torch.distributed as dist
+            flat = torch.cat([g_w.reshape(-1), g_b])
+            dist.all_reduce(flat)
+            g_w, g_b = flat[:g_w.numel()].reshape(g_w.shape), flat[g_w.numel():]
         return dict(loss=ce.detach(), y1=y1.detach(), nfe=nfe, grads={"ode": g_ode, "post_w": g_w, "post_b": g_b},
                     fwd_stats=ode.last_stats["fwd"], bwd_stats=ode.last_stats["bwd"])
 

@@ -26,6 +26,61 @@ last_stats = {"fwd": None, "bwd": None}   # controller statistics of the most re
 _workspaces = {}
 
 
+_dist = {"world": 1, "rank": 0}
+
+
+def _nccl_path():
+    try:
+        import nvidia.nccl as _n
+        import os
+        p = os.path.join(os.path.dirname(_n.__file__), "lib", "libnccl.so.2")
+        return p.encode() if os.path.exists(p) else None
+    except Exception:
+        return None
+
+
+def init_distributed(device=None):
+    """Make the solves on this process' GPU collective over the default torch.distributed group
+    (one process per GPU, batch sharded in equal contiguous row blocks, parameters replicated).
+    After this call every rank must enter odeint / odeint_aux_one (and their backward) together; the
+    ranks then follow the single-device step sequence of the concatenated batch and
+    parameter / time gradients come back globally summed."""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise RuntimeError("init_distributed: call torch.distributed.init_process_group first")
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    L = _cabi.lib()
+    h = _cabi.ctx(dev.index)
+    path = _nccl_path()
+    buf = (C.c_uint8 * 128)()
+    if rank == 0 and world > 1:
+        _cabi.check(L.eno_comm_unique_id(h, buf, path), h, "eno_comm_unique_id")
+    box = [bytes(buf)]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    idb = (C.c_uint8 * 128).from_buffer_copy(box[0])
+    with torch.cuda.device(dev):
+        _cabi.check(L.eno_comm_init(h, idb, rank, world, path), h, "eno_comm_init")
+    _dist["world"], _dist["rank"] = world, rank
+    _workspaces.clear()
+    return world, rank
+
+
+def shutdown_distributed(device=None):
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    _cabi.lib().eno_comm_destroy(_cabi.ctx(dev.index))
+    _dist["world"], _dist["rank"] = 1, 0
+
+
+def shard_rows(n_rows, world, rank):
+    """Contiguous equal row blocks (the collective solves need the same B on every rank)."""
+    if n_rows % world:
+        raise ValueError(f"global batch {n_rows} is not divisible by world size {world}")
+    per = n_rows // world
+    return slice(rank * per, (rank + 1) * per)
+
+
 def _workspace(device, nbytes):
     key = (device.index, )
     ws = _workspaces.get(key)

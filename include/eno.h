@@ -165,6 +165,21 @@ int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32
                 float* params_bar_out, void* stream);
 
 /*
+ * Multi-GPU, one process per GPU (no reference counterpart: the reference is single-device).  The batch
+ * is sharded in contiguous row blocks of equal size B per rank, parameters are replicated.  After
+ * eno_comm_init every eno_odeint_fwd / eno_odeint_bwd call on this ctx is COLLECTIVE: all ranks must
+ * call it with their shard; the error norm (lib/ode.py:518-527), the initial-step norms (86-104) and,
+ * in the adjoint, the batch-summed blocks params_bar / t0_bar are exchanged over NCCL every iteration so
+ * that all ranks follow the step sequence of the single-device solve on the concatenated batch.
+ * params_bar_out and ts_bar_out are then already global sums, identical on every rank.
+ * Rank 0 obtains `id` (128 bytes) from eno_comm_unique_id and ships it to the other ranks (e.g. with
+ * torch.distributed); `nccl_path` may name libnccl.so.2 explicitly (NULL: the copy already loaded).
+ */
+int32_t eno_comm_unique_id(eno_ctx* ctx, uint8_t* id_out /*[128]*/, const char* nccl_path);
+int32_t eno_comm_init(eno_ctx* ctx, const uint8_t* id /*[128]*/, int32_t rank, int32_t world, const char* nccl_path);
+int32_t eno_comm_destroy(eno_ctx* ctx);
+
+/*
  * Measurement hooks used by bench.py (no reference counterpart; the reference only wall-clocks the
  * whole jitted update, mnist.py:632-640).  With profiling on, the step kernels are bracketed by CUDA
  * events on the launch stream; eno_profile_read returns and clears the accumulated milliseconds and

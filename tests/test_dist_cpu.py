@@ -1,0 +1,77 @@
+"""world_size-2 gloo tests (CPU) of the host-side multi-GPU logic: row sharding, the rendezvous of the
+communicator id through torch.distributed, and the loud failure of the collective set-up when there is
+no CUDA device.  The device-side protocol itself is checked on GPUs by tests/dist_check.py."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+import easy_neural_ode_b200 as eno
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_rows_partitions_the_batch():
+    got = [eno.shard_rows(100, 4, r) for r in range(4)]
+    idx = torch.arange(100)
+    assert torch.equal(torch.cat([idx[s] for s in got]), idx)
+    assert all((s.stop - s.start) == 25 for s in got)
+    with pytest.raises(ValueError):
+        eno.shard_rows(100, 8, 0)      # the collective solves need equal shards
+
+
+def test_init_distributed_requires_a_process_group():
+    with pytest.raises(RuntimeError):
+        eno.init_distributed()
+
+
+WORKER = textwrap.dedent('''
+    import os, sys, torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    import easy_neural_ode_b200 as eno
+    from easy_neural_ode_b200 import _cabi
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    # 1. the id travels from rank 0 to everybody exactly as init_distributed ships it
+    box = [bytes(range(128)) if rank == 0 else bytes(128)]
+    dist.broadcast_object_list(box, src=0)
+    assert box[0] == bytes(range(128))
+    # 2. shards are disjoint and cover the batch; a sharded sum equals the global sum in fp64
+    x = torch.arange(96, dtype=torch.float64) ** 2
+    part = x[eno.shard_rows(96, world, rank)].sum().reshape(1)
+    parts = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(parts, part)
+    assert float(sum(parts)) == float(x.sum())
+    # 3. without a GPU the collective set-up fails loudly (no CPU fallback)
+    try:
+        eno.init_distributed()
+        raise SystemExit("init_distributed succeeded without a CUDA device")
+    except (_cabi.EnoLibraryError, RuntimeError, AssertionError):
+        pass
+    dist.destroy_process_group()
+    print("worker", rank, "ok")
+''') % ROOT
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU/gloo variant; GPUs run tests/dist_check.py")
+def test_gloo_world2_host_logic(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") == 2
+
+
+@pytest.mark.gpu
+def test_two_gpu_collective_step_matches_single_device():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "tests", "dist_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "DIST PARITY OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
