@@ -538,12 +538,26 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
       const int kchunk = (KB + kSlots - 1) / kSlots;
       int k = SPLITK ? grp * kchunk : 0;
       const int kend = SPLITK ? min(KB, k + kchunk) : KB;
-      for (; k + 4 <= kend; k += 4) {
-        float4 av[4], bv[4];
+      // software-pipelined: the next four rows of both operands are in flight while the current four
+      // feed the FMAs (the loop is bound by L2 latency, not by issue slots)
+      float4 av[4], bv[4];
+      bool have = (k + 4 <= kend);
+      if (have) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           av[u] = Ap[(size_t)(k + u) * lda];
           bv[u] = Bp[(size_t)(k + u) * ldb];
+        }
+      }
+      while (have) {
+        float4 an[4], bn[4];
+        const bool more = (k + 8 <= kend);
+        if (more) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            an[u] = Ap[(size_t)(k + 4 + u) * lda];
+            bn[u] = Bp[(size_t)(k + 4 + u) * ldb];
+          }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -553,6 +567,12 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
           for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+        k += 4;
+        have = more;
+        if (more) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { av[u] = an[u]; bv[u] = bn[u]; }
         }
       }
       for (; k < kend; ++k) {
