@@ -18,6 +18,7 @@ struct ClSmem {
   float *xz, *xzb;        // stage inputs [R][Dlp]
   float *y, *k;           // forward only: state and stage derivatives [R][Dlp], [s][R][Dlp]
   float *r, *rb, *kr;     // per-sample scalars [R], [R], [7][R]
+  float* aux;             // [36 R] scalar state / stage derivatives of the augmented forward solve
   double* dred;           // [kThreads] (forward finaliser)
 };
 
@@ -62,6 +63,7 @@ __device__ __forceinline__ ClSmem cl_carve(float* sm, int D, int H, const ClGeom
   s.r = sm; sm += 4 * ((R + 3) / 4);
   s.rb = sm; sm += 4 * ((R + 3) / 4);
   s.kr = sm; sm += 4 * ((7 * R + 3) / 4);
+  s.aux = sm; sm += 36 * R;
   return s;
 }
 
@@ -71,7 +73,7 @@ inline size_t cl_smem_bytes(int R, int D, int H, int stages, bool adjoint) {
   size_t f = (adjoint ? 0 : 2 * kThreads) + (size_t)g.Dl * g.ldw1 + (size_t)H * g.Dlp + 2 * H + 2 * g.Dlp + 4 * RD + RH;
   f += adjoint ? (6 * RD + 7 * RH) : ((size_t)(1 + stages) * RD);
   const size_t red_n = std::max((size_t)kKG * R * H, (size_t)kKGw * R * g.Dlp);
-  f += red_n + 2 * (size_t)R * g.Hs + 4 * R + 3 * 4 * ((R + 3) / 4) + 4 * ((7 * R + 3) / 4) + 16;
+  f += red_n + 2 * (size_t)R * g.Hs + 4 * R + 3 * 4 * ((R + 3) / 4) + 4 * ((7 * R + 3) / 4) + 36 * R + 16;
   return f * sizeof(float);
 }
 

@@ -8,6 +8,7 @@
 
 #include "dist.cuh"
 #include "adj_host.cuh"
+#include "cl_aug_fwd.cuh"
 #include "cl_kernels.cuh"
 #include "fwd_kernels.cuh"
 #include "tableaux.cuh"
@@ -105,7 +106,7 @@ int g_world = 1;   // ranks of this process group (set by eno_comm_init); sizes 
 size_t fwd_ws_bytes(int B, int D) {
   const size_t N = (size_t)B * D;
   return align_up(sizeof(Ctrl)) + align_up(3 * N * 4) * 2 + align_up(2 * N * 4) +
-         2 * align_up((size_t)kC * B * g_world * 8) + 1024;
+         2 * align_up((size_t)kC * B * g_world * 8) + 3 * align_up((size_t)9 * B * 4) + 1024;
 }
 
 template <int R>
@@ -203,11 +204,18 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
                        const float* ts, int32_t T, const float* params, const float* eps, float rtol, float atol,
                        int32_t mxstep, void* workspace, size_t workspace_bytes, float* ys_out, float* aux_out,
                        eno_stats* stats_host, eno_trace_row* trace_out, int32_t trace_cap, void* stream_) {
-  (void)eps;
-  (void)aux_out;
   if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_odeint_fwd: ctx is null");
   if (!desc_ok(desc)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd: unsupported dynamics desc (MLP sigmoid, D%4==0, H%4==0)");
-  if (desc->aug != ENO_AUG_NONE) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd: augmented forward not built yet");
+  const int aug = desc->aug;
+  const int n_aux = aug == ENO_AUG_ALL ? 3 : (aug == ENO_AUG_REG ? 1 : 0);
+  if (aug != ENO_AUG_NONE) {
+    if (aug != ENO_AUG_REG && aug != ENO_AUG_ALL) return fail(ctx, ENO_E_ARG, "eno_odeint_fwd: bad desc->aug");
+    if (tableau != ENO_TABLEAU_DOPRI5) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd: augmented states integrate with dopri5 only (odeint is always dopri5, lib/ode.py:746)");
+    if (!(desc->reg_order == 0 || desc->reg_order == 2 || desc->reg_order == 3)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd: reg_order must be 0, 2 or 3");
+    if (!aux_out || (aug == ENO_AUG_ALL && !eps)) return fail(ctx, ENO_E_ARG, "eno_odeint_fwd: augmented solve needs aux_out (and eps for ENO_AUG_ALL)");
+    if (ctx->path_mode == 1 || !cl_supported(desc->D, desc->H, kClRows, kAdjStages, true))
+      return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd: the augmented forward solve exists on the cluster-resident path only (weights must fit the cluster's shared memory)");
+  }
   if (B <= 0 || T < 1 || !y0 || !ts || !params || !ys_out || !workspace)
     return fail(ctx, ENO_E_ARG, "eno_odeint_fwd: null pointer or empty batch");
   if (((uintptr_t)params | (uintptr_t)y0 | (uintptr_t)ys_out | (uintptr_t)workspace) & 15)
@@ -228,6 +236,13 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   a.MID = cv.take<float>(2 * N);
   a.rowpart0 = cv.take<double>((size_t)kC * B * g_world);
   a.rowpart1 = cv.take<double>((size_t)kC * B * g_world);
+  AugFwdArgs A;
+  A.RSa = cv.take<float>((size_t)9 * B);
+  A.FRa = cv.take<float>((size_t)9 * B);
+  A.MIDa = cv.take<float>((size_t)9 * B);
+  A.eps = eps;
+  A.aux_out = aux_out;
+  A.n_aux = n_aux;
   a.w = mlp_weights_from_flat(params, D, H, nullptr, nullptr);
   a.B = B;
   a.N = N;
@@ -239,7 +254,8 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   const DistCtx& dc = ctx->dist;
   const bool dist = dc.active();
   const int world = dist ? dc.world : 1;
-  const bool use_cluster = ctx->path_mode != 1 && cl_supported(D, H, kClRows, tab.s < 2 ? 2 : tab.s, false);
+  const bool use_cluster = aug != ENO_AUG_NONE ||
+                           (ctx->path_mode != 1 && cl_supported(D, H, kClRows, tab.s < 2 ? 2 : tab.s, false));
   const int stride = use_cluster ? kC : 1;           // partial sums per sample
   const size_t n_loc = (size_t)stride * B;           // this rank's partial sums
   a.n_rp = (int)(n_loc * world);
@@ -252,18 +268,23 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   double* rp1 = const_cast<double*>(a.rp1_all);
 
   const int R = pick_rows_fwd(B, D, H, tab.s, ctx->sm_count);
-  const size_t smem = use_cluster ? cl_smem_bytes(kClRows, D, H, tab.s < 2 ? 2 : tab.s, false)
-                                  : fwd_smem_bytes(R, D, H, tab.s < 2 ? 2 : tab.s);
+  const size_t smem = aug != ENO_AUG_NONE ? cl_smem_bytes(kClRows, D, H, kAdjStages, true)
+                      : use_cluster       ? cl_smem_bytes(kClRows, D, H, tab.s < 2 ? 2 : tab.s, false)
+                                          : fwd_smem_bytes(R, D, H, tab.s < 2 ? 2 : tab.s);
   const int grid = use_cluster ? cl_grid(B) : (B + R - 1) / R;
   int launches = 0;
 
   ENO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tab, &tab, sizeof(Tableau), 0, cudaMemcpyHostToDevice, stream));
   k_ctrl_reset<<<1, 1, 0, stream>>>(a.ctrl, rtol, atol, T, mxstep <= 0 ? INT_MAX : mxstep, trace_out ? trace_cap : 0,
-                                    (float)(N * world));
+                                    (float)((N + (size_t)n_aux * B) * world));
   ++launches;
 
   auto launch = [&](int mode) -> cudaError_t {
     ++launches;
+    if (aug != ENO_AUG_NONE) {
+      A.f = a;
+      return cl_aug_fwd_launch(desc->reg_order, aug, mode, A, grid, smem, stream);
+    }
     if (use_cluster) return cl_fwd_launch(mode, a, grid, smem, stream);
     if (R == 1) return fwd_stream_launch<1>(mode, a, grid, smem, stream);
     if (R == 2) return fwd_stream_launch<2>(mode, a, grid, smem, stream);
@@ -296,9 +317,15 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
         if (finish(0)) return fail(ctx, ENO_E_CUDA, "eno_odeint_fwd: NCCL all-gather failed");
         // with several output times a step can leave targets behind mid-solve: evaluate them before
         // the next step recycles the ring; with a single target one output launch per chunk suffices
-        if (T > 2) { k_fwd_out<<<out_grid, 256, 0, stream>>>(a); ++launches; }
+        if (T > 2) {
+          k_fwd_out<<<out_grid, 256, 0, stream>>>(a); ++launches;
+          if (n_aux) { A.f = a; k_aux_out<<<(n_aux * B + 255) / 256, 256, 0, stream>>>(A); ++launches; }
+        }
       }
-      if (T <= 2) { k_fwd_out<<<out_grid, 256, 0, stream>>>(a); ++launches; }
+      if (T <= 2) {
+        k_fwd_out<<<out_grid, 256, 0, stream>>>(a); ++launches;
+        if (n_aux) { A.f = a; k_aux_out<<<(n_aux * B + 255) / 256, 256, 0, stream>>>(A); ++launches; }
+      }
       ENO_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, a.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
       ENO_CUDA(ctx, cudaStreamSynchronize(stream));
       if (ctx->mailbox->done) break;
@@ -314,6 +341,7 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   }
   ctx->hint_fwd = c.n_iters + 1 > 64 ? 64 : c.n_iters + 1;
   const int per_iter = tab.clip ? 2 * (tab.s - 1) : (tab.s - 1);
+  (void)eps;
   fill_stats(stats_host, c, launches, 2 + per_iter * c.n_iters);
   return c.status;
 }

@@ -203,8 +203,7 @@ def odeint(func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=math.inf):
     """Adaptive dopri5 solve; mirrors lib/ode.py:540-559.  -> (ys [T, B, D], nfe)."""
     _require_spec(func, "odeint")
     if func.kind != "plain":
-        raise NotImplementedError("odeint on the augmented closures (evaluation path, mnist.py:333-334) is not built yet; "
-                                  "training uses odeint_aux_one")
+        return _odeint_augmented(func, y0, t, args, rtol, atol, mxstep)
     spec = func.spec
     eps, params = _split_args(func, args)
     out_dev = y0.device
@@ -218,6 +217,50 @@ def odeint(func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=math.inf):
     if out_dev != ys.device:
         ys, nfe = ys.to(out_dev), nfe.to(out_dev)
     return ys, nfe
+
+
+def _odeint_augmented(func, y0, t, args, rtol, atol, mxstep, trace_cap=0):
+    """odeint on aug_dynamics / all_aug_dynamics (evaluation path, mnist.py:333-334, 343-348): the state is
+    the tuple (y, r) or (y, r, fro, kin); forward only (the scripts never differentiate this call).
+    -> ((ys [T,B,D], r [T,B], ...), nfe), every auxiliary output with the shape of its y0 leaf."""
+    spec = func.spec
+    eps, params = _split_args(func, args)
+    n_aux = 1 if func.kind == "aug" else 3
+    if len(y0) != 1 + n_aux:
+        raise TypeError(f"{func!r} integrates a state of {1 + n_aux} leaves, got {len(y0)}")
+    y_in = y0[0]
+    for leaf in y0[1:]:
+        if float(leaf.abs().max()) != 0.0:
+            raise NotImplementedError("augmented solves start from zero auxiliary state (aug_init, mnist.py:416-438)")
+    out_dev = y_in.device
+    dev = _dev(y_in)
+    y = _f32c(y_in.detach().reshape(-1, spec.dim), dev)
+    ts = _f32c(torch.as_tensor(t), dev)
+    pflat = _f32c(spec.flatten_params(params).detach(), dev)
+    epsd = _f32c(eps.reshape(-1, spec.dim), dev) if (eps is not None and n_aux == 3) else None
+    L = _cabi.lib()
+    h = _cabi.ctx(dev.index)
+    B, D = y.shape
+    T = ts.numel()
+    desc = spec.desc(_cabi.AUG_REG if n_aux == 1 else _cabi.AUG_ALL, eps is not None)
+    nbytes = L.eno_workspace_bytes(C.byref(desc), B, T, 0, 0)
+    ws = _workspace(dev, nbytes)
+    ys = torch.empty((T, B, D), dtype=torch.float32, device=dev)
+    aux = torch.zeros((T, n_aux, B), dtype=torch.float32, device=dev)
+    trace = torch.zeros((trace_cap, 4), dtype=torch.float32, device=dev) if trace_cap else None
+    st = _cabi.Stats()
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        rc = L.eno_odeint_fwd(h, C.byref(desc), 0, B, _ptr(y), _ptr(ts), T, _ptr(pflat), _ptr(epsd), float(rtol),
+                              float(atol), _mx(mxstep), _ptr(ws), ws.numel(), _ptr(ys), _ptr(aux), C.byref(st), _ptr(trace),
+                              trace_cap, stream)
+    _cabi.check(rc, h, "eno_odeint_fwd")
+    last_stats["fwd"] = st.as_dict()
+    if trace_cap:
+        last_stats["fwd_trace"] = trace[: st.n_iters].cpu()
+    outs = [ys.reshape((T,) + tuple(y_in.shape))] + [aux[:, q].reshape((T,) + tuple(y0[1 + q].shape)) for q in range(n_aux)]
+    nfe = torch.tensor(st.nfe, dtype=torch.float32, device=out_dev)
+    return tuple(o.to(out_dev) for o in outs), nfe
 
 
 def odeint_aux_one(fwd_func, rev_func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=math.inf):
