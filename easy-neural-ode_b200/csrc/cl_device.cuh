@@ -44,7 +44,7 @@ __device__ long long g_phase_last;
 #endif
 
 constexpr int kC = 4;          // CTAs per cluster
-constexpr int kKG = 7;         // k-groups of a product contracting over the local slice (K = Dl; 49 = 7 x 7 at D = 784)
+constexpr int kKG = 7;         // k-groups of a product contracting over the local slice (K = Dl; 49 = 7 x 7 at D = 784; 10 measured equal)
 constexpr int kKGw = 5;        // k-groups of a product contracting over H (25 = 5 x 5 at H = 100)
 constexpr int kRG = 2;         // row groups (measured: 1 vs 2 makes no difference; the products are latency-bound)
 
