@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="polled solves instead of the whole-step CUDA graph")
     ap.add_argument("--batch", type=int, default=B, help="per-GPU batch (development sweeps only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -143,6 +144,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    # stdout carries exactly one JSON line: NCCL's banner / debug output goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
     import torch
     import torch.distributed as dist
@@ -163,8 +166,13 @@ def main():
     dev_batches = [tuple(t.to(dev) for t in synth_batch(rank, s)) for s in range(8)]
     host_batches = [synth_batch(rank, s, pin=True) for s in range(8)]
 
+    use_graph = not args.no_graph
+
     def step(s, batch=None):
         images, labels, eps = batch if batch is not None else dev_batches[s % 8]
+        if use_graph:
+            # the whole update() as ONE CUDA-graph launch (deferred-mode solves, device-guarded update)
+            return model.update_graphed(images, labels, eps)
         # world > 1: the batch is sharded over ranks; inside the solves the error norm and the
         # batch-summed adjoint blocks are exchanged over NCCL every iteration, so params_bar comes back
         # globally reduced and every rank applies the same update
@@ -194,8 +202,12 @@ def main():
         evs[s][0].record()
         out = step(s)
         evs[s][1].record()
-        launches += out["fwd_stats"]["n_launches"] + sum(b["n_launches"] for b in out["bwd_stats"])
-        nfe_total += float(out["fwd_stats"]["nfe"])
+        if use_graph:
+            launches += model._launches
+            nfe_total += float(out["nfe"])
+        else:
+            launches += out["fwd_stats"]["n_launches"] + sum(b["n_launches"] for b in out["bwd_stats"])
+            nfe_total += float(out["fwd_stats"]["nfe"])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -214,7 +226,7 @@ def main():
         images, labels, eps = host_batches[s % 8]
         di, dl, de = images.to(dev, non_blocking=True), labels.to(dev, non_blocking=True), eps.to(dev, non_blocking=True)
         o = step(s, (di, dl, de))
-        return float(o["loss"].item())             # device -> host read of the step's result
+        return float(o["loss"])                    # device -> host read of the step's result
     for s in range(3):
         step_e2e(s)
     model.restore(snap)
@@ -236,6 +248,7 @@ def main():
     L = _cabi.lib()
     h = _cabi.ctx(dev.index)
     model.restore(snap)
+    use_graph = False                              # per-kernel events need the polled launch path
     L.eno_profile_enable(h, 1)
     for s in range(args.steps):
         step(s)
@@ -276,7 +289,10 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "nfe_per_s": nfe_total * B * world / (dev_ms * 1e-3),
-        "solver": {"fwd": out["fwd_stats"], "bwd": out["bwd_stats"][0]},
+        "solver": ({"fwd_iters": out["fwd_iters"], "bwd_iters": out["bwd_iters"], "graph_redone": out["redone"]}
+                   if not args.no_graph else {"fwd": out["fwd_stats"], "bwd": out["bwd_stats"][0]}),
+        "launch_mode": "whole update() replayed as one CUDA graph (deferred-mode solves)" if not args.no_graph
+                       else "polled solves",
         "roofline": roofline,
         "wall_s": wall,
     }
@@ -291,8 +307,15 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        eno.shutdown_distributed()
-        dist.destroy_process_group()
+        # Tear down in dependency order: the captured graph holds NCCL work of both communicators.  Drop it,
+        # drain the device, meet the other ranks once more, then leave without running communicator
+        # destructors (a destructor waiting on a peer that already left is the classic exit hang).
+        model._graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

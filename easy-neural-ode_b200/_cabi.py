@@ -19,7 +19,7 @@ TABLEAUX = {"dopri5": 0, "heun": 1, "fehlberg": 2, "bosh": 3, "rk_fehlberg": 4, 
 SYMBOLS = ["eno_abi_version", "eno_last_error_string", "eno_create", "eno_destroy", "eno_param_count",
            "eno_adjoint_state_size", "eno_workspace_bytes", "eno_odeint_fwd", "eno_odeint_bwd", "eno_rhs",
            "eno_profile_enable", "eno_profile_read", "eno_ffma_peak", "eno_comm_unique_id", "eno_comm_init",
-           "eno_comm_destroy"]
+           "eno_comm_destroy", "eno_set_deferred", "eno_read_stats"]
 
 
 class Desc(C.Structure):
@@ -86,6 +86,10 @@ def lib():
     L.eno_comm_init.argtypes = [vp, vp, i32, i32, C.c_char_p]
     L.eno_comm_destroy.restype = i32
     L.eno_comm_destroy.argtypes = [vp]
+    L.eno_set_deferred.restype = i32
+    L.eno_set_deferred.argtypes = [vp, i32, i32, i32]
+    L.eno_read_stats.restype = i32
+    L.eno_read_stats.argtypes = [vp, vp, C.POINTER(Stats), vp]
     _lib = L
     return L
 

@@ -2,6 +2,7 @@
 // streamed weights), launch sequence of lib/ode.py:1494-1529 per output segment.
 #pragma once
 #include <algorithm>
+#include <cstring>
 #include <string>
 
 #include "adj_kernels.cuh"
@@ -181,7 +182,8 @@ inline void adj_transposes(const AdjArgs& a, cudaStream_t st) {
   k_transpose<<<dim3((D + 31) / 32, (H + 31) / 32), blk, 0, st>>>(a.w.W2x, const_cast<float*>(a.w.W2xT), H, D);
 }
 
-inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, std::string* err, Ctrl* mailbox, int* hint, int sms, const eno_dynamics_desc* desc, int B,
+inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int deferred_iters, const Tableau* tab_host,
+                     std::string* err, Ctrl* mailbox, int* hint, int sms, const eno_dynamics_desc* desc, int B,
                      const float* ys, const float* ts, int T, const float* params, const float* g_y, const float* g_r,
                      float rtol, float atol, int mxstep, void* ws, size_t ws_bytes, float* y0_bar_out,
                      float* r0_bar_out, float* ts_bar_out, float* params_bar_out, eno_stats* stats,
@@ -204,9 +206,11 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, std::stri
     a.n_state = (float)(2 * (Ng + n_aux * Bg) + 1 + (desc->eps_in_args ? Ng : 0) + (size_t)a.P);
   }
   a.trace = trace;
-  Tableau tab;
-  fill_tableau(ENO_TABLEAU_DOPRI5, &tab);
-  ENO_ADJ_CHECK(cudaMemcpyToSymbolAsync(c_tab, &tab, sizeof(Tableau), 0, cudaMemcpyHostToDevice, st));
+  // tab_host lives in pinned memory owned by the context, so the copy stays valid if this call is being
+  // captured into a CUDA graph (deferred mode)
+  ENO_ADJ_CHECK(cudaMemcpyToSymbolAsync(c_tab, tab_host, sizeof(Tableau), 0, cudaMemcpyHostToDevice, st));
+  const bool deferred = deferred_iters > 0;
+  if (deferred && T != 2) { if (err) *err = "eno_odeint_bwd: deferred mode supports T == 2 only"; return ENO_E_UNSUPPORTED; }
   const AdjPlan plan = adj_plan(B, D, H, sms, path_mode, false);
   if (!plan.cluster) adj_transposes(a, st);
   adj_set_views(&a, plan.cluster ? kC : 1, rank, world);
@@ -259,7 +263,7 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, std::stri
     k_adj_pgrad<ADJ_INIT1><<<geo.grid, kSlots * kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
     if ((rc = exchange(ADJ_INIT1))) return rc;
     launches += dist ? 7 : 5;
-    int chunk = *hint;
+    int chunk = deferred ? deferred_iters : *hint;
     for (;;) {
       for (int k = 0; k < chunk; ++k) {
         int ps = prof->begin(PROF_ADJ_ROWS, st);
@@ -276,10 +280,15 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, std::stri
       // launch per chunk (a no-op unless the segment finished) is therefore enough.
       k_adj_out<<<egrid, 256, 0, st>>>(a);
       ++launches;
+      if (deferred) break;   // no host round-trip: the caller checks Ctrl.done later (eno_read_stats)
       ENO_ADJ_CHECK(cudaMemcpyAsync(mailbox, a.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
       ENO_ADJ_CHECK(cudaStreamSynchronize(st));
       if (mailbox->done) break;
       chunk = 4;
+    }
+    if (deferred) {
+      if (stats) { memset(stats, 0, sizeof(eno_stats)); stats->status = -100; stats->n_launches = launches; }
+      continue;
     }
     {
       int valid[PROF_KINDS] = {0, mailbox->n_iters, mailbox->n_iters, 0};
@@ -299,7 +308,7 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, std::stri
   k_adj_finish<<<(B + 255) / 256, 256, 0, st>>>(a, g_r, r0_bar_out, ts_bar_out);
   ENO_ADJ_CHECK(cudaMemcpyAsync(y0_bar_out, a.YBAR, N * 4, cudaMemcpyDeviceToDevice, st));
   ENO_ADJ_CHECK(cudaMemcpyAsync(params_bar_out, a.POUT, (size_t)a.P * 4, cudaMemcpyDeviceToDevice, st));
-  ENO_ADJ_CHECK(cudaStreamSynchronize(st));
+  if (!deferred) ENO_ADJ_CHECK(cudaStreamSynchronize(st));
   ENO_ADJ_CHECK(cudaGetLastError());
   return worst;
 }

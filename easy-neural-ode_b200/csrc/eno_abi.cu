@@ -25,6 +25,9 @@ struct eno_ctx {
   int path_mode = 0;        // 0 auto, 1 force streamed weights, 2 force cluster-resident (ENO_PATH)
   Profiler prof;
   DistCtx dist;             // world 1 unless eno_comm_init was called
+  Tableau* tabs = nullptr;  // pinned copies of all tableaux (sources of the constant-memory upload)
+  int deferred = 0;         // 1: enqueue a fixed number of iterations, never synchronise (graph capturable)
+  int spec_fwd = 0, spec_bwd = 0;
 };
 
 namespace {
@@ -157,6 +160,8 @@ int32_t eno_create(eno_ctx** out, int32_t device) {
   c->device = device;
   ENO_CUDA(c, cudaSetDevice(device));
   ENO_CUDA(c, cudaMallocHost(&c->mailbox, sizeof(Ctrl)));
+  ENO_CUDA(c, cudaMallocHost(&c->tabs, sizeof(Tableau) * ENO_NUM_TABLEAUX));
+  for (int i = 0; i < ENO_NUM_TABLEAUX; ++i) fill_tableau(i, &c->tabs[i]);
   cudaDeviceProp prop;
   ENO_CUDA(c, cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -178,6 +183,7 @@ int32_t eno_create(eno_ctx** out, int32_t device) {
 void eno_destroy(eno_ctx* ctx) {
   if (!ctx) return;
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+  if (ctx->tabs) cudaFreeHost(ctx->tabs);
   delete ctx;
 }
 
@@ -274,7 +280,8 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   const int grid = use_cluster ? cl_grid(B) : (B + R - 1) / R;
   int launches = 0;
 
-  ENO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tab, &tab, sizeof(Tableau), 0, cudaMemcpyHostToDevice, stream));
+  ENO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tab, &ctx->tabs[tableau], sizeof(Tableau), 0, cudaMemcpyHostToDevice, stream));
+  const bool deferred = ctx->deferred && ctx->spec_fwd > 0;
   k_ctrl_reset<<<1, 1, 0, stream>>>(a.ctrl, rtol, atol, T, mxstep <= 0 ? INT_MAX : mxstep, trace_out ? trace_cap : 0,
                                     (float)((N + (size_t)n_aux * B) * world));
   ++launches;
@@ -307,7 +314,7 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   ENO_CUDA(ctx, launch(2));
   if (finish(2)) return fail(ctx, ENO_E_CUDA, "eno_odeint_fwd: NCCL all-gather failed");
   {
-    int chunk = ctx->hint_fwd;
+    int chunk = deferred ? ctx->spec_fwd : ctx->hint_fwd;
     const int out_grid = (int)((N + 1023) / 1024) < 4 * ctx->sm_count ? (int)((N + 1023) / 1024) : 4 * ctx->sm_count;
     for (;;) {
       for (int i = 0; i < chunk; ++i) {
@@ -326,6 +333,7 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
         k_fwd_out<<<out_grid, 256, 0, stream>>>(a); ++launches;
         if (n_aux) { A.f = a; k_aux_out<<<(n_aux * B + 255) / 256, 256, 0, stream>>>(A); ++launches; }
       }
+      if (deferred) break;   // graph-capturable: no host round-trip, Ctrl is inspected later (eno_read_stats)
       ENO_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, a.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
       ENO_CUDA(ctx, cudaStreamSynchronize(stream));
       if (ctx->mailbox->done) break;
@@ -334,6 +342,10 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   }
 
   ENO_CUDA(ctx, cudaGetLastError());
+  if (deferred) {
+    if (stats_host) { memset(stats_host, 0, sizeof(eno_stats)); stats_host->status = -100; stats_host->n_launches = launches; }
+    return ENO_OK;
+  }
   const Ctrl& c = *ctx->mailbox;
   {
     int valid[PROF_KINDS] = {c.n_iters, 0, 0, 0};
@@ -379,9 +391,32 @@ int32_t eno_odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, c
   ENO_CUDA(ctx, cudaSetDevice(ctx->device));
   if (desc->aug != ENO_AUG_NONE && desc->aug != ENO_AUG_REG)
     return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: aug must be ENO_AUG_NONE or ENO_AUG_REG");
-  return adj_solve(&ctx->prof, ctx->path_mode, &ctx->dist, &ctx->err, ctx->mailbox, &ctx->hint_bwd, ctx->sm_count, desc, B, ys, ts, T, params, g_y, g_r, rtol,
+  return adj_solve(&ctx->prof, ctx->path_mode, &ctx->dist, (ctx->deferred ? ctx->spec_bwd : 0), &ctx->tabs[ENO_TABLEAU_DOPRI5], &ctx->err, ctx->mailbox, &ctx->hint_bwd, ctx->sm_count, desc, B, ys, ts, T, params, g_y, g_r, rtol,
                    atol, mxstep, workspace, workspace_bytes, y0_bar_out, r0_bar_out, ts_bar_out, params_bar_out,
                    stats_host, trace_out, trace_cap, static_cast<cudaStream_t>(stream_));
+}
+
+// ---- deferred launch mode (CUDA-graph capturable solves) ----------------------------------------
+int32_t eno_set_deferred(eno_ctx* ctx, int32_t on, int32_t fwd_iters, int32_t bwd_iters) {
+  if (!ctx) return ENO_E_ARG;
+  if (on && (fwd_iters <= 0 || bwd_iters <= 0)) return fail(ctx, ENO_E_ARG, "eno_set_deferred: iteration budgets must be positive");
+  ctx->deferred = on ? 1 : 0;
+  ctx->spec_fwd = fwd_iters;
+  ctx->spec_bwd = bwd_iters;
+  return ENO_OK;
+}
+
+int32_t eno_read_stats(eno_ctx* ctx, const void* workspace, eno_stats* out, void* stream_) {
+  if (!ctx || !workspace || !out) return fail(ctx, ENO_E_ARG, "eno_read_stats: null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+  // the controller block is the first object of both the forward and the backward workspace layout
+  ENO_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, workspace, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+  ENO_CUDA(ctx, cudaStreamSynchronize(stream));
+  const Ctrl& c = *ctx->mailbox;
+  fill_stats(out, c, 0, 2 + 6 * c.n_iters);
+  if (!c.done) out->status = -101;   // the iteration budget of the deferred launch was too small
+  return ENO_OK;
 }
 
 // ---- multi-GPU (one process per GPU) -----------------------------------------------------------

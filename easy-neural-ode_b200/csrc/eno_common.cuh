@@ -2,6 +2,7 @@
 // tableau constants, block primitives.  sm_100a only.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/eno.h"
@@ -52,6 +53,9 @@ struct Ctrl {
   int trace_cap;
   float n_state;           // N of the mean in error_ratio (as float)
 };
+
+// The host mirror (ode.py: CTRL_DONE_I32, CTRL_NITERS_I32) reads these two words straight out of a workspace.
+static_assert(offsetof(Ctrl, done) == 72 && offsetof(Ctrl, n_iters) == 80, "Ctrl layout is part of the host contract");
 
 // Optional per-kernel device timing (bench.py's roofline leg): event pairs around the launches of
 // one kernel kind, resolved after the solve's final synchronize.

@@ -87,6 +87,79 @@ class MnistNode:
         self.apply_grads(g["ode"], g["post_w"], g["post_b"])
         return out
 
+    # ---- whole-step CUDA graph ------------------------------------------------------------------
+    # The solves normally poll their device-side controller once per chunk of iterations.  In deferred
+    # mode (include/eno.h) they enqueue a fixed iteration budget and never synchronise, so the entire
+    # update() - PreODE, forward solve, head, adjoint solve, momentum - becomes ONE graph launch.  The
+    # parameter update is guarded on the device by the controllers' `done` flags; if a budget turns out too
+    # small the parameters are left untouched and the step is redone in polled mode with a bigger budget.
+    def update_graphed(self, images_u8, labels, eps):
+        """update() through a captured CUDA graph; returns dict(loss=float, redone=bool, ...)."""
+        if getattr(self, "_graph", None) is None:
+            out = self.update(images_u8, labels, eps)        # polled step: learns the iteration counts
+            if not getattr(self, "_graph_off", False):
+                try:
+                    self._capture(images_u8, labels, eps, out["fwd_stats"]["n_iters"], out["bwd_stats"][0]["n_iters"])
+                except Exception as e:                       # capture is an optimisation, never a requirement
+                    self._graph, self._graph_off, self._graph_error = None, True, repr(e)
+            return dict(loss=float(out["loss"]), redone=False, fwd_iters=out["fwd_stats"]["n_iters"],
+                        bwd_iters=out["bwd_stats"][0]["n_iters"], nfe=out["fwd_stats"]["nfe"])
+        for dst, src in zip(self._g_in, (images_u8, labels, eps)):
+            dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        loss, ok_f, n_f, ok_b, n_b = self._g_info.tolist()   # the step's one device -> host read
+        if not (ok_f and ok_b):
+            self._graph = None                               # budget too small: parameters were not touched
+            out = self.update(images_u8, labels, eps)
+            self._capture(images_u8, labels, eps, out["fwd_stats"]["n_iters"], out["bwd_stats"][0]["n_iters"])
+            return dict(loss=float(out["loss"]), redone=True, fwd_iters=out["fwd_stats"]["n_iters"],
+                        bwd_iters=out["bwd_stats"][0]["n_iters"], nfe=out["fwd_stats"]["nfe"])
+        n_f, n_b = int(n_f), int(n_b)
+        if (n_f > self._budget[0] - 2 or n_b > self._budget[1] - 2 or
+                2 * n_f + 16 < self._budget[0] or 2 * n_b + 16 < self._budget[1]):
+            self._capture(images_u8, labels, eps, n_f, n_b)   # keep the budgets ahead of the drifting counts
+        return dict(loss=loss, redone=False, fwd_iters=n_f, bwd_iters=n_b, nfe=2.0 + 6.0 * n_f)
+
+    def _capture(self, images_u8, labels, eps, n_f, n_b):
+        # iterations past termination cost one ~3 us no-op launch each; re-capturing costs milliseconds,
+        # so the budgets are generous (counts drift upwards as training stiffens the dynamics)
+        self._budget = (max(n_f + 8, (3 * n_f + 1) // 2), max(n_b + 8, (3 * n_b + 1) // 2))
+        first = getattr(self, "_g_in", None) is None
+        if first:
+            self._g_in = tuple(t.clone() for t in (images_u8, labels, eps))
+        snap = self.snapshot()
+        ode.set_deferred(True, self._budget[0], self._budget[1], self.device)
+        try:
+            if first:
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    self._graph_body()                        # warm-up on a side stream (allocations)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                self.restore(snap)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._g_info = self._graph_body()
+            self._graph = g
+            self._launches = ode.last_stats["fwd"]["n_launches"] + sum(b["n_launches"] for b in ode.last_stats["bwd"])
+        finally:
+            ode.set_deferred(False, device=self.device)
+        self.restore(snap)
+
+    def _graph_body(self):
+        out = self.loss_and_grads(*self._g_in)
+        wf = ode.workspace_tensor("fwd", self.device).view(torch.int32)
+        wb = ode.workspace_tensor("bwd", self.device).view(torch.int32)
+        ok = (wf[ode.CTRL_DONE_I32] != 0) & (wb[ode.CTRL_DONE_I32] != 0)
+        g = out["grads"]
+        for p, v, gr in ((self.p_ode, self.v_ode, g["ode"]), (self.post_w, self.v_w, g["post_w"]),
+                         (self.post_b, self.v_b, g["post_b"])):
+            v_new = self.mass * v + gr
+            v.copy_(torch.where(ok, v_new, v))                # NaN-safe: garbage gradients are never selected
+            p.copy_(torch.where(ok, p - self.lr * v_new, p))
+        return torch.stack([out["loss"].float(), wf[ode.CTRL_DONE_I32].float(), wf[ode.CTRL_NITERS_I32].float(),
+                            wb[ode.CTRL_DONE_I32].float(), wb[ode.CTRL_NITERS_I32].float()])
+
     def apply_grads(self, g_ode, g_w, g_b):
         """jax.experimental.optimizers.momentum: v <- mass*v + g ; x <- x - lr*v."""
         self.v_ode.mul_(self.mass).add_(g_ode); self.p_ode.sub_(self.lr * self.v_ode)

@@ -81,8 +81,42 @@ def shard_rows(n_rows, world, rank):
     return slice(rank * per, (rank + 1) * per)
 
 
-def _workspace(device, nbytes):
-    key = (device.index, )
+_deferred = {"on": False}
+
+
+def set_deferred(on, fwd_iters=0, bwd_iters=0, device=None):
+    """Switch the solves on this device between the default polled mode and the deferred mode of
+    include/eno.h (fixed iteration budgets, no host synchronisation: CUDA-graph capturable)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    h = _cabi.ctx(dev.index)
+    _cabi.check(_cabi.lib().eno_set_deferred(h, int(bool(on)), int(fwd_iters), int(bwd_iters)), h, "eno_set_deferred")
+    _deferred["on"] = bool(on)
+
+
+def workspace_tensor(kind, device=None):
+    """The cached workspace ("fwd" or "bwd") of the most recent solves on the device (uint8 tensor whose
+    first bytes are the device-side controller block)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return _workspaces.get((dev.index, kind))
+
+
+def read_deferred_stats(kind, device=None):
+    """Controller statistics of the last deferred solve; status -101 = iteration budget exhausted."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ws = workspace_tensor(kind, dev)
+    st = _cabi.Stats()
+    h = _cabi.ctx(dev.index)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _cabi.check(_cabi.lib().eno_read_stats(h, _ptr(ws), C.byref(st), stream), h, "eno_read_stats")
+    return st.as_dict()
+
+
+CTRL_DONE_I32 = 18      # int32 index of Ctrl.done / Ctrl.n_iters inside a workspace (csrc/eno_common.cuh)
+CTRL_NITERS_I32 = 20
+
+
+def _workspace(device, nbytes, kind="fwd"):
+    key = (device.index, kind)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
@@ -139,7 +173,7 @@ def _bwd_call(spec, aug, eps_in_args, ys, ts, pflat, g_y, g_r, rtol, atol, mxste
     T, B, D = ys.shape
     desc = spec.desc(aug, eps_in_args, reg_order=spec.reg_order if aug == _cabi.AUG_REG else 0)
     nbytes = L.eno_workspace_bytes(C.byref(desc), B, T, 0, 1)
-    ws = _workspace(device, nbytes)
+    ws = _workspace(device, nbytes, "bwd")
     y0_bar = torch.empty((B, D), dtype=torch.float32, device=device)
     r0_bar = torch.empty((B,), dtype=torch.float32, device=device)
     ts_bar = torch.empty((T,), dtype=torch.float32, device=device)
@@ -169,7 +203,10 @@ class _OdeintFn(torch.autograd.Function):
         T, B, _ = ys.shape
         # aux outputs of the split wrappers are zeros of shape [T, B, 1] (lib/ode.py:998-1004)
         rs = torch.zeros((T, B, 1), dtype=ys.dtype, device=ys.device)
-        nfe = torch.tensor(st["nfe"], dtype=torch.float32, device=ys.device)
+        if _deferred["on"]:   # not known yet (read_deferred_stats after the stream has drained)
+            nfe = torch.full((), float("nan"), dtype=torch.float32, device=ys.device)
+        else:
+            nfe = torch.tensor(st["nfe"], dtype=torch.float32, device=ys.device)
         ctx.mark_non_differentiable(nfe)
         return ys, rs, nfe
 
@@ -338,7 +375,7 @@ def rhs(spec, mode, y, t, params, y_bar=None, r_bar=None):
     pflat = _f32c(spec.flatten_params(params).detach(), dev)
     desc = spec.desc(_cabi.AUG_REG if mode else _cabi.AUG_NONE, True)
     nbytes = L.eno_workspace_bytes(C.byref(desc), B, 2, 0, 1)
-    ws = _workspace(dev, nbytes)
+    ws = _workspace(dev, nbytes, "bwd")
     dy = torch.empty_like(yd)
     r = torch.empty(B, device=dev)
     zb = torch.empty_like(yd)

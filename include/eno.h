@@ -165,6 +165,19 @@ int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32
                 float* params_bar_out, void* stream);
 
 /*
+ * Deferred launch mode (no reference counterpart).  By default a solve polls its device-side controller
+ * once per chunk of iterations.  With eno_set_deferred(ctx, 1, fwd_iters, bwd_iters) the calls enqueue the
+ * two initial-step launches plus EXACTLY that many iteration launches (iterations after termination exit
+ * at their first instruction) and return without synchronising: they can be captured into a CUDA graph,
+ * which removes every launch gap of a training step.  stats_host then only reports status -100
+ * ("deferred"); call eno_read_stats on the same workspace afterwards: status -101 means the budget was
+ * too small (the outputs are then meaningless and the step must be repeated with a larger budget).
+ * The backward call supports T == 2 in this mode.
+ */
+int32_t eno_set_deferred(eno_ctx* ctx, int32_t on, int32_t fwd_iters, int32_t bwd_iters);
+int32_t eno_read_stats(eno_ctx* ctx, const void* workspace, eno_stats* out, void* stream);
+
+/*
  * Multi-GPU, one process per GPU (no reference counterpart: the reference is single-device).  The batch
  * is sharded in contiguous row blocks of equal size B per rank, parameters are replicated.  After
  * eno_comm_init every eno_odeint_fwd / eno_odeint_bwd call on this ctx is COLLECTIVE: all ranks must
