@@ -174,3 +174,57 @@ def test_augmented_forward_mnist_size_vs_oracle(cuda):
         for a, b in zip(got, want):
             diff = float((a[-1].cpu().double() - b[-1].double()).abs().max())
             assert diff < bar * float(b[-1].abs().max()) + 2 * tol, (tol, diff)
+
+
+@pytest.mark.parametrize("Bn", [1, 7, 130])
+def test_ragged_batches_cluster_path_equals_streamed_path(cuda, Bn):
+    """Batches that are not a multiple of the cluster tile (4 samples), a single sample, and more tiles than
+    co-resident clusters (persistent tile loop): the two independent CUDA formulations must agree, and the
+    result must not depend on which other samples share the batch beyond the shared error norm."""
+    import subprocess, sys, os, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json, torch; sys.path.insert(0, %r)\n"
+        "import easy_neural_ode_b200 as eno\n"
+        "dev = torch.device('cuda:0'); spec = eno.MLPDynamics(784, 100, reg='r3')\n"
+        "p = spec.init_params(seed=0, device=dev, scale=2.0)\n"
+        "g = torch.Generator().manual_seed(5); x0 = torch.rand((%d, 784), generator=g).to(dev)\n"
+        "pf = spec.flatten_params(p).clone().requires_grad_(True)\n"
+        "(ys, rs), nfe = eno.odeint_aux_one(spec.fwd, spec.aug_dynamics, (x0, torch.zeros(%d, device=dev)),\n"
+        "                                    torch.tensor([0., 1.], device=dev), x0, pf, rtol=1e-6, atol=1e-6)\n"
+        "(ys[-1].square().sum() + 0.01 * rs[-1].sum()).backward()\n"
+        "print(json.dumps(dict(nfe=float(nfe), y=ys[-1].double().sum().item(), ya=ys[-1].abs().double().sum().item(),\n"
+        "                      g=pf.grad.double().abs().sum().item(), bwd=eno.last_stats['bwd'][0]['n_iters'])))\n"
+    ) % (root, Bn, Bn)
+    outs = {}
+    for path in ("cluster", "stream"):
+        env = dict(os.environ, ENO_PATH=path)
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs[path] = json.loads(res.stdout.strip().splitlines()[-1])
+    a, b = outs["cluster"], outs["stream"]
+    assert a["nfe"] == b["nfe"] and a["bwd"] == b["bwd"]
+    for k in ("y", "ya", "g"):
+        assert abs(a[k] - b[k]) <= 2e-5 * abs(b[k]) + 1e-9, (k, a[k], b[k])
+
+
+@pytest.mark.parametrize("name", ["heun", "bosh", "cash_karp", "owrenzen", "owrenzen5"])
+def test_tableau_sweep_mnist_shapes_vs_oracle(cuda, name):
+    """BASELINE configs[4]: the tableau sweep on the MNIST NODE (784 -> 100 -> 784), step-count parity with
+    the oracle at rtol = atol in {1e-3, 1e-5}."""
+    import easy_neural_ode_b200 as eno
+    from oracle import dynamics_oracle as do, ode_oracle as oo
+    Bn, D, H = 8, 784, 100
+    spec = eno.MLPDynamics(D, H)
+    p_cpu = do.init_mlp_params(D, H, seed=0, scale=2.0)
+    gen = torch.Generator().manual_seed(3)
+    x0 = torch.rand((Bn, D), generator=gen)
+    ts = torch.tensor([0., 1.])
+    p_gpu = {k: {kk: vv.to(cuda) for kk, vv in v.items()} for k, v in p_cpu.items()}
+    fun = lambda y, t: do.mlp_dynamics(p_cpu, y, t).reshape(-1)
+    for tol in (1e-3, 1e-5):
+        want, nfe_w, st = oo.solve(fun, x0.reshape(-1), ts, tol, tol, solver=name)
+        fn = getattr(eno, f"_{name}_odeint")
+        got, nfe_g = fn(spec.dynamics_wrap, tol, tol, math.inf, x0.to(cuda).reshape(-1), ts, p_gpu)
+        assert float(nfe_g) == float(nfe_w), (name, tol)
+        assert rel_err(got, want) < max(RTOL, 2 * tol)
