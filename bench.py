@@ -144,8 +144,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
-    # stdout carries exactly one JSON line: NCCL's banner / debug output goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr, so
+    # that banners printed by native libraries (NCCL prints its version on communicator creation) cannot
+    # end up in front of the result
+    sys.stdout.flush()
+    result_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -305,7 +309,7 @@ def main():
                                           f"0..{args.steps - 1}), oracle port, torch CPU fp32, {threads} threads; "
                                           f"last step nfe {info['nfe']}, adjoint iterations {info['bwd_iters']}"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=result_out, flush=True)
     if world > 1:
         # Tear down in dependency order: the captured graph holds NCCL work of both communicators.  Drop it,
         # drain the device, meet the other ranks once more, then leave without running communicator

@@ -140,6 +140,20 @@ inline void adj_set_views(AdjArgs* a, int stride, int rank, int world) {
   }
 }
 
+constexpr size_t kPgradSmem = (size_t)kSlots * kPStages * kPRows * 64 * sizeof(float);   // operand rings of k_adj_pgrad
+
+inline cudaError_t pgrad_prepare() {
+  static thread_local bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(k_adj_pgrad<ADJ_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPgradSmem))) return e;
+  if ((e = cudaFuncSetAttribute(k_adj_pgrad<ADJ_INIT0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPgradSmem))) return e;
+  if ((e = cudaFuncSetAttribute(k_adj_pgrad<ADJ_INIT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPgradSmem))) return e;
+  if ((e = cudaFuncSetAttribute(k_adj_pgrad<ADJ_RHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPgradSmem))) return e;
+  done = true;
+  return cudaSuccess;
+}
+
 // One launch of the per-sample kernel on the chosen path.
 struct AdjPlan {
   bool cluster;
@@ -212,6 +226,7 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
   const bool deferred = deferred_iters > 0;
   if (deferred && T != 2) { if (err) *err = "eno_odeint_bwd: deferred mode supports T == 2 only"; return ENO_E_UNSUPPORTED; }
   const AdjPlan plan = adj_plan(B, D, H, sms, path_mode, false);
+  ENO_ADJ_CHECK(pgrad_prepare());
   if (!plan.cluster) adj_transposes(a, st);
   adj_set_views(&a, plan.cluster ? kC : 1, rank, world);
   const PgradGeom geo = pgrad_geom(D, H);
@@ -257,10 +272,10 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
                                            trace ? trace_cap : 0);
     int rc;
     if ((rc = adj_rows_any(plan, K, ADJ_INIT0, a, 0.f, st, err))) return rc;
-    k_adj_pgrad<ADJ_INIT0><<<geo.grid, kSlots * kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
+    k_adj_pgrad<ADJ_INIT0><<<geo.grid, kSlots * kGroup, kPgradSmem, st>>>(a, 0.f, nullptr, nullptr);
     if ((rc = exchange(ADJ_INIT0))) return rc;
     if ((rc = adj_rows_any(plan, K, ADJ_INIT1, a, 0.f, st, err))) return rc;
-    k_adj_pgrad<ADJ_INIT1><<<geo.grid, kSlots * kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
+    k_adj_pgrad<ADJ_INIT1><<<geo.grid, kSlots * kGroup, kPgradSmem, st>>>(a, 0.f, nullptr, nullptr);
     if ((rc = exchange(ADJ_INIT1))) return rc;
     launches += dist ? 7 : 5;
     int chunk = deferred ? deferred_iters : *hint;
@@ -270,7 +285,7 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
         if ((rc = adj_rows_any(plan, K, ADJ_STEP, a, 0.f, st, err))) return rc;
         prof->end(ps, st);
         ps = prof->begin(PROF_ADJ_PGRAD, st);
-        k_adj_pgrad<ADJ_STEP><<<geo.grid, kSlots * kGroup, 0, st>>>(a, 0.f, nullptr, nullptr);
+        k_adj_pgrad<ADJ_STEP><<<geo.grid, kSlots * kGroup, kPgradSmem, st>>>(a, 0.f, nullptr, nullptr);
         prof->end(ps, st);
         if ((rc = exchange(ADJ_STEP))) return rc;
         launches += dist ? 3 : 2;
@@ -327,6 +342,7 @@ inline int adj_rhs(int path_mode, std::string* err, int sms, const eno_dynamics_
   adj_carve(ws, B, D, H, params, &a);
   a.np = (K == 0) ? 1 : K;
   const AdjPlan plan = adj_plan(B, D, H, sms, path_mode, true);
+  ENO_ADJ_CHECK(pgrad_prepare());
   if (!plan.cluster) adj_transposes(a, st);
   adj_set_views(&a, plan.cluster ? kC : 1, 0, 1);
   ENO_ADJ_CHECK(cudaMemcpyAsync(a.Z, y, N * 4, cudaMemcpyDeviceToDevice, st));
@@ -347,7 +363,7 @@ inline int adj_rhs(int path_mode, std::string* err, int sms, const eno_dynamics_
   if ((rc = adj_rows_any(plan, K, ADJ_RHS, a, -t, st, err))) return rc;
   if (mode == 2) {
     const PgradGeom geo = pgrad_geom(D, H);
-    k_adj_pgrad<ADJ_RHS><<<geo.grid, kSlots * kGroup, 0, st>>>(a, -t, params_bar_out, tbar_out);
+    k_adj_pgrad<ADJ_RHS><<<geo.grid, kSlots * kGroup, kPgradSmem, st>>>(a, -t, params_bar_out, tbar_out);
   }
   ENO_ADJ_CHECK(cudaGetLastError());
   ENO_ADJ_CHECK(cudaStreamSynchronize(st));

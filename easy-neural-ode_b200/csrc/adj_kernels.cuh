@@ -12,6 +12,8 @@
 //                 reduces the error norm over ALL blocks and runs the controller.
 // The shared blocks never feed back into the RHS, so no stage buffers are kept for them.
 #pragma once
+#include <cuda_pipeline.h>
+
 #include <string>
 
 #include "adj_device.cuh"
@@ -23,6 +25,8 @@ namespace eno {
 constexpr int kAdjStages = 7;    // dopri5 (odeint() is always dopri5, lib/ode.py:746)
 constexpr int kSlots = 6;        // new RHS evaluations per iteration
 constexpr int kTile = 32;        // pgrad output tile edge
+constexpr int kPStages = 4;      // cp.async stages in flight per pgrad thread group (8 x 4 measured best of 4x6, 8x4, 16x3)
+constexpr int kPRows = 8;        // contraction rows per stage
 constexpr int kGroup = 64;       // threads per stage group in pgrad (8x8 threads x 4x4 outputs)
 
 enum AdjMode { ADJ_STEP = 0, ADJ_INIT0 = 1, ADJ_INIT1 = 2, ADJ_RHS = 3 };
@@ -502,6 +506,7 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
   __shared__ float tile[NS][kTile * kTile];
   __shared__ int pidx[kTile * kTile];   // flat parameter index of each tile element (-1 = padding)
   __shared__ double dred[kSlots * kGroup];
+  extern __shared__ __align__(16) float ring[];   // [kSlots][kPStages][kPRows][64] operand staging (dynamic)
   const int D = a.w.D, H = a.w.H, B = a.B;
   const PgradGeom geo = pgrad_geom(D, H);
   const int grp = threadIdx.x / kGroup;
@@ -527,63 +532,60 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    if (grp < NS && mm < M && nn < N) {
-      const FactorSlot& sl = a.slot[SPLITK ? 0 : grp];
-      const float* Am = first ? sl.S : sl.Hh;   // [KB][M]
+    // Operand rows are staged through a per-group ring in shared memory with cp.async (LDGSTS): kPStages
+    // stages of 4 contraction rows are in flight while the FMAs consume the oldest one, which takes the
+    // L2 latency off the critical path without spending registers on prefetch buffers.
+    {
+      const bool active = grp < NS;
+      const FactorSlot& sl = a.slot[(SPLITK || !active) ? 0 : grp];
+      const float* Am = first ? sl.S : sl.Hh;   // [KB][M]   (rows live as [3][B][*]; the first np*B are valid)
       const float* Bm = first ? sl.A : sl.G;    // [KB][N]
-      // factor rows live as [3][B][*]; only the first np*B rows are valid and contiguous
-      const float4* Ap = reinterpret_cast<const float4*>(Am + mm);
-      const float4* Bp = reinterpret_cast<const float4*>(Bm + nn);
-      const size_t lda = (size_t)M / 4, ldb = (size_t)N / 4;
       const int kchunk = (KB + kSlots - 1) / kSlots;
-      int k = SPLITK ? grp * kchunk : 0;
-      const int kend = SPLITK ? min(KB, k + kchunk) : KB;
-      // software-pipelined: the next four rows of both operands are in flight while the current four
-      // feed the FMAs (the loop is bound by L2 latency, not by issue slots)
-      float4 av[4], bv[4];
-      bool have = (k + 4 <= kend);
-      if (have) {
+      const int kbeg = SPLITK ? grp * kchunk : 0;
+      const int kend = SPLITK ? min(KB, kbeg + kchunk) : KB;
+      float* rg = ring + (size_t)grp * kPStages * kPRows * 64;     // [kPStages][kPRows][A 32 | B 32]
+      // this thread's 16-byte piece of a stage: operand (A/B), row 0..3, float4 column 0..7
+      const int which = tig >> 5, lrow = (tig & 31) >> 3, lc4 = tig & 7;
+      const float* src_base = which ? Bm : Am;
+      const int ld = which ? N : M;
+      const int col = (which ? n0 : m0) + 4 * lc4;
+      const bool col_ok = col < ld;
+      const int nst = active ? (kend - kbeg + kPRows - 1) / kPRows : 0;
+      auto issue = [&](int st) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          av[u] = Ap[(size_t)(k + u) * lda];
-          bv[u] = Bp[(size_t)(k + u) * ldb];
+        for (int h = 0; h < kPRows / 4; ++h) {
+          const int r = lrow + 4 * h;
+          const int k = kbeg + kPRows * st + r;
+          float* dst = rg + ((size_t)(st % kPStages) * kPRows + r) * 64 + which * 32 + 4 * lc4;
+          const bool ok = col_ok && k < kend;
+          const float* src = ok ? src_base + (size_t)k * ld + col : src_base;
+          __pipeline_memcpy_async(dst, src, 16, ok ? 0 : 16);    // out-of-range pieces are zero-filled
         }
+      };
+      for (int st = 0; st < kPStages - 1; ++st) {
+        if (st < nst) issue(st);
+        __pipeline_commit();
       }
-      while (have) {
-        float4 an[4], bn[4];
-        const bool more = (k + 8 <= kend);
-        if (more) {
+      for (int st = 0; st < nst; ++st) {
+        __pipeline_wait_prior(kPStages - 2);
+        asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kGroup) : "memory");   // stage st visible to the group
+        const float* sb = rg + (size_t)(st % kPStages) * kPRows * 64;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            an[u] = Ap[(size_t)(k + 4 + u) * lda];
-            bn[u] = Bp[(size_t)(k + 4 + u) * ldb];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float ar[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
-          const float br[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
+        for (int u = 0; u < kPRows; ++u) {
+          const float4 a4 = *reinterpret_cast<const float4*>(sb + u * 64 + ty * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(sb + u * 64 + 32 + tx * 4);
+          const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
+          const float br[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
           for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
         }
-        k += 4;
-        have = more;
-        if (more) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) { av[u] = an[u]; bv[u] = bn[u]; }
-        }
+        asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kGroup) : "memory");   // everyone done with the slot being refilled
+        if (st + kPStages - 1 < nst) issue(st + kPStages - 1);
+        __pipeline_commit();
       }
-      for (; k < kend; ++k) {
-        const float4 a4 = Ap[(size_t)k * lda], b4 = Bp[(size_t)k * ldb];
-        const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
-        const float br[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
-      }
+      __pipeline_wait_prior(0);
     }
     if (grp < NS) {
 #pragma unroll
