@@ -85,10 +85,43 @@ struct ClWeights {
   int D, H;
 };
 
-// cooperative copy of this CTA's weight slices into shared memory (once per launch)
+// ---- bulk asynchronous copies (TMA engine, cp.async.bulk) of the weight slices ------------------------
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(mbar)) : "memory");
+}
+
+// Copy of this CTA's weight slices into shared memory, once per launch.  The two matrices (157 KB at
+// D = 784, H = 100) travel as bulk asynchronous copies issued by one thread and tracked by an mbarrier -
+// no register staging, full L2 -> shared-memory bandwidth; the four small vectors use ordinary loads and
+// overlap with them.  W1's slice is contiguous in global memory (rows d0..d0+Dl of W1x) when the row stride
+// needs no padding; W2's slice is one 4*Dl-byte segment per row.
 __device__ __forceinline__ void cl_load_weights(const MlpWeights& w, const ClGeom& g, float* W1s, float* W2s,
                                                 float* vec /*[2H + 2Dlp]: b1, w1t, b2 slice, w2t slice*/) {
   const int H = w.H, D = w.D;
+  __shared__ __align__(8) unsigned long long mbar;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && g.Dl > 0) {
+    const unsigned total = 2u * (unsigned)g.Dl * (unsigned)H * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&mbar)), "r"(total) : "memory");
+    if (g.ldw1 == H) {
+      // one contiguous block; split so that every copy stays well below the 1 MB bulk limit
+      const unsigned bytes = (unsigned)g.Dl * (unsigned)H * 4u;
+      const unsigned half = (bytes / 2u) & ~15u;
+      bulk_g2s(W1s, w.W1x + (size_t)g.d0 * H, half, &mbar);
+      bulk_g2s(reinterpret_cast<char*>(W1s) + half, reinterpret_cast<const char*>(w.W1x + (size_t)g.d0 * H) + half,
+               bytes - half, &mbar);
+    } else {
+      for (int d = 0; d < g.Dl; ++d) bulk_g2s(W1s + (size_t)d * g.ldw1, w.W1x + (size_t)(g.d0 + d) * H, (unsigned)H * 4u, &mbar);
+    }
+    for (int n = 0; n < H; ++n) bulk_g2s(W2s + (size_t)n * g.Dlp, w.W2x + (size_t)n * D + g.d0, (unsigned)g.Dl * 4u, &mbar);
+  }
   for (int i = threadIdx.x; i < H; i += blockDim.x) {
     vec[i] = __ldg(w.b1 + i);
     vec[H + i] = __ldg(w.w1t + i);
@@ -97,17 +130,15 @@ __device__ __forceinline__ void cl_load_weights(const MlpWeights& w, const ClGeo
     vec[2 * H + i] = (i < g.Dl) ? __ldg(w.b2 + g.d0 + i) : 0.f;
     vec[2 * H + g.Dlp + i] = (i < g.Dl) ? __ldg(w.w2t + g.d0 + i) : 0.f;
   }
-  const int h4 = H >> 2;
-  for (int i = threadIdx.x; i < g.Dl * h4; i += blockDim.x) {
-    const int d = i / h4, c = i - d * h4;
-    reinterpret_cast<float4*>(W1s + (size_t)d * g.ldw1)[c] =
-        __ldg(reinterpret_cast<const float4*>(w.W1x + (size_t)(g.d0 + d) * H) + c);
-  }
-  const int d4 = g.Dl >> 2;
-  for (int i = threadIdx.x; i < H * d4; i += blockDim.x) {
-    const int n = i / d4, c = i - n * d4;
-    reinterpret_cast<float4*>(W2s + (size_t)n * g.Dlp)[c] =
-        __ldg(reinterpret_cast<const float4*>(w.W2x + (size_t)n * D + g.d0) + c);
+  if (g.Dl > 0) {
+    // every thread waits for the transaction count to drain (phase parity 0: the barrier is used once);
+    // the spin is bounded so that a lost copy traps instead of hanging the device
+    unsigned done = 0;
+    for (int spin = 0; spin < (1 << 24) && !done; ++spin) {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_addr(&mbar)) : "memory");
+    }
+    if (!done) __trap();
   }
 }
 

@@ -104,3 +104,36 @@ def test_mnist_train_step_vs_oracle(cuda):
         assert rel_err(out["loss"], want["loss"]) < RTOL
         assert rel_err(out["grads"]["ode"], flat_from_params(want["grads"]["ode"])) < bar
         assert rel_err(out["grads"]["post_w"], want["grads"]["post"]["w"]) < RTOL
+
+
+def test_plain_odeint_adjoint_multiple_output_times(cuda):
+    """odeint() with T = 5 output times and cotangents at every time: the adjoint runs T-1 backward segments
+    (lib/ode.py:1510-1529), carries y_bar / t0_bar / params_bar across them and returns ts_bar for every time.
+    Plain dynamics (no regulariser): state (y, y_bar, t0_bar, params_bar)."""
+    import easy_neural_ode_b200 as eno
+    from oracle import dynamics_oracle as do, ode_oracle as oo
+    Bn, D, H = 6, 16, 8
+    spec = eno.MLPDynamics(D, H)
+    p_cpu = do.init_mlp_params(D, H, seed=4, scale=2.0)
+    gen = torch.Generator().manual_seed(11)
+    x0 = torch.rand((Bn, D), generator=gen)
+    gys = torch.randn((5, Bn, D), generator=gen)
+    ts = torch.tensor([0., 0.2, 0.5, 0.6, 1.0])
+    tol = 1e-6
+    f = lambda y, t, p: do.mlp_dynamics(p, y.reshape(Bn, D), t).reshape(-1)
+    ys_w, nfe_w, st = oo.solve(lambda y, t: f(y, t, p_cpu), x0.reshape(-1), ts, tol, tol)
+    bst = []
+    want = oo.odeint_rev(f, tol, tol, math.inf, ys_w, ts, (p_cpu,), gys.reshape(5, -1), bst)
+
+    pflat = flat_from_params(p_cpu).to(cuda).requires_grad_(True)
+    xg = x0.to(cuda).requires_grad_(True)
+    tg = ts.to(cuda).requires_grad_(True)
+    ys, nfe = eno.odeint(spec.dynamics_wrap, xg, tg, pflat, rtol=tol, atol=tol)
+    assert float(nfe) == float(nfe_w)
+    assert rel_err(ys, ys_w.reshape(5, Bn, D)) < RTOL
+    (ys * gys.to(cuda)).sum().backward()
+    got_iters = [s["n_iters"] for s in eno.last_stats["bwd"]]
+    assert got_iters == [s["n_iters"] for s in bst]
+    assert rel_err(xg.grad, want[0].reshape(Bn, D)) < RTOL
+    assert rel_err(tg.grad, want[1]) < 2e-5
+    assert rel_err(pflat.grad, flat_from_params(want[2])) < RTOL
