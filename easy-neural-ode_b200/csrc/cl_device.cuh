@@ -23,30 +23,49 @@ namespace cg = cooperative_groups;
 
 // Optional phase clocks (build with -DENO_PHASES): thread 0 of CTA 0 accumulates clock64() deltas by
 // phase kind.  Development aid only; compiled out of the product library.
-enum PhaseKind { PH_PROLOGUE = 0, PH_ELEM, PH_MV_DL, PH_MV_H, PH_ALLRED, PH_REDLOC, PH_STORE, PH_SCALAR, PH_COMBINE, PH_NKINDS };
+enum PhaseKind { PH_PROLOGUE = 0, PH_ELEM, PH_MV_DL, PH_MV_H, PH_ALLRED, PH_REDLOC, PH_STORE, PH_SCALAR, PH_COMBINE,
+                 PH_WAIT_MV, PH_AR_LOCAL, PH_AR_CSYNC, PH_AR_REMOTE, PH_NKINDS };
 #ifdef ENO_PHASES
-__device__ long long g_phase_cycles[PH_NKINDS];
-__device__ long long g_phase_count[PH_NKINDS];
-__device__ long long g_phase_last;
+__device__ long long g_phase_cycles[32];
+__device__ long long g_phase_count[32];
+// thread 0 of CTA 0 keeps the clocks in SHARED memory (a tick costs a few cycles) and flushes once
+__device__ __forceinline__ long long* ph_slots() { __shared__ long long s[72]; return s; }
 #define ENO_TICK(kind)                                                        \
   do {                                                                        \
     if (blockIdx.x == 0 && threadIdx.x == 0) {                                \
+      long long* s_ = ph_slots();                                             \
       const long long now_ = clock64();                                       \
-      g_phase_cycles[kind] += now_ - g_phase_last;                            \
-      g_phase_count[kind] += 1;                                               \
-      g_phase_last = now_;                                                    \
+      s_[kind] += now_ - s_[64];                                              \
+      s_[32 + kind] += 1;                                                     \
+      s_[64] = clock64();                                                     \
     }                                                                         \
   } while (0)
-#define ENO_TICK_START() do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_last = clock64(); } while (0)
+#define ENO_TICK_START()                                                      \
+  do {                                                                        \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                \
+      long long* s_ = ph_slots();                                             \
+      for (int i_ = 0; i_ < 64; ++i_) s_[i_] = 0;                             \
+      s_[64] = clock64();                                                     \
+    }                                                                         \
+  } while (0)
+#define ENO_TICK_FLUSH()                                                      \
+  do {                                                                        \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                \
+      long long* s_ = ph_slots();                                             \
+      for (int i_ = 0; i_ < 32; ++i_) { g_phase_cycles[i_] += s_[i_]; g_phase_count[i_] += s_[32 + i_]; } \
+    }                                                                         \
+  } while (0)
 #else
 #define ENO_TICK(kind) do {} while (0)
 #define ENO_TICK_START() do {} while (0)
+#define ENO_TICK_FLUSH() do {} while (0)
 #endif
 
 constexpr int kC = 4;          // CTAs per cluster
-constexpr int kKG = 7;         // k-groups of a product contracting over the local slice (K = Dl; 49 = 7 x 7 at D = 784; 10 measured equal)
-constexpr int kKGw = 5;        // k-groups of a product contracting over H (25 = 5 x 5 at H = 100)
-constexpr int kRG = 2;         // row groups (measured: 1 vs 2 makes no difference; the products are latency-bound)
+constexpr int kKG = 14;        // k-groups of a product contracting over the local slice (K = Dl = 49 float4 rows at D = 784)
+constexpr int kKGw = 7;        // k-groups of a product contracting over H (25 float4 rows at H = 100)
+constexpr int kRG = 1;         // row groups: 1 = every weight word is read from shared memory ONCE per product and
+                               // feeds all R samples (the products are shared-memory-wavefront bound)
 
 struct ClGeom {
   int rank;   // CTA rank in cluster
@@ -247,6 +266,7 @@ __device__ __forceinline__ void mv_k(const float* __restrict__ W, int ldw, int N
 template <int R, typename Epi>
 __device__ __forceinline__ void reduce_local(const float* red, int KG, int N, Epi epi) {
   __syncthreads();
+  ENO_TICK(PH_WAIT_MV);
   for (int idx = threadIdx.x; idx < R * N; idx += blockDim.x) {
     const int r = idx / N, n = idx - r * N;
     float s = 0.f;
@@ -272,6 +292,7 @@ __device__ __forceinline__ void allreduce_H(cg::cluster_group& cluster, ClComm& 
                                             int KG, int H, const float* scal, int nscal, Epi epi, EpiS epis) {
   float* mine = cm.part[cm.phase];
   __syncthreads();
+  ENO_TICK(PH_WAIT_MV);
   for (int idx = threadIdx.x; idx < R * H; idx += blockDim.x) {
     const int r = idx / H, n = idx - r * H;
     float s = 0.f;
@@ -282,7 +303,9 @@ __device__ __forceinline__ void allreduce_H(cg::cluster_group& cluster, ClComm& 
     const int r = threadIdx.x / nscal, j = threadIdx.x - r * nscal;
     mine[r * g.Hs + H + j] = scal[r * 4 + j];
   }
+  ENO_TICK(PH_AR_LOCAL);
   cluster.sync();
+  ENO_TICK(PH_AR_CSYNC);
   const float* p0 = cluster.map_shared_rank(mine, 0);
   const float* p1 = cluster.map_shared_rank(mine, 1);
   const float* p2 = cluster.map_shared_rank(mine, 2);
@@ -299,6 +322,7 @@ __device__ __forceinline__ void allreduce_H(cg::cluster_group& cluster, ClComm& 
     epis(r, j, ((p0[o] + p1[o]) + p2[o]) + p3[o]);
   }
   cm.phase ^= 1;
+  ENO_TICK(PH_AR_REMOTE);
   __syncthreads();
   ENO_TICK(PH_ALLRED);
 }

@@ -41,9 +41,12 @@ __device__ __forceinline__ ClSmem cl_carve(float* sm, int D, int H, const ClGeom
     s.xzb = sm; sm += RD;
     s.m.y1 = sm; sm += RD;
     s.m.y2 = sm; sm += RD;
-    s.m.gf = sm; sm += RD;
-    s.m.gy1 = sm; sm += RD;
-    s.m.zacc = sm; sm += RD;
+    // three reverse-sweep vectors reuse storage whose forward-sweep contents are dead by then
+    // (cl_aug_reverse): y2 is last read when y2_bar is formed, u after the product that consumes it,
+    // the stage input after the first sigmoid
+    s.m.gf = s.m.y2;
+    s.m.gy1 = s.m.u;
+    s.m.zacc = s.xz;
     s.m.a1 = sm; sm += RH; s.m.h1 = sm; sm += RH; s.m.a2 = sm; sm += RH; s.m.h2 = sm; sm += RH;
     s.m.ga = sm; sm += RH; s.m.ga1 = sm; sm += RH; s.m.ga2 = sm; sm += RH;
     s.y = s.k = nullptr;
@@ -71,7 +74,7 @@ inline size_t cl_smem_bytes(int R, int D, int H, int stages, bool adjoint) {
   const ClGeom g = cl_geom(D, H, 0);
   const size_t RD = (size_t)R * g.Dlp, RH = (size_t)R * H;
   size_t f = (adjoint ? 0 : 2 * kThreads) + (size_t)g.Dl * g.ldw1 + (size_t)H * g.Dlp + 2 * H + 2 * g.Dlp + 4 * RD + RH;
-  f += adjoint ? (6 * RD + 7 * RH) : ((size_t)(1 + stages) * RD);
+  f += adjoint ? (3 * RD + 7 * RH) : ((size_t)(1 + stages) * RD);
   const size_t red_n = std::max((size_t)kKG * R * H, (size_t)kKGw * R * g.Dlp);
   f += red_n + 2 * (size_t)R * g.Hs + 4 * R + 3 * 4 * ((R + 3) / 4) + 4 * ((7 * R + 3) / 4) + 36 * R + 16;
   return f * sizeof(float);
@@ -529,6 +532,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
     __syncthreads();
     ENO_TICK(PH_COMBINE);
   }
+  ENO_TICK_FLUSH();
   cluster.sync();
 }
 

@@ -504,9 +504,10 @@ int32_t eno_ffma_peak(eno_ctx* ctx, double* tflops_out, void* stream_) {
 #ifdef ENO_PHASES
 // development aid: read and clear the phase clocks of the cluster kernels
 int32_t eno_debug_phases(long long* cycles, long long* counts) {
-  long long zero[PH_NKINDS] = {0};
+  long long zero[32] = {0};
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(cycles, g_phase_cycles, sizeof(long long) * PH_NKINDS);
+  (void)sizeof(zero);
   cudaMemcpyFromSymbol(counts, g_phase_count, sizeof(long long) * PH_NKINDS);
   cudaMemcpyToSymbol(g_phase_cycles, zero, sizeof(zero));
   cudaMemcpyToSymbol(g_phase_count, zero, sizeof(zero));

@@ -13,14 +13,14 @@ eps = (torch.randint(0, 2, (B, 784), generator=gen).float() * 2 - 1).to(dev)
 m = mnist_step.MnistNode(reg="r3", lam=6e-5, device=dev)
 L = _cabi.lib()
 L.eno_debug_phases.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
-cyc = (C.c_longlong * 16)(); cnt = (C.c_longlong * 16)()
+cyc = (C.c_longlong * 32)(); cnt = (C.c_longlong * 32)()
 for _ in range(2): m.loss_and_grads(images, labels, eps)
 L.eno_debug_phases(cyc, cnt)
 x0 = (images.float() / 255.).reshape(B, -1)
-# backward only: run fwd (phases also tick in k_cl_fwd through cl_primal) then clear, then full step
+# only the ADJOINT step kernel starts/flushes the clocks (forward-kernel ticks land in a dead slot array)
 out = m.loss_and_grads(images, labels, eps)
 n = L.eno_debug_phases(cyc, cnt)
-names = ["prologue", "elem", "mv over Dl", "mv over H", "allreduce", "reduce_local", "store(+elem)", "scalar", "combine"]
+names = ["prologue", "stage input(+sync)", "mv over Dl (thread 0)", "mv over H (thread 0)", "allreduce: end sync", "reduce_local body+sync", "store(+elem+sync)", "scalar", "combine", "wait mv stragglers", "allred local", "allred cluster.sync", "allred remote+epi"]
 tot = sum(cyc[i] for i in range(n))
 print("one train step (fwd+bwd kernels, CTA 0), total cycles", tot)
 for i in range(n):
