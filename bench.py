@@ -238,10 +238,15 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    dbg = []
     for s in range(args.steps):
+        t1 = time.perf_counter()
         step_e2e(s)
+        dbg.append(round((time.perf_counter() - t1) * 1e3, 2))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("ENO_BENCH_DEBUG"):
+        print("e2e per-step ms:", dbg, file=sys.stderr)
     t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -275,7 +280,8 @@ def main():
     achieved = flop_rows / (rows_ms * 1e-3) / 1e12 if rows_ms > 0 else 0.0
     roofline = {"kernel": "k_adj_rows<STEP> (adjoint dopri5 iteration, per-sample blocks)", "bound": "tensor",
                 "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": rows_ms, "launches_timed": int(cnt[1]),
+                "traffic": 2.02e6,   # dram__bytes_read + write per launch, ncu --set full (profiles/r1_ncu_v2_kernels.txt)
+                "peak_source": peak_src, "avg_launch_ms": rows_ms, "launches_timed": int(cnt[1]),
                 "fp32_ffma_peak_tflops": ffma.value, "frac_of_fp32_ffma": achieved / ffma.value if ffma.value else None,
                 "other_kernels_ms": {"k_fwd_step": ms[0] / max(cnt[0], 1), "k_adj_pgrad<STEP>": ms[2] / max(cnt[2], 1)},
                 "note": "fp32 FFMA kernel; the tensor pipe is the contract's denominator, the fp32 pipe is the one it uses"}
@@ -314,7 +320,7 @@ def main():
         # Tear down in dependency order: the captured graph holds NCCL work of both communicators.  Drop it,
         # drain the device, meet the other ranks once more, then leave without running communicator
         # destructors (a destructor waiting on a peer that already left is the classic exit hang).
-        model._graph = None
+        model._graphs = {}
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()

@@ -94,43 +94,59 @@ class MnistNode:
     # parameter update is guarded on the device by the controllers' `done` flags; if a budget turns out too
     # small the parameters are left untouched and the step is redone in polled mode with a bigger budget.
     def update_graphed(self, images_u8, labels, eps):
-        """update() through a captured CUDA graph; returns dict(loss=float, redone=bool, ...)."""
-        if getattr(self, "_graph", None) is None:
-            out = self.update(images_u8, labels, eps)        # polled step: learns the iteration counts
-            if not getattr(self, "_graph_off", False):
-                try:
-                    self._capture(images_u8, labels, eps, out["fwd_stats"]["n_iters"], out["bwd_stats"][0]["n_iters"])
-                except Exception as e:                       # capture is an optimisation, never a requirement
-                    self._graph, self._graph_off, self._graph_error = None, True, repr(e)
+        """update() through a captured CUDA graph; returns dict(loss=float, redone=bool, ...).
+
+        Graphs are cached per pair of iteration-budget levels (powers of two); the level is chosen from the
+        iteration counts of the previous step (they drift slowly).  The first call captures a small ladder
+        of levels up front, the way a tracing compiler pays its compile time in the warm-up."""
+        if getattr(self, "_graph_off", False):
+            out = self.update(images_u8, labels, eps)
             return dict(loss=float(out["loss"]), redone=False, fwd_iters=out["fwd_stats"]["n_iters"],
                         bwd_iters=out["bwd_stats"][0]["n_iters"], nfe=out["fwd_stats"]["nfe"])
+        if not hasattr(self, "_graphs"):
+            out = self.update(images_u8, labels, eps)        # polled step: learns the iteration counts
+            self._graphs, self._last = {}, (out["fwd_stats"]["n_iters"], out["bwd_stats"][0]["n_iters"])
+            self._g_in = tuple(t.clone() for t in (images_u8, labels, eps))
+            try:
+                lf, lb = self._level(self._last[0]), self._level(self._last[1])
+                for key in ((lf, lb), (lf, 2 * lb), (2 * lf, 2 * lb), (2 * lf, 4 * lb), (4 * lf, 4 * lb)):
+                    self._capture(key)
+            except Exception as e:                           # capture is an optimisation, never a requirement
+                self._graph_off, self._graph_error = True, repr(e)
+            return dict(loss=float(out["loss"]), redone=False, fwd_iters=self._last[0], bwd_iters=self._last[1],
+                        nfe=out["fwd_stats"]["nfe"])
+        key = (self._level(self._last[0]), self._level(self._last[1]))
+        if key not in self._graphs:
+            self._capture(key)
+        graph, info, self._launches = self._graphs[key]
         for dst, src in zip(self._g_in, (images_u8, labels, eps)):
             dst.copy_(src, non_blocking=True)
-        self._graph.replay()
-        loss, ok_f, n_f, ok_b, n_b = self._g_info.tolist()   # the step's one device -> host read
+        graph.replay()
+        loss, ok_f, n_f, ok_b, n_b = info.tolist()           # the step's one device -> host read
         if not (ok_f and ok_b):
-            self._graph = None                               # budget too small: parameters were not touched
+            # an iteration budget was too small: the guarded update left the parameters untouched; redo the
+            # step in polled mode and move to the level it needs
             out = self.update(images_u8, labels, eps)
-            self._capture(images_u8, labels, eps, out["fwd_stats"]["n_iters"], out["bwd_stats"][0]["n_iters"])
-            return dict(loss=float(out["loss"]), redone=True, fwd_iters=out["fwd_stats"]["n_iters"],
-                        bwd_iters=out["bwd_stats"][0]["n_iters"], nfe=out["fwd_stats"]["nfe"])
-        n_f, n_b = int(n_f), int(n_b)
-        if (n_f > self._budget[0] - 2 or n_b > self._budget[1] - 2 or
-                2 * n_f + 16 < self._budget[0] or 2 * n_b + 16 < self._budget[1]):
-            self._capture(images_u8, labels, eps, n_f, n_b)   # keep the budgets ahead of the drifting counts
-        return dict(loss=loss, redone=False, fwd_iters=n_f, bwd_iters=n_b, nfe=2.0 + 6.0 * n_f)
+            self._last = (out["fwd_stats"]["n_iters"], out["bwd_stats"][0]["n_iters"])
+            return dict(loss=float(out["loss"]), redone=True, fwd_iters=self._last[0], bwd_iters=self._last[1],
+                        nfe=out["fwd_stats"]["nfe"])
+        self._last = (int(n_f), int(n_b))
+        return dict(loss=loss, redone=False, fwd_iters=self._last[0], bwd_iters=self._last[1], nfe=2.0 + 6.0 * n_f)
 
-    def _capture(self, images_u8, labels, eps, n_f, n_b):
-        # iterations past termination cost one ~3 us no-op launch each; re-capturing costs milliseconds,
-        # so the budgets are generous (counts drift upwards as training stiffens the dynamics)
-        self._budget = (max(n_f + 8, (3 * n_f + 1) // 2), max(n_b + 8, (3 * n_b + 1) // 2))
-        first = getattr(self, "_g_in", None) is None
-        if first:
-            self._g_in = tuple(t.clone() for t in (images_u8, labels, eps))
+    @staticmethod
+    def _level(n):
+        """Iteration budget for an observed count n: next power of two above n + 4 (at least 16).  Launches
+        past termination cost ~3 us each; a level change costs a capture (milliseconds) once."""
+        lvl = 16
+        while lvl < n + 4:
+            lvl *= 2
+        return lvl
+
+    def _capture(self, key):
         snap = self.snapshot()
-        ode.set_deferred(True, self._budget[0], self._budget[1], self.device)
+        ode.set_deferred(True, key[0], key[1], self.device)
         try:
-            if first:
+            if not self._graphs:
                 side = torch.cuda.Stream(device=self.device)
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side):
@@ -139,9 +155,9 @@ class MnistNode:
                 self.restore(snap)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._g_info = self._graph_body()
-            self._graph = g
-            self._launches = ode.last_stats["fwd"]["n_launches"] + sum(b["n_launches"] for b in ode.last_stats["bwd"])
+                info = self._graph_body()
+            launches = ode.last_stats["fwd"]["n_launches"] + sum(b["n_launches"] for b in ode.last_stats["bwd"])
+            self._graphs[key] = (g, info, launches)
         finally:
             ode.set_deferred(False, device=self.device)
         self.restore(snap)
