@@ -236,3 +236,35 @@ def test_tableau_sweep_mnist_shapes_vs_oracle(cuda, name):
         got, nfe_g = fn(spec.dynamics_wrap, tol, tol, math.inf, x0.to(cuda).reshape(-1), ts, p_gpu)
         assert float(nfe_g) == float(nfe_w), (name, tol)
         assert rel_err(got, want) < max(RTOL, 2 * tol)
+
+
+def test_host_tensors_round_trip_and_usage_errors(case, cuda):
+    """Inputs that live on the host are copied to the device for the call and results come back on the host
+    (the e2e path of bench.py); usage errors surface as exceptions with the library's message, never as a
+    silent fallback."""
+    import ctypes as C
+    eno, g, spec, params, x0 = case
+    from easy_neural_ode_b200 import _cabi
+    p_host = {k: {kk: vv.cpu() for kk, vv in v.items()} for k, v in params.items()}
+    ys_h, nfe_h = eno.odeint(spec.dynamics_wrap, x0.cpu(), torch.tensor([0., 1.]), p_host, rtol=1e-5, atol=1e-5)
+    ys_d, nfe_d = eno.odeint(spec.dynamics_wrap, x0, torch.tensor([0., 1.]), params, rtol=1e-5, atol=1e-5)
+    assert ys_h.device.type == "cpu" and float(nfe_h) == float(nfe_d)
+    assert torch.equal(ys_h, ys_d.cpu())
+    # a workspace that is too small is rejected before any launch
+    L = _cabi.lib()
+    h = _cabi.ctx(cuda.index)
+    desc = spec.desc()
+    B, D = x0.shape
+    ys = torch.empty((2, B, D), device=cuda)
+    ts = torch.tensor([0., 1.], device=cuda)
+    pf = spec.flatten_params(params).contiguous()
+    ws = torch.empty(1024, dtype=torch.uint8, device=cuda)
+    st = _cabi.Stats()
+    rc = L.eno_odeint_fwd(h, C.byref(desc), 0, B, x0.data_ptr(), ts.data_ptr(), 2, pf.data_ptr(), None, 1e-5, 1e-5, 0,
+                          ws.data_ptr(), ws.numel(), ys.data_ptr(), None, C.byref(st), None, 0, None)
+    assert rc == -3 and b"workspace" in L.eno_last_error_string(h)
+    rc = L.eno_odeint_fwd(h, C.byref(desc), 42, B, x0.data_ptr(), ts.data_ptr(), 2, pf.data_ptr(), None, 1e-5, 1e-5, 0,
+                          ws.data_ptr(), 1 << 30, ys.data_ptr(), None, C.byref(st), None, 0, None)
+    assert rc == -1 and b"tableau" in L.eno_last_error_string(h)
+    with pytest.raises(TypeError):
+        eno.odeint(spec.aug_dynamics, (x0,), torch.tensor([0., 1.]), None, params)   # wrong state arity
