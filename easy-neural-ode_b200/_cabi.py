@@ -11,13 +11,13 @@ LIB_PATH = os.environ.get("ENO_LIB") or os.path.join(_HERE, "libeno.so")   # ENO
 
 ENO_OK, ENO_MXSTEP, ENO_DT_UNDERFLOW, ENO_NONFINITE = 0, 1, 2, 3
 ARCH_MLP_SIGMOID = 0
-AUG_NONE, AUG_REG, AUG_ALL = 0, 1, 2
+AUG_NONE, AUG_REG, AUG_ALL, AUG_FIN = 0, 1, 2, 3
 TABLEAUX = {"dopri5": 0, "heun": 1, "fehlberg": 2, "bosh": 3, "rk_fehlberg": 4, "cash_karp": 5,
             "owrenzen": 6, "owrenzen5": 7, "tanyam": 8}
 
 # every symbol include/eno.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["eno_abi_version", "eno_last_error_string", "eno_create", "eno_destroy", "eno_param_count",
-           "eno_adjoint_state_size", "eno_workspace_bytes", "eno_odeint_fwd", "eno_odeint_bwd", "eno_rhs",
+           "eno_adjoint_state_size", "eno_workspace_bytes", "eno_odeint_fwd", "eno_odeint_bwd", "eno_odeint_bwd_sepaux", "eno_rhs",
            "eno_profile_enable", "eno_profile_read", "eno_ffma_peak", "eno_comm_unique_id", "eno_comm_init",
            "eno_comm_destroy", "eno_set_deferred", "eno_read_stats"]
 
@@ -72,8 +72,11 @@ def lib():
     L.eno_odeint_bwd.restype = i32
     L.eno_odeint_bwd.argtypes = [vp, C.POINTER(Desc), i32, vp, vp, i32, vp, vp, vp, f32, f32, i32, vp, sz, vp, vp, vp,
                                  vp, C.POINTER(Stats), vp, i32, vp]
+    L.eno_odeint_bwd_sepaux.restype = i32
+    L.eno_odeint_bwd_sepaux.argtypes = [vp, C.POINTER(Desc), i32, vp, vp, i32, vp, vp, vp, vp, f32, f32, i32, vp, sz, vp, vp,
+                                        vp, vp, vp, C.POINTER(Stats), vp, i32, vp]
     L.eno_rhs.restype = i32
-    L.eno_rhs.argtypes = [vp, C.POINTER(Desc), i32, i32, vp, f32, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, vp]
+    L.eno_rhs.argtypes = [vp, C.POINTER(Desc), i32, i32, vp, f32, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]
     L.eno_profile_enable.restype = i32
     L.eno_profile_enable.argtypes = [vp, i32]
     L.eno_profile_read.restype = i32

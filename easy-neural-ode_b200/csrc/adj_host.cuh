@@ -17,13 +17,14 @@ namespace eno {
 // ======================================================================================
 inline size_t adj_align(size_t x) { return (x + 255) / 256 * 256; }
 
-inline size_t adj_ws_bytes(int B, int D, int H, int world = 1) {
+inline size_t adj_ws_bytes(int B, int D, int H, int world = 1, bool fin = false) {
   const size_t N = (size_t)B * D, P = (size_t)(D + 1) * H + H + (size_t)(H + 1) * D + D;
   const PgradGeom g = pgrad_geom(D, H);
   size_t s = 0;
   s += adj_align(sizeof(Ctrl)) + adj_align(sizeof(AdjScalars));
   s += 4 * adj_align(3 * N * 4);                    // Z, ZB, FZ, FZB
-  s += 2 * adj_align(3 * (size_t)B * 4) + adj_align((size_t)B * 4);  // RS, FR, RB
+  s += 2 * adj_align(3 * 2 * (size_t)B * 4) + adj_align(2 * (size_t)B * 4);  // RS, FR, RB (up to 2 scalars per sample)
+  if (fin) s += 2 * adj_align(3 * N * 4) + adj_align(2 * N * 4) + adj_align(N * 4);   // ZE, FZE, MIDZE, EBAR
   s += adj_align(2 * N * 4);                        // MIDZB
   s += 2 * adj_align(3 * P * 4) + adj_align(2 * P * 4);             // PB, FP, MIDP
   const size_t npp = std::max((size_t)g.grid, (P + 255) / 256);
@@ -46,7 +47,7 @@ struct AdjCarver {
   }
 };
 
-inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArgs* a, int world = 1) {
+inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArgs* a, int world = 1, bool fin = false) {
   const size_t N = (size_t)B * D, P = (size_t)(D + 1) * H + H + (size_t)(H + 1) * D + D;
   const PgradGeom g = pgrad_geom(D, H);
   AdjCarver cv{static_cast<char*>(ws)};
@@ -54,7 +55,13 @@ inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArg
   a->sc = cv.take<AdjScalars>(1);
   a->Z = cv.take<float>(3 * N); a->ZB = cv.take<float>(3 * N);
   a->FZ = cv.take<float>(3 * N); a->FZB = cv.take<float>(3 * N);
-  a->RS = cv.take<float>(3 * (size_t)B); a->FR = cv.take<float>(3 * (size_t)B); a->RB = cv.take<float>(B);
+  a->RS = cv.take<float>(3 * 2 * (size_t)B); a->FR = cv.take<float>(3 * 2 * (size_t)B); a->RB = cv.take<float>(2 * (size_t)B);
+  a->na = fin ? 2 : 1;
+  a->fin = fin ? 1 : 0;
+  if (fin) {
+    a->ZE = cv.take<float>(3 * N); a->FZE = cv.take<float>(3 * N);
+    a->MIDZE = cv.take<float>(2 * N); a->EBAR = cv.take<float>(N);
+  }
   a->MIDZB = cv.take<float>(2 * N);
   a->PB = cv.take<float>(3 * P); a->FP = cv.take<float>(3 * P); a->MIDP = cv.take<float>(2 * P);
   for (int j = 0; j < kSlots; ++j) {
@@ -198,24 +205,28 @@ inline void adj_transposes(const AdjArgs& a, cudaStream_t st) {
 
 inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int deferred_iters, const Tableau* tab_host,
                      std::string* err, Ctrl* mailbox, int* hint, int sms, const eno_dynamics_desc* desc, int B,
-                     const float* ys, const float* ts, int T, const float* params, const float* g_y, const float* g_r,
-                     float rtol, float atol, int mxstep, void* ws, size_t ws_bytes, float* y0_bar_out,
-                     float* r0_bar_out, float* ts_bar_out, float* params_bar_out, eno_stats* stats,
+                     const float* ys, const float* ts, int T, const float* params, const float* eps, const float* g_y,
+                     const float* g_r, float rtol, float atol, int mxstep, void* ws, size_t ws_bytes, float* y0_bar_out,
+                     float* r0_bar_out, float* eps_bar_out, float* ts_bar_out, float* params_bar_out, eno_stats* stats,
                      eno_trace_row* trace, int trace_cap, cudaStream_t st) {
-  const int D = desc->D, H = desc->H, K = desc->reg_order;
+  const bool fin = desc->aug == ENO_AUG_FIN;
+  const int D = desc->D, H = desc->H, K = fin ? 2 : desc->reg_order;
   if (!(K == 0 || K == 2 || K == 3)) { if (err) *err = "eno_odeint_bwd: reg_order must be 0, 2 or 3"; return ENO_E_UNSUPPORTED; }
+  if (fin && !eps) { if (err) *err = "eno_odeint_bwd: ENO_AUG_FIN needs eps"; return ENO_E_ARG; }
   if (B <= 0 || T < 1 || !ys || !ts || !params || !g_y || !g_r || !ws || !y0_bar_out || !r0_bar_out || !ts_bar_out ||
       !params_bar_out) { if (err) *err = "eno_odeint_bwd: null pointer or empty batch"; return ENO_E_ARG; }
   const bool dist = dc && dc->active();
   const int world = dist ? dc->world : 1, rank = dist ? dc->rank : 0;
-  if (ws_bytes < adj_ws_bytes(B, D, H, world)) { if (err) *err = "eno_odeint_bwd: workspace too small"; return ENO_E_WORKSPACE; }
+  if (ws_bytes < adj_ws_bytes(B, D, H, world, fin)) { if (err) *err = "eno_odeint_bwd: workspace too small"; return ENO_E_WORKSPACE; }
   const size_t N = (size_t)B * D;
   AdjArgs a = {};
-  adj_carve(ws, B, D, H, params, &a, world);
+  adj_carve(ws, B, D, H, params, &a, world, fin);
+  a.eps = eps;
+  const size_t na = (size_t)a.na;
   a.dist = dist ? 1 : 0;
   a.np = (K == 0) ? 1 : K;
   {
-    const size_t n_aux = (desc->aug == ENO_AUG_NONE) ? 0 : 1;
+    const size_t n_aux = (desc->aug == ENO_AUG_NONE) ? 0 : na;
     const size_t Ng = N * world, Bg = (size_t)B * world;   // the ODE state spans the GLOBAL batch
     a.n_state = (float)(2 * (Ng + n_aux * Bg) + 1 + (desc->eps_in_args ? Ng : 0) + (size_t)a.P);
   }
@@ -226,6 +237,10 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
   const bool deferred = deferred_iters > 0;
   if (deferred && T != 2) { if (err) *err = "eno_odeint_bwd: deferred mode supports T == 2 only"; return ENO_E_UNSUPPORTED; }
   const AdjPlan plan = adj_plan(B, D, H, sms, path_mode, false);
+  if (fin && !plan.cluster) {
+    if (err) *err = "eno_odeint_bwd: ENO_AUG_FIN runs on the cluster-resident path only (shape or ENO_PATH excludes it)";
+    return ENO_E_UNSUPPORTED;
+  }
   ENO_ADJ_CHECK(pgrad_prepare());
   if (!plan.cluster) adj_transposes(a, st);
   adj_set_views(&a, plan.cluster ? kC : 1, rank, world);
@@ -255,7 +270,8 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
   int worst = ENO_OK;
   if (T == 1) {   // nothing to integrate: y0_bar = g[0], everything else zero (empty scan)
     ENO_ADJ_CHECK(cudaMemcpyAsync(y0_bar_out, g_y, N * 4, cudaMemcpyDeviceToDevice, st));
-    ENO_ADJ_CHECK(cudaMemcpyAsync(r0_bar_out, g_r, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    ENO_ADJ_CHECK(cudaMemcpyAsync(r0_bar_out, g_r, na * B * 4, cudaMemcpyDeviceToDevice, st));
+    if (eps_bar_out) ENO_ADJ_CHECK(cudaMemsetAsync(eps_bar_out, 0, N * 4, st));
     ENO_ADJ_CHECK(cudaMemsetAsync(ts_bar_out, 0, 4, st));
     ENO_ADJ_CHECK(cudaMemsetAsync(params_bar_out, 0, (size_t)a.P * 4, st));
     ENO_ADJ_CHECK(cudaStreamSynchronize(st));
@@ -265,7 +281,7 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
     int launches = 0;
     const int first = (i == T - 1);
     a.g_y = g_y + (size_t)i * N;
-    a.g_r = g_r + (size_t)i * B;
+    a.g_r = g_r + (size_t)i * na * B;
     a.g_y_prev = g_y + (size_t)(i - 1) * N;
     a.tbar_out = ts_bar_out + i;
     k_adj_seg_begin<<<egrid, 256, 0, st>>>(a, ys + (size_t)i * N, a.g_y, a.g_r, ts, i, first, rtol, atol, mx,
@@ -322,6 +338,11 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
   }
   k_adj_finish<<<(B + 255) / 256, 256, 0, st>>>(a, g_r, r0_bar_out, ts_bar_out);
   ENO_ADJ_CHECK(cudaMemcpyAsync(y0_bar_out, a.YBAR, N * 4, cudaMemcpyDeviceToDevice, st));
+  if (eps_bar_out) {
+    // reg_type 'our' never reads eps: its cotangent stays identically zero (it only dilutes the error norm)
+    if (fin) ENO_ADJ_CHECK(cudaMemcpyAsync(eps_bar_out, a.EBAR, N * 4, cudaMemcpyDeviceToDevice, st));
+    else ENO_ADJ_CHECK(cudaMemsetAsync(eps_bar_out, 0, N * 4, st));
+  }
   ENO_ADJ_CHECK(cudaMemcpyAsync(params_bar_out, a.POUT, (size_t)a.P * 4, cudaMemcpyDeviceToDevice, st));
   if (!deferred) ENO_ADJ_CHECK(cudaStreamSynchronize(st));
   ENO_ADJ_CHECK(cudaGetLastError());
@@ -329,35 +350,46 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
 }
 
 inline int adj_rhs(int path_mode, std::string* err, int sms, const eno_dynamics_desc* desc, int mode, int B, const float* y, float t,
-                   const float* params, const float* y_bar, const float* r_bar, void* ws, size_t ws_bytes, float* dy_out,
-                   float* aux_out, float* ybar_dot_out, float* tbar_out, float* params_bar_out, cudaStream_t st) {
-  const int D = desc->D, H = desc->H, K = desc->reg_order;
+                   const float* params, const float* eps, const float* y_bar, const float* r_bar, void* ws, size_t ws_bytes,
+                   float* dy_out, float* aux_out, float* ybar_dot_out, float* tbar_out, float* params_bar_out,
+                   float* eps_bar_dot_out, cudaStream_t st) {
+  const bool fin = desc->aug == ENO_AUG_FIN;
+  const int D = desc->D, H = desc->H, K = fin ? 2 : desc->reg_order;
   if (!(K == 0 || K == 2 || K == 3)) { if (err) *err = "eno_rhs: reg_order must be 0, 2 or 3"; return ENO_E_UNSUPPORTED; }
-  if (!ws || ws_bytes < adj_ws_bytes(B, D, H)) { if (err) *err = "eno_rhs: workspace too small"; return ENO_E_WORKSPACE; }
+  if (fin && !eps) { if (err) *err = "eno_rhs: ENO_AUG_FIN needs eps"; return ENO_E_ARG; }
+  if (!ws || ws_bytes < adj_ws_bytes(B, D, H, 1, fin)) { if (err) *err = "eno_rhs: workspace too small"; return ENO_E_WORKSPACE; }
   if (mode == 2 && (!y_bar || !r_bar || !ybar_dot_out || !tbar_out || !params_bar_out || !aux_out)) {
     if (err) *err = "eno_rhs: mode 2 needs y_bar, r_bar and all outputs"; return ENO_E_ARG;
   }
   const size_t N = (size_t)B * D;
   AdjArgs a = {};
-  adj_carve(ws, B, D, H, params, &a);
+  adj_carve(ws, B, D, H, params, &a, 1, fin);
   a.np = (K == 0) ? 1 : K;
+  a.eps = eps;
+  const size_t na = (size_t)a.na;
   const AdjPlan plan = adj_plan(B, D, H, sms, path_mode, true);
+  if (fin && !plan.cluster) {
+    if (err) *err = "eno_rhs: ENO_AUG_FIN runs on the cluster-resident path only";
+    return ENO_E_UNSUPPORTED;
+  }
   ENO_ADJ_CHECK(pgrad_prepare());
   if (!plan.cluster) adj_transposes(a, st);
   adj_set_views(&a, plan.cluster ? kC : 1, 0, 1);
   ENO_ADJ_CHECK(cudaMemcpyAsync(a.Z, y, N * 4, cudaMemcpyDeviceToDevice, st));
   if (mode == 2) {
     ENO_ADJ_CHECK(cudaMemcpyAsync(a.ZB, y_bar, N * 4, cudaMemcpyDeviceToDevice, st));
-    ENO_ADJ_CHECK(cudaMemcpyAsync(a.RB, r_bar, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+    ENO_ADJ_CHECK(cudaMemcpyAsync(a.RB, r_bar, na * B * 4, cudaMemcpyDeviceToDevice, st));
   } else {
     ENO_ADJ_CHECK(cudaMemsetAsync(a.ZB, 0, N * 4, st));
-    ENO_ADJ_CHECK(cudaMemsetAsync(a.RB, 0, (size_t)B * 4, st));
+    ENO_ADJ_CHECK(cudaMemsetAsync(a.RB, 0, na * B * 4, st));
   }
-  ENO_ADJ_CHECK(cudaMemsetAsync(a.RS, 0, (size_t)B * 4, st));
+  ENO_ADJ_CHECK(cudaMemsetAsync(a.RS, 0, na * B * 4, st));
+  if (fin) ENO_ADJ_CHECK(cudaMemsetAsync(a.ZE, 0, N * 4, st));
   ENO_ADJ_CHECK(cudaMemsetAsync(a.ctrl, 0, sizeof(Ctrl), st));
   a.rhs_dy = dy_out;
   a.rhs_r = aux_out;
   a.rhs_zb = ybar_dot_out;
+  a.rhs_eb = eps_bar_dot_out;
   int rc;
   // solver time tau = -t, so that the kernel's t = -tau is the caller's t
   if ((rc = adj_rows_any(plan, K, ADJ_RHS, a, -t, st, err))) return rc;

@@ -50,9 +50,16 @@ struct AdjArgs {
   // per-sample rings
   float *Z, *ZB;           // [3][N]
   float *FZ, *FZB;         // [3][N]
-  float *RS, *FR;          // [3][B]
-  float* RB;               // [B]      r_bar (constant during a segment)
+  float *RS, *FR;          // [3][na][B]
+  float* RB;               // [na][B]  r_bar (constant during a segment)
   float *MIDZB;            // [2][N]   (only y_bar's interpolant is ever read)
+  // "fin" dynamics (ENO_AUG_FIN): two scalar states per sample and the eps_bar block
+  int na;                  // scalar states per sample: 1, or 2 (fro, kin)
+  int fin;
+  const float* eps;        // [N]
+  float *ZE, *FZE;         // [3][N]   eps_bar ring and its derivative
+  float* MIDZE;            // [2][N]
+  float* EBAR;             // [N]      eps_bar after the segment
   // shared block
   float *PB, *FP;          // [3][P]
   float* MIDP;             // [2][P]
@@ -67,13 +74,13 @@ struct AdjArgs {
   int dist;                                // 1: multi-GPU split (local contraction | NCCL | finish)
   // segment inputs / outputs
   const float* g_y;        // [N]   g[i] (for t_bar)
-  const float* g_r;        // [B]
+  const float* g_r;        // [na][B]
   float* YBAR;             // [N]   y_bar after the segment (+ g[i-1])
   const float* g_y_prev;   // [N]   g[i-1]
   float* POUT;             // [P]
   float* tbar_out;         // scalar: ts_bar[i]
   // eno_rhs outputs
-  float *rhs_dy, *rhs_r, *rhs_zb;
+  float *rhs_dy, *rhs_r, *rhs_zb, *rhs_eb;
   eno_trace_row* trace;
 };
 
@@ -622,7 +629,8 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
         for (int r = rb; r < re; ++r) acc += F0[(size_t)r * W + o];
       } else {
         const int n = o - W;
-        if (a.np >= 2) for (int r = rb; r < re; ++r) acc += fmaf(t_stage, F0[(size_t)r * W + n], F1[(size_t)r * W + n]);
+        // the jvp of the fin dynamics is taken wrt y only: its tangent pass has no w1t / w2t terms
+        if (a.np >= 2 && !a.fin) for (int r = rb; r < re; ++r) acc += fmaf(t_stage, F0[(size_t)r * W + n], F1[(size_t)r * W + n]);
         else for (int r = rb; r < re; ++r) acc += t_stage * F0[(size_t)r * W + n];
       }
     }
@@ -822,10 +830,12 @@ __global__ void k_adj_seg_begin(AdjArgs a, const float* ys_i, const float* g_y_i
     a.Z[k] = ys_i[k];
     a.ZB[k] = first ? g_y_i[k] : a.YBAR[k];
   }
-  for (size_t k = tid; k < (size_t)a.B; k += nth) {
+  for (size_t k = tid; k < (size_t)a.na * a.B; k += nth) {
     a.RS[k] = 0.f;   // the split wrappers' residual aux state is zeros (lib/ode.py:1003, 1679)
     a.RB[k] = first ? g_r_i[k] : a.RB[k] + g_r_i[k];
   }
+  if (a.fin)
+    for (size_t k = tid; k < a.N; k += nth) a.ZE[k] = first ? 0.f : a.EBAR[k];
   for (size_t k = tid; k < (size_t)a.P; k += nth) a.PB[k] = first ? 0.f : a.POUT[k];
   if (tid == 0) {
     Ctrl* c = a.ctrl;
@@ -870,6 +880,10 @@ __global__ void k_adj_out(AdjArgs a) {
                            a.FZB[(size_t)prev * a.N + k], a.FZB[(size_t)cur * a.N + k]);
     a.YBAR[k] = v + a.g_y_prev[k];
   }
+  if (a.fin)
+    for (size_t k = tid; k < a.N; k += nth)
+      a.EBAR[k] = interp(a.ZE[(size_t)prev * a.N + k], a.ZE[(size_t)cur * a.N + k], a.MIDZE[(size_t)mid * a.N + k],
+                         a.FZE[(size_t)prev * a.N + k], a.FZE[(size_t)cur * a.N + k]);
   for (size_t k = tid; k < (size_t)a.P; k += nth)
     a.POUT[k] = interp(a.PB[(size_t)prev * a.P + k], a.PB[(size_t)cur * a.P + k], a.MIDP[(size_t)mid * a.P + k],
                        a.FP[(size_t)prev * a.P + k], a.FP[(size_t)cur * a.P + k]);
@@ -879,7 +893,7 @@ __global__ void k_adj_out(AdjArgs a) {
 
 __global__ void k_adj_finish(AdjArgs a, const float* g_r0, float* r0_bar_out, float* ts_bar0) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-  for (size_t k = tid; k < (size_t)a.B; k += nth) r0_bar_out[k] = a.RB[k] + g_r0[k];
+  for (size_t k = tid; k < (size_t)a.na * a.B; k += nth) r0_bar_out[k] = a.RB[k] + g_r0[k];
   if (tid == 0) *ts_bar0 = a.sc->t0_out;
 }
 

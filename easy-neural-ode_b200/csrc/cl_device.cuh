@@ -592,4 +592,120 @@ __device__ __forceinline__ void cl_aug_reverse(cg::cluster_group& cluster, ClCom
   ENO_TICK(PH_SCALAR);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// "fin" augmented dynamics (mnist.py:294-313 with --reg_type fin; the same structure as the FFJORD
+// Hutchinson term of ffjord_tabular.py:250-268): next to f the RHS returns
+//     dfro = mean_d (J eps)^2        (J = df/dz, a forward-mode product with the fixed probe eps)
+//     dkin = mean_d f^2
+// The tangent pass is the first-order Taylor pass above with z' = eps instead of f and WITHOUT the time
+// tangent (jvp wrt y only: no w1t / w2t terms).  Its reverse sweep additionally yields the cotangent of
+// eps, which is a block of the adjoint state (lib/ode.py:1498-1504 differentiates wrt every arg).
+// On return of cl_fin_forward: f, y1 = J eps (local slices), h, a1, h1 replicated,
+// scal[r*4+0] = local partial of sum_d (J eps)^2, scal[r*4+1] = of sum_d f^2.
+template <int R>
+__device__ __forceinline__ void cl_fin_forward(cg::cluster_group& cluster, ClComm& cm, const ClGeom& g,
+                                               const ClWeights& w, float t, const float* z, const float* eps_g,
+                                               const ClScratch& m, const FactorSlot* slot, int row0, int B) {
+  const int D = w.D, H = w.H, Dl = g.Dl, Dlp = g.Dlp;
+  const size_t BD = (size_t)B * D, BH = (size_t)B * H;
+  cl_primal<R>(cluster, cm, g, w, t, z, m.f, m);
+  if (slot) {
+    cl_store_D<R>(slot->S, m.s, g, D, row0, B);
+    cl_store_H<R>(slot->Hh, m.h, g, H, row0, B);
+  }
+  for (int i = threadIdx.x; i < R * Dlp; i += blockDim.x) {
+    const int r = i / Dlp, d = i - r * Dlp;
+    const float s = m.s[i];
+    const bool ok = d < Dl && row0 + r < B;
+    m.u[i] = ok ? s * (1.f - s) * __ldg(eps_g + (size_t)(row0 + r) * D + g.d0 + d) : 0.f;
+  }
+  __syncthreads();
+  if (slot) cl_store_D<R>(slot->S + BD, m.u, g, D, row0, B);
+  mv_n<R>(w.W1, g.ldw1, Dl, H, m.u, Dlp, m.red, kKG);
+  allreduce_H<R>(cluster, cm, g, m.red, kKG, H, nullptr, 0,
+                 [&](int r, int n, float sum) {
+                   const float h = m.h[r * H + n];
+                   m.a1[r * H + n] = sum;
+                   m.h1[r * H + n] = h * (1.f - h) * sum;
+                 },
+                 [&](int, int, float) {});
+  if (slot) cl_store_H<R>(slot->Hh + BH, m.h1, g, H, row0, B);
+  mv_n<R>(w.W2, Dlp, H, Dl, m.h1, H, m.red, kKGw);
+  reduce_local<R>(m.red, kKGw, Dl, [&](int r, int d, float sum) { m.y1[r * Dlp + d] = sum; });
+  cl_sumsq_local<R>(m.y1, g, m.scal, 0);
+  cl_sumsq_local<R>(m.f, g, m.scal, 1);
+  __syncthreads();
+}
+
+// Reverse sweep of the fin dynamics.  zb: cotangent of f (local slice); rb2[r], rb2[R + r]: cotangents of
+// dfro, dkin.  On return: zacc = vjp wrt z, ebar = vjp wrt eps (local slices; ebar aliases u),
+// rdot2[r] = dfro, rdot2[R + r] = dkin (all ranks), factors + per-CTA t_bar pieces stored.
+template <int R>
+__device__ __forceinline__ void cl_fin_reverse(cg::cluster_group& cluster, ClComm& cm, const ClGeom& g,
+                                               const ClWeights& w, const float* zb, const float* rb2,
+                                               const float* eps_g, const ClScratch& m, float* rdot2,
+                                               const FactorSlot& slot, int row0, int B) {
+  const int D = w.D, H = w.H, Dl = g.Dl, Dlp = g.Dlp;
+  const size_t BD = (size_t)B * D, BH = (size_t)B * H;
+  const float invD2 = 2.0f / (float)D;
+  const float invD = 1.0f / (float)D;
+  // cotangent of e = J eps; cotangent of f from its own adjoint and from dkin
+  for (int i = threadIdx.x; i < R * Dlp; i += blockDim.x) {
+    const int r = i / Dlp;
+    m.gy1[i] = rb2[r] * invD2 * m.y1[i];
+    m.gf[i] = zb[i] + rb2[R + r] * invD2 * m.f[i];
+  }
+  __syncthreads();
+  cl_store_D<R>(slot.G + BD, m.gy1, g, D, row0, B);
+  mv_k<R>(w.W2, Dlp, H, Dl, m.gy1, Dlp, m.red, kKG);
+  allreduce_H<R>(cluster, cm, g, m.red, kKG, H, m.scal, 2,
+                 [&](int r, int n, float hb1) {
+                   const float h = m.h[r * H + n];
+                   const float hp = h * (1.f - h);
+                   m.ga[r * H + n] = hb1 * hp * (1.f - 2.f * h) * m.a1[r * H + n];
+                   m.ga1[r * H + n] = hb1 * hp;
+                 },
+                 [&](int r, int j, float v) { rdot2[j * R + r] = v * invD; });
+  cl_store_H<R>(slot.A + BH, m.ga1, g, H, row0, B);
+  mv_k<R>(w.W1, g.ldw1, Dl, H, m.ga1, H, m.red, kKGw);
+  // gy1 (= u) is dead once its product and factor store are done: its storage takes eps_bar
+  float* ebar = m.gy1;
+  reduce_local<R>(m.red, kKGw, Dl, [&](int r, int d, float sb1) {
+    const int i = r * Dlp + d;
+    const float s = m.s[i];
+    const float sp = s * (1.f - s);
+    const float ev = (row0 + r < B) ? __ldg(eps_g + (size_t)(row0 + r) * D + g.d0 + d) : 0.f;
+    m.zacc[i] = sb1 * sp * (1.f - 2.f * s) * ev;
+    ebar[i] = sb1 * sp;
+  });
+  cl_store_D<R>(slot.G, m.gf, g, D, row0, B);
+  mv_k<R>(w.W2, Dlp, H, Dl, m.gf, Dlp, m.red, kKG);
+  allreduce_H<R>(cluster, cm, g, m.red, kKG, H, nullptr, 0,
+                 [&](int r, int n, float hb) {
+                   const float h = m.h[r * H + n];
+                   m.ga[r * H + n] += hb * h * (1.f - h);
+                 },
+                 [&](int, int, float) {});
+  cl_store_H<R>(slot.A, m.ga, g, H, row0, B);
+  mv_k<R>(w.W1, g.ldw1, Dl, H, m.ga, H, m.red, kKGw);
+  reduce_local<R>(m.red, kKGw, Dl, [&](int r, int d, float sb) {
+    const int i = r * Dlp + d;
+    const float s = m.s[i];
+    m.zacc[i] += sb * s * (1.f - s);
+  });
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = warp; r < R; r += nw) {
+      double acc = 0.0;
+      for (int d = lane; d < Dl; d += 32) acc += (double)(m.gf[r * Dlp + d] * w.w2t[d]);
+      if (g.rank == 0)
+        for (int n = lane; n < H; n += 32) acc += (double)(m.ga[r * H + n] * w.w1t[n]);
+      acc = warp_sum(acc);
+      if (lane == 0 && row0 + r < B) slot.tbar[(size_t)(row0 + r) * kC + g.rank] = (float)acc;
+    }
+  }
+  __syncthreads();
+}
+
 }  // namespace eno

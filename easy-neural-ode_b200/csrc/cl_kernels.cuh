@@ -285,7 +285,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_fwd(FwdArgs a) {
 // adjoint per-sample blocks.  Stage derivatives live in REGISTERS (each thread owns EPT elements of
 // the tile's local slice for the whole iteration); shared memory only holds the RHS working set.
 // ------------------------------------------------------------------------------------------
-template <int R, int K, int MODE, int DT, int HT>
+// FIN = the "fin" augmented dynamics (cl_fin_forward / cl_fin_reverse): two scalar states per sample and
+// the eps_bar block, which never feeds back into the RHS and is therefore carried as running stage
+// combinations (solution, error, mid-point) instead of stage buffers.
+template <int R, int K, int MODE, int DT, int HT, bool FIN = false>
 __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rhs_tau) {
   Ctrl* c = a.ctrl;
   if (MODE == ADJ_STEP && c->done) return;
@@ -305,6 +308,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
   const float tau = (MODE == ADJ_STEP) ? c->t : (MODE == ADJ_RHS ? rhs_tau : a.sc->seg_ts[0]);
   const float dt = (MODE == ADJ_STEP) ? c->dt : c->h0;
   const size_t B = a.B;
+  constexpr int NA = FIN ? 2 : 1;   // scalar states per sample
+  float* const sr = FIN ? S.aux : S.r;                 // [NA][R] state
+  float* const srb = FIN ? S.aux + 2 * R : S.rb;       // [NA][R] cotangent (constant during a segment)
+  float* const skr = FIN ? S.aux + 4 * R : S.kr;       // [7][NA][R] stage derivatives
+  float* const srd = FIN ? S.aux + 18 * R : S.m.rdot;  // [NA][R] RHS output
   __syncthreads();
   ENO_TICK(PH_PROLOGUE);
 
@@ -313,6 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
   for (int tile = blockIdx.x / kC; tile < n_tiles; tile += n_clusters) {
     const int row0 = tile * R;
     float z[EPT], zb[EPT], kz[kAdjStages][EPT], kzb[kAdjStages][EPT];
+    float ze[EPT], ke0[EPT], kel[EPT], se[EPT], ee[EPT], me[EPT];   // eps_bar block (FIN only)
     size_t gi[EPT];
     bool ok[EPT];
 #pragma unroll
@@ -330,12 +339,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
       }
 #pragma unroll
       for (int st = 1; st < kAdjStages; ++st) kz[st][j] = kzb[st][j] = 0.f;
+      ze[j] = ke0[j] = kel[j] = se[j] = ee[j] = me[j] = 0.f;
+      if (FIN) {
+        ze[j] = ok[j] ? a.ZE[(size_t)cur * a.N + gi[j]] : 0.f;
+        if (MODE == ADJ_STEP || MODE == ADJ_INIT1) ke0[j] = ok[j] ? a.FZE[(size_t)cur * a.N + gi[j]] : 0.f;
+        se[j] = c_tab.c_sol[0] * ke0[j];
+        ee[j] = c_tab.c_err[0] * ke0[j];
+        me[j] = c_tab.c_mid[0] * ke0[j];
+      }
     }
-    if (threadIdx.x < R) {
-      const bool okr = row0 + threadIdx.x < a.B;
-      S.r[threadIdx.x] = okr ? a.RS[(size_t)cur * B + row0 + threadIdx.x] : 0.f;
-      S.rb[threadIdx.x] = okr ? a.RB[row0 + threadIdx.x] : 0.f;
-      S.kr[threadIdx.x] = (okr && (MODE == ADJ_STEP || MODE == ADJ_INIT1)) ? a.FR[(size_t)cur * B + row0 + threadIdx.x] : 0.f;
+    if (threadIdx.x < NA * R) {
+      const int q = threadIdx.x / R, r = threadIdx.x - q * R;
+      const bool okr = row0 + r < a.B;
+      sr[threadIdx.x] = okr ? a.RS[((size_t)cur * NA + q) * B + row0 + r] : 0.f;
+      srb[threadIdx.x] = okr ? a.RB[(size_t)q * B + row0 + r] : 0.f;
+      skr[threadIdx.x] = (okr && (MODE == ADJ_STEP || MODE == ADJ_INIT1)) ? a.FR[((size_t)cur * NA + q) * B + row0 + r] : 0.f;
     }
 
     constexpr int NEVAL = (MODE == ADJ_STEP) ? kAdjStages - 1 : 1;
@@ -371,8 +389,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
       __syncthreads();
       ENO_TICK(PH_ELEM);
       const FactorSlot& slot = a.slot[(MODE == ADJ_STEP) ? ev - 1 : 0];
-      cl_aug_forward<R, K>(cluster, S.cm, g, w, -tev, S.xz, S.m, &slot, row0, a.B);
-      cl_aug_reverse<R, K>(cluster, S.cm, g, w, S.xzb, S.rb, S.m, slot, row0, a.B);
+      if (FIN) {
+        cl_fin_forward<R>(cluster, S.cm, g, w, -tev, S.xz, a.eps, S.m, &slot, row0, a.B);
+        cl_fin_reverse<R>(cluster, S.cm, g, w, S.xzb, srb, a.eps, S.m, srd, slot, row0, a.B);
+      } else {
+        cl_aug_forward<R, K>(cluster, S.cm, g, w, -tev, S.xz, S.m, &slot, row0, a.B);
+        cl_aug_reverse<R, K>(cluster, S.cm, g, w, S.xzb, S.rb, S.m, slot, row0, a.B);
+      }
 #pragma unroll
       for (int j = 0; j < EPT; ++j) {
         const int e = threadIdx.x + j * kThreads;
@@ -381,8 +404,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
 #pragma unroll
         for (int st = 1; st < kAdjStages; ++st)
           if (st == ev) { kz[st][j] = vf; kzb[st][j] = vb; }
+        if (FIN) {
+          kel[j] = (e < RD) ? S.m.gy1[e] : 0.f;   // eps_bar' (cl_fin_reverse leaves it in gy1's storage)
+          if (MODE == ADJ_STEP) {
+            se[j] = fmaf(c_tab.c_sol[ev], kel[j], se[j]);
+            ee[j] = fmaf(c_tab.c_err[ev], kel[j], ee[j]);
+            me[j] = fmaf(c_tab.c_mid[ev], kel[j], me[j]);
+          }
+        }
       }
-      if (threadIdx.x < R) S.kr[ev * R + threadIdx.x] = -S.m.rdot[threadIdx.x];
+      if (threadIdx.x < NA * R) skr[ev * NA * R + threadIdx.x] = -srd[threadIdx.x];
       __syncthreads();
       ENO_TICK(PH_SCALAR);
     }
@@ -393,9 +424,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
         if (ok[j]) {
           a.rhs_dy[gi[j]] = -kz[1][j];
           if (a.rhs_zb) a.rhs_zb[gi[j]] = kzb[1][j];
+          if (FIN && a.rhs_eb) a.rhs_eb[gi[j]] = kel[j];
         }
-      if (g.rank == 0 && threadIdx.x < R && row0 + threadIdx.x < a.B && a.rhs_r)
-        a.rhs_r[row0 + threadIdx.x] = -S.kr[R + threadIdx.x];
+      if (g.rank == 0 && threadIdx.x < NA * R && a.rhs_r) {
+        const int q = threadIdx.x / R, r = threadIdx.x - q * R;
+        if (row0 + r < a.B) a.rhs_r[(size_t)q * B + row0 + r] = -skr[NA * R + threadIdx.x];
+      }
       continue;
     }
 
@@ -408,8 +442,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
           const float kzv = kz[1][j], kbv = kzb[1][j];
           const float sz = atol + fabsf(z[j]) * rtol, szb = atol + fabsf(zb[j]) * rtol;
           const float q0a = z[j] / sz, q0b = zb[j] / szb, q1a = kzv / sz, q1b = kbv / szb;
-          S.m.u[e] = ok[j] ? q0a * q0a + q0b * q0b : 0.f;
-          S.xz[e] = ok[j] ? q1a * q1a + q1b * q1b : 0.f;
+          float p0 = q0a * q0a + q0b * q0b, p1 = q1a * q1a + q1b * q1b;
+          if (FIN) {
+            const float sze = atol + fabsf(ze[j]) * rtol;
+            const float q0e = ze[j] / sze, q1e = kel[j] / sze;
+            p0 = fmaf(q0e, q0e, p0);
+            p1 = fmaf(q1e, q1e, p1);
+            if (ok[j]) a.FZE[(size_t)cur * a.N + gi[j]] = kel[j];
+          }
+          S.m.u[e] = ok[j] ? p0 : 0.f;
+          S.xz[e] = ok[j] ? p1 : 0.f;
           S.xzb[e] = ok[j] ? (-kzv) * a.g_y[gi[j]] : 0.f;
           if (ok[j]) {
             a.FZ[(size_t)cur * a.N + gi[j]] = kzv;
@@ -419,14 +461,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
       }
       if (threadIdx.x < R) {
         const int r = threadIdx.x;
-        const float rr = S.r[r], rbv = S.rb[r], kr = S.kr[R + r];
-        const float sr = atol + fabsf(rr) * rtol, srb = atol + fabsf(rbv) * rtol;
-        const float q0 = rr / sr, q0b = rbv / srb, q1 = kr / sr;
         const bool okr = row0 + r < a.B;
-        S.m.scal[r * 4 + 0] = q0 * q0 + q0b * q0b;
-        S.m.scal[r * 4 + 1] = q1 * q1;
-        S.m.scal[r * 4 + 2] = okr ? (-kr) * a.g_r[row0 + r] : 0.f;
-        if (okr && g.rank == 0) a.FR[(size_t)cur * B + row0 + r] = kr;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+          const float rr = sr[q * R + r], rbv = srb[q * R + r], kr = skr[NA * R + q * R + r];
+          const float tr = atol + fabsf(rr) * rtol, trb = atol + fabsf(rbv) * rtol;
+          const float q0 = rr / tr, q0b = rbv / trb, q1 = kr / tr;
+          a0 += q0 * q0 + q0b * q0b;
+          a1 += q1 * q1;
+          if (okr) {
+            a2 += (-kr) * a.g_r[(size_t)q * B + row0 + r];
+            if (g.rank == 0) a.FR[((size_t)cur * NA + q) * B + row0 + r] = kr;
+          }
+        }
+        S.m.scal[r * 4 + 0] = a0;
+        S.m.scal[r * 4 + 1] = a1;
+        S.m.scal[r * 4 + 2] = a2;
       }
       __syncthreads();
       {
@@ -458,14 +509,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
         if (e < RD) {
           const float sz = atol + fabsf(z[j]) * rtol, szb = atol + fabsf(zb[j]) * rtol;
           const float qa = (kz[1][j] - kz[0][j]) / sz, qb = (kzb[1][j] - kzb[0][j]) / szb;
-          S.m.u[e] = ok[j] ? qa * qa + qb * qb : 0.f;
+          float p = qa * qa + qb * qb;
+          if (FIN) {
+            const float qe = (kel[j] - ke0[j]) / (atol + fabsf(ze[j]) * rtol);
+            p = fmaf(qe, qe, p);
+          }
+          S.m.u[e] = ok[j] ? p : 0.f;
         }
       }
       if (threadIdx.x < R) {
         const int r = threadIdx.x;
-        const float sr = atol + fabsf(S.r[r]) * rtol;
-        const float q = (S.kr[R + r] - S.kr[r]) / sr;
-        S.m.rdot[r] = q * q;
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+          const float tr = atol + fabsf(sr[q * R + r]) * rtol;
+          const float d = (skr[NA * R + q * R + r] - skr[q * R + r]) / tr;
+          acc += d * d;
+        }
+        S.m.rdot[r] = acc;
       }
       __syncthreads();
       cl_row_sums<R>(S.m.u, g, row0, a.B, a.rowpart0, S.m.rdot);
@@ -491,7 +552,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
         const float tz = atol + rtol * fmaxf(fabsf(z[j]), fabsf(z1));
         const float tb = atol + rtol * fmaxf(fabsf(zb[j]), fabsf(zb1));
         const float qz = dt * ez / tz, qb = dt * eb / tb;
-        S.m.u[e] = ok[j] ? qz * qz + qb * qb : 0.f;
+        float p = qz * qz + qb * qb;
+        if (FIN) {
+          const float ze1 = fmaf(dt, se[j], ze[j]);
+          const float te = atol + rtol * fmaxf(fabsf(ze[j]), fabsf(ze1));
+          const float qe = dt * ee[j] / te;
+          p = fmaf(qe, qe, p);
+          if (ok[j]) {
+            a.ZE[(size_t)cand * a.N + gi[j]] = ze1;
+            a.FZE[(size_t)cand * a.N + gi[j]] = kel[j];
+            a.MIDZE[(size_t)midw * a.N + gi[j]] = fmaf(dt, me[j], ze[j]);
+          }
+        }
+        S.m.u[e] = ok[j] ? p : 0.f;
         if (ok[j]) {
           a.Z[(size_t)cand * a.N + gi[j]] = z1;
           a.ZB[(size_t)cand * a.N + gi[j]] = zb1;
@@ -503,20 +576,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
     }
     if (threadIdx.x < R) {
       const int r = threadIdx.x;
-      float sr = 0.f, er = 0.f;
-      for (int q = 0; q < kAdjStages; ++q) {
-        sr = fmaf(c_tab.c_sol[q], S.kr[q * R + r], sr);
-        er = fmaf(c_tab.c_err[q], S.kr[q * R + r], er);
+      float acc = 0.f;
+#pragma unroll
+      for (int qa = 0; qa < NA; ++qa) {
+        float cs = 0.f, er = 0.f;
+        for (int q = 0; q < kAdjStages; ++q) {
+          cs = fmaf(c_tab.c_sol[q], skr[q * NA * R + qa * R + r], cs);
+          er = fmaf(c_tab.c_err[q], skr[q * NA * R + qa * R + r], er);
+        }
+        const float r0 = sr[qa * R + r];
+        const float r1 = fmaf(dt, cs, r0);
+        const float tr = atol + rtol * fmaxf(fabsf(r0), fabsf(r1));
+        const float q = dt * er / tr;
+        acc += q * q;
+        if (g.rank == 0 && row0 + r < a.B) {
+          a.RS[((size_t)cand * NA + qa) * B + row0 + r] = r1;
+          a.FR[((size_t)cand * NA + qa) * B + row0 + r] = skr[(kAdjStages - 1) * NA * R + qa * R + r];
+        }
       }
-      const float r0 = S.r[r];
-      const float r1 = fmaf(dt, sr, r0);
-      const float tr = atol + rtol * fmaxf(fabsf(r0), fabsf(r1));
-      const float q = dt * er / tr;
-      S.m.scal[r * 4 + 0] = q * q;
-      if (g.rank == 0 && row0 + r < a.B) {
-        a.RS[(size_t)cand * B + row0 + r] = r1;
-        a.FR[(size_t)cand * B + row0 + r] = S.kr[(kAdjStages - 1) * R + r];
-      }
+      S.m.scal[r * 4 + 0] = acc;
     }
     __syncthreads();
     {
@@ -573,17 +651,21 @@ inline int cl_grid(int B) {
 // index arithmetic folds, the product loops unroll); any other shape runs the generic one.
 inline bool cl_is_mnist(int D, int H) { return D == 784 && H == 100; }
 
-template <int K, int DT, int HT>
+template <int K, int DT, int HT, bool FIN = false>
 inline cudaError_t cl_adj_rows_launch(int mode, const AdjArgs& a, int grid, size_t smem, float rhs_tau, cudaStream_t st) {
   switch (mode) {
-    case ADJ_STEP: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_STEP, DT, HT>, grid, smem, st, a, rhs_tau);
-    case ADJ_INIT0: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_INIT0, DT, HT>, grid, smem, st, a, rhs_tau);
-    case ADJ_INIT1: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_INIT1, DT, HT>, grid, smem, st, a, rhs_tau);
-    default: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_RHS, DT, HT>, grid, smem, st, a, rhs_tau);
+    case ADJ_STEP: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_STEP, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
+    case ADJ_INIT0: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_INIT0, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
+    case ADJ_INIT1: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_INIT1, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
+    default: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_RHS, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
   }
 }
 
 inline cudaError_t cl_adj_rows(int K, int mode, const AdjArgs& a, int grid, size_t smem, float rhs_tau, cudaStream_t st) {
+  if (a.fin) {
+    if (cl_is_mnist(a.w.D, a.w.H)) return cl_adj_rows_launch<2, 784, 100, true>(mode, a, grid, smem, rhs_tau, st);
+    return cl_adj_rows_launch<2, 0, 0, true>(mode, a, grid, smem, rhs_tau, st);
+  }
   if (cl_is_mnist(a.w.D, a.w.H)) {
     if (K == 0) return cl_adj_rows_launch<0, 784, 100>(mode, a, grid, smem, rhs_tau, st);
     if (K == 2) return cl_adj_rows_launch<2, 784, 100>(mode, a, grid, smem, rhs_tau, st);

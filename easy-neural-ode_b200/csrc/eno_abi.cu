@@ -194,7 +194,7 @@ int64_t eno_param_count(const eno_dynamics_desc* d) {
 
 int64_t eno_adjoint_state_size(const eno_dynamics_desc* d, int32_t B) {
   if (!d) return -1;
-  const int64_t n_aux = (d->aug == ENO_AUG_NONE) ? 0 : 1;
+  const int64_t n_aux = (d->aug == ENO_AUG_NONE) ? 0 : (d->aug == ENO_AUG_FIN ? 2 : 1);
   return 2 * ((int64_t)B * d->D + n_aux * B) + 1 + (d->eps_in_args ? (int64_t)B * d->D : 0) + eno_param_count(d);
 }
 
@@ -203,7 +203,7 @@ size_t eno_workspace_bytes(const eno_dynamics_desc* d, int32_t B, int32_t T, int
   (void)tableau;
   if (!desc_ok(d) || B <= 0) return 0;
   if (mode == 0) return fwd_ws_bytes(B, d->D);
-  return adj_ws_bytes(B, d->D, d->H, g_world);
+  return adj_ws_bytes(B, d->D, d->H, g_world, d->aug == ENO_AUG_FIN);
 }
 
 int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tableau, int32_t B, const float* y0,
@@ -361,8 +361,7 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
 int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32_t B, const float* y, float t,
                 const float* params, const float* eps, const float* y_bar, const float* r_bar, void* workspace,
                 size_t workspace_bytes, float* dy_out, float* aux_out, float* ybar_dot_out, float* tbar_out,
-                float* params_bar_out, void* stream_) {
-  (void)eps;
+                float* params_bar_out, float* eps_bar_dot_out, void* stream_) {
   if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_rhs: ctx is null");
   if (!desc_ok(desc)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_rhs: unsupported dynamics desc");
   if (B <= 0 || !y || !params || !dy_out) return fail(ctx, ENO_E_ARG, "eno_rhs: null pointer or empty batch");
@@ -377,8 +376,25 @@ int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32
     ENO_CUDA(ctx, cudaStreamSynchronize(stream));
     return ENO_OK;
   }
-  return adj_rhs(ctx->path_mode, &ctx->err, ctx->sm_count, desc, mode, B, y, t, params, y_bar, r_bar, workspace,
-                 workspace_bytes, dy_out, aux_out, ybar_dot_out, tbar_out, params_bar_out, stream);
+  return adj_rhs(ctx->path_mode, &ctx->err, ctx->sm_count, desc, mode, B, y, t, params, eps, y_bar, r_bar, workspace,
+                 workspace_bytes, dy_out, aux_out, ybar_dot_out, tbar_out, params_bar_out, eps_bar_dot_out, stream);
+}
+
+int32_t eno_odeint_bwd_sepaux(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, const float* ys, const float* ts,
+                              int32_t T, const float* params, const float* eps, const float* g_y, const float* g_aux,
+                              float rtol, float atol, int32_t mxstep, void* workspace, size_t workspace_bytes,
+                              float* y0_bar_out, float* aux0_bar_out, float* eps_bar_out, float* ts_bar_out,
+                              float* params_bar_out, eno_stats* stats_host, eno_trace_row* trace_out, int32_t trace_cap,
+                              void* stream_) {
+  if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_odeint_bwd: ctx is null");
+  if (!desc_ok(desc)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: unsupported dynamics desc");
+  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (desc->aug != ENO_AUG_NONE && desc->aug != ENO_AUG_REG && desc->aug != ENO_AUG_FIN)
+    return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: aug must be ENO_AUG_NONE, ENO_AUG_REG or ENO_AUG_FIN");
+  return adj_solve(&ctx->prof, ctx->path_mode, &ctx->dist, (ctx->deferred ? ctx->spec_bwd : 0), &ctx->tabs[ENO_TABLEAU_DOPRI5],
+                   &ctx->err, ctx->mailbox, &ctx->hint_bwd, ctx->sm_count, desc, B, ys, ts, T, params, eps, g_y, g_aux, rtol,
+                   atol, mxstep, workspace, workspace_bytes, y0_bar_out, aux0_bar_out, eps_bar_out, ts_bar_out,
+                   params_bar_out, stats_host, trace_out, trace_cap, static_cast<cudaStream_t>(stream_));
 }
 
 int32_t eno_odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, const float* ys, const float* ts,
@@ -386,14 +402,11 @@ int32_t eno_odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, c
                        int32_t mxstep, void* workspace, size_t workspace_bytes, float* y0_bar_out,
                        float* r0_bar_out, float* ts_bar_out, float* params_bar_out, eno_stats* stats_host,
                        eno_trace_row* trace_out, int32_t trace_cap, void* stream_) {
-  if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_odeint_bwd: ctx is null");
-  if (!desc_ok(desc)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: unsupported dynamics desc");
-  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (desc->aug != ENO_AUG_NONE && desc->aug != ENO_AUG_REG)
-    return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: aug must be ENO_AUG_NONE or ENO_AUG_REG");
-  return adj_solve(&ctx->prof, ctx->path_mode, &ctx->dist, (ctx->deferred ? ctx->spec_bwd : 0), &ctx->tabs[ENO_TABLEAU_DOPRI5], &ctx->err, ctx->mailbox, &ctx->hint_bwd, ctx->sm_count, desc, B, ys, ts, T, params, g_y, g_r, rtol,
-                   atol, mxstep, workspace, workspace_bytes, y0_bar_out, r0_bar_out, ts_bar_out, params_bar_out,
-                   stats_host, trace_out, trace_cap, static_cast<cudaStream_t>(stream_));
+  if (desc && desc->aug == ENO_AUG_FIN)
+    return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: ENO_AUG_FIN reads eps; call eno_odeint_bwd_sepaux");
+  return eno_odeint_bwd_sepaux(ctx, desc, B, ys, ts, T, params, nullptr, g_y, g_r, rtol, atol, mxstep, workspace,
+                               workspace_bytes, y0_bar_out, r0_bar_out, nullptr, ts_bar_out, params_bar_out, stats_host,
+                               trace_out, trace_cap, stream_);
 }
 
 // ---- deferred launch mode (CUDA-graph capturable solves) ----------------------------------------

@@ -38,7 +38,7 @@ class MLPDynamics:
     Closures (same names as in init_model):
       dynamics_wrap(x, t, params)                   mnist.py:285
       fwd(y, t, eps, params)                        the lambda at mnist.py:331
-      aug_dynamics(yr, t, eps, params)              mnist.py:302-313
+      aug_dynamics(yr, t, eps, params)              mnist.py:302-313  (both --reg_type arms)
       all_aug_dynamics(yr, t, eps, params)          mnist.py:315-324
     """
 
@@ -49,17 +49,18 @@ class MLPDynamics:
             raise ValueError(f"--reg must be one of {['none'] + REGS}")
         if reg in REGS[2:]:
             raise NotImplementedError("Taylor orders above r3 are not built (BASELINE configs use r2/r3)")
-        if reg_type != "our":
-            raise NotImplementedError("--reg_type fin (Finlay regulariser) is not built yet")
+        if reg_type not in ("our", "fin"):
+            raise ValueError("--reg_type must be 'our' or 'fin' (mnist.py:49)")
         self.dim, self.hidden, self.reg, self.reg_type = dim, hidden, reg, reg_type
         self.reg_order = 0 if reg == "none" else REGS.index(reg) + 2
         self.dynamics_wrap = EnoFunc(self, "plain", ("params",))
         self.fwd = EnoFunc(self, "plain", ("eps", "params"))
-        self.aug_dynamics = EnoFunc(self, "aug", ("eps", "params"))
+        # reg_type 'our': (dy, r_K); 'fin': (dy, dfro, dkin) from a jvp with eps (mnist.py:302-313)
+        self.aug_dynamics = EnoFunc(self, "aug" if reg_type == "our" else "fin", ("eps", "params"))
         self.all_aug_dynamics = EnoFunc(self, "all", ("eps", "params"))
 
     def __repr__(self):
-        return f"MLPDynamics(dim={self.dim}, hidden={self.hidden}, reg={self.reg!r})"
+        return f"MLPDynamics(dim={self.dim}, hidden={self.hidden}, reg={self.reg!r}, reg_type={self.reg_type!r})"
 
     @property
     def n_params(self):

@@ -4,6 +4,7 @@ Same names, argument order and return tuples as the reference:
 
     odeint(func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=inf) -> (ys, nfe)       lib/ode.py:540-559
     odeint_aux_one(fwd_func, rev_func, y0, t, *args, rtol, atol, mxstep)                 lib/ode.py:657-676
+    odeint_sepaux(fwd_func, rev_func, y0, t, *args, rtol, atol, mxstep)                  lib/ode.py:678-697
     _heun_odeint / _bosh_odeint / ... (func, rtol, atol, mxstep, y0, ts, *args)          lib/ode.py:1048-1390
 
 ``func`` must be a dynamics-spec closure (dynamics.EnoFunc); an arbitrary Python
@@ -166,27 +167,37 @@ def _fwd_call(spec, solver, y0, ts, pflat, rtol, atol, mxstep, trace_cap=0):
     return ys, st.as_dict(), trace
 
 
-def _bwd_call(spec, aug, eps_in_args, ys, ts, pflat, g_y, g_r, rtol, atol, mxstep, trace_cap=0):
+def _bwd_call(spec, aug, eps_in_args, ys, ts, pflat, g_y, g_r, rtol, atol, mxstep, trace_cap=0, eps=None):
+    """eno_odeint_bwd (aug NONE / REG) or eno_odeint_bwd_sepaux (aug FIN: g_r is [T, 2, B] and eps is read).
+    -> (y0_bar, r0_bar [B] or [2, B], ts_bar, params_bar, stats, trace, eps_bar or None)."""
     L = _cabi.lib()
     device = ys.device
     h = _cabi.ctx(device.index)
     T, B, D = ys.shape
+    fin = aug == _cabi.AUG_FIN
     desc = spec.desc(aug, eps_in_args, reg_order=spec.reg_order if aug == _cabi.AUG_REG else 0)
     nbytes = L.eno_workspace_bytes(C.byref(desc), B, T, 0, 1)
     ws = _workspace(device, nbytes, "bwd")
     y0_bar = torch.empty((B, D), dtype=torch.float32, device=device)
-    r0_bar = torch.empty((B,), dtype=torch.float32, device=device)
+    r0_bar = torch.empty((2, B) if fin else (B,), dtype=torch.float32, device=device)
     ts_bar = torch.empty((T,), dtype=torch.float32, device=device)
     p_bar = torch.empty((spec.n_params,), dtype=torch.float32, device=device)
+    eps_bar = torch.empty((B, D), dtype=torch.float32, device=device) if fin else None
     trace = torch.zeros((trace_cap, 4), dtype=torch.float32, device=device) if trace_cap else None
     st = (_cabi.Stats * max(T - 1, 1))()
     stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
     with torch.cuda.device(device):
-        rc = L.eno_odeint_bwd(h, C.byref(desc), B, _ptr(ys), _ptr(ts), T, _ptr(pflat), _ptr(g_y), _ptr(g_r),
-                              float(rtol), float(atol), _mx(mxstep), _ptr(ws), ws.numel(), _ptr(y0_bar), _ptr(r0_bar),
-                              _ptr(ts_bar), _ptr(p_bar), st, _ptr(trace), trace_cap, stream)
+        if fin:
+            rc = L.eno_odeint_bwd_sepaux(h, C.byref(desc), B, _ptr(ys), _ptr(ts), T, _ptr(pflat), _ptr(eps), _ptr(g_y),
+                                         _ptr(g_r), float(rtol), float(atol), _mx(mxstep), _ptr(ws), ws.numel(),
+                                         _ptr(y0_bar), _ptr(r0_bar), _ptr(eps_bar), _ptr(ts_bar), _ptr(p_bar), st,
+                                         _ptr(trace), trace_cap, stream)
+        else:
+            rc = L.eno_odeint_bwd(h, C.byref(desc), B, _ptr(ys), _ptr(ts), T, _ptr(pflat), _ptr(g_y), _ptr(g_r),
+                                  float(rtol), float(atol), _mx(mxstep), _ptr(ws), ws.numel(), _ptr(y0_bar), _ptr(r0_bar),
+                                  _ptr(ts_bar), _ptr(p_bar), st, _ptr(trace), trace_cap, stream)
     _cabi.check(rc, h, "eno_odeint_bwd")
-    return y0_bar, r0_bar, ts_bar, p_bar, [s.as_dict() for s in st][:max(T - 1, 0)], trace
+    return y0_bar, r0_bar, ts_bar, p_bar, [s.as_dict() for s in st][:max(T - 1, 0)], trace, eps_bar
 
 
 class _OdeintFn(torch.autograd.Function):
@@ -217,10 +228,45 @@ class _OdeintFn(torch.autograd.Function):
         T, B, D = ys.shape
         g_y = g_ys.contiguous().float()
         g_r = g_rs.reshape(T, B).contiguous().float()
-        y0_bar, r0_bar, ts_bar, p_bar, st, _ = _bwd_call(ctx.spec, ctx.aug, ctx.eps_in_args, ys, ts, pflat, g_y, g_r,
-                                                        rtol, atol, mxstep)
+        y0_bar, r0_bar, ts_bar, p_bar, st, _, _ = _bwd_call(ctx.spec, ctx.aug, ctx.eps_in_args, ys, ts, pflat, g_y, g_r,
+                                                           rtol, atol, mxstep)
         last_stats["bwd"] = st
         return None, None, None, None, None, None, y0_bar, r0_bar, ts_bar, p_bar
+
+
+class _OdeintSepauxFn(torch.autograd.Function):
+    """custom_vjp pair of odeint_sepaux (_odeint_sepaux_fwd/_rev, lib/ode.py:1482-1484, 1686-1693) for the
+    'fin' aug_dynamics: forward = the plain solve, two zero aux outputs; backward = the adjoint of
+    (dy, dfro, dkin), which reads eps and carries eps_bar."""
+
+    @staticmethod
+    def forward(ctx, spec, rtol, atol, mxstep, y0, a0, b0, ts, eps, pflat):
+        ys, st, _ = _fwd_call(spec, "dopri5", y0, ts, pflat, rtol, atol, mxstep)
+        last_stats["fwd"] = st
+        ctx.spec = spec
+        ctx.tols = (rtol, atol, mxstep)
+        ctx.save_for_backward(ys, ts, eps, pflat)
+        T, B, _ = ys.shape
+        z1 = torch.zeros((T, B, 1), dtype=ys.dtype, device=ys.device)   # lib/ode.py:1011-1018
+        z2 = torch.zeros((T, B, 1), dtype=ys.dtype, device=ys.device)
+        if _deferred["on"]:
+            nfe = torch.full((), float("nan"), dtype=torch.float32, device=ys.device)
+        else:
+            nfe = torch.tensor(st["nfe"], dtype=torch.float32, device=ys.device)
+        ctx.mark_non_differentiable(nfe)
+        return ys, z1, z2, nfe
+
+    @staticmethod
+    def backward(ctx, g_ys, g_a, g_b, _g_nfe):
+        ys, ts, eps, pflat = ctx.saved_tensors
+        rtol, atol, mxstep = ctx.tols
+        T, B, D = ys.shape
+        g_y = g_ys.contiguous().float()
+        g_aux = torch.stack([g_a.reshape(T, B), g_b.reshape(T, B)], dim=1).contiguous().float()   # [T, 2, B]
+        y0_bar, r0_bar, ts_bar, p_bar, st, _, eps_bar = _bwd_call(ctx.spec, _cabi.AUG_FIN, True, ys, ts, pflat, g_y,
+                                                                 g_aux, rtol, atol, mxstep, eps=eps)
+        last_stats["bwd"] = st
+        return None, None, None, None, y0_bar, r0_bar[0], r0_bar[1], ts_bar, eps_bar, p_bar
 
 
 def _split_args(func, args):
@@ -323,6 +369,35 @@ def odeint_aux_one(fwd_func, rev_func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, m
     return (ys, rs), nfe
 
 
+def odeint_sepaux(fwd_func, rev_func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=math.inf):
+    """Split solve with two auxiliary states, lib/ode.py:678-697 (mnist.py:83, 326-332 with --reg_type fin):
+    forward integrates ``y0[0]`` with ``fwd_func`` and returns zeros for both auxiliary states; backward
+    runs the adjoint with ``rev_func`` = aug_dynamics('fin') on (y, fro, kin).
+    -> ((ys [T,B,D], fro [T,B,1], kin [T,B,1]), nfe)."""
+    _require_spec(fwd_func, "odeint_sepaux")
+    _require_spec(rev_func, "odeint_sepaux")
+    if fwd_func.kind != "plain" or rev_func.kind != "fin" or fwd_func.spec is not rev_func.spec:
+        raise TypeError("odeint_sepaux expects (spec.fwd, spec.aug_dynamics) of one dynamics spec built with reg_type='fin'")
+    spec = fwd_func.spec
+    eps, params = _split_args(rev_func, args)
+    if eps is None:
+        raise TypeError("odeint_sepaux: the 'fin' dynamics read eps (mnist.py:294-300)")
+    if len(y0) != 3:
+        raise TypeError(f"odeint_sepaux integrates (y, fro, kin); got a state of {len(y0)} leaves")
+    y_in, a_in, b_in = y0
+    out_dev = y_in.device
+    dev = _dev(y_in)
+    y = _f32c(y_in.reshape(-1, spec.dim), dev)
+    a0, b0 = _f32c(a_in.reshape(-1), dev), _f32c(b_in.reshape(-1), dev)
+    ts = _f32c(torch.as_tensor(t), dev)
+    epsd = _f32c(eps.reshape(-1, spec.dim), dev)
+    pflat = _f32c(spec.flatten_params(params), dev)
+    ys, fro, kin, nfe = _OdeintSepauxFn.apply(spec, rtol, atol, mxstep, y, a0, b0, ts, epsd, pflat)
+    if out_dev != ys.device:
+        ys, fro, kin, nfe = ys.to(out_dev), fro.to(out_dev), kin.to(out_dev), nfe.to(out_dev)
+    return (ys, fro, kin), nfe
+
+
 def _tableau_odeint(solver):
     def run(func, rtol, atol, mxstep, y0, ts, *args):
         _require_spec(func, f"_{solver}_odeint")
@@ -365,31 +440,39 @@ def solve_with_trace(spec, solver, y0, ts, params, rtol, atol, mxstep=math.inf, 
     return ys, st, trace[: st["n_iters"]].cpu()
 
 
-def rhs(spec, mode, y, t, params, y_bar=None, r_bar=None):
-    """One evaluation of the integrated function (eno_rhs): mode 0 f, 1 (f, r_K), 2 the VJP."""
+def rhs(spec, mode, y, t, params, y_bar=None, r_bar=None, eps=None):
+    """One evaluation of the integrated function (eno_rhs): mode 0 f, 1 (f, r_K), 2 the VJP.
+    With ``eps`` the 'fin' dynamics are evaluated instead: aux = (dfro, dkin) [2, B], r_bar is [2, B] and
+    mode 2 also returns the cotangent of eps."""
     L = _cabi.lib()
     dev = _dev(y)
     h = _cabi.ctx(dev.index)
     yd = _f32c(y.reshape(-1, spec.dim), dev)
     B, D = yd.shape
     pflat = _f32c(spec.flatten_params(params).detach(), dev)
-    desc = spec.desc(_cabi.AUG_REG if mode else _cabi.AUG_NONE, True)
+    fin = eps is not None and mode != 0
+    desc = spec.desc((_cabi.AUG_FIN if fin else _cabi.AUG_REG) if mode else _cabi.AUG_NONE, True)
     nbytes = L.eno_workspace_bytes(C.byref(desc), B, 2, 0, 1)
     ws = _workspace(dev, nbytes, "bwd")
     dy = torch.empty_like(yd)
-    r = torch.empty(B, device=dev)
+    r = torch.empty((2, B) if fin else (B,), device=dev)
+    epsd = _f32c(eps.reshape(-1, D), dev) if fin else None
+    eb = torch.empty_like(yd) if fin else None
     zb = torch.empty_like(yd)
     tbar = torch.empty(1, device=dev)
     pbar = torch.empty(spec.n_params, device=dev)
     yb = _f32c(y_bar.reshape(-1, D), dev) if y_bar is not None else None
     rb = _f32c(r_bar.reshape(-1), dev) if r_bar is not None else None
+    if fin and mode != 2:   # the fin dynamics exist as the adjoint RHS only: evaluate it with zero cotangents
+        yb, rb = torch.zeros_like(yd), torch.zeros(2 * B, device=dev)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     with torch.cuda.device(dev):
-        rc = L.eno_rhs(h, C.byref(desc), mode, B, _ptr(yd), float(t), _ptr(pflat), None, _ptr(yb), _ptr(rb),
-                       _ptr(ws), ws.numel(), _ptr(dy), _ptr(r), _ptr(zb), _ptr(tbar), _ptr(pbar), stream)
+        rc = L.eno_rhs(h, C.byref(desc), 2 if fin else mode, B, _ptr(yd), float(t), _ptr(pflat), _ptr(epsd), _ptr(yb),
+                       _ptr(rb), _ptr(ws), ws.numel(), _ptr(dy), _ptr(r), _ptr(zb), _ptr(tbar), _ptr(pbar), _ptr(eb),
+                       stream)
     _cabi.check(rc, h, "eno_rhs")
     if mode == 0:
         return dy
     if mode == 1:
         return dy, r
-    return dy, r, zb, tbar, pbar
+    return (dy, r, zb, tbar, pbar, eb) if fin else (dy, r, zb, tbar, pbar)

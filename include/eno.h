@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ENO_ABI_VERSION 1
+#define ENO_ABI_VERSION 2
 
 /* status codes */
 #define ENO_OK 0
@@ -62,6 +62,7 @@ extern "C" {
 #define ENO_AUG_NONE 0 /* dynamics_wrap            mnist.py:285            */
 #define ENO_AUG_REG 1  /* aug_dynamics 'our'       mnist.py:302-308: (dy, r_K) */
 #define ENO_AUG_ALL 2  /* all_aug_dynamics         mnist.py:315-324: (dy, r_K, fro, kin) */
+#define ENO_AUG_FIN 3  /* aug_dynamics 'fin'       mnist.py:294-313: (dy, dfro, dkin), reads eps (backward only) */
 
 typedef struct eno_ctx eno_ctx;
 
@@ -104,7 +105,7 @@ void eno_destroy(eno_ctx* ctx);
 /* Number of parameters of a dynamics family: (D+1)*H + H + (H+1)*D + D. */
 int64_t eno_param_count(const eno_dynamics_desc* desc);
 /* Length of the flat adjoint ODE state, lib/ode.py:1516-1519:
- * 2*(B*D + n_aux*B) + 1 + (eps_in_args ? B*D : 0) + P,  n_aux = 1 for ENO_AUG_REG, 0 for NONE. */
+ * 2*(B*D + n_aux*B) + 1 + (eps_in_args ? B*D : 0) + P,  n_aux = 1 for ENO_AUG_REG, 2 for ENO_AUG_FIN, 0 for NONE. */
 int64_t eno_adjoint_state_size(const eno_dynamics_desc* desc, int32_t B);
 
 /* Scratch the solve needs (device bytes). mode: 0 forward, 1 backward. */
@@ -151,6 +152,25 @@ int32_t eno_odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, c
                        eno_trace_row* trace_out, int32_t trace_cap, void* stream);
 
 /*
+ * Backward solve for rev_funcs that read eps.  Replaces
+ *   _odeint_rev as reached through _odeint_sepaux_rev        lib/ode.py:1686-1693
+ * (odeint_sepaux, lib/ode.py:678-697, 1006-1018) for rev_func = aug_dynamics(reg_type 'fin')
+ * (mnist.py:294-313): per sample the augmented state is (y [D], fro, kin), the RHS is
+ * (f, mean_d (J eps)^2, mean_d f^2) with J eps = jvp(f wrt y, eps), and eps_bar is a live block of the
+ * adjoint state.  With ENO_AUG_NONE / ENO_AUG_REG it is eno_odeint_bwd (eps may be NULL).
+ *
+ *   eps   [B, D]               g_aux [T, n_aux, B]  cotangents of the aux outputs (n_aux = 2: fro, kin)
+ *   aux0_bar_out [n_aux, B]    eps_bar_out [B, D] or NULL
+ * Runs on the cluster-resident path only (ENO_E_UNSUPPORTED otherwise).
+ */
+int32_t eno_odeint_bwd_sepaux(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, const float* ys, const float* ts,
+                              int32_t T, const float* params, const float* eps, const float* g_y, const float* g_aux,
+                              float rtol, float atol, int32_t mxstep, void* workspace, size_t workspace_bytes,
+                              float* y0_bar_out, float* aux0_bar_out, float* eps_bar_out, float* ts_bar_out,
+                              float* params_bar_out, eno_stats* stats_host, eno_trace_row* trace_out, int32_t trace_cap,
+                              void* stream);
+
+/*
  * One evaluation of the integrated function (unit-test hook), the closures of
  * mnist.py:285-324.
  *   mode 0: dy = f(y, t)                                       -> dy_out [B,D]
@@ -158,11 +178,13 @@ int32_t eno_odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, c
  *   mode 2: vjp of aug_dynamics('our') at (y, t) with cotangent (y_bar [B,D], r_bar [B])
  *           -> dy_out, aux_out [1,B], ybar_dot_out [B,D], tbar_out [1], params_bar_out [P]
  *              (lib/ode.py:1498-1504)
+ *           With ENO_AUG_FIN (eps required): aux_out [2,B] = (dfro, dkin), r_bar [2,B], and
+ *           eps_bar_dot_out [B,D] (or NULL) receives the cotangent of eps.
  */
 int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32_t B, const float* y, float t,
                 const float* params, const float* eps, const float* y_bar, const float* r_bar, void* workspace,
                 size_t workspace_bytes, float* dy_out, float* aux_out, float* ybar_dot_out, float* tbar_out,
-                float* params_bar_out, void* stream);
+                float* params_bar_out, float* eps_bar_dot_out, void* stream);
 
 /*
  * Deferred launch mode (no reference counterpart).  By default a solve polls its device-side controller

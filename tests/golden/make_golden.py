@@ -40,6 +40,39 @@ def mlp_case(B, D, H, seed, scale):
     return params, x0, eps, gy
 
 
+def fin_case(ref, do, B, D, H, params, x0, eps, gy):
+    """odeint_sepaux forward + adjoint with the 'fin' aug_dynamics (mnist.py:294-313, lib/ode.py:678-697,
+    1686-1693): two tolerances on ts = [0, 1] and a three-point grid with cotangents at every time."""
+    rec = dict(B=B, D=D, H=H, x0=x0.numpy(), params=flat_params(params), eps=eps.numpy(), gy=gy.numpy(),
+               g_fro=0.01, g_kin=0.02)
+    cl = do.make_mnist_closures("none", reg_type="fin")
+    y0 = (x0, torch.zeros(B), torch.zeros(B))
+    fwd_w = ref.ravel_first_arg(cl["fwd"], ravel_pytree(y0[0])[1])
+    rev_w = ref.ravel_first_arg(cl["aug_dynamics"], ravel_pytree(y0)[1])
+    for tag, tol, ts in [("5", 1e-5, torch.tensor([0., 1.])), ("d", 1.4e-8, torch.tensor([0., 1.])),
+                         ("m", 1e-6, torch.tensor([0., 0.4, 1.]))]:
+        (res, nfe), saved = ref._odeint_sepaux_fwd(fwd_w, rev_w, tol, tol, math.inf, y0, ts, eps, params)
+        g = tuple(torch.zeros_like(r) for r in res)
+        if tag == "m":
+            for i in range(len(ts)):
+                g[0][i] = gy * (0.5 + i)
+                g[1][i] = 0.01 * (1 + i)
+                g[2][i] = 0.02 * (3 - i)
+        else:
+            g[0][-1] = gy
+            g[1][-1] = 0.01
+            g[2][-1] = 0.02
+        out = ref._odeint_sepaux_rev(fwd_w, rev_w, tol, tol, math.inf, saved, (g, None))
+        k = f"fin_{tag}"
+        rec[f"{k}_ts"], rec[f"{k}_tol"] = ts.numpy(), tol
+        rec[f"{k}_y"], rec[f"{k}_nfe"] = res[0].numpy(), float(nfe)
+        rec[f"{k}_x0_bar"] = out[0][0].numpy()
+        rec[f"{k}_fro0_bar"], rec[f"{k}_kin0_bar"] = out[0][1].numpy(), out[0][2].numpy()
+        rec[f"{k}_ts_bar"], rec[f"{k}_eps_bar"] = out[1].numpy(), out[2].numpy()
+        rec[f"{k}_params_bar"] = flat_params(out[3])
+    np.savez(os.path.join(OUT, "mlp_adjoint_fin.npz"), **rec)
+
+
 def main():
     ref = load_reference_ode()
     torch.set_num_threads(8)
@@ -111,6 +144,8 @@ def main():
     rec["all_y1"], rec["all_r"], rec["all_fro"], rec["all_kin"], rec["all_nfe"] = (
         ya[-1].numpy(), ra[-1].numpy(), fro[-1].numpy(), kin[-1].numpy(), float(nfe))
     np.savez(os.path.join(OUT, "mlp_adjoint.npz"), **rec)
+
+    fin_case(ref, do, B, D, H, params, x0, eps, gy)
 
     # ---- plain adjoint on the pendulum (lib/ode.py:1720-1722, 1765-1774), multi-output
     def pend(y, t, m, g):

@@ -74,6 +74,76 @@ def test_odeint_aux_one_golden(case, cuda, reg, tag):
     assert rel_err(pflat.grad, g[f"{k}_params_bar"]) < bar
 
 
+def _needs_cluster_path():
+    import os
+    if os.environ.get("ENO_PATH") == "stream":
+        pytest.skip("the 'fin' adjoint exists on the cluster-resident path only")
+
+
+def test_fin_rhs_and_vjp_match_torch_func(cuda):
+    """(dy, dfro, dkin) of mnist.py:294-313 and its VJP wrt (y, t, eps, params) against torch.func in fp64."""
+    _needs_cluster_path()
+    import easy_neural_ode_b200 as eno
+    from oracle import dynamics_oracle as do
+    g = load("mlp_adjoint_fin.npz")
+    B, D, H = int(g["B"]), int(g["D"]), int(g["H"])
+    params = params_from_flat(g["params"], D, H, device=cuda)
+    spec = eno.MLPDynamics(D, H, reg_type="fin")
+    x0, eps, yb = (torch.as_tensor(g[k], device=cuda) for k in ("x0", "eps", "gy"))
+    rb = torch.stack([torch.linspace(0.5, 1.5, B), torch.linspace(-0.3, 0.9, B)]).to(cuda)
+    t = 0.37
+    dy, aux, zb, tbar, pbar, eb = eno.rhs(spec, 2, x0, t, params, yb, rb, eps=eps)
+    cl = do.make_mnist_closures("none", reg_type="fin")
+    dbl = lambda p: {k: {kk: vv.detach().cpu().double() for kk, vv in v.items()} for k, v in p.items()}
+    func = lambda y, tt, e, p: cl["aug_dynamics"]((y,), tt, e, p)
+    (dy_w, fro_w, kin_w), pull = torch.func.vjp(func, x0.cpu().double(), torch.tensor(t, dtype=torch.float64),
+                                                eps.cpu().double(), dbl(params))
+    zb_w, tb_w, eb_w, pb_w = pull((yb.cpu().double(), rb[0].cpu().double(), rb[1].cpu().double()))
+    assert rel_err(dy, dy_w) < 1e-5
+    assert rel_err(aux[0], fro_w) < 1e-5 and rel_err(aux[1], kin_w) < 1e-5
+    assert rel_err(zb, zb_w) < 2e-5
+    assert rel_err(eb, eb_w) < 2e-5
+    assert rel_err(tbar, tb_w) < 2e-5
+    assert rel_err(pbar, flat_from_params(pb_w)) < 2e-5
+
+
+@pytest.mark.parametrize("tag", ["5", "d", "m"])
+def test_odeint_sepaux_fin_golden(cuda, tag):
+    """odeint_sepaux (lib/ode.py:678-697) with the 'fin' dynamics against the unmodified reference solver:
+    ts = [0, 1] at two tolerances, and a three-point grid with cotangents at every output time (eps_bar and
+    the two scalar cotangents are carried across segments)."""
+    _needs_cluster_path()
+    import easy_neural_ode_b200 as eno
+    g = load("mlp_adjoint_fin.npz")
+    B, D, H = int(g["B"]), int(g["D"]), int(g["H"])
+    k = f"fin_{tag}"
+    tol = float(g[f"{k}_tol"])
+    spec = eno.MLPDynamics(D, H, reg_type="fin")
+    x0 = torch.as_tensor(g["x0"], device=cuda).requires_grad_(True)
+    eps = torch.as_tensor(g["eps"], device=cuda).requires_grad_(True)
+    pflat = torch.as_tensor(g["params"], device=cuda).requires_grad_(True)
+    ts = torch.as_tensor(g[f"{k}_ts"], device=cuda).requires_grad_(True)
+    a0 = torch.zeros(B, device=cuda, requires_grad=True)
+    b0 = torch.zeros(B, device=cuda, requires_grad=True)
+    (ys, fro, kin), nfe = eno.odeint_sepaux(spec.fwd, spec.aug_dynamics, (x0, a0, b0), ts, eps, pflat, rtol=tol, atol=tol)
+    assert float(nfe) == float(g[f"{k}_nfe"])
+    assert rel_err(ys, g[f"{k}_y"]) < RTOL
+    assert float(fro.abs().max()) == 0.0 and fro.shape == (ts.numel(), B, 1) and kin.shape == fro.shape
+    gy = torch.as_tensor(g["gy"], device=cuda)
+    if tag == "m":
+        loss = sum((ys[i] * gy * (0.5 + i)).sum() + 0.01 * (1 + i) * fro[i].sum() + 0.02 * (3 - i) * kin[i].sum()
+                   for i in range(ts.numel()))
+    else:
+        loss = (ys[-1] * gy).sum() + float(g["g_fro"]) * fro[-1].sum() + float(g["g_kin"]) * kin[-1].sum()
+    loss.backward()
+    bar = RTOL if tag == "d" else 5e-5   # as for odeint_aux_one: solver-accuracy level at loose tolerances
+    assert rel_err(x0.grad, g[f"{k}_x0_bar"]) < bar
+    assert rel_err(ts.grad, g[f"{k}_ts_bar"]) < bar
+    assert rel_err(pflat.grad, g[f"{k}_params_bar"]) < bar
+    assert rel_err(eps.grad, g[f"{k}_eps_bar"]) < 10 * bar   # eps_bar is ~1e-4: close to the solver's atol
+    assert rel_err(a0.grad, g[f"{k}_fro0_bar"]) < bar and rel_err(b0.grad, g[f"{k}_kin0_bar"]) < bar
+
+
 def test_mnist_train_step_vs_oracle(cuda):
     """C1: B=100 synthetic 28x28, --reg r3 --lam 6e-5, script-default tolerances."""
     import easy_neural_ode_b200 as eno

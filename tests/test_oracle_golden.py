@@ -92,6 +92,36 @@ def test_split_solve_and_adjoint(reg):
     np.testing.assert_allclose(flat_from_params(out[3]).numpy(), g[f"{k}_params_bar"], rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("tag", ["5", "m"])
+def test_sepaux_fin_solve_and_adjoint(tag):
+    """odeint_sepaux with the 'fin' aug_dynamics (lib/ode.py:678-697, 1686-1693; mnist.py:294-313):
+    eps is read by the RHS, so eps_bar is a live block of the adjoint state."""
+    g = load("mlp_adjoint_fin.npz")
+    B, D, H = int(g["B"]), int(g["D"]), int(g["H"])
+    params = params_from_flat(g["params"], D, H)
+    x0, eps, gy = (torch.as_tensor(g[k]) for k in ("x0", "eps", "gy"))
+    cl = do.make_mnist_closures("none", reg_type="fin")
+    k = f"fin_{tag}"
+    ts, tol = torch.as_tensor(g[f"{k}_ts"]), float(g[f"{k}_tol"])
+    res, nfe = oo.odeint_split_fwd(cl["fwd"], (x0, torch.zeros(B), torch.zeros(B)), ts, eps, params, n_aux=2,
+                                   rtol=tol, atol=tol)
+    assert nfe == float(g[f"{k}_nfe"])
+    np.testing.assert_allclose(res[0].numpy(), g[f"{k}_y"], **TIGHT)
+    gg = tuple(torch.zeros_like(r) for r in res)
+    if tag == "m":
+        for i in range(len(ts)):
+            gg[0][i] = gy * (0.5 + i)
+            gg[1][i] = 0.01 * (1 + i)
+            gg[2][i] = 0.02 * (3 - i)
+    else:
+        gg[0][-1], gg[1][-1], gg[2][-1] = gy, float(g["g_fro"]), float(g["g_kin"])
+    out = oo.odeint_split_rev(cl["aug_dynamics"], tol, tol, math.inf, res, ts, (eps, params), gg)
+    np.testing.assert_allclose(out[0][0].numpy(), g[f"{k}_x0_bar"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out[1].numpy(), g[f"{k}_ts_bar"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out[2].numpy(), g[f"{k}_eps_bar"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(flat_from_params(out[3]).numpy(), g[f"{k}_params_bar"], rtol=1e-5, atol=1e-6)
+
+
 def test_pendulum_adjoint_multi_segment():
     g = load("pendulum.npz")
 
