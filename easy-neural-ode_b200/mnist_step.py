@@ -1,6 +1,7 @@
 """Thin driver reproducing one ``update()`` of mnist.py (553-559) around the ODE path:
 PreODE (173-192) -> odeint_aux_one (330-341) -> PostODE (225-238) -> CE + lam*mean(r) (462-471)
--> jax.grad (528) -> momentum SGD (530-540).
+-> jax.grad (528) -> momentum SGD (530-540).  With reg_type='fin' the ODE block is odeint_sepaux and the
+loss is CE + lam_fro*mean(fro) + lam_kin*mean(kin) (mnist.py:83, 472-478).
 
 Only what is needed to drive the hot path and to report the headline metric (train steps/s);
 the head (sigmoid + Linear(10) on [B, 784]) is a handful of tiny torch ops, everything inside the
@@ -14,9 +15,10 @@ from . import ode
 
 class MnistNode:
     def __init__(self, reg="r3", lam=6e-5, rtol=1.4e-8, atol=1.4e-8, device="cuda", dim=784, hidden=100,
-                 lr=1e-1, mass=0.9, n_cls=10, world=1):
-        self.spec = MLPDynamics(dim, hidden, reg=reg)
+                 lr=1e-1, mass=0.9, n_cls=10, world=1, reg_type="our", lam_fro=0.0, lam_kin=0.0):
+        self.spec = MLPDynamics(dim, hidden, reg=reg, reg_type=reg_type)
         self.lam, self.rtol, self.atol = lam, rtol, atol
+        self.reg_type, self.lam_fro, self.lam_kin = reg_type, lam_fro, lam_kin
         self.device = torch.device(device)
         self.lr, self.mass = lr, mass
         self.dim, self.n_cls = dim, n_cls
@@ -61,14 +63,22 @@ class MnistNode:
         p_ode = self.p_ode.detach().requires_grad_(True)
         w = self.post_w.detach().requires_grad_(True)
         b = self.post_b.detach().requires_grad_(True)
-        y0 = (x0, torch.zeros(B, device=self.device))
-        (ys, rs), nfe = ode.odeint_aux_one(self.spec.fwd, self.spec.aug_dynamics, y0, self.ts, eps, p_ode,
-                                           rtol=self.rtol, atol=self.atol)
-        y1, r1 = ys[-1], rs[-1]
+        if self.reg_type == "fin":
+            y0 = (x0, torch.zeros(B, device=self.device), torch.zeros(B, device=self.device))
+            (ys, fro, kin), nfe = ode.odeint_sepaux(self.spec.fwd, self.spec.aug_dynamics, y0, self.ts, eps, p_ode,
+                                                    rtol=self.rtol, atol=self.atol)
+            y1 = ys[-1]
+            reg_term = self.lam_fro * fro[-1].mean() + self.lam_kin * kin[-1].mean()
+        else:
+            y0 = (x0, torch.zeros(B, device=self.device))
+            (ys, rs), nfe = ode.odeint_aux_one(self.spec.fwd, self.spec.aug_dynamics, y0, self.ts, eps, p_ode,
+                                               rtol=self.rtol, atol=self.atol)
+            y1 = ys[-1]
+            reg_term = self.lam * rs[-1].mean()
         logits = torch.sigmoid(y1) @ w + b
         ce = torch.nn.functional.cross_entropy(logits, labels)
-        # this rank's share of loss_fn (mnist.py:462-471) over the global batch of world * B samples
-        loss = (ce + self.lam * r1.mean()) / self.world
+        # this rank's share of loss_fn (mnist.py:462-478) over the global batch of world * B samples
+        loss = (ce + reg_term) / self.world
         g_ode, g_w, g_b = torch.autograd.grad(loss, (p_ode, w, b))
         if self.world > 1:
             # the adjoint's params_bar is already the global sum (exchanged per iteration inside the

@@ -174,15 +174,28 @@ def head_loss_and_grad(post, y1, labels):
 
 
 def train_step_grads(ode_params, post, x0, labels, eps, lam, reg="r3", rtol=1.4e-8, atol=1.4e-8,
-                     collect=None):
-    """loss_fn + jax.grad of mnist.py:462-471, 528 for reg_type 'our', lam_w = 0.
+                     collect=None, reg_type="our", lam_fro=0.0, lam_kin=0.0):
+    """loss_fn + jax.grad of mnist.py:462-478, 528, lam_w = 0; reg_type 'our' (odeint_aux_one, lam * mean r) or
+    'fin' (odeint_sepaux, lam_fro * mean fro + lam_kin * mean kin).
 
     -> dict(loss, y1, nfe, grads={'ode':..., 'post':...}, x0_bar, fwd_stats, bwd_stats)
     """
     from . import ode_oracle as oo
-    cl = make_mnist_closures(reg, "our")
+    cl = make_mnist_closures(reg, reg_type)
     B = x0.shape[0]
     ts = torch.tensor([0., 1.], dtype=x0.dtype)
+    if reg_type == "fin":
+        zero = torch.zeros(B, dtype=x0.dtype)
+        (ys, fs, ks), nfe, fst = oo.odeint_split_fwd(cl["fwd"], (x0, zero, zero.clone()), ts, eps, ode_params, n_aux=2,
+                                                     rtol=rtol, atol=atol, return_stats=True)
+        loss, gy, gpost = head_loss_and_grad(post, ys[-1], labels)
+        g_y, g_f, g_k = torch.zeros_like(ys), torch.zeros_like(fs), torch.zeros_like(ks)
+        g_y[-1], g_f[-1], g_k[-1] = gy, lam_fro / B, lam_kin / B
+        bst = []
+        y0_bar, ts_bar, eps_bar, params_bar = oo.odeint_split_rev(
+            cl["aug_dynamics"], rtol, atol, math.inf, (ys, fs, ks), ts, (eps, ode_params), (g_y, g_f, g_k), bst)
+        return dict(loss=loss, y1=ys[-1], nfe=nfe, grads={"ode": params_bar, "post": gpost},
+                    x0_bar=y0_bar[0], ts_bar=ts_bar, eps_bar=eps_bar, fwd_stats=fst, bwd_stats=bst)
     y0 = (x0, torch.zeros(B, dtype=x0.dtype))
     (ys, rs), nfe, fst = oo.odeint_split_fwd(cl["fwd"], y0, ts, eps, ode_params, n_aux=1,
                                              rtol=rtol, atol=atol, return_stats=True)

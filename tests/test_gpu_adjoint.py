@@ -176,6 +176,33 @@ def test_mnist_train_step_vs_oracle(cuda):
         assert rel_err(out["grads"]["post_w"], want["grads"]["post"]["w"]) < RTOL
 
 
+def test_mnist_fin_train_step_vs_oracle(cuda):
+    """C1 shape with --reg_type fin --lam_fro 1e-2 --lam_kin 1e-2 (the RNODE arm the paper compares with):
+    odeint_sepaux forward + adjoint at MNIST size against the oracle, default tolerances."""
+    _needs_cluster_path()
+    from easy_neural_ode_b200 import mnist_step
+    from oracle import dynamics_oracle as do
+    B, D, H = 100, 784, 100
+    gen = torch.Generator().manual_seed(0)
+    images = torch.randint(0, 256, (B, 28, 28, 1), generator=gen, dtype=torch.uint8)
+    labels = torch.randint(0, 10, (B,), generator=gen)
+    eps = torch.randint(0, 2, (B, D), generator=gen).float() * 2 - 1
+    p_ode = do.init_mlp_params(D, H, seed=0)
+    p_post = do.init_post_params(D, seed=1)
+    tol = 1.4e-8
+    want = do.train_step_grads(p_ode, p_post, do.pre_ode(images), labels, eps, 0.0, reg="none", rtol=tol, atol=tol,
+                               reg_type="fin", lam_fro=1e-2, lam_kin=1e-2)
+    model = mnist_step.MnistNode(reg="none", rtol=tol, atol=tol, device=cuda, reg_type="fin", lam_fro=1e-2, lam_kin=1e-2)
+    model.load_params(p_ode, p_post)
+    out = model.loss_and_grads(images.to(cuda), labels.to(cuda), eps.to(cuda))
+    assert float(out["nfe"]) == float(want["nfe"])
+    assert out["bwd_stats"][0]["n_iters"] == want["bwd_stats"][0]["n_iters"]
+    assert out["bwd_stats"][0]["n_accepted"] == want["bwd_stats"][0]["n_accepted"]
+    assert rel_err(out["y1"], want["y1"]) < RTOL
+    assert rel_err(out["grads"]["ode"], flat_from_params(want["grads"]["ode"])) < RTOL
+    assert rel_err(out["grads"]["post_w"], want["grads"]["post"]["w"]) < RTOL
+
+
 def test_plain_odeint_adjoint_multiple_output_times(cuda):
     """odeint() with T = 5 output times and cotangents at every time: the adjoint runs T-1 backward segments
     (lib/ode.py:1510-1529), carries y_bar / t0_bar / params_bar across them and returns ts_bar for every time.
