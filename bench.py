@@ -283,7 +283,9 @@ def main():
                 "traffic": 2.02e6,   # dram__bytes_read + write per launch, ncu --set full (profiles/r1_ncu_v2_kernels.txt)
                 "peak_source": peak_src, "avg_launch_ms": rows_ms, "launches_timed": int(cnt[1]),
                 "fp32_ffma_peak_tflops": ffma.value, "frac_of_fp32_ffma": achieved / ffma.value if ffma.value else None,
-                "other_kernels_ms": {"k_fwd_step": ms[0] / max(cnt[0], 1), "k_adj_pgrad<STEP>": ms[2] / max(cnt[2], 1)},
+                "other_kernels_ms": {"k_fwd_step": ms[0] / max(cnt[0], 1), "k_adj_pgrad<STEP>": ms[2] / max(cnt[2], 1),
+                                     **({"exchange (NCCL group + replicated finish kernel), per iteration, fwd and adjoint":
+                                         ms[3] / max(cnt[3], 1)} if world > 1 else {})},
                 "note": "fp32 FFMA kernel; the tensor pipe is the contract's denominator, the fp32 pipe is the one it uses"}
 
     line = {

@@ -303,7 +303,9 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
         ps = prof->begin(PROF_ADJ_PGRAD, st);
         k_adj_pgrad<ADJ_STEP><<<geo.grid, kSlots * kGroup, kPgradSmem, st>>>(a, 0.f, nullptr, nullptr);
         prof->end(ps, st);
+        ps = dist ? prof->begin(PROF_EXCHANGE, st) : -1;
         if ((rc = exchange(ADJ_STEP))) return rc;
+        prof->end(ps, st);
         launches += dist ? 3 : 2;
       }
       // A segment has one target, so a dense output can only become pending on the iteration that ends
@@ -322,7 +324,7 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
       continue;
     }
     {
-      int valid[PROF_KINDS] = {0, mailbox->n_iters, mailbox->n_iters, 0};
+      int valid[PROF_KINDS] = {0, mailbox->n_iters, mailbox->n_iters, dist ? mailbox->n_iters : 0};
       prof->resolve(valid);
     }
     *hint = mailbox->n_iters + 1 > 64 ? 64 : mailbox->n_iters + 1;

@@ -321,7 +321,9 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
         const int ps_ = ctx->prof.begin(PROF_FWD_STEP, stream);
         ENO_CUDA(ctx, launch(0));
         ctx->prof.end(ps_, stream);
+        const int px_ = dist ? ctx->prof.begin(PROF_EXCHANGE, stream) : -1;
         if (finish(0)) return fail(ctx, ENO_E_CUDA, "eno_odeint_fwd: NCCL all-gather failed");
+        ctx->prof.end(px_, stream);
         // with several output times a step can leave targets behind mid-solve: evaluate them before
         // the next step recycles the ring; with a single target one output launch per chunk suffices
         if (T > 2) {
@@ -348,7 +350,7 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   }
   const Ctrl& c = *ctx->mailbox;
   {
-    int valid[PROF_KINDS] = {c.n_iters, 0, 0, 0};
+    int valid[PROF_KINDS] = {c.n_iters, 0, 0, dist ? c.n_iters : 0};
     ctx->prof.resolve(valid);
   }
   ctx->hint_fwd = c.n_iters + 1 > 64 ? 64 : c.n_iters + 1;

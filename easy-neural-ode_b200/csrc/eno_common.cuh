@@ -59,7 +59,7 @@ static_assert(offsetof(Ctrl, done) == 72 && offsetof(Ctrl, n_iters) == 80, "Ctrl
 
 // Optional per-kernel device timing (bench.py's roofline leg): event pairs around the launches of
 // one kernel kind, resolved after the solve's final synchronize.
-enum ProfKind { PROF_FWD_STEP = 0, PROF_ADJ_ROWS = 1, PROF_ADJ_PGRAD = 2, PROF_KINDS = 4 };
+enum ProfKind { PROF_FWD_STEP = 0, PROF_ADJ_ROWS = 1, PROF_ADJ_PGRAD = 2, PROF_EXCHANGE = 3, PROF_KINDS = 4 };
 struct Profiler {
   bool enabled = false;
   static constexpr int kMax = 512;

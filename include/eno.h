@@ -219,7 +219,7 @@ int32_t eno_comm_destroy(eno_ctx* ctx);
  * whole jitted update, mnist.py:632-640).  With profiling on, the step kernels are bracketed by CUDA
  * events on the launch stream; eno_profile_read returns and clears the accumulated milliseconds and
  * launch counts per kernel kind: [0] forward step, [1] adjoint per-sample step, [2] adjoint
- * parameter-gradient step, [3] unused.  eno_ffma_peak measures the non-tensor fp32 FMA peak (TFLOP/s).
+ * parameter-gradient step, [3] multi-GPU exchange (NCCL group + replicated finish kernel).  eno_ffma_peak measures the non-tensor fp32 FMA peak (TFLOP/s).
  */
 int32_t eno_profile_enable(eno_ctx* ctx, int32_t on);
 int32_t eno_profile_read(eno_ctx* ctx, double* ms_out /*[4]*/, int64_t* count_out /*[4]*/);
