@@ -28,19 +28,22 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     Bg = int(os.environ.get("ENO_DIST_B", "96"))
     tol = float(os.environ.get("ENO_DIST_TOL", "1.4e-8"))
+    # ENO_DIST_REGTYPE=fin runs the odeint_sepaux / 'fin' arm (eps_bar block, two scalar states per sample)
+    kw = (dict(reg="none", reg_type="fin", lam_fro=1e-2, lam_kin=1e-2) if os.environ.get("ENO_DIST_REGTYPE") == "fin"
+          else dict(reg="r3", lam=6e-5))
     gen = torch.Generator().manual_seed(0)
     images = torch.randint(0, 256, (Bg, 28, 28, 1), generator=gen, dtype=torch.uint8).to(dev)
     labels = torch.randint(0, 10, (Bg,), generator=gen).to(dev)
     eps = (torch.randint(0, 2, (Bg, 784), generator=gen).float() * 2 - 1).to(dev)
 
     # single-device reference on the full batch (every rank computes it redundantly, before going collective)
-    ref_model = mnist_step.MnistNode(reg="r3", lam=6e-5, rtol=tol, atol=tol, device=dev)
+    ref_model = mnist_step.MnistNode(rtol=tol, atol=tol, device=dev, **kw)
     want = ref_model.loss_and_grads(images, labels, eps)
     want_f, want_b = dict(want["fwd_stats"]), dict(want["bwd_stats"][0])
 
     eno.init_distributed()
     sl = eno.shard_rows(Bg, world, rank)
-    model = mnist_step.MnistNode(reg="r3", lam=6e-5, rtol=tol, atol=tol, device=dev, world=world)
+    model = mnist_step.MnistNode(rtol=tol, atol=tol, device=dev, world=world, **kw)
     got = model.loss_and_grads(images[sl], labels[sl], eps[sl])
     f, b = got["fwd_stats"], got["bwd_stats"][0]
     errs = dict(y1=rel(got["y1"], want["y1"][sl]), g_ode=rel(got["grads"]["ode"], want["grads"]["ode"]),

@@ -203,6 +203,29 @@ def test_mnist_fin_train_step_vs_oracle(cuda):
     assert rel_err(out["grads"]["post_w"], want["grads"]["post"]["w"]) < RTOL
 
 
+@pytest.mark.parametrize("reg_type", ["our", "fin"])
+def test_whole_step_graph_matches_polled_updates(cuda, reg_type):
+    """update_graphed (the whole update() replayed as one CUDA graph over deferred-mode solves) must leave
+    exactly the parameters the polled update() leaves, for both regulariser arms."""
+    if reg_type == "fin":
+        _needs_cluster_path()
+    from easy_neural_ode_b200 import mnist_step
+    B, D = 100, 784
+    gen = torch.Generator().manual_seed(3)
+    batches = [(torch.randint(0, 256, (B, 28, 28, 1), generator=gen, dtype=torch.uint8).to(cuda),
+                torch.randint(0, 10, (B,), generator=gen).to(cuda),
+                (torch.randint(0, 2, (B, D), generator=gen).float() * 2 - 1).to(cuda)) for _ in range(4)]
+    kw = dict(reg="none", reg_type="fin", lam_fro=1e-2, lam_kin=1e-2) if reg_type == "fin" else dict(reg="r3", lam=6e-5)
+    a = mnist_step.MnistNode(device=cuda, **kw)
+    b = mnist_step.MnistNode(device=cuda, **kw)
+    for batch in batches:
+        a.update(*batch)
+    infos = [b.update_graphed(*batch) for batch in batches]
+    assert not getattr(b, "_graph_off", False), getattr(b, "_graph_error", None)
+    assert all(not i["redone"] for i in infos)
+    assert torch.equal(a.p_ode, b.p_ode) and torch.equal(a.post_w, b.post_w) and torch.equal(a.v_ode, b.v_ode)
+
+
 def test_plain_odeint_adjoint_multiple_output_times(cuda):
     """odeint() with T = 5 output times and cotangents at every time: the adjoint runs T-1 backward segments
     (lib/ode.py:1510-1529), carries y_bar / t0_bar / params_bar across them and returns ts_bar for every time.
