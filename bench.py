@@ -138,6 +138,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="polled solves instead of the whole-step CUDA graph")
     ap.add_argument("--batch", type=int, default=B, help="per-GPU batch (development sweeps only)")
+    ap.add_argument("--reg-type", default="our", choices=["our", "fin"],
+                    help="development only: 'fin' times the --reg_type fin arm (odeint_sepaux, lam_fro = lam_kin = 1e-2); "
+                         "the headline metric is the default 'our' (--reg r3)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -165,7 +168,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         eno.init_distributed()   # solves become collective: one global adaptive step sequence
 
-    model = mnist_step.MnistNode(reg="r3", lam=LAM, rtol=TOL, atol=TOL, device=dev, dim=D, hidden=H, world=world)
+    if args.reg_type == "fin":
+        model = mnist_step.MnistNode(reg="none", rtol=TOL, atol=TOL, device=dev, dim=D, hidden=H, world=world,
+                                     reg_type="fin", lam_fro=1e-2, lam_kin=1e-2)
+    else:
+        model = mnist_step.MnistNode(reg="r3", lam=LAM, rtol=TOL, atol=TOL, device=dev, dim=D, hidden=H, world=world)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     dev_batches = [tuple(t.to(dev) for t in synth_batch(rank, s)) for s in range(8)]
     host_batches = [synth_batch(rank, s, pin=True) for s in range(8)]
@@ -292,7 +299,10 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "rtol": TOL, "atol": TOL,
+        "config": {"workload": WORKLOAD if args.reg_type == "our" else
+                   "mnist.py Neural ODE classifier, dopri5, --reg_type fin --lam_fro 1e-2 --lam_kin 1e-2, batch 100 synthetic 28x28 "
+                   "(development run, not the headline config)",
+                   "global_batch": B * world, "per_gpu_batch": B, "rtol": TOL, "atol": TOL,
                    "parallelism": (f"dp{world}: batch sharded {B}/GPU, ONE global adaptive step sequence (per-iteration NCCL "
                                    "all-gather of error-norm partials + all-reduce of the params_bar stage sums)")
                    if world > 1 else "single GPU",

@@ -70,3 +70,26 @@ def test_empty_time_grid_returns_initial_state_only():
     f = lambda y, t: -y
     ys, nfe, st = oo.solve(f, torch.ones(3), torch.tensor([0.5]), 1e-5, 1e-5)
     assert ys.shape == (1, 3) and nfe == 2.0 and st["n_iters"] == 0
+
+
+def test_sepaux_surface_rejects_mismatched_closures():
+    """odeint_sepaux mirrors lib/ode.py:678-697: (fwd_func, rev_func, (y, fro, kin), t, eps, params); the rev_func
+    must be the 'fin' aug_dynamics of the same spec, and the usage errors surface before any device work."""
+    import easy_neural_ode_b200 as eno
+    our = eno.MLPDynamics(16, 8, reg="r3")
+    fin = eno.MLPDynamics(16, 8, reg_type="fin")
+    assert fin.aug_dynamics.kind == "fin" and our.aug_dynamics.kind == "aug"
+    y0 = (torch.zeros(2, 16), torch.zeros(2), torch.zeros(2))
+    ts = torch.tensor([0., 1.])
+    eps = torch.ones(2, 16)
+    p = fin.init_params()
+    with pytest.raises(TypeError):
+        eno.odeint_sepaux(our.fwd, our.aug_dynamics, y0, ts, eps, p)          # 'our' closure on the sepaux surface
+    with pytest.raises(TypeError):
+        eno.odeint_sepaux(fin.fwd, our.aug_dynamics, y0, ts, eps, p)          # closures of different specs
+    with pytest.raises(TypeError):
+        eno.odeint_sepaux(fin.fwd, fin.aug_dynamics, y0[:2], ts, eps, p)      # wrong state arity
+    with pytest.raises(TypeError):
+        eno.odeint_aux_one(fin.fwd, fin.aug_dynamics, y0[:2], ts, eps, p)     # 'fin' closure on the aux_one surface
+    with pytest.raises(ValueError):
+        eno.MLPDynamics(16, 8, reg_type="other")
