@@ -17,7 +17,7 @@ TABLEAUX = {"dopri5": 0, "heun": 1, "fehlberg": 2, "bosh": 3, "rk_fehlberg": 4, 
 
 # every symbol include/eno.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["eno_abi_version", "eno_last_error_string", "eno_create", "eno_destroy", "eno_param_count",
-           "eno_adjoint_state_size", "eno_workspace_bytes", "eno_odeint_fwd", "eno_odeint_bwd", "eno_odeint_bwd_sepaux", "eno_rhs",
+           "eno_adjoint_state_size", "eno_workspace_bytes", "eno_odeint_fwd", "eno_odeint_fwd_vmap", "eno_odeint_bwd", "eno_odeint_bwd_sepaux", "eno_rhs",
            "eno_profile_enable", "eno_profile_read", "eno_ffma_peak", "eno_comm_unique_id", "eno_comm_init",
            "eno_comm_destroy", "eno_set_deferred", "eno_read_stats"]
 
@@ -69,6 +69,8 @@ def lib():
     L.eno_odeint_fwd.restype = i32
     L.eno_odeint_fwd.argtypes = [vp, C.POINTER(Desc), i32, i32, vp, vp, i32, vp, vp, f32, f32, i32, vp, sz, vp, vp,
                                  C.POINTER(Stats), vp, i32, vp]
+    L.eno_odeint_fwd_vmap.restype = i32
+    L.eno_odeint_fwd_vmap.argtypes = [vp, C.POINTER(Desc), i32, vp, vp, i32, vp, f32, f32, i32, vp, vp, vp, vp, vp]
     L.eno_odeint_bwd.restype = i32
     L.eno_odeint_bwd.argtypes = [vp, C.POINTER(Desc), i32, vp, vp, i32, vp, vp, vp, f32, f32, i32, vp, sz, vp, vp, vp,
                                  vp, C.POINTER(Stats), vp, i32, vp]

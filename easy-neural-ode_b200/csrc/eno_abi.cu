@@ -10,6 +10,7 @@
 #include "adj_host.cuh"
 #include "cl_aug_fwd.cuh"
 #include "cl_kernels.cuh"
+#include "cl_vmap.cuh"
 #include "fwd_kernels.cuh"
 #include "tableaux.cuh"
 
@@ -358,6 +359,37 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   (void)eps;
   fill_stats(stats_host, c, launches, 2 + per_iter * c.n_iters);
   return c.status;
+}
+
+int32_t eno_odeint_fwd_vmap(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, const float* y0, const float* ts,
+                            int32_t T, const float* params, float rtol, float atol, int32_t mxstep, float* ys_out,
+                            float* nfe_out, int32_t* iters_out, int32_t* status_out, void* stream_) {
+  if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_odeint_fwd_vmap: ctx is null");
+  if (!desc_ok(desc)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd_vmap: unsupported dynamics desc (MLP sigmoid, D%4==0, H%4==0)");
+  if (desc->aug != ENO_AUG_NONE) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd_vmap: plain dynamics only (mnist.py:350-353 vmaps odeint(dynamics_wrap, ...))");
+  if (T != 2) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd_vmap: T must be 2 (ts = [t0, t1])");
+  if (B <= 0 || !y0 || !ts || !params || !ys_out || !nfe_out) return fail(ctx, ENO_E_ARG, "eno_odeint_fwd_vmap: null pointer or empty batch");
+  if (ctx->path_mode == 1 || !cl_supported(desc->D, desc->H, kClRows, kAdjStages, false))
+    return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd_vmap: runs on the cluster-resident path only (weights must fit the cluster's shared memory)");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+  ENO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tab, &ctx->tabs[ENO_TABLEAU_DOPRI5], sizeof(Tableau), 0, cudaMemcpyHostToDevice, stream));
+  VmapArgs a = {};
+  a.w = mlp_weights_from_flat(params, desc->D, desc->H, nullptr, nullptr);
+  a.B = B;
+  a.y0 = y0;
+  a.ts = ts;
+  a.rtol = rtol;
+  a.atol = atol;
+  a.mxstep = mxstep <= 0 ? INT_MAX : mxstep;
+  a.ys_out = ys_out;
+  a.nfe_out = nfe_out;
+  a.iters_out = iters_out;
+  a.status_out = status_out;
+  ENO_CUDA(ctx, cl_fwd_vmap_launch(a, cl_grid(B), cl_smem_bytes(kClRows, desc->D, desc->H, kAdjStages, false), stream));
+  ENO_CUDA(ctx, cudaGetLastError());
+  ENO_CUDA(ctx, cudaStreamSynchronize(stream));
+  return ENO_OK;
 }
 
 int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32_t B, const float* y, float t,

@@ -398,6 +398,40 @@ def odeint_sepaux(fwd_func, rev_func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mx
     return (ys, fro, kin), nfe
 
 
+def odeint_vmap(func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=math.inf):
+    """``jax.vmap(lambda y0, t, *args: odeint(func, y0, t, *args), (0, None, None))`` - the per-example solves of
+    mnist.py:350-353 (``--vmap`` NFE count): every row of ``y0`` is integrated as its own problem, with its own
+    initial step, accept / reject sequence and NFE.  One kernel launch runs all of them to completion.
+    Forward only (the script never differentiates it).  -> (ys [T=2, B, D], nfe [B])."""
+    _require_spec(func, "odeint_vmap")
+    if func.kind != "plain":
+        raise TypeError("odeint_vmap: only the plain dynamics are vmapped by the reference (mnist.py:351)")
+    spec = func.spec
+    _, params = _split_args(func, args)
+    out_dev = y0.device
+    dev = _dev(y0)
+    y = _f32c(y0.detach().reshape(-1, spec.dim), dev)
+    ts = _f32c(torch.as_tensor(t), dev)
+    if ts.numel() != 2:
+        raise NotImplementedError("odeint_vmap: t must be [t0, t1]")
+    pflat = _f32c(spec.flatten_params(params).detach(), dev)
+    L = _cabi.lib()
+    h = _cabi.ctx(dev.index)
+    B, D = y.shape
+    ys = torch.empty((2, B, D), dtype=torch.float32, device=dev)
+    nfe = torch.empty((B,), dtype=torch.float32, device=dev)
+    iters = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    desc = spec.desc(_cabi.AUG_NONE)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        rc = L.eno_odeint_fwd_vmap(h, C.byref(desc), B, _ptr(y), _ptr(ts), 2, _ptr(pflat), float(rtol), float(atol),
+                                   _mx(mxstep), _ptr(ys), _ptr(nfe), _ptr(iters), _ptr(status), stream)
+    _cabi.check(rc, h, "eno_odeint_fwd_vmap")
+    last_stats["vmap"] = {"iters": iters[:, 0].cpu(), "accepted": iters[:, 1].cpu(), "status": status.cpu()}
+    return ys.reshape((2,) + tuple(y0.shape)).to(out_dev), nfe.to(out_dev)
+
+
 def _tableau_odeint(solver):
     def run(func, rtol, atol, mxstep, y0, ts, *args):
         _require_spec(func, f"_{solver}_odeint")

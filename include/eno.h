@@ -133,6 +133,20 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
                        eno_stats* stats_host, eno_trace_row* trace_out, int32_t trace_cap, void* stream);
 
 /*
+ * Per-example forward solves: every sample is its own dopri5 problem with its own step sequence.  Replaces
+ *   jax.vmap(lambda y0, t, params: odeint(dynamics_wrap, y0, t, params)[1], (0, None, None))   mnist.py:350-353
+ * (the `--vmap` NFE count of the evaluation path; each lane runs lib/ode.py:823-862 on a state of D elements).
+ * One launch runs all B solves to completion; there is no workspace and no host round-trip per step.
+ *
+ *   y0 [B, D]   ts [2] (device)   ys_out [2, B, D]   nfe_out [B] (2 + 6 * iterations of that sample)
+ *   iters_out [B, 2] or NULL: iterations and accepted steps;  status_out [B] or NULL: ENO_OK / ENO_MXSTEP / ...
+ * Runs on the cluster-resident path only (ENO_E_UNSUPPORTED otherwise).
+ */
+int32_t eno_odeint_fwd_vmap(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, const float* y0, const float* ts,
+                            int32_t T, const float* params, float rtol, float atol, int32_t mxstep, float* ys_out,
+                            float* nfe_out, int32_t* iters_out, int32_t* status_out, void* stream);
+
+/*
  * Backward (adjoint) solve.  Replaces
  *   _odeint_rev(func, rtol, atol, mxstep, res, g)             lib/ode.py:1494-1529
  *   as reached through _odeint_aux_one_rev                    lib/ode.py:1677-1684

@@ -115,6 +115,11 @@ def mlp_taylor_closed(params, z, t, order):
     return out
 
 
+def mlp_dynamics_xtp(x, t, params):
+    """dynamics_wrap of mnist.py:285 (argument order of the solver: state, time, *args)."""
+    return mlp_dynamics(params, x, t)
+
+
 def make_mnist_closures(reg="r3", reg_type="our"):
     """The closures init_model() builds (mnist.py:285-334), over explicit params."""
     def dynamics_wrap(x, t, params):

@@ -73,6 +73,22 @@ def fin_case(ref, do, B, D, H, params, x0, eps, gy):
     np.savez(os.path.join(OUT, "mlp_adjoint_fin.npz"), **rec)
 
 
+def vmap_case(ref, do, B, D, H, params, x0):
+    """Per-example solves (mnist.py:350-353 vmaps odeint over the batch): the reference solver is run on every
+    sample separately, which is what each vmap lane computes; plus one mxstep-limited run."""
+    cl = do.make_mnist_closures("none")
+    ts = torch.tensor([0., 1.])
+    rec = dict(B=B, D=D, H=H, x0=x0.numpy(), params=flat_params(params))
+    for tag, tol, mx in [("5", 1e-5, math.inf), ("6", 1e-6, math.inf), ("mx2", 1e-5, 2)]:
+        ys, nfes = [], []
+        for b in range(B):
+            y, nfe = ref.odeint(cl["dynamics_wrap"], x0[b:b + 1], ts, params, rtol=tol, atol=tol, mxstep=mx)
+            ys.append(y[:, 0].numpy())
+            nfes.append(float(nfe))
+        rec[f"vmap_{tag}_y"], rec[f"vmap_{tag}_nfe"], rec[f"vmap_{tag}_tol"] = np.stack(ys, 1), np.array(nfes), tol
+    np.savez(os.path.join(OUT, "mlp_vmap.npz"), **rec)
+
+
 def main():
     ref = load_reference_ode()
     torch.set_num_threads(8)
@@ -146,6 +162,7 @@ def main():
     np.savez(os.path.join(OUT, "mlp_adjoint.npz"), **rec)
 
     fin_case(ref, do, B, D, H, params, x0, eps, gy)
+    vmap_case(ref, do, B, D, H, params, x0)
 
     # ---- plain adjoint on the pendulum (lib/ode.py:1720-1722, 1765-1774), multi-output
     def pend(y, t, m, g):

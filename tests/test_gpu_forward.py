@@ -268,3 +268,54 @@ def test_host_tensors_round_trip_and_usage_errors(case, cuda):
     assert rc == -1 and b"tableau" in L.eno_last_error_string(h)
     with pytest.raises(TypeError):
         eno.odeint(spec.aug_dynamics, (x0,), torch.tensor([0., 1.]), None, params)   # wrong state arity
+
+
+@pytest.mark.parametrize("tag", ["5", "6", "mx2"])
+def test_odeint_vmap_golden(cuda, tag):
+    """Per-example solves (mnist.py:350-353, --vmap) in one launch against the unmodified reference solver run on
+    every sample separately: per-sample NFE exact, values rtol 1e-5; `mx2` leaves the loops after 2 iterations
+    (the output is then the last interpolant extrapolated, lib/ode.py:848-850)."""
+    _needs_cluster_path()
+    import easy_neural_ode_b200 as eno
+    g = load("mlp_vmap.npz")
+    B, D, H = int(g["B"]), int(g["D"]), int(g["H"])
+    spec = eno.MLPDynamics(D, H)
+    params = params_from_flat(g["params"], D, H, device=cuda)
+    x0 = torch.as_tensor(g["x0"], device=cuda)
+    tol = float(g[f"vmap_{tag}_tol"])
+    ys, nfe = eno.odeint_vmap(spec.dynamics_wrap, x0, torch.tensor([0., 1.]), params, rtol=tol, atol=tol,
+                              mxstep=2 if tag == "mx2" else math.inf)
+    assert ys.shape == (2, B, D) and nfe.shape == (B,)
+    assert nfe.cpu().tolist() == g[f"vmap_{tag}_nfe"].tolist()
+    # at tol = 1e-5 two fp32 implementations agree to the solve's own accuracy (DESIGN.md section 2)
+    assert rel_err(ys, g[f"vmap_{tag}_y"]) < {"5": 5e-5, "6": RTOL, "mx2": 1e-4}[tag]
+    st = eno.last_stats["vmap"]["status"].tolist()
+    assert st == ([1] * B if tag == "mx2" else [0] * B)
+
+
+def test_odeint_vmap_mnist_shape_vs_per_sample_oracle(cuda):
+    """C1 shape, ragged batch (B = 10 is not a multiple of the 4-sample tile): every sample's NFE and final
+    state against the oracle solving that sample alone; the per-sample step sequences differ from each other
+    and from the batch solve's (whose error norm is a mean over all samples)."""
+    _needs_cluster_path()
+    import easy_neural_ode_b200 as eno
+    from oracle import dynamics_oracle as do, ode_oracle as oo
+    B, D, H = 10, 784, 100
+    spec = eno.MLPDynamics(D, H)
+    p_cpu = do.init_mlp_params(D, H, seed=2, scale=3.0)
+    gen = torch.Generator().manual_seed(5)
+    x0 = torch.rand((B, D), generator=gen) * torch.linspace(0.2, 2.0, B)[:, None]
+    ts = torch.tensor([0., 1.])
+    tol = 1e-6
+    params = {k: {kk: vv.to(cuda) for kk, vv in v.items()} for k, v in p_cpu.items()}
+    ys, nfe = eno.odeint_vmap(spec.dynamics_wrap, x0.to(cuda), ts, params, rtol=tol, atol=tol)
+    want_nfe, want_y = [], []
+    for b in range(B):
+        y, n = oo.odeint(do.mlp_dynamics_xtp, x0[b:b + 1], ts, p_cpu, rtol=tol, atol=tol)
+        want_nfe.append(float(n))
+        want_y.append(y[-1, 0])
+    assert nfe.cpu().tolist() == want_nfe
+    assert rel_err(ys[-1], torch.stack(want_y)) < RTOL
+    # and the batch solve is a different computation: one step sequence for all samples
+    _, nfe_batch = eno.odeint(spec.dynamics_wrap, x0.to(cuda), ts, params, rtol=tol, atol=tol)
+    assert float(nfe_batch) >= min(want_nfe)

@@ -122,6 +122,21 @@ def test_sepaux_fin_solve_and_adjoint(tag):
     np.testing.assert_allclose(flat_from_params(out[3]).numpy(), g[f"{k}_params_bar"], rtol=1e-5, atol=1e-6)
 
 
+def test_per_example_solves_golden():
+    """mnist.py:350-353 (--vmap): every sample as its own problem; includes an mxstep-limited (extrapolated) run."""
+    g = load("mlp_vmap.npz")
+    B, D, H = int(g["B"]), int(g["D"]), int(g["H"])
+    params = params_from_flat(g["params"], D, H)
+    x0 = torch.as_tensor(g["x0"])
+    ts = torch.tensor([0., 1.])
+    for tag, mx in [("5", math.inf), ("mx2", 2)]:
+        tol = float(g[f"vmap_{tag}_tol"])
+        for b in range(B):
+            ys, nfe = oo.odeint(do.mlp_dynamics_xtp, x0[b:b + 1], ts, params, rtol=tol, atol=tol, mxstep=mx)
+            assert nfe == float(g[f"vmap_{tag}_nfe"][b])
+            np.testing.assert_allclose(ys[:, 0].numpy(), g[f"vmap_{tag}_y"][:, b], **TIGHT)
+
+
 def test_pendulum_adjoint_multi_segment():
     g = load("pendulum.npz")
 
