@@ -1,6 +1,6 @@
 // "Cluster-resident" formulation of the MLP dynamics and its Taylor / adjoint sweeps.
 //
-// A thread-block cluster of kC = 4 CTAs owns a tile of R samples.  The state width D is split
+// A thread-block cluster of kC = 5 CTAs owns a tile of R samples.  The state width D is split
 // into kC column slices; CTA `rank` keeps, for the whole launch, its slice of BOTH weight
 // matrices in shared memory:
 //     W1 rows  d0..d0+Dl  ([Dl][H])   - used as  a[n]  = sum_{d local} x[d] W1[d][n]   (partial over d)
@@ -61,7 +61,8 @@ __device__ __forceinline__ long long* ph_slots() { __shared__ long long s[72]; r
 #define ENO_TICK_FLUSH() do {} while (0)
 #endif
 
-constexpr int kC = 4;          // CTAs per cluster
+constexpr int kC = 5;          // CTAs per cluster: 25 clusters x 5 = 125 of the 148 SMs at B = 100 (26 such clusters can be
+                               // co-resident, tools/probe/cluster_occ.cu; 4-CTA clusters used 100 SMs and were 5 % slower per step)
 constexpr int kKG = 14;        // k-groups of a product contracting over the local slice (K = Dl = 49 float4 rows at D = 784)
 constexpr int kKGw = 7;        // k-groups of a product contracting over H (25 float4 rows at H = 100)
 constexpr int kRG = 1;         // row groups: 1 = every weight word is read from shared memory ONCE per product and
@@ -217,6 +218,7 @@ __device__ __forceinline__ void mv_k(const float* __restrict__ W, int ldw, int N
                                      int ldx, float* __restrict__ red, int KG) {
   constexpr int TR = R / kRG;
   const int NQ = N >> 2;
+  if (NQ == 0) return;   // a CTA whose column slice is empty (D/4 < kC) has nothing to produce
   const int per = NQ * KG;
   const int rg = threadIdx.x / per;
   if (rg < kRG) {
@@ -286,7 +288,7 @@ struct ClComm {
 
 // All-reduce over the cluster of R x (H + nscal) partial sums.  `red` holds the k-group partials of
 // this CTA's layer-1 product; `scal[r*4 + j]` (may be null) holds up to 4 per-sample scalar partials.
-// Sum order over CTAs is fixed (rank 0..3), so every CTA obtains bit-identical results.
+// Sum order over CTAs is fixed (rank 0..kC-1), so every CTA obtains bit-identical results.
 template <int R, typename Epi, typename EpiS>
 __device__ __forceinline__ void allreduce_H(cg::cluster_group& cluster, ClComm& cm, const ClGeom& g, const float* red,
                                             int KG, int H, const float* scal, int nscal, Epi epi, EpiS epis) {
@@ -306,20 +308,27 @@ __device__ __forceinline__ void allreduce_H(cg::cluster_group& cluster, ClComm& 
   ENO_TICK(PH_AR_LOCAL);
   cluster.sync();
   ENO_TICK(PH_AR_CSYNC);
-  const float* p0 = cluster.map_shared_rank(mine, 0);
-  const float* p1 = cluster.map_shared_rank(mine, 1);
-  const float* p2 = cluster.map_shared_rank(mine, 2);
-  const float* p3 = cluster.map_shared_rank(mine, 3);
+  const float* pk[kC];
+#pragma unroll
+  for (int k = 0; k < kC; ++k) pk[k] = cluster.map_shared_rank(mine, k);
   for (int idx = threadIdx.x; idx < R * H; idx += blockDim.x) {
     const int r = idx / H, n = idx - r * H;
     const int o = r * g.Hs + n;
-    const float s = ((p0[o] + p1[o]) + p2[o]) + p3[o];
+    float v[kC];
+#pragma unroll
+    for (int k = 0; k < kC; ++k) v[k] = pk[k][o];   // all remote loads in flight before the adds
+    float s = v[0];
+#pragma unroll
+    for (int k = 1; k < kC; ++k) s += v[k];
     epi(r, n, s);
   }
   if (scal && threadIdx.x < R * nscal) {
     const int r = threadIdx.x / nscal, j = threadIdx.x - r * nscal;
     const int o = r * g.Hs + H + j;
-    epis(r, j, ((p0[o] + p1[o]) + p2[o]) + p3[o]);
+    float s = pk[0][o];
+#pragma unroll
+    for (int k = 1; k < kC; ++k) s += pk[k][o];
+    epis(r, j, s);
   }
   cm.phase ^= 1;
   ENO_TICK(PH_AR_REMOTE);

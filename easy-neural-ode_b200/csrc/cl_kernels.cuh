@@ -1,6 +1,6 @@
 // Cluster-resident step kernels (the fast path when the weight slices fit in shared memory):
 // same controller protocol, workspace and outputs as fwd_kernels.cuh / adj_kernels.cuh, but a
-// 4-CTA cluster owns a tile of R samples, keeps its weight slices in shared memory for the whole
+// 5-CTA cluster owns a tile of R samples, keeps its weight slices in shared memory for the whole
 // launch, loops persistently over tiles, and exchanges only R x H partial sums over DSMEM.
 #pragma once
 #include "adj_kernels.cuh"
@@ -82,7 +82,7 @@ inline size_t cl_smem_bytes(int R, int D, int H, int stages, bool adjoint) {
 
 // Can the cluster path run this problem?  (thread-count and divisibility limits of mv_n / mv_k)
 inline bool cl_supported(int D, int H, int R, int stages, bool adjoint) {
-  if (D % 4 || H % 4 || D / 4 < kC) return false;
+  if (D % 4 || H % 4 || D < 4) return false;   // D/4 < kC: the trailing CTAs of a cluster own empty slices
   const ClGeom g = cl_geom(D, H, 0);
   if (adjoint && R * g.Dlp > 2 * kThreads) return false;   // EPT = 2 register-resident elements per thread
   if ((H / 4) * kKG * kRG > kThreads) return false;
@@ -640,7 +640,7 @@ inline cudaError_t launch_cluster(void (*kernel)(KArgs...), int grid, size_t sme
 }
 
 constexpr int kClRows = 4;           // samples per cluster tile
-constexpr int kClMaxClusters = 33;   // 4-CTA clusters co-resident on 148 SMs (132 SMs usable)
+constexpr int kClMaxClusters = 26;   // 5-CTA clusters co-resident on 148 SMs (measured with cudaOccupancyMaxActiveClusters)
 
 inline int cl_grid(int B) {
   const int tiles = (B + kClRows - 1) / kClRows;

@@ -3,10 +3,10 @@
 // i.e. every sample is its own dopri5 problem (state [D], error norm and initial step over its D elements,
 // lib/ode.py:86-104, 518-538, 823-862) with its own t, dt, accept / reject sequence and NFE.
 //
-// Nothing couples the samples, so there is no grid-wide event at all: a 4-CTA cluster keeps its weight
+// Nothing couples the samples, so there is no grid-wide event at all: a 5-CTA cluster keeps its weight
 // slices in shared memory (cl_device.cuh), takes a tile of R samples and runs their complete solves -
 // initial step, every iteration, dense output at t1 - before moving to the next tile.  The per-sample
-// norms are sums of per-CTA partials exchanged over distributed shared memory in rank order, so all four
+// norms are sums of per-CTA partials exchanged over distributed shared memory in rank order, so all
 // CTAs hold bit-identical controller state and take the same branches.  Rows of a tile that finish early
 // idle until the slowest row of the tile is done.
 #pragma once
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_fwd_vmap(VmapArgs a) {
         any[0] = n;
       }
       __syncthreads();
-      if (!any[0]) break;   // identical on all four CTAs: their controller state is bit-identical
+      if (!any[0]) break;   // identical on all CTAs of the cluster: their controller state is bit-identical
       for (int st = 1; st < s; ++st) {
         for (int i = threadIdx.x; i < RD; i += blockDim.x) {
           float accv = 0.f;
