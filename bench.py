@@ -287,7 +287,7 @@ def main():
     achieved = flop_rows / (rows_ms * 1e-3) / 1e12 if rows_ms > 0 else 0.0
     roofline = {"kernel": "k_adj_rows<STEP> (adjoint dopri5 iteration, per-sample blocks)", "bound": "tensor",
                 "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                "traffic": 2.02e6,   # dram__bytes_read + write per launch, ncu --set full (profiles/r1_ncu_v2_kernels.txt)
+                "traffic": 2.02e6,   # dram__bytes_read + write per launch, ncu --set full (profiles/r1_ncu_v4_kernels.txt)
                 "peak_source": peak_src, "avg_launch_ms": rows_ms, "launches_timed": int(cnt[1]),
                 "fp32_ffma_peak_tflops": ffma.value, "frac_of_fp32_ffma": achieved / ffma.value if ffma.value else None,
                 "other_kernels_ms": {"k_fwd_step": ms[0] / max(cnt[0], 1), "k_adj_pgrad<STEP>": ms[2] / max(cnt[2], 1),
