@@ -28,8 +28,8 @@ inline size_t adj_ws_bytes(int B, int D, int H, int world = 1, bool fin = false)
   s += adj_align(2 * N * 4);                        // MIDZB
   s += 2 * adj_align(3 * P * 4) + adj_align(2 * P * 4);             // PB, FP, MIDP
   const size_t npp = std::max((size_t)g.grid, (P + 255) / 256);
-  s += kSlots * (2 * adj_align(3 * N * 4) + 2 * adj_align(3 * (size_t)B * H * 4) + adj_align((size_t)kC * B * world * 4));
-  s += 3 * adj_align((size_t)kC * B * world * 8) + 2 * adj_align(npp * 8);
+  s += kSlots * (2 * adj_align(3 * N * 4) + 2 * adj_align(3 * (size_t)B * H * 4));
+  s += adj_align((size_t)6 * kC * B * world * 8) + 2 * adj_align(npp * 8);   // xrec (one record per rank), ppart0/1
   if (world > 1) s += adj_align(4 * P * 4);          // pcomb
   s += adj_align(N * 4) + adj_align(P * 4);         // YBAR, POUT
   s += 2 * adj_align((size_t)D * H * 4);            // transposes
@@ -69,11 +69,11 @@ inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArg
     a->slot[j].G = cv.take<float>(3 * N);
     a->slot[j].A = cv.take<float>(3 * (size_t)B * H);
     a->slot[j].Hh = cv.take<float>(3 * (size_t)B * H);
-    a->slot[j].tbar = cv.take<float>((size_t)kC * B * world);
+    a->slot[j].tbar = nullptr;   // adj_set_views
   }
-  a->rowpart0 = cv.take<double>((size_t)kC * B * world); a->rowpart1 = cv.take<double>((size_t)kC * B * world);
-  a->rowpart2 = cv.take<double>((size_t)kC * B * world);
-  a->n_rp = B;
+  a->xrec = cv.take<double>((size_t)6 * kC * B * world);
+  a->rowpart0 = a->rowpart1 = a->rowpart2 = nullptr;
+  a->n_rp = a->n_loc = B;
   const size_t npp = std::max((size_t)g.grid, (P + 255) / 256);
   a->ppart0 = cv.take<double>(npp); a->ppart1 = cv.take<double>(npp);
   a->pcomb = (world > 1) ? cv.take<float>(4 * P) : nullptr;
@@ -135,15 +135,25 @@ inline int adj_rows(int R, int K, int mode, const AdjArgs& a, int grid, size_t s
   return ENO_E_UNSUPPORTED;
 }
 
-// Point the kernels' write views at this rank's chunk of the gathered partial-sum arrays.
+// Everything a rank contributes to the controller besides the params_bar block lives in ONE record of
+// 6 * n_loc doubles, so that the multi-GPU exchange is a single all-gather (plus the params_bar all-reduce):
+//   [ rp0: n_loc doubles | t_bar pieces of slots 0..5: 6 * n_loc floats | rp1: n_loc doubles | rp2: n_loc doubles ]
+// Point the kernels' write views at this rank's record and the readers at rank 0's (block_sum_records).
 inline void adj_set_views(AdjArgs* a, int stride, int rank, int world) {
   const size_t n_loc = (size_t)stride * a->B;
+  a->n_loc = (int)n_loc;
   a->n_rp = (int)(n_loc * world);
-  a->rp0_all = a->rowpart0; a->rp1_all = a->rowpart1; a->rp2_all = a->rowpart2;
-  a->rowpart0 += (size_t)rank * n_loc; a->rowpart1 += (size_t)rank * n_loc; a->rowpart2 += (size_t)rank * n_loc;
+  a->rp0_all = a->xrec;
+  a->rp1_all = a->xrec + 4 * n_loc;
+  a->rp2_all = a->xrec + 5 * n_loc;
+  double* mine = a->xrec + (size_t)rank * 6 * n_loc;
+  a->rowpart0 = mine;
+  a->rowpart1 = mine + 4 * n_loc;
+  a->rowpart2 = mine + 5 * n_loc;
+  float* f0 = reinterpret_cast<float*>(a->xrec) + 2 * n_loc;   // rank 0's t_bar pieces
   for (int j = 0; j < kSlots; ++j) {
-    a->tbar_all[j] = a->slot[j].tbar;
-    a->slot[j].tbar += (size_t)rank * n_loc;
+    a->tbar_all[j] = f0 + (size_t)j * n_loc;
+    a->slot[j].tbar = f0 + (size_t)rank * 12 * n_loc + (size_t)j * n_loc;
   }
 }
 
@@ -252,12 +262,7 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
     if (!dist) return 0;
     int rc = dc->api.GroupStart();
     rc |= dc->allreduce(a.pcomb, (mode == ADJ_STEP ? 4 : 1) * (size_t)a.P, st);
-    rc |= dc->gather(const_cast<double*>(a.rp0_all), n_loc, st);
-    if (mode == ADJ_INIT0) {
-      rc |= dc->gather(const_cast<double*>(a.rp1_all), n_loc, st);
-      rc |= dc->gather(const_cast<double*>(a.rp2_all), n_loc, st);
-    }
-    for (int j = 0; j < (mode == ADJ_STEP ? kSlots : 1); ++j) rc |= dc->gather(const_cast<float*>(a.tbar_all[j]), n_loc, st);
+    rc |= dc->gather(a.xrec, 6 * n_loc, st);   // every rank's record: norm partials + t_bar pieces
     rc |= dc->api.GroupEnd();
     if (rc) { if (err) *err = "eno_odeint_bwd: NCCL exchange failed"; return ENO_E_CUDA; }
     if (mode == ADJ_STEP) k_adj_pfinish<ADJ_STEP><<<pf_grid, 256, 0, st>>>(a);

@@ -44,7 +44,11 @@ struct AdjArgs {
   AdjScalars* sc;
   MlpWeights w;
   int B, P, np;            // np = Taylor passes whose factors exist (1, 2 or 3)
-  int n_rp;                // entries of the per-sample partial-sum arrays: B (streamed) or kC*B (cluster)
+  int n_rp;                // entries of the per-sample partial-sum arrays over ALL ranks: world * n_loc
+  int n_loc;               // ... of this rank: B (streamed) or kC*B (cluster)
+  double* xrec;            // [world] records of 6*n_loc doubles: rp0 | t_bar pieces of the 6 slots (floats) | rp1 | rp2
+                           // - everything a rank contributes to the controller besides params_bar, so that the
+                           //   multi-GPU exchange is ONE all-gather
   size_t N;                // B * D
   float n_state;
   // per-sample rings
@@ -67,8 +71,8 @@ struct AdjArgs {
   FactorSlot slot[kSlots];
   // partial sums
   double *rowpart0, *rowpart1, *rowpart2;  // per-sample partials of THIS rank's rows (views into rp*_all)
-  const double *rp0_all, *rp1_all, *rp2_all;   // all ranks, canonical global row order, n_rp entries
-  const float* tbar_all[kSlots];           // same for the per-sample t_bar pieces of every slot
+  const double *rp0_all, *rp1_all, *rp2_all;   // rank 0's entries; rank r's are 6*n_loc doubles further (block_sum_records)
+  const float* tbar_all[kSlots];           // same for the per-sample t_bar pieces of every slot (12*n_loc floats per rank)
   double *ppart0, *ppart1;                 // [pgrad grid]
   float* pcomb;                            // [4][P] multi-GPU: this rank's share of the stage combinations
   int dist;                                // 1: multi-GPU split (local contraction | NCCL | finish)
@@ -386,12 +390,12 @@ __device__ __forceinline__ void adj_finalize(AdjArgs& a, Ctrl* c, double* dred, 
   __shared__ double fin[12];
   {
     double v;
-    v = block_sum_global(a.rp0_all, a.n_rp, dred); if (threadIdx.x == 0) fin[0] = v; __syncthreads();
+    v = block_sum_records(a.rp0_all, a.n_rp, a.n_loc, 6 * a.n_loc, dred); if (threadIdx.x == 0) fin[0] = v; __syncthreads();
     v = block_sum_global(a.ppart0, n_pp, dred); if (threadIdx.x == 0) fin[1] = v; __syncthreads();
     if (MODE == ADJ_INIT0) {
-      v = block_sum_global(a.rp1_all, a.n_rp, dred); if (threadIdx.x == 0) fin[2] = v; __syncthreads();
+      v = block_sum_records(a.rp1_all, a.n_rp, a.n_loc, 6 * a.n_loc, dred); if (threadIdx.x == 0) fin[2] = v; __syncthreads();
       v = block_sum_global(a.ppart1, n_pp, dred); if (threadIdx.x == 0) fin[3] = v; __syncthreads();
-      v = block_sum_global(a.rp2_all, a.n_rp, dred); if (threadIdx.x == 0) fin[4] = v; __syncthreads();
+      v = block_sum_records(a.rp2_all, a.n_rp, a.n_loc, 6 * a.n_loc, dred); if (threadIdx.x == 0) fin[4] = v; __syncthreads();
     }
     // stage derivatives of t0_bar: sums of the per-sample t_bar contributions
     for (int j = 0; j < (SPLITK ? 1 : NS); ++j) {
@@ -399,7 +403,10 @@ __device__ __forceinline__ void adj_finalize(AdjArgs& a, Ctrl* c, double* dred, 
       const int per = (a.n_rp + blockDim.x - 1) / blockDim.x;
       const int b0 = threadIdx.x * per, b1 = min(a.n_rp, b0 + per);
       double acc = 0.0;
-      for (int i = b0; i < b1; ++i) acc += (double)tb[i];
+      for (int i = b0; i < b1; ++i) {
+        const int r = i / a.n_loc;
+        acc += (double)tb[(size_t)r * 12 * a.n_loc + (i - r * a.n_loc)];
+      }
       dred[threadIdx.x] = acc;
       __syncthreads();
       for (int o = 256; o > 0; o >>= 1) {

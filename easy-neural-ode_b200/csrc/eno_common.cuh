@@ -122,6 +122,31 @@ __device__ __forceinline__ double block_sum_global(const double* __restrict__ v,
   return sm[0];
 }
 
+// The same sum over n logical entries stored as records: entry i lives at v[(i / n_loc) * rec + (i % n_loc)]
+// (one record per rank, see adj_host.cuh).  Chunking and tree are those of block_sum_global, so a packed
+// layout gives bit-identical sums.
+template <typename T>
+__device__ __forceinline__ double block_sum_records(const T* __restrict__ v, int n, int n_loc, int rec, double* sm) {
+  const int nt = blockDim.x;
+  const int per = (n + nt - 1) / nt;
+  const int b = threadIdx.x * per;
+  const int e = min(n, b + per);
+  double acc = 0.0;
+  for (int i = b; i < e; ++i) {
+    const int r = i / n_loc;
+    acc += (double)v[(size_t)r * rec + (i - r * n_loc)];
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  int o = 1;
+  while (o < nt) o <<= 1;
+  for (o >>= 1; o > 0; o >>= 1) {
+    if (threadIdx.x < o && threadIdx.x + o < nt) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  return sm[0];
+}
+
 // optimal_step_size, lib/ode.py:529-538, in fp32 like the reference's traced scalars.
 __device__ __forceinline__ float next_dt(float last, float ratio, int order) {
   const float dfactor = (ratio < 1.0f) ? 1.0f : 0.2f;
