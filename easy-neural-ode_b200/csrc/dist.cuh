@@ -4,8 +4,9 @@
 //
 // What travels per solver iteration:
 //   forward : all-gather of the per-sample fp64 partial sums of (err/tol)^2  (kC * B_global doubles)
-//   adjoint : the same + per-sample t_bar pieces, and ONE all-reduce of the four stage combinations of
-//             the params_bar block (4 P floats): everything downstream of the batch sum is linear.
+//   adjoint : ONE all-gather of a packed per-rank record (the same partial sums + the per-sample t_bar pieces
+//             of all six stages, adj_host.cuh) and ONE all-reduce of the four stage combinations of the
+//             params_bar block (4 P floats): everything downstream of the batch sum is linear.
 // After the exchange every rank holds bit-identical inputs and runs the same one-CTA controller, so the
 // global accept / reject sequence is the single-device sequence for the concatenated batch.
 #pragma once
