@@ -18,7 +18,7 @@ TABLEAUX = {"dopri5": 0, "heun": 1, "fehlberg": 2, "bosh": 3, "rk_fehlberg": 4, 
 # every symbol include/eno.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["eno_abi_version", "eno_last_error_string", "eno_create", "eno_destroy", "eno_param_count",
            "eno_adjoint_state_size", "eno_workspace_bytes", "eno_odeint_fwd", "eno_odeint_fwd_vmap", "eno_odeint_bwd", "eno_odeint_bwd_sepaux", "eno_rhs",
-           "eno_profile_enable", "eno_profile_read", "eno_ffma_peak", "eno_comm_unique_id", "eno_comm_init",
+           "eno_mnist_head", "eno_momentum_update", "eno_profile_enable", "eno_profile_read", "eno_ffma_peak", "eno_comm_unique_id", "eno_comm_init",
            "eno_comm_destroy", "eno_set_deferred", "eno_read_stats"]
 
 
@@ -79,6 +79,10 @@ def lib():
                                         vp, vp, vp, C.POINTER(Stats), vp, i32, vp]
     L.eno_rhs.restype = i32
     L.eno_rhs.argtypes = [vp, C.POINTER(Desc), i32, i32, vp, f32, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]
+    L.eno_mnist_head.restype = i32
+    L.eno_mnist_head.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp]
+    L.eno_momentum_update.restype = i32
+    L.eno_momentum_update.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), f32, f32, vp, vp, vp]
     L.eno_profile_enable.restype = i32
     L.eno_profile_enable.argtypes = [vp, i32]
     L.eno_profile_read.restype = i32

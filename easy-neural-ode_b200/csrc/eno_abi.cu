@@ -12,6 +12,7 @@
 #include "cl_kernels.cuh"
 #include "cl_vmap.cuh"
 #include "fwd_kernels.cuh"
+#include "head_kernels.cuh"
 #include "tableaux.cuh"
 
 using namespace eno;
@@ -441,6 +442,47 @@ int32_t eno_odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, c
   return eno_odeint_bwd_sepaux(ctx, desc, B, ys, ts, T, params, nullptr, g_y, g_r, rtol, atol, mxstep, workspace,
                                workspace_bytes, y0_bar_out, r0_bar_out, nullptr, ts_bar_out, params_bar_out, stats_host,
                                trace_out, trace_cap, stream_);
+}
+
+// ---- the rest of mnist.py's update() around the ODE block (head_kernels.cuh) ----------------------
+int32_t eno_mnist_head(eno_ctx* ctx, int32_t B, int32_t D, int32_t C, const float* y1, const int64_t* labels, const float* W,
+                       const float* b, float inv_count, float* scratch, float* loss_out, float* gy_out, float* gW_out,
+                       float* gb_out, void* stream_) {
+  if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_mnist_head: ctx is null");
+  if (B <= 0 || D <= 0 || C <= 0 || C > kHeadMaxClasses) return fail(ctx, ENO_E_ARG, "eno_mnist_head: bad sizes (classes <= 32)");
+  if (!y1 || !labels || !W || !b || !scratch || !loss_out || !gy_out || !gW_out || !gb_out)
+    return fail(ctx, ENO_E_ARG, "eno_mnist_head: null pointer");
+  if ((size_t)D * 4 > 48 * 1024) return fail(ctx, ENO_E_UNSUPPORTED, "eno_mnist_head: D too large for the row kernel");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+  float* s = scratch;                       // [B][D]
+  float* dl = scratch + (size_t)B * D;      // [B][C]
+  float* loss_rows = dl + (size_t)B * C;    // [B]
+  k_head_rows<<<B, 256, (size_t)D * 4, stream>>>(y1, labels, W, b, D, C, inv_count, s, dl, loss_rows, gy_out);
+  const int n = D * C + C + 1;
+  k_head_wgrad<<<(n + 255) / 256, 256, 0, stream>>>(s, dl, loss_rows, B, D, C, gW_out, gb_out, loss_out);
+  ENO_CUDA(ctx, cudaGetLastError());
+  return ENO_OK;
+}
+
+int32_t eno_momentum_update(eno_ctx* ctx, int32_t n_blocks, float* const* params, float* const* velocity,
+                            const float* const* grads, const int64_t* sizes, float lr, float mass, const int32_t* ok_a,
+                            const int32_t* ok_b, void* stream_) {
+  if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_momentum_update: ctx is null");
+  if (n_blocks < 1 || n_blocks > 3 || !params || !velocity || !grads || !sizes)
+    return fail(ctx, ENO_E_ARG, "eno_momentum_update: 1..3 parameter blocks");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+  MomentumBlocks m = {};
+  long long total = 0;
+  for (int k = 0; k < n_blocks; ++k) {
+    m.p[k] = params[k]; m.v[k] = velocity[k]; m.g[k] = grads[k]; m.n[k] = sizes[k];
+    total = sizes[k] > total ? sizes[k] : total;
+  }
+  const int grid = (int)((total + 255) / 256 < 4LL * ctx->sm_count ? (total + 255) / 256 : 4LL * ctx->sm_count);
+  k_momentum<<<grid > 0 ? grid : 1, 256, 0, stream>>>(m, lr, mass, ok_a, ok_b);
+  ENO_CUDA(ctx, cudaGetLastError());
+  return ENO_OK;
 }
 
 // ---- deferred launch mode (CUDA-graph capturable solves) ----------------------------------------

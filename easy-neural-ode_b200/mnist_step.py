@@ -3,14 +3,18 @@ PreODE (173-192) -> odeint_aux_one (330-341) -> PostODE (225-238) -> CE + lam*me
 -> jax.grad (528) -> momentum SGD (530-540).  With reg_type='fin' the ODE block is odeint_sepaux and the
 loss is CE + lam_fro*mean(fro) + lam_kin*mean(kin) (mnist.py:83, 472-478).
 
-Only what is needed to drive the hot path and to report the headline metric (train steps/s);
-the head (sigmoid + Linear(10) on [B, 784]) is a handful of tiny torch ops, everything inside the
-ODE block is libeno.so.
+Only what is needed to drive the hot path and to report the headline metric (train steps/s).  Everything
+on the device is libeno.so: the ODE block, and - since the ~40 small framework launches of the head and the
+optimiser were 8 % of a step - PostODE + loss + its gradients (eno_mnist_head) and the momentum update
+(eno_momentum_update) too.  ``loss_and_grads_autograd`` keeps the torch.autograd formulation over the public
+odeint_aux_one / odeint_sepaux surface; the tests hold the two against each other.
 """
+import ctypes as C
+
 import torch
 
 from .dynamics import MLPDynamics
-from . import ode
+from . import ode, _cabi
 
 
 class MnistNode:
@@ -56,8 +60,77 @@ class MnistNode:
         self.v_w = torch.zeros_like(self.post_w)
         self.v_b = torch.zeros_like(self.post_b)
 
+    # ---- library-only formulation (default) ---------------------------------------------------------
+    def _buffers(self, B):
+        """Per-batch-size device buffers of the fused head: cotangents handed to the adjoint, scratch, outputs."""
+        if getattr(self, "_buf_B", None) == B:
+            return self._buf
+        D, Cn, dev = self.dim, self.n_cls, self.device
+        fin = self.reg_type == "fin"
+        g_y = torch.zeros((2, B, D), device=dev)                      # cotangent of ys: only the last time is hit
+        n = B * self.world
+        if fin:
+            g_r = torch.zeros((2, 2, B), device=dev)
+            g_r[1, 0], g_r[1, 1] = self.lam_fro / n, self.lam_kin / n   # d(lam * mean(reg))/d reg[b], mnist.py:462-478
+        else:
+            g_r = torch.zeros((2, B), device=dev)
+            g_r[1] = self.lam / n
+        self._buf = dict(g_y=g_y, g_r=g_r, scratch=torch.empty(B * D + B * Cn + B, device=dev),
+                         loss=torch.zeros(1, device=dev), gwb=torch.empty(D * Cn + Cn, device=dev))
+        self._buf_B = B
+        return self._buf
+
     def loss_and_grads(self, images_u8, labels, eps):
-        """images [B,28,28,1] uint8, labels [B] int64, eps [B,784] Rademacher; all on self.device."""
+        """images [B,28,28,1] uint8, labels [B] int64, eps [B,784] Rademacher; all on self.device.
+        forward solve -> eno_mnist_head -> adjoint solve; no autograd graph is built."""
+        B = images_u8.shape[0]
+        D, Cn = self.dim, self.n_cls
+        buf = self._buffers(B)
+        L = _cabi.lib()
+        h = _cabi.ctx(self.device.index)
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        x0 = (images_u8.to(torch.float32) / 255.).reshape(B, -1)
+        ys, st_f, _ = ode._fwd_call(self.spec, "dopri5", x0, self.ts, self.p_ode, self.rtol, self.atol, float("inf"))
+        gw, gb = buf["gwb"][:D * Cn].view(D, Cn), buf["gwb"][D * Cn:]
+        with torch.cuda.device(self.device):
+            rc = L.eno_mnist_head(h, B, D, Cn, ode._ptr(ys[1]), ode._ptr(labels), ode._ptr(self.post_w), ode._ptr(self.post_b),
+                                  1.0 / (B * self.world), ode._ptr(buf["scratch"]), ode._ptr(buf["loss"]),
+                                  ode._ptr(buf["g_y"][1]), ode._ptr(gw), ode._ptr(gb), stream)
+        _cabi.check(rc, h, "eno_mnist_head")
+        if self.world > 1:
+            # the adjoint's params_bar is already the global sum (exchanged per iteration inside the
+            # solve); the 7,850 head gradients are summed here
+            import torch.distributed as dist
+            dist.all_reduce(buf["gwb"])
+        fin = self.reg_type == "fin"
+        out = ode._bwd_call(self.spec, _cabi.AUG_FIN if fin else _cabi.AUG_REG, True, ys, self.ts, self.p_ode, buf["g_y"],
+                            buf["g_r"], self.rtol, self.atol, float("inf"), eps=eps.contiguous() if fin else None)
+        p_bar, st_b = out[3], out[4]
+        ode.last_stats["fwd"], ode.last_stats["bwd"] = st_f, st_b
+        if ode._deferred["on"]:
+            nfe = torch.full((), float("nan"), device=self.device)
+        else:
+            nfe = torch.tensor(st_f["nfe"], dtype=torch.float32, device=self.device)
+        return dict(loss=buf["loss"][0], y1=ys[1], nfe=nfe, grads={"ode": p_bar, "post_w": gw, "post_b": gb},
+                    fwd_stats=st_f, bwd_stats=st_b)
+
+    def _momentum(self, g_ode, g_w, g_b, ok_a=None, ok_b=None):
+        """optimizers.momentum (mnist.py:530-540) for the three parameter blocks in one launch."""
+        L = _cabi.lib()
+        h = _cabi.ctx(self.device.index)
+        vp = C.c_void_p
+        ps = (vp * 3)(self.p_ode.data_ptr(), self.post_w.data_ptr(), self.post_b.data_ptr())
+        vs = (vp * 3)(self.v_ode.data_ptr(), self.v_w.data_ptr(), self.v_b.data_ptr())
+        gs = (vp * 3)(g_ode.data_ptr(), g_w.data_ptr(), g_b.data_ptr())
+        ns = (C.c_int64 * 3)(self.p_ode.numel(), self.post_w.numel(), self.post_b.numel())
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        with torch.cuda.device(self.device):
+            rc = L.eno_momentum_update(h, 3, ps, vs, gs, ns, float(self.lr), float(self.mass), ok_a, ok_b, stream)
+        _cabi.check(rc, h, "eno_momentum_update")
+
+    # ---- torch.autograd formulation over the public solver surface -----------------------------------
+    def loss_and_grads_autograd(self, images_u8, labels, eps):
+        """The same through odeint_aux_one / odeint_sepaux and torch.autograd (head and loss as torch ops)."""
         B = images_u8.shape[0]
         x0 = (images_u8.to(torch.float32) / 255.).reshape(B, -1)
         p_ode = self.p_ode.detach().requires_grad_(True)
@@ -132,7 +205,10 @@ class MnistNode:
         for dst, src in zip(self._g_in, (images_u8, labels, eps)):
             dst.copy_(src, non_blocking=True)
         graph.replay()
-        loss, ok_f, n_f, ok_b, n_b = info.tolist()           # the step's one device -> host read
+        raw = info.cpu()                                     # the step's one device -> host read
+        loss = float(raw[:1].view(torch.float32))
+        span = ode.CTRL_NITERS_I32 - ode.CTRL_DONE_I32
+        ok_f, n_f, ok_b, n_b = int(raw[1]), int(raw[1 + span]), int(raw[2 + span]), int(raw[2 + 2 * span])
         if not (ok_f and ok_b):
             # an iteration budget was too small: the guarded update left the parameters untouched; redo the
             # step in polled mode and move to the level it needs
@@ -176,18 +252,14 @@ class MnistNode:
         out = self.loss_and_grads(*self._g_in)
         wf = ode.workspace_tensor("fwd", self.device).view(torch.int32)
         wb = ode.workspace_tensor("bwd", self.device).view(torch.int32)
-        ok = (wf[ode.CTRL_DONE_I32] != 0) & (wb[ode.CTRL_DONE_I32] != 0)
         g = out["grads"]
-        for p, v, gr in ((self.p_ode, self.v_ode, g["ode"]), (self.post_w, self.v_w, g["post_w"]),
-                         (self.post_b, self.v_b, g["post_b"])):
-            v_new = self.mass * v + gr
-            v.copy_(torch.where(ok, v_new, v))                # NaN-safe: garbage gradients are never selected
-            p.copy_(torch.where(ok, p - self.lr * v_new, p))
-        return torch.stack([out["loss"].float(), wf[ode.CTRL_DONE_I32].float(), wf[ode.CTRL_NITERS_I32].float(),
-                            wb[ode.CTRL_DONE_I32].float(), wb[ode.CTRL_NITERS_I32].float()])
+        # guarded on the device by the two `done` words: garbage gradients never reach the parameters
+        self._momentum(g["ode"], g["post_w"], g["post_b"],
+                       C.c_void_p(wf.data_ptr() + 4 * ode.CTRL_DONE_I32), C.c_void_p(wb.data_ptr() + 4 * ode.CTRL_DONE_I32))
+        # one launch: [loss bits | fwd done, -, n_iters | bwd done, -, n_iters] as int32 (decoded on the host)
+        d, n = ode.CTRL_DONE_I32, ode.CTRL_NITERS_I32
+        return torch.cat([out["loss"].reshape(1).view(torch.int32), wf[d:n + 1], wb[d:n + 1]])
 
     def apply_grads(self, g_ode, g_w, g_b):
         """jax.experimental.optimizers.momentum: v <- mass*v + g ; x <- x - lr*v."""
-        self.v_ode.mul_(self.mass).add_(g_ode); self.p_ode.sub_(self.lr * self.v_ode)
-        self.v_w.mul_(self.mass).add_(g_w); self.post_w.sub_(self.lr * self.v_w)
-        self.v_b.mul_(self.mass).add_(g_b); self.post_b.sub_(self.lr * self.v_b)
+        self._momentum(g_ode.contiguous(), g_w.contiguous(), g_b.contiguous())

@@ -201,6 +201,25 @@ int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32
                 float* params_bar_out, float* eps_bar_dot_out, void* stream);
 
 /*
+ * The rest of mnist.py's update() around the ODE block, so that a train step is library launches only.
+ * eno_mnist_head replaces PostODE + the loss and its gradients (mnist.py:225-238, 90-94, 449-452, 528):
+ *   logits = sigmoid(y1) @ W + b;  loss = mean softmax cross-entropy;  inv_count = 1 / (global batch)
+ *   y1 [B, D]  labels [B] int64  W [D, C]  b [C]  scratch [B*D + B*C + B] floats
+ *   -> loss_out [1] (mean over this call's B rows), gy_out [B, D] = d(sum_r loss_r * inv_count)/dy1,
+ *      gW_out [D, C], gb_out [C] (sums over this call's rows; all-reduce them across ranks)
+ * eno_momentum_update replaces optimizers.momentum (mnist.py:530-540) for up to three parameter blocks in one
+ * launch: v <- mass * v + g; x <- x - lr * v, applied only if both guard words (device int32, may be NULL)
+ * are non-zero - in deferred mode they are the solves' `done` flags (first word pairs of the workspaces).
+ * Both calls only enqueue work (CUDA-graph capturable).
+ */
+int32_t eno_mnist_head(eno_ctx* ctx, int32_t B, int32_t D, int32_t C, const float* y1, const int64_t* labels, const float* W,
+                       const float* b, float inv_count, float* scratch, float* loss_out, float* gy_out, float* gW_out,
+                       float* gb_out, void* stream);
+int32_t eno_momentum_update(eno_ctx* ctx, int32_t n_blocks, float* const* params, float* const* velocity,
+                            const float* const* grads, const int64_t* sizes, float lr, float mass, const int32_t* ok_a,
+                            const int32_t* ok_b, void* stream);
+
+/*
  * Deferred launch mode (no reference counterpart).  By default a solve polls its device-side controller
  * once per chunk of iterations.  With eno_set_deferred(ctx, 1, fwd_iters, bwd_iters) the calls enqueue the
  * two initial-step launches plus EXACTLY that many iteration launches (iterations after termination exit

@@ -204,6 +204,34 @@ def test_mnist_fin_train_step_vs_oracle(cuda):
 
 
 @pytest.mark.parametrize("reg_type", ["our", "fin"])
+def test_library_head_matches_autograd_formulation(cuda, reg_type):
+    """MnistNode.loss_and_grads (forward solve -> eno_mnist_head -> adjoint solve, no autograd graph) against the
+    torch.autograd formulation over the public odeint_aux_one / odeint_sepaux surface with the head as torch ops;
+    and one momentum step of each leaves the same parameters."""
+    if reg_type == "fin":
+        _needs_cluster_path()
+    from easy_neural_ode_b200 import mnist_step
+    B, D = 100, 784
+    gen = torch.Generator().manual_seed(7)
+    images = torch.randint(0, 256, (B, 28, 28, 1), generator=gen, dtype=torch.uint8).to(cuda)
+    labels = torch.randint(0, 10, (B,), generator=gen).to(cuda)
+    eps = (torch.randint(0, 2, (B, D), generator=gen).float() * 2 - 1).to(cuda)
+    kw = dict(reg="none", reg_type="fin", lam_fro=1e-2, lam_kin=1e-2) if reg_type == "fin" else dict(reg="r3", lam=6e-5)
+    m = mnist_step.MnistNode(device=cuda, **kw)
+    m.post_b += 0.1 * torch.randn(10, generator=gen).to(cuda)
+    got = m.loss_and_grads(images, labels, eps)
+    want = m.loss_and_grads_autograd(images, labels, eps)
+    assert rel_err(got["loss"], want["loss"]) < 1e-6
+    assert float(got["nfe"]) == float(want["nfe"])
+    for k in ("ode", "post_w", "post_b"):
+        assert rel_err(got["grads"][k], want["grads"][k]) < 1e-5, k
+    p0, v0 = m.p_ode.clone(), m.v_ode.clone()
+    m.apply_grads(got["grads"]["ode"], got["grads"]["post_w"], got["grads"]["post_b"])
+    v_want = m.mass * v0 + got["grads"]["ode"]
+    assert torch.allclose(m.v_ode, v_want, rtol=1e-6, atol=0) and torch.allclose(m.p_ode, p0 - m.lr * v_want, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("reg_type", ["our", "fin"])
 def test_whole_step_graph_matches_polled_updates(cuda, reg_type):
     """update_graphed (the whole update() replayed as one CUDA graph over deferred-mode solves) must leave
     exactly the parameters the polled update() leaves, for both regulariser arms."""
