@@ -459,8 +459,8 @@ int32_t eno_mnist_head(eno_ctx* ctx, int32_t B, int32_t D, int32_t C, const floa
   float* dl = scratch + (size_t)B * D;      // [B][C]
   float* loss_rows = dl + (size_t)B * C;    // [B]
   k_head_rows<<<B, 256, (size_t)D * 4, stream>>>(y1, labels, W, b, D, C, inv_count, s, dl, loss_rows, gy_out);
-  const int n = D * C + C + 1;
-  k_head_wgrad<<<(n + 255) / 256, 256, 0, stream>>>(s, dl, loss_rows, B, D, C, gW_out, gb_out, loss_out);
+  const int n = D * C + C + 1;   // one warp per output
+  k_head_wgrad<<<(n + 7) / 8, 256, 0, stream>>>(s, dl, loss_rows, B, D, C, gW_out, gb_out, loss_out);
   ENO_CUDA(ctx, cudaGetLastError());
   return ENO_OK;
 }

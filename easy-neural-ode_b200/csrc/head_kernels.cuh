@@ -61,26 +61,32 @@ __global__ void __launch_bounds__(256) k_head_rows(const float* __restrict__ y1,
   }
 }
 
-// gW[d][c] = sum_r s[r][d] dl[r][c];  gb[c] = sum_r dl[r][c];  loss = mean_r loss_rows   (row order)
+// gW[d][c] = sum_r s[r][d] dl[r][c];  gb[c] = sum_r dl[r][c];  loss = mean_r loss_rows.
+// One warp per output: lanes stride the rows (a serial loop over B rows is B dependent L2 latencies), then a
+// fixed-shape shuffle tree - deterministic.
 __global__ void __launch_bounds__(256) k_head_wgrad(const float* __restrict__ s, const float* __restrict__ dl,
                                                     const float* __restrict__ loss_rows, int B, int D, int C,
                                                     float* __restrict__ gW, float* __restrict__ gb, float* __restrict__ loss_out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  float acc = 0.f;
   if (idx < D * C) {
     const int d = idx / C, c = idx - d * C;
-    float acc = 0.f;
-    for (int r = 0; r < B; ++r) acc = fmaf(s[(size_t)r * D + d], dl[(size_t)r * C + c], acc);
-    gW[idx] = acc;
+    for (int r = lane; r < B; r += 32) acc = fmaf(s[(size_t)r * D + d], dl[(size_t)r * C + c], acc);
   } else if (idx < D * C + C) {
     const int c = idx - D * C;
-    float acc = 0.f;
-    for (int r = 0; r < B; ++r) acc += dl[(size_t)r * C + c];
-    gb[c] = acc;
+    for (int r = lane; r < B; r += 32) acc += dl[(size_t)r * C + c];
   } else if (idx == D * C + C) {
-    float acc = 0.f;
-    for (int r = 0; r < B; ++r) acc += loss_rows[r];
-    *loss_out = acc / (float)B;
+    for (int r = lane; r < B; r += 32) acc += loss_rows[r];
+  } else {
+    return;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane != 0) return;
+  if (idx < D * C) gW[idx] = acc;
+  else if (idx < D * C + C) gb[idx - D * C] = acc;
+  else *loss_out = acc / (float)B;
 }
 
 // momentum SGD over up to three parameter blocks in one launch; the update is applied only when both guard
