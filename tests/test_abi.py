@@ -59,6 +59,10 @@ def test_sizes_reported_by_the_library():
     assert L.eno_adjoint_state_size(C.byref(d0), 100) == 2 * 78400 + 1 + 158568
     assert L.eno_workspace_bytes(C.byref(d), 100, 2, 0, 0) > 8 * 78400 * 4
     assert L.eno_workspace_bytes(C.byref(d), 100, 2, 0, 1) > 0
+    # 'fin' arm: two scalar states per sample and a live eps_bar block -> larger state, larger workspace
+    dfin = spec.desc(_cabi.AUG_FIN, True, reg_order=0)
+    assert L.eno_adjoint_state_size(C.byref(dfin), 100) == 2 * (78400 + 2 * 100) + 1 + 78400 + 158568
+    assert L.eno_workspace_bytes(C.byref(dfin), 100, 2, 0, 1) > L.eno_workspace_bytes(C.byref(d), 100, 2, 0, 1)
     bad = _cabi.Desc(0, 783, 100, 3, 1, 1)
     assert L.eno_workspace_bytes(C.byref(bad), 100, 2, 0, 0) == 0              # D % 4 != 0 is unsupported
 
@@ -82,3 +86,8 @@ def test_null_arguments_are_usage_errors():
     assert L.eno_odeint_bwd(None, None, 1, None, None, 2, None, None, None, 1e-5, 1e-5, 0, None, 0, None, None, None,
                             None, None, None, 0, None) == -1
     assert L.eno_profile_enable(None, 1) == -1
+    assert L.eno_odeint_bwd_sepaux(None, None, 1, None, None, 2, None, None, None, None, 1e-5, 1e-5, 0, None, 0, None, None,
+                                   None, None, None, None, None, 0, None) == -1
+    assert L.eno_odeint_fwd_vmap(None, None, 1, None, None, 2, None, 1e-5, 1e-5, 0, None, None, None, None, None) == -1
+    assert L.eno_mnist_head(None, 1, 4, 2, None, None, None, None, 1.0, None, None, None, None, None, None) == -1
+    assert L.eno_momentum_update(None, 1, None, None, None, None, 0.1, 0.9, None, None, None) == -1
