@@ -254,6 +254,46 @@ def test_whole_step_graph_matches_polled_updates(cuda, reg_type):
     assert torch.equal(a.p_ode, b.p_ode) and torch.equal(a.post_w, b.post_w) and torch.equal(a.v_ode, b.v_ode)
 
 
+@pytest.mark.parametrize("reg_type", ["our", "fin"])
+def test_adjoint_more_tiles_than_clusters(cuda, reg_type):
+    """B = 110 samples = 28 four-sample tiles, more than the 26 co-resident clusters: some clusters loop over two
+    tiles (the last one ragged).  Split solve + adjoint against the oracle, both regulariser arms."""
+    if reg_type == "fin":
+        _needs_cluster_path()
+    import easy_neural_ode_b200 as eno
+    from oracle import dynamics_oracle as do, ode_oracle as oo
+    Bn, D, H = 110, 16, 8
+    tol = 1e-6
+    p_cpu = do.init_mlp_params(D, H, seed=5, scale=2.0)
+    gen = torch.Generator().manual_seed(21)
+    x0 = torch.rand((Bn, D), generator=gen)
+    eps = torch.randint(0, 2, (Bn, D), generator=gen).float() * 2 - 1
+    gy = torch.randn((Bn, D), generator=gen)
+    ts = torch.tensor([0., 1.])
+    fin = reg_type == "fin"
+    spec = eno.MLPDynamics(D, H, reg="none" if fin else "r3", reg_type=reg_type)
+    cl = do.make_mnist_closures("none" if fin else "r3", reg_type=reg_type)
+    n_aux = 2 if fin else 1
+    zeros = tuple(torch.zeros(Bn) for _ in range(n_aux))
+    res, nfe_w = oo.odeint_split_fwd(cl["fwd"], (x0,) + zeros, ts, eps, p_cpu, n_aux=n_aux, rtol=tol, atol=tol)
+    gg = tuple(torch.zeros_like(r) for r in res)
+    gg[0][-1] = gy
+    for q in range(n_aux):
+        gg[1 + q][-1] = 0.01 * (q + 1)
+    want = oo.odeint_split_rev(cl["aug_dynamics"], tol, tol, math.inf, res, ts, (eps, p_cpu), gg)
+    pflat = flat_from_params(p_cpu).to(cuda).requires_grad_(True)
+    xd = x0.to(cuda).requires_grad_(True)
+    y0 = (xd,) + tuple(z.to(cuda) for z in zeros)
+    call = eno.odeint_sepaux if fin else eno.odeint_aux_one
+    outs, nfe = call(spec.fwd, spec.aug_dynamics, y0, ts.to(cuda), eps.to(cuda), pflat, rtol=tol, atol=tol)
+    assert float(nfe) == float(nfe_w)
+    loss = (outs[0][-1] * gy.to(cuda)).sum() + sum(0.01 * (q + 1) * outs[1 + q][-1].sum() for q in range(n_aux))
+    loss.backward()
+    assert rel_err(outs[0][-1], res[0][-1]) < RTOL
+    assert rel_err(xd.grad, want[0][0]) < 2e-5
+    assert rel_err(pflat.grad, flat_from_params(want[3])) < 2e-5
+
+
 def test_plain_odeint_adjoint_multiple_output_times(cuda):
     """odeint() with T = 5 output times and cotangents at every time: the adjoint runs T-1 backward segments
     (lib/ode.py:1510-1529), carries y_bar / t0_bar / params_bar across them and returns ts_bar for every time.
