@@ -79,8 +79,10 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_train_steps(n_steps, warmup, threads):
-    """The oracle port of one update() on host cores; returns (seconds per step, info)."""
+def cpu_train_steps(n_steps, warmup, threads, shards=1, budget_s=None):
+    """The oracle port of one update() on host cores; returns (seconds per step, info).
+    ``shards`` > 1: the global batch of a weak-scaling run (the per-GPU batches of all ranks, concatenated);
+    ``budget_s``: stop after that many seconds of timed steps (bounded sample)."""
     import torch
     from oracle import dynamics_oracle as do
     torch.set_num_threads(threads)
@@ -89,7 +91,10 @@ def cpu_train_steps(n_steps, warmup, threads):
     vel = None
     times, info = [], {}
     for s in range(-warmup, n_steps):
-        images, labels, eps = synth_batch(0, max(s, 0))
+        if budget_s is not None and times and sum(times) > budget_s:
+            break
+        parts = [synth_batch(r, max(s, 0)) for r in range(shards)]
+        images, labels, eps = (torch.cat([p[k] for p in parts]) for k in range(3))
         t0 = time.perf_counter()
         out = do.train_step_grads(p_ode, p_post, do.pre_ode(images), labels, eps, LAM, reg="r3", rtol=TOL, atol=TOL)
         if s >= 0:   # warm-up evaluations (s < 0) do not move the parameters
@@ -100,7 +105,7 @@ def cpu_train_steps(n_steps, warmup, threads):
             p_ode, p_post = params["ode"], params["post"]
             times.append(time.perf_counter() - t0)
         info = dict(nfe=float(out["nfe"]), fwd_iters=out["fwd_stats"]["n_iters"],
-                    bwd_iters=out["bwd_stats"][0]["n_iters"])
+                    bwd_iters=out["bwd_stats"][0]["n_iters"], steps_timed=len(times))
     return sum(times) / len(times), info
 
 
@@ -111,19 +116,21 @@ def run_reference(args, rank, world):
         return
     threads = len(os.sched_getaffinity(0))
     steps = max(1, min(args.steps, 40))
-    sec, info = cpu_train_steps(steps, 1, threads)
+    # same workload as the b200 arm at this N: weak scaling, the global batch is B per GPU
+    sec, info = cpu_train_steps(steps, 1, threads, shards=max(args.gpus, 1), budget_s=150.0)
+    steps = info["steps_timed"]
     val = 1.0 / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B, "rtol": TOL, "atol": TOL},
+        "config": {"workload": WORKLOAD, "global_batch": B * max(args.gpus, 1), "per_gpu_batch": B, "rtol": TOL, "atol": TOL},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"train steps 0..{steps - 1} from the initial parameters (forward solve + adjoint + "
                                    f"momentum update each) after 1 untimed warm-up evaluation, torch CPU fp32, {threads} threads; "
                                    f"last step nfe {info['nfe']}, adjoint iterations {info['bwd_iters']}"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "nfe_per_s": info["nfe"] * B * val,
+        "nfe_per_s": info["nfe"] * B * max(args.gpus, 1) * val,
     }
     print(json.dumps(line), flush=True)
 
