@@ -292,7 +292,7 @@ def main():
     rows_ms = ms[1] / max(cnt[1], 1)
     flop_rows = 6.0 * B * 12 * 2 * D * H + 70.0 * 2 * B * D   # DESIGN.md "Algorithmic work"
     achieved = flop_rows / (rows_ms * 1e-3) / 1e12 if rows_ms > 0 else 0.0
-    roofline = {"kernel": "k_adj_rows<STEP> (adjoint dopri5 iteration, per-sample blocks)", "bound": "tensor",
+    roofline = {"kernel": "k_cl_adj_rows<STEP> (adjoint dopri5 iteration, per-sample blocks; k_adj_rows on the streamed path)", "bound": "tensor",
                 "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                 "traffic": 2.02e6,   # dram__bytes_read + write per launch, ncu --set full (profiles/r1_ncu_v4_kernels.txt)
                 "peak_source": peak_src, "avg_launch_ms": rows_ms, "launches_timed": int(cnt[1]),
