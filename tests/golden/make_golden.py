@@ -89,6 +89,30 @@ def vmap_case(ref, do, B, D, H, params, x0):
     np.savez(os.path.join(OUT, "mlp_vmap.npz"), **rec)
 
 
+def css_case(ref):
+    """ffjord_tabular.py's odeint_sepaux call (reg_type 'our': state (y, logp, r)) with ConcatSquash dynamics on
+    small dims: groundwork for BASELINE config C2 (oracle/ffjord_oracle.py)."""
+    from oracle import ffjord_oracle as fo
+    B, D, H, seed, scale, tol = 5, 6, 12, 3, 1.5, 1e-5
+    params = fo.init_css_params(D, H, seed=seed, scale=scale)
+    g = torch.Generator().manual_seed(9)
+    x0 = torch.randn((B, D), generator=g)
+    eps = torch.randn((B, D), generator=g)
+    gy = torch.randn((B, D), generator=g)
+    cl = fo.make_ffjord_closures("r2", "our")
+    ts = torch.tensor([0., 1.])
+    y0 = (x0, torch.zeros(B, 1), torch.zeros(B, 1))
+    fwd_w = ref.ravel_first_arg(cl["fwd"], ravel_pytree(y0[0])[1])
+    rev_w = ref.ravel_first_arg(cl["aug_dynamics"], ravel_pytree(y0)[1])
+    (res, nfe), saved = ref._odeint_sepaux_fwd(fwd_w, rev_w, tol, tol, math.inf, y0, ts, eps, params)
+    gg = tuple(torch.zeros_like(r) for r in res)
+    gg[0][-1], gg[1][-1], gg[2][-1] = gy, 1.0 / B, 0.01 / B
+    out = ref._odeint_sepaux_rev(fwd_w, rev_w, tol, tol, math.inf, saved, (gg, None))
+    np.savez(os.path.join(OUT, "css_sepaux.npz"), B=B, D=D, H=H, seed=seed, scale=scale, tol=tol, x0=x0.numpy(),
+             eps=eps.numpy(), gy=gy.numpy(), y=res[0].numpy(), nfe=float(nfe), x0_bar=out[0][0].numpy(),
+             ts_bar=out[1].numpy(), eps_bar=out[2].numpy(), params_bar=flat_params(out[3]))
+
+
 def main():
     ref = load_reference_ode()
     torch.set_num_threads(8)
@@ -163,6 +187,7 @@ def main():
 
     fin_case(ref, do, B, D, H, params, x0, eps, gy)
     vmap_case(ref, do, B, D, H, params, x0)
+    css_case(ref)
 
     # ---- plain adjoint on the pendulum (lib/ode.py:1720-1722, 1765-1774), multi-output
     def pend(y, t, m, g):
