@@ -13,6 +13,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_sessionstart(session):
+    """The C-ABI library is a build product (git-ignored).  On a checkout that has not been built yet, build it
+    once (nvcc cross-compiles without a GPU; a few minutes) instead of failing every test that loads it."""
+    lib = os.path.join(ROOT, "easy-neural-ode_b200", "libeno.so")
+    if not os.path.exists(lib):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
