@@ -113,6 +113,20 @@ def css_case(ref):
              ts_bar=out[1].numpy(), eps_bar=out[2].numpy(), params_bar=flat_params(out[3]))
 
 
+def latent_case(ref):
+    """One trajectory of latent_ode.py's generative solve (latent_ode.py:344-350): odeint on (z, r) with the R3
+    augmented GenDynamics over 5 output times.  Groundwork for BASELINE config C3 (oracle/latent_oracle.py)."""
+    from oracle import latent_oracle as lo
+    D, U, layers, seed, scale, tol = 8, 12, 2, 4, 1.5, 1e-6
+    params = lo.init_gen_params(D, U, layers, seed=seed, scale=scale)
+    z0 = 0.5 * torch.randn((1, D), generator=torch.Generator().manual_seed(6))
+    ts = torch.tensor([0., 0.2, 0.45, 0.8, 1.0])
+    cl = lo.make_latent_closures("r3")
+    (zs, rs), nfe = ref.odeint(cl["aug_dynamics"], (z0, torch.zeros(())), ts, params, rtol=tol, atol=tol)
+    np.savez(os.path.join(OUT, "latent_gen.npz"), D=D, U=U, layers=layers, seed=seed, scale=scale, tol=tol,
+             z0=z0.numpy(), ts=ts.numpy(), zs=zs.numpy(), rs=rs.numpy(), nfe=float(nfe))
+
+
 def main():
     ref = load_reference_ode()
     torch.set_num_threads(8)
@@ -188,6 +202,7 @@ def main():
     fin_case(ref, do, B, D, H, params, x0, eps, gy)
     vmap_case(ref, do, B, D, H, params, x0)
     css_case(ref)
+    latent_case(ref)
 
     # ---- plain adjoint on the pendulum (lib/ode.py:1720-1722, 1765-1774), multi-output
     def pend(y, t, m, g):
