@@ -10,8 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ENO_LIB") or os.path.join(_HERE, "libeno.so")   # ENO_LIB: development variants only
 
 ENO_OK, ENO_MXSTEP, ENO_DT_UNDERFLOW, ENO_NONFINITE = 0, 1, 2, 3
-ARCH_MLP_SIGMOID = 0
-AUG_NONE, AUG_REG, AUG_ALL, AUG_FIN = 0, 1, 2, 3
+ARCH_MLP_SIGMOID, ARCH_CONCATSQUASH = 0, 1
+AUG_NONE, AUG_REG, AUG_ALL, AUG_FIN, AUG_FFJORD = 0, 1, 2, 3, 4
 TABLEAUX = {"dopri5": 0, "heun": 1, "fehlberg": 2, "bosh": 3, "rk_fehlberg": 4, "cash_karp": 5,
             "owrenzen": 6, "owrenzen5": 7, "tanyam": 8}
 
@@ -19,12 +19,12 @@ TABLEAUX = {"dopri5": 0, "heun": 1, "fehlberg": 2, "bosh": 3, "rk_fehlberg": 4, 
 SYMBOLS = ["eno_abi_version", "eno_last_error_string", "eno_create", "eno_destroy", "eno_param_count",
            "eno_adjoint_state_size", "eno_workspace_bytes", "eno_odeint_fwd", "eno_odeint_fwd_vmap", "eno_odeint_bwd", "eno_odeint_bwd_sepaux", "eno_rhs",
            "eno_mnist_head", "eno_momentum_update", "eno_profile_enable", "eno_profile_read", "eno_ffma_peak", "eno_comm_unique_id", "eno_comm_init",
-           "eno_comm_destroy", "eno_set_deferred", "eno_read_stats"]
+           "eno_comm_destroy", "eno_set_deferred", "eno_read_stats", "eno_gemm_tf32x3"]
 
 
 class Desc(C.Structure):
     _fields_ = [("arch", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("reg_order", C.c_int32),
-                ("aug", C.c_int32), ("eps_in_args", C.c_int32)]
+                ("aug", C.c_int32), ("eps_in_args", C.c_int32), ("n_hidden", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -99,6 +99,8 @@ def lib():
     L.eno_set_deferred.argtypes = [vp, i32, i32, i32]
     L.eno_read_stats.restype = i32
     L.eno_read_stats.argtypes = [vp, vp, C.POINTER(Stats), vp]
+    L.eno_gemm_tf32x3.restype = i32
+    L.eno_gemm_tf32x3.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, i32, vp]
     _lib = L
     return L
 

@@ -1,0 +1,583 @@
+// Second translation unit of libeno.so: the GEMM-pipeline engine for wide dynamics networks - the ConcatSquash
+// stacks of ffjord_tabular.py (BASELINE config C2).  Stage contractions run on tcgen05 as 3xTF32 (gemm_tc.cuh) with
+// fused epilogues (css_rhs.cuh); the adaptive dopri5 loop is a flat-state driver with a device-resident controller
+// (css_kernels.cuh); one loop iteration (6 right-hand sides + controller) is captured once into a CUDA graph and
+// replayed, so the host only polls the controller once per chunk of iterations.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "css_api.h"
+#include "css_kernels.cuh"
+#include "eno_ctx.cuh"
+#include "tableaux.cuh"
+
+using namespace eno;
+
+namespace {
+
+thread_local std::string g_css_err;
+
+int css_fail(eno_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  g_css_err = msg;
+  return code;
+}
+
+#define CSS_CUDA(ctx, expr)                                                                                       \
+  do {                                                                                                            \
+    cudaError_t e_ = (expr);                                                                                      \
+    if (e_ != cudaSuccess) return css_fail(ctx, ENO_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+inline size_t up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+inline int ld4(int w) { return (w + 3) / 4 * 4; }
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t n) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += up(n * sizeof(T));
+    return p;
+  }
+};
+
+struct Plan {
+  css::Net net;
+  css::Flat flat;
+  size_t P = 0;
+  float* params = nullptr;   // copies inside the workspace, so that a captured iteration graph only names the workspace
+  float* eps = nullptr;
+  float* seg_ts = nullptr;
+  size_t bytes = 0;
+  size_t zero_from = 0, zero_bytes = 0;   // transposed operands: their padding columns must read as zero
+};
+
+int aux_count(int aug) {
+  switch (aug) {
+    case ENO_AUG_NONE: return 0;
+    case ENO_AUG_FFJORD: return 1;
+    case ENO_AUG_REG: return 2;
+    case ENO_AUG_FIN: return 3;
+    case ENO_AUG_ALL: return 4;
+  }
+  return -1;
+}
+
+// mode: 0 forward solve, 1 adjoint solve
+void plan_build(const eno_dynamics_desc* d, int B, int T, int mode, void* ws, Plan* p) {
+  css::Net& n = p->net;
+  css::Flat& f = p->flat;
+  memset(&n, 0, sizeof(n));
+  memset(&f, 0, sizeof(f));
+  const int D = d->D, H = d->H, L = d->n_hidden + 1;
+  n.B = B; n.Bp = (B + 127) / 128 * 128; n.D = D; n.H = H; n.L = L;
+  n.mode = mode ? css::MODE_ADJ : (d->aug == ENO_AUG_NONE ? css::MODE_PLAIN : css::MODE_AUG);
+  n.fin = (d->aug == ENO_AUG_FIN);
+  switch (d->aug) {
+    case ENO_AUG_NONE: n.nq = 0; break;
+    case ENO_AUG_FFJORD: case ENO_AUG_FIN: n.nq = 1; break;
+    default: n.nq = d->reg_order ? 2 : 1;
+  }
+  n.ldD = ld4(D);
+  n.hmax = std::max(H, D);
+  size_t po = 0;
+  for (int l = 0; l < L; ++l) {
+    n.din[l] = l == 0 ? D : H;
+    n.dout[l] = l == L - 1 ? D : H;
+    n.ldi[l] = ld4(n.din[l]);
+    n.ldo[l] = ld4(n.dout[l]);
+    n.poff[l] = po;
+    po += (size_t)n.din[l] * n.dout[l] + 4 * (size_t)n.dout[l];
+  }
+  p->P = po;
+  const size_t BD = (size_t)B * D;
+  const int na = aux_count(d->aug);
+  f.B = B; f.D = D; f.n_aux = na;
+  f.oAUX = BD;
+  if (mode) {
+    f.oYB = BD + (size_t)na * B;
+    f.oAUXB = f.oYB + BD;
+    f.oT0 = f.oAUXB + (size_t)na * B;
+    f.oEB = f.oT0 + 1;
+    f.oPR = f.oEB + BD;
+    f.N = f.oPR + p->P;
+    f.n_feed = f.oAUXB;    // y, aux, y_bar (the aux_bar blocks are constants read from the state ring)
+    f.tsign = -1.f;
+  } else {
+    f.N = BD + (size_t)na * B;
+    f.n_feed = BD;
+    f.tsign = 1.f;
+  }
+  const bool adj = mode != 0;
+  Carver cv{static_cast<char*>(ws)};
+  f.ctrl = cv.take<Ctrl>(1);
+  f.Y = cv.take<float>(3 * f.N);
+  f.F = cv.take<float>(3 * f.N);
+  f.KS = cv.take<float>(5 * f.N);
+  f.MID = cv.take<float>(2 * f.N);
+  f.YS = cv.take<float>(f.n_feed);
+  f.n_part = 2048;
+  f.part = cv.take<double>(2 * (size_t)f.n_part);
+  f.out = cv.take<float>((size_t)std::max(T, 2) * f.N);
+  p->params = cv.take<float>(p->P);
+  p->eps = cv.take<float>(BD);
+  p->seg_ts = cv.take<float>(4);
+  n.eps = p->eps;
+  n.tval = cv.take<float>(4);
+  for (int l = 0; l < L; ++l) {
+    const float* base = p->params ? p->params + n.poff[l] : nullptr;
+    const size_t dd = (size_t)n.din[l] * n.dout[l];
+    n.b[l] = base;
+    n.W[l] = base ? base + n.dout[l] : nullptr;
+    n.wb[l] = base ? base + n.dout[l] + dd : nullptr;
+    n.bg[l] = base ? base + 2 * (size_t)n.dout[l] + dd : nullptr;
+    n.wg[l] = base ? base + 3 * (size_t)n.dout[l] + dd : nullptr;
+    n.WT2[l] = cv.take<float>(2 * (size_t)n.dout[l] * n.ldi[l]);
+    if (adj) n.W2[l] = cv.take<float>(2 * (size_t)n.din[l] * n.ldo[l]);
+    n.G[l] = cv.take<float>(n.dout[l]);
+    n.G1[l] = cv.take<float>(n.dout[l]);
+    n.CC[l] = cv.take<float>(n.dout[l]);
+    n.X2[l] = cv.take<float>(2 * n.xplane(l));
+    n.LIN[l] = cv.take<float>((size_t)B * n.ldo[l]);
+    if (l < L - 1) n.S[l] = cv.take<float>((size_t)B * n.ldo[l]);
+    if (adj) {
+      n.A1[l] = cv.take<float>(2 * (size_t)B * n.ldo[l]);
+      n.V[l] = cv.take<float>(2 * (size_t)B * n.ldo[l]);
+      n.WQ[l] = cv.take<float>(2 * (size_t)B * n.ldo[l]);
+      n.WW[l] = cv.take<float>((size_t)B * n.ldo[l]);
+      n.AB2[l] = cv.take<float>(2 * n.abplane(l));
+      n.WP[l] = cv.take<float>(3 * (size_t)n.din[l] * n.dout[l]);
+    }
+  }
+  n.cr_chunks = 16;
+  if (adj) {
+    n.CR = cv.take<float>((size_t)L * n.cr_chunks * 4 * n.hmax);
+    n.TC = cv.take<float>((size_t)L * n.hmax);
+    n.XB1 = cv.take<float>(2 * (size_t)B * n.ldD);
+    n.EBD = cv.take<float>((size_t)B * n.ldD);
+    n.YBDOT = cv.take<float>((size_t)B * n.ldD);
+  }
+  n.F = cv.take<float>((size_t)B * n.ldD);
+  n.JE = cv.take<float>((size_t)B * n.ldD);
+  n.Y1 = cv.take<float>((size_t)B * n.ldD);
+  n.DIV = cv.take<float>(B); n.RR = cv.take<float>(B); n.FRO = cv.take<float>(B); n.KIN = cv.take<float>(B);
+  p->zero_from = cv.off;
+  if (adj)
+    for (int l = 0; l < L; ++l) {
+      n.XT2[l] = cv.take<float>(2 * n.xtplane(l));
+      n.ABT2[l] = cv.take<float>(2 * n.abtplane(l));
+    }
+  p->zero_bytes = cv.off - p->zero_from;
+  p->bytes = cv.off + 1024;
+}
+
+int pick_bn(int M, int N) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("ENO_CSS_BN"); forced = e ? atoi(e) : 0; }
+  if (N < 128) return 64;
+  if (forced == 64 || forced == 128) return forced;
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  return tiles < 100 ? 64 : 128;
+}
+
+template <class Epi>
+cudaError_t gemm(const tc::GemmOperand& A, const tc::GemmOperand& Bm, int M, int N, int splits, const int* done, const Epi& epi,
+                 cudaStream_t st, std::string* err) {
+  return pick_bn(M, N) == 128 ? tc::launch_gemm<128>(A, Bm, M, N, splits, done, epi, st, err)
+                              : tc::launch_gemm<64>(A, Bm, M, N, splits, done, epi, st, err);
+}
+
+#define CSS_G(expr)                                                                   \
+  do {                                                                                \
+    cudaError_t e_ = (expr);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      if (err->empty()) *err = std::string(#expr) + ": " + cudaGetErrorString(e_);    \
+      return ENO_E_CUDA;                                                              \
+    }                                                                                 \
+  } while (0)
+
+// One evaluation of the integrated function into the stage slot (or k_override).
+int css_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, int sms, cudaStream_t st, std::string* err) {
+  const css::Net& n = p.net;
+  const css::Flat& f = p.flat;
+  const int L = n.L, B = n.B, Bp = n.Bp;
+  const int* done = (init_mode == css::ST_STAGE) ? &f.ctrl->done : nullptr;
+  const int egrid = std::min<int>((int)((std::max(f.n_feed, (size_t)n.hmax) + 255) / 256), 4 * sms);
+  css::k_css_stage<<<egrid, 256, 0, st>>>(f, n, stage, init_mode);
+  // forward: primal stream, then the tangent streams stacked
+  for (int l = 0; l < L; ++l) {
+    tc::GemmOperand A{n.X2[l], 3 * Bp, n.din[l], n.ldi[l], n.xplane(l), 0};
+    tc::GemmOperand W{n.WT2[l], n.dout[l], n.din[l], n.ldi[l], (size_t)n.dout[l] * n.ldi[l], 0};
+    CSS_G(gemm(A, W, B, n.dout[l], 1, done, css::EpiPrimal{n, l}, st, err));
+  }
+  if (n.nq > 0) {
+    for (int l = 0; l < L; ++l) {
+      tc::GemmOperand A{n.X2[l], 3 * Bp, n.din[l], n.ldi[l], n.xplane(l), Bp};
+      tc::GemmOperand W{n.WT2[l], n.dout[l], n.din[l], n.ldi[l], (size_t)n.dout[l] * n.ldi[l], 0};
+      CSS_G(gemm(A, W, n.nq * Bp, n.dout[l], 1, done, css::EpiTangent{n, l}, st, err));
+    }
+  }
+  if (n.mode != css::MODE_PLAIN) css::k_css_seed<<<(B * 32 + 255) / 256, 256, 0, st>>>(f, n);
+  if (n.mode == css::MODE_ADJ) {
+    // reverse: tangent streams
+    if (n.nq > 0) {
+      for (int l = L - 1; l >= 0; --l) {
+        tc::GemmOperand A{n.AB2[l], 3 * Bp, n.dout[l], n.ldo[l], n.abplane(l), Bp};
+        tc::GemmOperand W{n.W2[l], n.din[l], n.dout[l], n.ldo[l], (size_t)n.din[l] * n.ldo[l], 0};
+        if (l > 0) CSS_G(gemm(A, W, n.nq * Bp, n.din[l], 1, done, css::EpiTanRev{n, l}, st, err));
+        else CSS_G(gemm(A, W, n.nq * Bp, n.din[l], 1, done, css::EpiTanRev0{n}, st, err));
+      }
+    }
+    css::k_css_seed2<<<std::min((int)(((size_t)B * n.D + 255) / 256), 4 * sms), 256, 0, st>>>(f, n);
+    for (int l = L - 1; l >= 0; --l) {
+      tc::GemmOperand A{n.AB2[l], 3 * Bp, n.dout[l], n.ldo[l], n.abplane(l), 0};
+      tc::GemmOperand W{n.W2[l], n.din[l], n.dout[l], n.ldo[l], (size_t)n.din[l] * n.ldo[l], 0};
+      if (l > 0) CSS_G(gemm(A, W, B, n.din[l], 1, done, css::EpiPrimRev{n, l}, st, err));
+      else CSS_G(gemm(A, W, B, n.din[l], 1, done, css::EpiPrimRev0{n}, st, err));
+    }
+    // weight gradients: contraction over the batch, one K-split per row stream
+    for (int l = 0; l < L; ++l) {
+      const int K = (1 + n.nq) * Bp;
+      tc::GemmOperand A{n.XT2[l], n.din[l], K, 3 * Bp, n.xtplane(l), 0};
+      tc::GemmOperand Bt{n.ABT2[l], n.dout[l], K, 3 * Bp, n.abtplane(l), 0};
+      CSS_G(gemm(A, Bt, n.din[l], n.dout[l], 1 + n.nq, done, css::EpiWgrad{n.WP[l], n.din[l], n.dout[l]}, st, err));
+    }
+    css::k_css_colred<<<dim3((n.hmax + 31) / 32, n.cr_chunks, L), dim3(32, 8), 0, st>>>(f, n);
+    css::k_css_colfin<<<(n.hmax + 127) / 128, 128, 0, st>>>(f, n, stage, init_mode, k_override ? k_override + f.oPR : nullptr);
+  }
+  const size_t work = std::max((size_t)B * n.D, n.mode == css::MODE_ADJ ? (size_t)n.H * n.H : (size_t)1);
+  css::k_css_assemble<<<std::min((int)((work + 255) / 256), 8 * sms), 256, 0, st>>>(f, n, stage, init_mode, k_override);
+  CSS_G(cudaGetLastError());
+  return 0;
+}
+
+int css_prepare(eno_ctx* ctx, Plan& p, const float* params, const float* eps, cudaStream_t st) {
+  const css::Net& n = p.net;
+  Tableau* tab = &ctx->tabs[ENO_TABLEAU_DOPRI5];
+  CSS_CUDA(ctx, cudaMemcpyToSymbolAsync(css::c_tab, tab, sizeof(Tableau), 0, cudaMemcpyHostToDevice, st));
+  CSS_CUDA(ctx, cudaMemcpyAsync(p.params, params, p.P * 4, cudaMemcpyDeviceToDevice, st));
+  if (eps) CSS_CUDA(ctx, cudaMemcpyAsync(p.eps, eps, (size_t)n.B * n.D * 4, cudaMemcpyDeviceToDevice, st));
+  else CSS_CUDA(ctx, cudaMemsetAsync(p.eps, 0, (size_t)n.B * n.D * 4, st));
+  if (p.zero_bytes) CSS_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<char*>(p.flat.ctrl) + p.zero_from, 0, p.zero_bytes, st));
+  for (int l = 0; l < n.L; ++l) {
+    // forward operand: W^T [dout][din];  reverse operand: W [din][dout]
+    tc::k_split_planes<<<512, 256, 0, st>>>(n.W[l], n.din[l], n.dout[l], n.dout[l], n.WT2[l], n.ldi[l], (size_t)n.dout[l] * n.ldi[l], 1);
+    if (n.W2[l])
+      tc::k_split_planes<<<512, 256, 0, st>>>(n.W[l], n.din[l], n.dout[l], n.dout[l], n.W2[l], n.ldo[l], (size_t)n.din[l] * n.ldo[l], 0);
+  }
+  if (n.nq > 0) css::k_css_eps<<<std::min((int)(((size_t)n.B * n.D + 255) / 256), 1024), 256, 0, st>>>(n);
+  CSS_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+// cached graph of one loop iteration, keyed by everything its kernel arguments depend on
+struct GraphKey {
+  void* ws; int B, D, H, L, aug, reg, mode, T;
+  bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
+};
+struct CssState {
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  int use_graph = 1;
+  int hint[2] = {8, 8};
+};
+
+CssState* state_of(eno_ctx* ctx) {
+  if (!ctx->css) {
+    CssState* s = new CssState();
+    if (const char* e = getenv("ENO_CSS_GRAPH")) s->use_graph = atoi(e);
+    ctx->css = s;
+  }
+  return static_cast<CssState*>(ctx->css);
+}
+
+int enqueue_iteration(const Plan& p, int sms, cudaStream_t st, std::string* err) {
+  for (int s = 1; s <= 6; ++s) {
+    int rc = css_rhs_launch(p, s, css::ST_STAGE, nullptr, sms, st, err);
+    if (rc) return rc;
+  }
+  const int fgrid = std::min<int>((int)((p.flat.N + 255) / 256), p.flat.n_part);
+  css::k_flat_finish<<<fgrid, 256, 0, st>>>(p.flat);
+  css::k_flat_out<<<std::min<int>((int)((p.flat.N + 255) / 256), 4 * sms), 256, 0, st>>>(p.flat);
+  return 0;
+}
+
+// Runs the adaptive loop to completion on an initialised state (Y[0] / out[0] set, controller reset).
+int run_loop(eno_ctx* ctx, const Plan& p, const GraphKey& key, int which, eno_stats* stats, int* launches, cudaStream_t st) {
+  CssState* S = state_of(ctx);
+  std::string err;
+  const int sms = ctx->sm_count;
+  int rc;
+  // initial step: f0, norms, f(y0 + h0 f0), norms
+  if ((rc = css_rhs_launch(p, 0, css::ST_INIT0, nullptr, sms, st, &err))) return css_fail(ctx, rc, err);
+  const int igrid = std::min<int>((int)((p.flat.N + 255) / 256), p.flat.n_part);
+  css::k_flat_init<<<igrid, 256, 0, st>>>(p.flat, 0);
+  if ((rc = css_rhs_launch(p, 0, css::ST_INIT1, nullptr, sms, st, &err))) return css_fail(ctx, rc, err);
+  css::k_flat_init<<<igrid, 256, 0, st>>>(p.flat, 1);
+  cudaGraphExec_t exec = nullptr;
+  if (S->use_graph) {
+    auto it = S->graphs.find(key);
+    if (it != S->graphs.end()) exec = it->second;
+    else {
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        rc = enqueue_iteration(p, sms, st, &err);
+        cudaError_t e = cudaStreamEndCapture(st, &g);
+        if (rc == 0 && e == cudaSuccess && g && cudaGraphInstantiate(&exec, g, 0) == cudaSuccess) S->graphs[key] = exec;
+        else { exec = nullptr; cudaGetLastError(); }
+        if (g) cudaGraphDestroy(g);
+      } else cudaGetLastError();
+    }
+  }
+  int chunk = S->hint[which];
+  int n_launched_iters = 0;
+  for (;;) {
+    for (int k = 0; k < chunk; ++k) {
+      if (exec) CSS_CUDA(ctx, cudaGraphLaunch(exec, st));
+      else if ((rc = enqueue_iteration(p, sms, st, &err))) return css_fail(ctx, rc, err);
+      ++n_launched_iters;
+    }
+    CSS_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, p.flat.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+    CSS_CUDA(ctx, cudaStreamSynchronize(st));
+    if (ctx->mailbox->done) break;
+    chunk = 2;
+  }
+  const Ctrl& c = *ctx->mailbox;
+  S->hint[which] = std::min(64, c.n_iters + 1);
+  if (stats) {
+    stats->nfe = (float)c.nfe; stats->n_iters = c.n_iters; stats->n_accepted = c.n_accepted; stats->status = c.status;
+    stats->last_dt = c.dt; stats->last_t = c.t; stats->n_rhs = 2 + 6 * c.n_iters;
+    stats->n_launches = n_launched_iters;   // iteration graphs (or direct iteration sequences) enqueued
+  }
+  if (launches) *launches += n_launched_iters;
+  return c.status;
+}
+
+}  // namespace
+
+namespace eno {
+namespace css {
+
+bool desc_ok(const eno_dynamics_desc* d) {
+  return d && d->arch == ENO_ARCH_CONCATSQUASH && d->D > 0 && d->H > 0 && d->n_hidden >= 1 && d->n_hidden + 1 <= kMaxLayers &&
+         aux_count(d->aug) >= 0 && (d->reg_order == 0 || d->reg_order == 2);
+}
+
+int64_t param_count(const eno_dynamics_desc* d) {
+  int64_t P = 0;
+  const int L = d->n_hidden + 1;
+  for (int l = 0; l < L; ++l) {
+    const int64_t din = l == 0 ? d->D : d->H, dout = l == L - 1 ? d->D : d->H;
+    P += din * dout + 4 * dout;
+  }
+  return P;
+}
+
+int n_aux(const eno_dynamics_desc* d) { return aux_count(d->aug); }
+
+int64_t adjoint_state_size(const eno_dynamics_desc* d, int B) {
+  const int64_t BD = (int64_t)B * d->D, na = aux_count(d->aug);
+  return 2 * (BD + na * B) + 1 + BD + param_count(d);
+}
+
+size_t workspace_bytes(const eno_dynamics_desc* d, int B, int T, int mode) {
+  if (!desc_ok(d) || B <= 0) return 0;
+  Plan p;
+  plan_build(d, B, T, mode, nullptr, &p);
+  return p.bytes;
+}
+
+int odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* y0, const float* ts, int T, const float* params,
+               const float* eps, float rtol, float atol, int mxstep, void* ws, size_t ws_bytes, float* ys_out, float* aux_out,
+               eno_stats* stats, eno_trace_row* trace, int trace_cap, cudaStream_t st) {
+  if (!desc_ok(desc)) return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd: unsupported ConcatSquash descriptor");
+  if (B <= 0 || T < 1 || !y0 || !ts || !params || !ws || !ys_out) return css_fail(ctx, ENO_E_ARG, "eno_odeint_fwd: null pointer or empty batch");
+  const int na = aux_count(desc->aug);
+  if (na > 0 && !eps) return css_fail(ctx, ENO_E_ARG, "eno_odeint_fwd: the FFJORD closures read eps");
+  if (na > 0 && !aux_out) return css_fail(ctx, ENO_E_ARG, "eno_odeint_fwd: aux_out is required for augmented dynamics");
+  Plan p;
+  plan_build(desc, B, T, 0, ws, &p);
+  if (ws_bytes < p.bytes) return css_fail(ctx, ENO_E_WORKSPACE, "eno_odeint_fwd: workspace too small");
+  CSS_CUDA(ctx, cudaSetDevice(ctx->device));
+  p.flat.ts = ts;
+  p.flat.trace = trace;
+  int rc;
+  if ((rc = css_prepare(ctx, p, params, eps, st))) return rc;
+  const size_t N = p.flat.N, BD = (size_t)B * desc->D;
+  css::k_flat_reset<<<1, 1, 0, st>>>(p.flat.ctrl, rtol, atol, T, mxstep <= 0 ? INT_MAX : mxstep, trace ? trace_cap : 0, (float)N);
+  css::k_css_fwd_begin<<<std::min<int>((int)((N + 255) / 256), 1024), 256, 0, st>>>(p.flat, y0, nullptr);
+  int launches = 0;
+  int status = ENO_OK;
+  if (T > 1) {
+    GraphKey key{ws, B, desc->D, desc->H, desc->n_hidden, desc->aug, desc->reg_order, 0, T};
+    status = run_loop(ctx, p, key, 0, stats, &launches, st);
+    if (status < 0) return status;
+  } else if (stats) memset(stats, 0, sizeof(*stats));
+  // un-flatten the trajectory: out [T][N] -> ys [T][B][D], aux [T][n_aux][B]
+  CSS_CUDA(ctx, cudaMemcpy2DAsync(ys_out, BD * 4, p.flat.out, N * 4, BD * 4, T, cudaMemcpyDeviceToDevice, st));
+  if (na > 0)
+    CSS_CUDA(ctx, cudaMemcpy2DAsync(aux_out, (size_t)na * B * 4, p.flat.out + BD, N * 4, (size_t)na * B * 4, T, cudaMemcpyDeviceToDevice, st));
+  CSS_CUDA(ctx, cudaStreamSynchronize(st));
+  return status;
+}
+
+int odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* ys, const float* ts, int T, const float* params,
+               const float* eps, const float* g_y, const float* g_aux, float rtol, float atol, int mxstep, void* ws,
+               size_t ws_bytes, float* y0_bar_out, float* aux0_bar_out, float* eps_bar_out, float* ts_bar_out,
+               float* params_bar_out, eno_stats* stats, eno_trace_row* trace, int trace_cap, cudaStream_t st) {
+  if (!desc_ok(desc)) return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: unsupported ConcatSquash descriptor");
+  const int na = aux_count(desc->aug);
+  if (desc->aug != ENO_AUG_REG && desc->aug != ENO_AUG_FIN)
+    return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: the FFJORD adjoint integrates aug_dynamics ('our' or 'fin')");
+  if (B <= 0 || T < 1 || !ys || !ts || !params || !eps || !g_y || !g_aux || !ws || !y0_bar_out || !aux0_bar_out || !ts_bar_out ||
+      !params_bar_out)
+    return css_fail(ctx, ENO_E_ARG, "eno_odeint_bwd: null pointer or empty batch");
+  Plan p;
+  plan_build(desc, B, 2, 1, ws, &p);
+  if (ws_bytes < p.bytes) return css_fail(ctx, ENO_E_WORKSPACE, "eno_odeint_bwd: workspace too small");
+  CSS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t N = p.flat.N, BD = (size_t)B * desc->D, AB = (size_t)na * B;
+  if (T == 1) {
+    CSS_CUDA(ctx, cudaMemcpyAsync(y0_bar_out, g_y, BD * 4, cudaMemcpyDeviceToDevice, st));
+    CSS_CUDA(ctx, cudaMemcpyAsync(aux0_bar_out, g_aux, AB * 4, cudaMemcpyDeviceToDevice, st));
+    if (eps_bar_out) CSS_CUDA(ctx, cudaMemsetAsync(eps_bar_out, 0, BD * 4, st));
+    CSS_CUDA(ctx, cudaMemsetAsync(ts_bar_out, 0, 4, st));
+    CSS_CUDA(ctx, cudaMemsetAsync(params_bar_out, 0, p.P * 4, st));
+    CSS_CUDA(ctx, cudaStreamSynchronize(st));
+    return ENO_OK;
+  }
+  int rc;
+  if ((rc = css_prepare(ctx, p, params, eps, st))) return rc;
+  p.flat.ts = p.seg_ts;
+  p.flat.trace = trace;
+  const int egrid = std::min<int>((int)((N + 255) / 256), 2048);
+  int worst = ENO_OK, launches = 0;
+  std::string err;
+  for (int i = T - 1; i >= 1; --i) {
+    const float* gy_i = g_y + (size_t)i * BD;
+    const float* ga_i = g_aux + (size_t)i * AB;
+    css::k_css_seg_ts<<<1, 1, 0, st>>>(ts, i, p.seg_ts);
+    css::k_flat_reset<<<1, 1, 0, st>>>(p.flat.ctrl, rtol, atol, 2, mxstep <= 0 ? INT_MAX : mxstep, trace ? trace_cap : 0, (float)N);
+    css::k_css_adj_begin<<<egrid, 256, 0, st>>>(p.flat, ys + (size_t)i * BD, nullptr, gy_i, ga_i, i == T - 1);
+    // t_bar needs func(ys[i], ts[i]): the forward half of one evaluation (scratch slot: stage buffer 1)
+    if ((rc = css_rhs_launch(p, 0, css::ST_PROBE, p.flat.KS + N, ctx->sm_count, st, &err))) return css_fail(ctx, rc, err);
+    css::k_css_tbar<<<1, 512, 0, st>>>(p.flat, p.net, gy_i, ga_i, ts_bar_out + i);
+    GraphKey key{ws, B, desc->D, desc->H, desc->n_hidden, desc->aug, desc->reg_order, 1, 2};
+    int status = run_loop(ctx, p, key, 1, stats ? stats + (T - 1 - i) : nullptr, &launches, st);
+    if (status < 0) return status;
+    if (status != ENO_OK && worst == ENO_OK) worst = status;
+    p.flat.trace = nullptr;   // only the first segment is traced
+  }
+  css::k_css_adj_finish<<<egrid, 256, 0, st>>>(p.flat, g_y, g_aux, y0_bar_out, aux0_bar_out, eps_bar_out, ts_bar_out, params_bar_out, p.P);
+  CSS_CUDA(ctx, cudaGetLastError());
+  CSS_CUDA(ctx, cudaStreamSynchronize(st));
+  return worst;
+}
+
+// eno_rhs for ConcatSquash dynamics.  mode 0: f;  1: the augmented closure named by desc->aug;  2: its vjp.
+int rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int mode, int B, const float* y, float t, const float* params,
+        const float* eps, const float* y_bar, const float* aux_bar, void* ws, size_t ws_bytes, float* dy_out, float* aux_out,
+        float* ybar_dot_out, float* tbar_out, float* params_bar_out, float* eps_bar_dot_out, cudaStream_t st) {
+  if (!desc_ok(desc)) return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_rhs: unsupported ConcatSquash descriptor");
+  if (!y || !params || !ws || !dy_out || B <= 0) return css_fail(ctx, ENO_E_ARG, "eno_rhs: null pointer or empty batch");
+  eno_dynamics_desc d = *desc;
+  if (mode == 0) d.aug = ENO_AUG_NONE;
+  const int na = aux_count(d.aug);
+  if (mode > 0 && (!eps || !aux_out)) return css_fail(ctx, ENO_E_ARG, "eno_rhs: augmented modes need eps and aux_out");
+  if (mode == 2 && (!y_bar || !aux_bar || !ybar_dot_out || !tbar_out || !params_bar_out))
+    return css_fail(ctx, ENO_E_ARG, "eno_rhs: mode 2 needs y_bar, aux_bar and all outputs");
+  Plan p;
+  plan_build(&d, B, 2, mode == 2 ? 1 : 0, ws, &p);
+  if (ws_bytes < p.bytes) return css_fail(ctx, ENO_E_WORKSPACE, "eno_rhs: workspace too small");
+  CSS_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = css_prepare(ctx, p, params, eps, st))) return rc;
+  const size_t N = p.flat.N, BD = (size_t)B * d.D, AB = (size_t)na * B;
+  // solver time of the evaluation: ts[0] = tsign * t
+  const float tau = p.flat.tsign * t;
+  CSS_CUDA(ctx, cudaMemcpyAsync(p.seg_ts, &tau, 4, cudaMemcpyHostToDevice, st));
+  p.flat.ts = p.seg_ts;
+  css::k_flat_reset<<<1, 1, 0, st>>>(p.flat.ctrl, 1.f, 1.f, 2, INT_MAX, 0, (float)N);
+  CSS_CUDA(ctx, cudaMemsetAsync(p.flat.Y, 0, N * 4, st));
+  CSS_CUDA(ctx, cudaMemcpyAsync(p.flat.Y, y, BD * 4, cudaMemcpyDeviceToDevice, st));
+  if (mode == 2) {
+    CSS_CUDA(ctx, cudaMemcpyAsync(p.flat.Y + p.flat.oYB, y_bar, BD * 4, cudaMemcpyDeviceToDevice, st));
+    CSS_CUDA(ctx, cudaMemcpyAsync(p.flat.Y + p.flat.oAUXB, aux_bar, AB * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  std::string err;
+  float* k = p.flat.KS;
+  if ((rc = css_rhs_launch(p, 0, css::ST_PROBE, k, ctx->sm_count, st, &err))) return css_fail(ctx, rc, err);
+  const float sgn = (mode == 2) ? -1.f : 1.f;   // the adjoint slot holds -f, +div, -r
+  css::k_css_scale_copy<<<256, 256, 0, st>>>(k, sgn, BD, dy_out);
+  if (na > 0 && aux_out) css::k_css_scale_copy<<<64, 256, 0, st>>>(k + p.flat.oAUX, sgn, AB, aux_out);
+  if (mode == 2) {
+    CSS_CUDA(ctx, cudaMemcpyAsync(ybar_dot_out, k + p.flat.oYB, BD * 4, cudaMemcpyDeviceToDevice, st));
+    CSS_CUDA(ctx, cudaMemcpyAsync(tbar_out, k + p.flat.oT0, 4, cudaMemcpyDeviceToDevice, st));
+    CSS_CUDA(ctx, cudaMemcpyAsync(params_bar_out, k + p.flat.oPR, p.P * 4, cudaMemcpyDeviceToDevice, st));
+    if (eps_bar_dot_out) CSS_CUDA(ctx, cudaMemcpyAsync(eps_bar_dot_out, k + p.flat.oEB, BD * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  CSS_CUDA(ctx, cudaGetLastError());
+  CSS_CUDA(ctx, cudaStreamSynchronize(st));
+  return ENO_OK;
+}
+
+void destroy(eno_ctx* ctx) {
+  if (!ctx || !ctx->css) return;
+  CssState* s = static_cast<CssState*>(ctx->css);
+  for (auto& kv : s->graphs) cudaGraphExecDestroy(kv.second);
+  delete s;
+  ctx->css = nullptr;
+}
+
+}  // namespace css
+}  // namespace eno
+
+extern "C" {
+
+// Unit-test hook of the tensor-core contraction (declared in include/eno.h).
+int32_t eno_gemm_tf32x3(eno_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B,
+                        int32_t ldb, float* C, int32_t ldc, int32_t bn, int32_t splits, void* stream) {
+  if (!ctx || !A || !B || !C || M <= 0 || N <= 0 || K <= 0 || splits < 1 || (bn != 64 && bn != 128))
+    return css_fail(ctx, ENO_E_ARG, "eno_gemm_tf32x3: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CSS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int ka = (K + 3) / 4 * 4;
+  float *a2 = nullptr, *b2 = nullptr, *part = nullptr;
+  CSS_CUDA(ctx, cudaMalloc(&a2, (size_t)2 * M * ka * 4));
+  CSS_CUDA(ctx, cudaMalloc(&b2, (size_t)2 * N * ka * 4));
+  CSS_CUDA(ctx, cudaMemsetAsync(a2, 0, (size_t)2 * M * ka * 4, st));
+  CSS_CUDA(ctx, cudaMemsetAsync(b2, 0, (size_t)2 * N * ka * 4, st));
+  tc::k_split_planes<<<1024, 256, 0, st>>>(A, M, K, lda, a2, ka, (size_t)M * ka, 0);
+  tc::k_split_planes<<<1024, 256, 0, st>>>(B, N, K, ldb, b2, ka, (size_t)N * ka, 0);
+  tc::GemmOperand oa{a2, M, K, ka, (size_t)M * ka, 0}, ob{b2, N, K, ka, (size_t)N * ka, 0};
+  tc::EpiStore epi;
+  if (splits > 1) {
+    CSS_CUDA(ctx, cudaMalloc(&part, (size_t)splits * M * N * 4));
+    epi = tc::EpiStore{part, M, N, N, (size_t)M * N};
+  } else {
+    epi = tc::EpiStore{C, M, N, ldc, 0};
+  }
+  std::string err;
+  cudaError_t e = (bn == 128) ? tc::launch_gemm<128>(oa, ob, M, N, splits, nullptr, epi, st, &err)
+                              : tc::launch_gemm<64>(oa, ob, M, N, splits, nullptr, epi, st, &err);
+  if (e != cudaSuccess) {
+    cudaFree(a2); cudaFree(b2); if (part) cudaFree(part);
+    return css_fail(ctx, ENO_E_CUDA, "eno_gemm_tf32x3: " + (err.empty() ? std::string(cudaGetErrorString(e)) : err));
+  }
+  if (splits > 1) tc::k_sum_splits<<<256, 256, 0, st>>>(part, splits, (size_t)M * N, N, C, ldc);
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaFree(a2); cudaFree(b2); if (part) cudaFree(part);
+  if (es != cudaSuccess) return css_fail(ctx, ENO_E_CUDA, std::string("eno_gemm_tf32x3: ") + cudaGetErrorString(es));
+  return ENO_OK;
+}
+
+}  // extern "C"

@@ -6,7 +6,8 @@
 #include <cstring>
 #include <string>
 
-#include "dist.cuh"
+#include "eno_ctx.cuh"
+#include "css_api.h"
 #include "adj_host.cuh"
 #include "cl_aug_fwd.cuh"
 #include "cl_kernels.cuh"
@@ -17,20 +18,6 @@
 
 using namespace eno;
 
-struct eno_ctx {
-  int device = 0;
-  Ctrl* mailbox = nullptr;  // pinned host copy of the device controller
-  std::string err;
-  int hint_fwd = 8;         // launches to enqueue before the first poll
-  int hint_bwd = 8;
-  int sm_count = 148;
-  int path_mode = 0;        // 0 auto, 1 force streamed weights, 2 force cluster-resident (ENO_PATH)
-  Profiler prof;
-  DistCtx dist;             // world 1 unless eno_comm_init was called
-  Tableau* tabs = nullptr;  // pinned copies of all tableaux (sources of the constant-memory upload)
-  int deferred = 0;         // 1: enqueue a fixed number of iterations, never synchronise (graph capturable)
-  int spec_fwd = 0, spec_bwd = 0;
-};
 
 namespace {
 
@@ -184,6 +171,7 @@ int32_t eno_create(eno_ctx** out, int32_t device) {
 
 void eno_destroy(eno_ctx* ctx) {
   if (!ctx) return;
+  css::destroy(ctx);
   if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
   if (ctx->tabs) cudaFreeHost(ctx->tabs);
   delete ctx;
@@ -191,18 +179,20 @@ void eno_destroy(eno_ctx* ctx) {
 
 int64_t eno_param_count(const eno_dynamics_desc* d) {
   if (!d) return -1;
+  if (d->arch == ENO_ARCH_CONCATSQUASH) return css::desc_ok(d) ? css::param_count(d) : -1;
   return (int64_t)(d->D + 1) * d->H + d->H + (int64_t)(d->H + 1) * d->D + d->D;
 }
 
 int64_t eno_adjoint_state_size(const eno_dynamics_desc* d, int32_t B) {
   if (!d) return -1;
+  if (d->arch == ENO_ARCH_CONCATSQUASH) return css::desc_ok(d) ? css::adjoint_state_size(d, B) : -1;
   const int64_t n_aux = (d->aug == ENO_AUG_NONE) ? 0 : (d->aug == ENO_AUG_FIN ? 2 : 1);
   return 2 * ((int64_t)B * d->D + n_aux * B) + 1 + (d->eps_in_args ? (int64_t)B * d->D : 0) + eno_param_count(d);
 }
 
 size_t eno_workspace_bytes(const eno_dynamics_desc* d, int32_t B, int32_t T, int32_t tableau, int32_t mode) {
-  (void)T;
   (void)tableau;
+  if (d && d->arch == ENO_ARCH_CONCATSQUASH) return css::workspace_bytes(d, B, T, mode);
   if (!desc_ok(d) || B <= 0) return 0;
   if (mode == 0) return fwd_ws_bytes(B, d->D);
   return adj_ws_bytes(B, d->D, d->H, g_world, d->aug == ENO_AUG_FIN);
@@ -212,6 +202,12 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
                        const float* ts, int32_t T, const float* params, const float* eps, float rtol, float atol,
                        int32_t mxstep, void* workspace, size_t workspace_bytes, float* ys_out, float* aux_out,
                        eno_stats* stats_host, eno_trace_row* trace_out, int32_t trace_cap, void* stream_) {
+  if (ctx && desc && desc->arch == ENO_ARCH_CONCATSQUASH) {
+    if (tableau != ENO_TABLEAU_DOPRI5)
+      return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd: the ConcatSquash dynamics run dopri5 only (the tableau sweep is defined on the MNIST dynamics)");
+    return css::odeint_fwd(ctx, desc, B, y0, ts, T, params, eps, rtol, atol, mxstep, workspace, workspace_bytes, ys_out, aux_out,
+                           stats_host, trace_out, trace_cap, static_cast<cudaStream_t>(stream_));
+  }
   if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_odeint_fwd: ctx is null");
   if (!desc_ok(desc)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd: unsupported dynamics desc (MLP sigmoid, D%4==0, H%4==0)");
   const int aug = desc->aug;
@@ -398,6 +394,9 @@ int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32
                 size_t workspace_bytes, float* dy_out, float* aux_out, float* ybar_dot_out, float* tbar_out,
                 float* params_bar_out, float* eps_bar_dot_out, void* stream_) {
   if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_rhs: ctx is null");
+  if (desc && desc->arch == ENO_ARCH_CONCATSQUASH)
+    return css::rhs(ctx, desc, mode, B, y, t, params, eps, y_bar, r_bar, workspace, workspace_bytes, dy_out, aux_out, ybar_dot_out,
+                    tbar_out, params_bar_out, eps_bar_dot_out, static_cast<cudaStream_t>(stream_));
   if (!desc_ok(desc)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_rhs: unsupported dynamics desc");
   if (B <= 0 || !y || !params || !dy_out) return fail(ctx, ENO_E_ARG, "eno_rhs: null pointer or empty batch");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -422,6 +421,10 @@ int32_t eno_odeint_bwd_sepaux(eno_ctx* ctx, const eno_dynamics_desc* desc, int32
                               float* params_bar_out, eno_stats* stats_host, eno_trace_row* trace_out, int32_t trace_cap,
                               void* stream_) {
   if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_odeint_bwd: ctx is null");
+  if (desc && desc->arch == ENO_ARCH_CONCATSQUASH)
+    return css::odeint_bwd(ctx, desc, B, ys, ts, T, params, eps, g_y, g_aux, rtol, atol, mxstep, workspace, workspace_bytes,
+                           y0_bar_out, aux0_bar_out, eps_bar_out, ts_bar_out, params_bar_out, stats_host, trace_out, trace_cap,
+                           static_cast<cudaStream_t>(stream_));
   if (!desc_ok(desc)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: unsupported dynamics desc");
   ENO_CUDA(ctx, cudaSetDevice(ctx->device));
   if (desc->aug != ENO_AUG_NONE && desc->aug != ENO_AUG_REG && desc->aug != ENO_AUG_FIN)

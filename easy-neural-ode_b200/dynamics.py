@@ -69,7 +69,11 @@ class MLPDynamics:
 
     def desc(self, aug=_cabi.AUG_NONE, eps_in_args=False, reg_order=None):
         return _cabi.Desc(_cabi.ARCH_MLP_SIGMOID, self.dim, self.hidden,
-                          self.reg_order if reg_order is None else reg_order, aug, int(eps_in_args))
+                          self.reg_order if reg_order is None else reg_order, aug, int(eps_in_args), 0)
+
+    # closure kind -> (ENO_AUG_*, number of auxiliary state leaves)
+    AUG_OF_KIND = {"aug": (_cabi.AUG_REG, 1), "all": (_cabi.AUG_ALL, 3), "fin": (_cabi.AUG_FIN, 2)}
+    eps_kinds = ("all", "fin")     # closures that read eps
 
     # ---- parameters: Haiku dict layout <-> flat vector in ravel_pytree order ---------------
     def init_params(self, seed=0, device="cpu", scale=1.0):
@@ -99,3 +103,95 @@ class MLPDynamics:
         o1, o2, o3 = H, H + (D + 1) * H, H + (D + 1) * H + D
         return {L1: {"b": flat[:o1], "w": flat[o1:o2].reshape(D + 1, H)},
                 L2: {"b": flat[o2:o3], "w": flat[o3:].reshape(H + 1, D)}}
+
+
+class ConcatSquashDynamics:
+    """NN_Dynamics of ffjord_tabular.py:163-193: ``num_layers`` hidden ConcatSquashLinear layers of width ``hidden`` and
+    one back to ``dim``, softplus (``_logaddexp``, 92-103) between them:  u = (x W + b) * sigmoid(w_g t + b_g) + w_b t.
+
+    ``reg`` / ``reg_type`` are the script flags (ffjord_tabular.py:38, 52); any ``reg != 'none'`` means the fixed K = 2
+    Taylor term of the script's sol_recursive (116-136).  Closures, named as in init_model (235-297):
+      dynamics_wrap(x, t, params)                235
+      fwd(y, t, eps, params)                     the lambda at 303
+      ffjord_dynamics((y, p), t, eps, params)    250-258   (dy, -div)
+      aug_dynamics(ypr, t, eps, params)          270-284   (dy, -div, r) or, reg_type 'fin', (dy, -div, dfro, dkin)
+      all_aug_dynamics(ypr, t, eps, params)      286-297   (dy, -div, r, dfro, dkin)
+    Parameters: the Haiku dict of the module ({layer: {"w", "b", "w_gate", "b_gate", "w_bias"}}, the flattened form the
+    oracle uses) or one flat vector in ravel order, per layer [b | W | w_bias | b_gate | w_gate] (sub-modules linear,
+    linear_1 (hyper-bias, no bias term), linear_2 (hyper-gate) in sorted-key order).
+    """
+
+    def __init__(self, dim, hidden, num_layers=2, reg="none", reg_type="our"):
+        if reg not in ["none"] + REGS:
+            raise ValueError(f"--reg must be one of {['none'] + REGS}")
+        if reg_type not in ("our", "fin"):
+            raise ValueError("--reg_type must be 'our' or 'fin' (ffjord_tabular.py:52)")
+        if not 1 <= num_layers <= 5:
+            raise ValueError("ConcatSquashDynamics supports 1..5 hidden layers")
+        self.dim, self.hidden, self.num_layers, self.reg, self.reg_type = dim, hidden, num_layers, reg, reg_type
+        self.reg_order = 0 if reg == "none" else 2
+        self.dims = [dim] + [hidden] * num_layers + [dim]
+        self.dynamics_wrap = EnoFunc(self, "plain", ("params",))
+        self.fwd = EnoFunc(self, "plain", ("eps", "params"))
+        self.ffjord_dynamics = EnoFunc(self, "ffjord", ("eps", "params"))
+        self.aug_dynamics = EnoFunc(self, "aug" if reg_type == "our" else "fin", ("eps", "params"))
+        self.all_aug_dynamics = EnoFunc(self, "all", ("eps", "params"))
+
+    AUG_OF_KIND = {"ffjord": (_cabi.AUG_FFJORD, 1), "aug": (_cabi.AUG_REG, 2), "fin": (_cabi.AUG_FIN, 3), "all": (_cabi.AUG_ALL, 4)}
+    eps_kinds = ("ffjord", "aug", "fin", "all")
+
+    def __repr__(self):
+        return (f"ConcatSquashDynamics(dim={self.dim}, hidden={self.hidden}, num_layers={self.num_layers}, "
+                f"reg={self.reg!r}, reg_type={self.reg_type!r})")
+
+    @property
+    def layer_names(self):
+        return ["nn__dynamics/concat_squash_linear" + ("" if i == 0 else f"_{i}") for i in range(len(self.dims) - 1)]
+
+    @property
+    def n_params(self):
+        return sum(i * o + 4 * o for i, o in zip(self.dims[:-1], self.dims[1:]))
+
+    def desc(self, aug=_cabi.AUG_NONE, eps_in_args=False, reg_order=None):
+        return _cabi.Desc(_cabi.ARCH_CONCATSQUASH, self.dim, self.hidden,
+                          self.reg_order if reg_order is None else reg_order, aug, int(eps_in_args), self.num_layers)
+
+    def init_params(self, seed=0, device="cpu", scale=1.0):
+        """Haiku default init: truncated normal (+-2 sigma), sigma = 1/sqrt(fan_in) (fan_in = 1 for the two
+        hyper-networks of the scalar t); biases 0."""
+        g = torch.Generator().manual_seed(seed)
+
+        def tn(shape, fan_in):
+            w = torch.empty(shape, dtype=torch.float64)
+            torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=g)
+            return (w * (scale / math.sqrt(fan_in))).float().to(device)
+
+        params = {}
+        for name, d_in, d_out in zip(self.layer_names, self.dims[:-1], self.dims[1:]):
+            params[name] = {"w": tn((d_in, d_out), d_in), "b": torch.zeros(d_out, device=device),
+                            "w_gate": tn((1, d_out), 1), "b_gate": torch.zeros(d_out, device=device),
+                            "w_bias": tn((1, d_out), 1)}
+        return params
+
+    def flatten_params(self, params):
+        if isinstance(params, torch.Tensor):
+            if params.numel() != self.n_params:
+                raise ValueError(f"flat params must have {self.n_params} elements")
+            return params.reshape(-1)
+        parts = []
+        for n in self.layer_names:
+            p = params[n]
+            parts += [p["b"].reshape(-1), p["w"].reshape(-1), p["w_bias"].reshape(-1), p["b_gate"].reshape(-1),
+                      p["w_gate"].reshape(-1)]
+        return torch.cat(parts)
+
+    def unflatten_params(self, flat):
+        out, o = {}, 0
+        for n, d_in, d_out in zip(self.layer_names, self.dims[:-1], self.dims[1:]):
+            b = flat[o:o + d_out]; o += d_out
+            w = flat[o:o + d_in * d_out].reshape(d_in, d_out); o += d_in * d_out
+            wb = flat[o:o + d_out].reshape(1, d_out); o += d_out
+            bg = flat[o:o + d_out]; o += d_out
+            wg = flat[o:o + d_out].reshape(1, d_out); o += d_out
+            out[n] = {"w": w, "b": b, "w_gate": wg, "b_gate": bg, "w_bias": wb}
+        return out

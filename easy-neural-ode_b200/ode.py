@@ -269,6 +269,86 @@ class _OdeintSepauxFn(torch.autograd.Function):
         return None, None, None, None, y0_bar, r0_bar[0], r0_bar[1], ts_bar, eps_bar, p_bar
 
 
+def _bwd_call_split(spec, aug, n_aux, ys, ts, pflat, eps, g_y, g_aux, rtol, atol, mxstep):
+    """eno_odeint_bwd_sepaux for a dynamics family whose rev_func carries ``n_aux`` auxiliary states (g_aux [T, n_aux, B]).
+    -> (y0_bar, aux0_bar [n_aux, B], ts_bar, params_bar, eps_bar, stats)."""
+    L = _cabi.lib()
+    device = ys.device
+    h = _cabi.ctx(device.index)
+    T, B, D = ys.shape
+    desc = spec.desc(aug, True)
+    nbytes = L.eno_workspace_bytes(C.byref(desc), B, T, 0, 1)
+    ws = _workspace(device, nbytes, "bwd")
+    y0_bar = torch.empty((B, D), dtype=torch.float32, device=device)
+    a0_bar = torch.empty((n_aux, B), dtype=torch.float32, device=device)
+    ts_bar = torch.empty((T,), dtype=torch.float32, device=device)
+    p_bar = torch.empty((spec.n_params,), dtype=torch.float32, device=device)
+    eps_bar = torch.empty((B, D), dtype=torch.float32, device=device)
+    st = (_cabi.Stats * max(T - 1, 1))()
+    stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    with torch.cuda.device(device):
+        rc = L.eno_odeint_bwd_sepaux(h, C.byref(desc), B, _ptr(ys), _ptr(ts), T, _ptr(pflat), _ptr(eps), _ptr(g_y),
+                                     _ptr(g_aux), float(rtol), float(atol), _mx(mxstep), _ptr(ws), ws.numel(),
+                                     _ptr(y0_bar), _ptr(a0_bar), _ptr(eps_bar), _ptr(ts_bar), _ptr(p_bar), st, None, 0, stream)
+    _cabi.check(rc, h, "eno_odeint_bwd_sepaux")
+    return y0_bar, a0_bar, ts_bar, p_bar, eps_bar, [s.as_dict() for s in st][:max(T - 1, 0)]
+
+
+class _OdeintSplitFn(torch.autograd.Function):
+    """custom_vjp pairs of odeint_sepaux / odeint_fin_sepaux for the FFJORD closures (lib/ode.py:1006-1032 primal,
+    1482-1488 fwd, 1686-1693 rev; defvjp 1714-1715): forward = the plain solve of y0[0] with fwd_func, zeros for the
+    n_aux auxiliary states; backward = the adjoint of rev_func on (y, aux...)."""
+
+    @staticmethod
+    def forward(ctx, spec, aug, n_aux, rtol, atol, mxstep, y0, ts, eps, pflat, *aux0):
+        ys, st, _ = _fwd_call(spec, "dopri5", y0, ts, pflat, rtol, atol, mxstep)
+        last_stats["fwd"] = st
+        ctx.spec, ctx.aug, ctx.n_aux = spec, aug, n_aux
+        ctx.tols = (rtol, atol, mxstep)
+        ctx.save_for_backward(ys, ts, eps, pflat)
+        T, B, _ = ys.shape
+        zs = tuple(torch.zeros((T, B, 1), dtype=ys.dtype, device=ys.device) for _ in range(n_aux))
+        nfe = torch.tensor(st["nfe"], dtype=torch.float32, device=ys.device)
+        ctx.mark_non_differentiable(nfe)
+        return (ys,) + zs + (nfe,)
+
+    @staticmethod
+    def backward(ctx, g_ys, *rest):
+        ys, ts, eps, pflat = ctx.saved_tensors
+        rtol, atol, mxstep = ctx.tols
+        T, B, D = ys.shape
+        n_aux = ctx.n_aux
+        g_y = g_ys.contiguous().float()
+        g_aux = torch.stack([g.reshape(T, B) for g in rest[:n_aux]], dim=1).contiguous().float()   # [T, n_aux, B]
+        y0_bar, a0_bar, ts_bar, p_bar, eps_bar, st = _bwd_call_split(ctx.spec, ctx.aug, n_aux, ys, ts, pflat, eps, g_y, g_aux,
+                                                                      rtol, atol, mxstep)
+        last_stats["bwd"] = st
+        return (None,) * 6 + (y0_bar, ts_bar, eps_bar, p_bar) + tuple(a0_bar[q] for q in range(n_aux))
+
+
+def _odeint_split(name, kind, fwd_func, rev_func, y0, t, args, rtol, atol, mxstep):
+    spec = fwd_func.spec
+    aug, n_aux = spec.AUG_OF_KIND[kind]
+    eps, params = _split_args(rev_func, args)
+    if eps is None:
+        raise TypeError(f"{name}: the FFJORD closures read eps (ffjord_tabular.py:250-268)")
+    if len(y0) != 1 + n_aux:
+        raise TypeError(f"{name} integrates a state of {1 + n_aux} leaves with this rev_func; got {len(y0)}")
+    y_in = y0[0]
+    out_dev = y_in.device
+    dev = _dev(y_in)
+    y = _f32c(y_in.reshape(-1, spec.dim), dev)
+    aux0 = tuple(_f32c(a.reshape(-1), dev) for a in y0[1:])
+    ts = _f32c(torch.as_tensor(t), dev)
+    epsd = _f32c(eps.reshape(-1, spec.dim), dev)
+    pflat = _f32c(spec.flatten_params(params), dev)
+    out = _OdeintSplitFn.apply(spec, aug, n_aux, rtol, atol, mxstep, y, ts, epsd, pflat, *aux0)
+    if out_dev != out[0].device:
+        out = tuple(o.to(out_dev) for o in out)
+    return tuple(out[:-1]), out[-1]
+
+
+
 def _split_args(func, args):
     if len(args) != len(func.arg_names):
         raise TypeError(f"{func!r} expects args {func.arg_names}, got {len(args)}")
@@ -308,7 +388,7 @@ def _odeint_augmented(func, y0, t, args, rtol, atol, mxstep, trace_cap=0):
     -> ((ys [T,B,D], r [T,B], ...), nfe), every auxiliary output with the shape of its y0 leaf."""
     spec = func.spec
     eps, params = _split_args(func, args)
-    n_aux = 1 if func.kind == "aug" else 3
+    aug_const, n_aux = spec.AUG_OF_KIND[func.kind]
     if len(y0) != 1 + n_aux:
         raise TypeError(f"{func!r} integrates a state of {1 + n_aux} leaves, got {len(y0)}")
     y_in = y0[0]
@@ -320,12 +400,15 @@ def _odeint_augmented(func, y0, t, args, rtol, atol, mxstep, trace_cap=0):
     y = _f32c(y_in.detach().reshape(-1, spec.dim), dev)
     ts = _f32c(torch.as_tensor(t), dev)
     pflat = _f32c(spec.flatten_params(params).detach(), dev)
-    epsd = _f32c(eps.reshape(-1, spec.dim), dev) if (eps is not None and n_aux == 3) else None
+    reads_eps = func.kind in spec.eps_kinds
+    if reads_eps and eps is None:
+        raise TypeError(f"{func!r} reads eps")
+    epsd = _f32c(eps.reshape(-1, spec.dim), dev) if reads_eps else None
     L = _cabi.lib()
     h = _cabi.ctx(dev.index)
     B, D = y.shape
     T = ts.numel()
-    desc = spec.desc(_cabi.AUG_REG if n_aux == 1 else _cabi.AUG_ALL, eps is not None)
+    desc = spec.desc(aug_const, eps is not None)
     nbytes = L.eno_workspace_bytes(C.byref(desc), B, T, 0, 0)
     ws = _workspace(dev, nbytes)
     ys = torch.empty((T, B, D), dtype=torch.float32, device=dev)
@@ -376,6 +459,11 @@ def odeint_sepaux(fwd_func, rev_func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mx
     -> ((ys [T,B,D], fro [T,B,1], kin [T,B,1]), nfe)."""
     _require_spec(fwd_func, "odeint_sepaux")
     _require_spec(rev_func, "odeint_sepaux")
+    if getattr(fwd_func.spec, "num_layers", None) is not None:
+        # FFJORD closures (ffjord_tabular.py:299-304): rev_func = aug_dynamics 'our' on (y, delta_logp, r)
+        if fwd_func.kind != "plain" or rev_func.kind != "aug" or fwd_func.spec is not rev_func.spec:
+            raise TypeError("odeint_sepaux expects (spec.fwd, spec.aug_dynamics) of one ConcatSquashDynamics built with reg_type='our'")
+        return _odeint_split("odeint_sepaux", "aug", fwd_func, rev_func, y0, t, args, rtol, atol, mxstep)
     if fwd_func.kind != "plain" or rev_func.kind != "fin" or fwd_func.spec is not rev_func.spec:
         raise TypeError("odeint_sepaux expects (spec.fwd, spec.aug_dynamics) of one dynamics spec built with reg_type='fin'")
     spec = fwd_func.spec
@@ -396,6 +484,20 @@ def odeint_sepaux(fwd_func, rev_func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mx
     if out_dev != ys.device:
         ys, fro, kin, nfe = ys.to(out_dev), fro.to(out_dev), kin.to(out_dev), nfe.to(out_dev)
     return (ys, fro, kin), nfe
+
+
+def odeint_fin_sepaux(fwd_func, rev_func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=math.inf):
+    """Split solve with three auxiliary states, lib/ode.py:699-718 (jit wrapper 790-794, primal 1020-1032, fwd rule 1486-1488,
+    rev rule shared with odeint_sepaux, defvjp 1715): what the FFJORD scripts call with ``--reg_type fin``
+    (ffjord_mnist.py:78).  Forward integrates ``y0[0]`` with ``fwd_func`` and returns zeros for (delta_logp, fro, kin);
+    backward runs the adjoint with ``rev_func`` = aug_dynamics('fin') = (dy, -div, mean (J eps)^2, mean f^2).
+    -> ((ys [T,B,D], delta_logp [T,B,1], fro [T,B,1], kin [T,B,1]), nfe)."""
+    _require_spec(fwd_func, "odeint_fin_sepaux")
+    _require_spec(rev_func, "odeint_fin_sepaux")
+    if (getattr(fwd_func.spec, "num_layers", None) is None or fwd_func.kind != "plain" or rev_func.kind != "fin"
+            or fwd_func.spec is not rev_func.spec):
+        raise TypeError("odeint_fin_sepaux expects (spec.fwd, spec.aug_dynamics) of one ConcatSquashDynamics built with reg_type='fin'")
+    return _odeint_split("odeint_fin_sepaux", "fin", fwd_func, rev_func, y0, t, args, rtol, atol, mxstep)
 
 
 def odeint_vmap(func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=math.inf):
@@ -472,6 +574,46 @@ def solve_with_trace(spec, solver, y0, ts, params, rtol, atol, mxstep=math.inf, 
     pflat = _f32c(spec.flatten_params(params).detach(), dev)
     ys, st, trace = _fwd_call(spec, solver, y, tsd, pflat, rtol, atol, mxstep, trace_cap)
     return ys, st, trace[: st["n_iters"]].cpu()
+
+
+def rhs_closure(func, mode, y, t, *args, y_bar=None, aux_bar=None):
+    """One evaluation of a dynamics-spec closure (eno_rhs) for the FFJORD closures: mode 0 -> dy; mode 1 -> (dy, aux
+    [n_aux, B]) = what ``func`` returns; mode 2 -> (dy, aux, vjp_y, vjp_t, vjp_params, vjp_eps), the pull-back of
+    (y_bar [B,D], aux_bar [n_aux,B]) through ``func`` at (y, t) - the adjoint's right-hand side, lib/ode.py:1498-1504."""
+    _require_spec(func, "rhs_closure")
+    spec = func.spec
+    eps, params = _split_args(func, args)
+    L = _cabi.lib()
+    dev = _dev(y)
+    h = _cabi.ctx(dev.index)
+    yd = _f32c(y.reshape(-1, spec.dim), dev)
+    B, D = yd.shape
+    pflat = _f32c(spec.flatten_params(params).detach(), dev)
+    if func.kind == "plain":
+        aug, n_aux = _cabi.AUG_NONE, 0
+    else:
+        aug, n_aux = spec.AUG_OF_KIND[func.kind]
+    desc = spec.desc(aug, eps is not None)
+    nbytes = L.eno_workspace_bytes(C.byref(desc), B, 2, 0, 1 if mode == 2 else 0)
+    ws = _workspace(dev, nbytes, "bwd" if mode == 2 else "fwd")
+    dy = torch.empty_like(yd)
+    aux = torch.empty((max(n_aux, 1), B), device=dev)
+    epsd = _f32c(eps.reshape(-1, D), dev) if eps is not None else None
+    zb, eb = torch.empty_like(yd), torch.empty_like(yd)
+    tbar = torch.empty(1, device=dev)
+    pbar = torch.empty(spec.n_params, device=dev)
+    yb = _f32c(y_bar.reshape(-1, D), dev) if y_bar is not None else None
+    ab = _f32c(aux_bar.reshape(n_aux, B), dev) if aux_bar is not None else None
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        rc = L.eno_rhs(h, C.byref(desc), mode, B, _ptr(yd), float(t), _ptr(pflat), _ptr(epsd), _ptr(yb), _ptr(ab), _ptr(ws),
+                       ws.numel(), _ptr(dy), _ptr(aux), _ptr(zb), _ptr(tbar), _ptr(pbar), _ptr(eb), stream)
+    _cabi.check(rc, h, "eno_rhs")
+    if mode == 0:
+        return dy
+    if mode == 1:
+        return dy, aux[:n_aux]
+    return dy, aux[:n_aux], zb, tbar, pbar, eb
 
 
 def rhs(spec, mode, y, t, params, y_bar=None, r_bar=None, eps=None):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ENO_ABI_VERSION 2
+#define ENO_ABI_VERSION 3
 
 /* status codes */
 #define ENO_OK 0
@@ -57,12 +57,22 @@ extern "C" {
 /* dynamics families (the reference's Python `func` cannot be called from a kernel;
  * the spec names the closure instead) */
 #define ENO_ARCH_MLP_SIGMOID 0 /* MLPDynamics, mnist.py:195-222 */
+#define ENO_ARCH_CONCATSQUASH 1 /* NN_Dynamics of ConcatSquashLinear layers, softplus, ffjord_tabular.py:140-193:
+                                   D -> H (x n_hidden) -> D; flat parameters per layer in Haiku ravel order
+                                   [ b (out) | W (in x out) | w_hyper_bias (out) | b_gate (out) | w_gate (out) ] */
 
 /* what the integrated function returns besides dy/dt (the reference's closures) */
 #define ENO_AUG_NONE 0 /* dynamics_wrap            mnist.py:285            */
 #define ENO_AUG_REG 1  /* aug_dynamics 'our'       mnist.py:302-308: (dy, r_K) */
 #define ENO_AUG_ALL 2  /* all_aug_dynamics         mnist.py:315-324: (dy, r_K, fro, kin) */
 #define ENO_AUG_FIN 3  /* aug_dynamics 'fin'       mnist.py:294-313: (dy, dfro, dkin), reads eps (backward only) */
+#define ENO_AUG_FFJORD 4 /* ffjord_dynamics       ffjord_tabular.py:250-258: (dy, -div), div = sum eps * (J eps)          */
+/* For ENO_ARCH_CONCATSQUASH the closures are those of ffjord_tabular.py:250-297, all reading eps:
+ *   ENO_AUG_FFJORD (dy, -div)                      ffjord_dynamics, the NFE count of nfe_fn (forward only)
+ *   ENO_AUG_REG    (dy, -div, r_2)                 aug_dynamics 'our' (r = 0 when reg_order == 0); the adjoint of odeint_sepaux
+ *   ENO_AUG_FIN    (dy, -div, dfro, dkin)          aug_dynamics 'fin'; the adjoint of odeint_fin_sepaux
+ *   ENO_AUG_ALL    (dy, -div, r_2, dfro, dkin)     all_aug_dynamics (evaluation, forward only)
+ * reg_order is 0 or 2: sol_recursive of the FFJORD scripts stops at K = 2 whatever --reg says (ffjord_tabular.py:133-136). */
 
 typedef struct eno_ctx eno_ctx;
 
@@ -76,6 +86,7 @@ typedef struct eno_dynamics_desc {
   int32_t eps_in_args; /* 1 when the reference call passes eps among *args (mnist.py:330-332):
                         its cotangent eps_bar (identically 0 for reg_type 'our') is then
                         part of the adjoint state and dilutes the error mean            */
+  int32_t n_hidden;  /* ENO_ARCH_CONCATSQUASH: hidden layers (--num_layers, ffjord_tabular.py:56); else ignored */
 } eno_dynamics_desc;
 
 typedef struct eno_stats {
@@ -257,6 +268,16 @@ int32_t eno_comm_destroy(eno_ctx* ctx);
 int32_t eno_profile_enable(eno_ctx* ctx, int32_t on);
 int32_t eno_profile_read(eno_ctx* ctx, double* ms_out /*[4]*/, int64_t* count_out /*[4]*/);
 int32_t eno_ffma_peak(eno_ctx* ctx, double* tflops_out, void* stream);
+
+/*
+ * Unit-test hook of the tensor-core contraction used by the wide-network path (no reference counterpart; the
+ * reference's contractions are XLA dots inside ffjord_tabular.py:151-152): C[M, N] = A[M, K] * B[N, K]^T in fp32
+ * accuracy, computed as the 3-pass tf32 split on tcgen05 with TMEM accumulators and TMA operand loads.
+ * lda / ldb / ldc in elements, multiples of 4; bn: accumulator tile width, 64 or 128; splits >= 1: K partitions
+ * summed in a fixed order.  Allocates its own scratch; synchronises the stream.
+ */
+int32_t eno_gemm_tf32x3(eno_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B,
+                        int32_t ldb, float* C, int32_t ldc, int32_t bn, int32_t splits, void* stream);
 
 #ifdef __cplusplus
 }
