@@ -79,6 +79,26 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bench_config(world, workload=None):
+    """The `config` object of the JSON line; IDENTICAL in both arms (the reference arm runs the b200 arm's config)."""
+    return {"workload": workload or WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "rtol": TOL, "atol": TOL,
+            "parallelism": (f"dp{world}: batch sharded {B}/GPU, ONE global adaptive step sequence (per-iteration exchange of the "
+                            "error-norm partials and of the params_bar stage sums); the reference arm solves the "
+                            "concatenated global batch on the host") if world > 1 else "single GPU",
+            "l2": "flushed between steps (256 MiB device write, outside the per-step events)",
+            "trajectory": "train steps 0..K-1 from the initial parameters (seeded), identical in every leg and arm"}
+
+
+def traffic_from_profiles(kernel_key):
+    """dram bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` summary
+    (profiles/roofline_traffic.json, written by tools/ncu_summary.py); None when no capture is committed."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        return rec.get(kernel_key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def cpu_train_steps(n_steps, warmup, threads, shards=1, budget_s=None):
     """The oracle port of one update() on host cores; returns (seconds per step, info).
     ``shards`` > 1: the global batch of a weak-scaling run (the per-GPU batches of all ranks, concatenated);
@@ -119,20 +139,189 @@ def run_reference(args, rank, world):
     # same workload as the b200 arm at this N: weak scaling, the global batch is B per GPU
     sec, info = cpu_train_steps(steps, 1, threads, shards=max(args.gpus, 1), budget_s=150.0)
     steps = info["steps_timed"]
-    val = 1.0 / sec
+    # same unit as the b200 arm: per-GPU-batch (batch-100) train steps per second over the whole job - one step of
+    # the concatenated global batch is `shards` of them
+    shards = max(args.gpus, 1)
+    val = shards / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B * max(args.gpus, 1), "per_gpu_batch": B, "rtol": TOL, "atol": TOL},
+        "config": bench_config(shards),
+        "global_steps_per_s": 1.0 / sec, "samples_per_s": B * shards / sec,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"train steps 0..{steps - 1} from the initial parameters (forward solve + adjoint + "
                                    f"momentum update each) after 1 untimed warm-up evaluation, torch CPU fp32, {threads} threads; "
                                    f"last step nfe {info['nfe']}, adjoint iterations {info['bwd_iters']}"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "nfe_per_s": info["nfe"] * B * max(args.gpus, 1) * val,
+        # the reference's own NFE counter (2 + 6 * iterations of the last timed step's forward solve) per second of
+        # global solves; "sample_nfe_per_s" multiplies by the samples each evaluation covers
+        "nfe_per_s": info["nfe"] / sec, "sample_nfe_per_s": info["nfe"] * B * shards / sec,
     }
     print(json.dumps(line), flush=True)
+
+
+# ---- BASELINE configs[1]: ffjord_tabular.py, MINIBOONE-shaped 43-d data, --reg r2 --lam 1e-2, batch 1000 ---------------
+FJ = dict(B=1000, D=43, HF=20, LAYERS=2, LAM=1e-2, LAM_W=1e-6, TOL=1.4e-8)
+FJ_WORKLOAD = ("ffjord_tabular.py FFJORD, synthetic MINIBOONE-shaped 43-d data, ConcatSquash 43-860-860-43 softplus, dopri5, "
+               "--reg r2 --lam 1e-2 --lam_w 1e-6, Hutchinson trace (N(0,1) probe), batch 1000 (configs[1])")
+
+
+def fj_batch(rank, step, pin=False):
+    import torch
+    g = torch.Generator().manual_seed(4321 + 97 * rank + (step % 8))
+    x = torch.randn((FJ["B"], FJ["D"]), generator=g)
+    eps = torch.randn((FJ["B"], FJ["D"]), generator=g)
+    if pin:
+        x, eps = x.pin_memory(), eps.pin_memory()
+    return x, eps
+
+
+def fj_config(world):
+    return {"workload": FJ_WORKLOAD, "global_batch": FJ["B"] * world, "per_gpu_batch": FJ["B"], "rtol": FJ["TOL"], "atol": FJ["TOL"],
+            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (development)",
+            "l2": "flushed between steps (256 MiB device write, outside the per-step events)",
+            "trajectory": "train steps 0..K-1 from the initial parameters (seeded), identical in every leg and arm"}
+
+
+def fj_cpu_steps(n_steps, warmup, threads, budget_s=None):
+    """Oracle port of one update() of ffjord_tabular.py (547-553) on host cores -> (seconds per step, info)."""
+    import torch
+    from oracle import ffjord_oracle as fo
+    torch.set_num_threads(threads)
+    params = fo.init_css_params(FJ["D"], FJ["D"] * FJ["HF"], n_hidden_layers=FJ["LAYERS"], seed=0, scale=1.0)
+    m, v = fo.adam_init(params)
+    times, info = [], {}
+    for s in range(-warmup, n_steps):
+        if budget_s is not None and times and sum(times) > budget_s:
+            break
+        x, eps = fj_batch(0, max(s, 0))
+        t0 = time.perf_counter()
+        out = fo.train_step_grads(params, x, eps, lam=FJ["LAM"], lam_w=FJ["LAM_W"], reg="r2", rtol=FJ["TOL"], atol=FJ["TOL"])
+        if s >= 0:
+            params, m, v = fo.adam_update(params, m, v, out["grads"], s, 1e-3)
+            times.append(time.perf_counter() - t0)
+        info = dict(nfe=float(out["nfe"]), fwd_iters=out["fwd_stats"]["n_iters"], bwd_iters=out["bwd_stats"][0]["n_iters"],
+                    steps_timed=len(times), loss=float(out["loss"]))
+    return sum(times) / len(times), info
+
+
+def fj_reference(args):
+    threads = len(os.sched_getaffinity(0))
+    steps = max(1, min(args.steps, 20))
+    sec, info = fj_cpu_steps(steps, 1, threads, budget_s=120.0)
+    val = 1.0 / sec
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": fj_config(1), "samples_per_s": FJ["B"] / sec,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"train steps 0..{info['steps_timed'] - 1} from the initial parameters, oracle port, torch CPU "
+                                       f"fp32, {threads} threads; last step nfe {info['nfe']}, adjoint iterations {info['bwd_iters']}"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "nfe_per_s": info["nfe"] / sec}
+    print(json.dumps(line), flush=True)
+
+
+def fj_main(args, result_out, rank, local_rank, world):
+    """`--workload ffjord_tabular`: one update() of ffjord_tabular.py per step (forward solve of y, loss head, adjoint solve of
+    aug_dynamics with the Hutchinson term and the K = 2 Taylor regulariser, Adam).  Contractions: tcgen05 3xTF32."""
+    import torch
+    import easy_neural_ode_b200 as eno
+    from easy_neural_ode_b200 import ffjord_step, _cabi
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    model = ffjord_step.TabularFfjord(dim=FJ["D"], hdim_factor=FJ["HF"], num_layers=FJ["LAYERS"], reg="r2", lam=FJ["LAM"],
+                                      lam_w=FJ["LAM_W"], rtol=FJ["TOL"], atol=FJ["TOL"], device=dev, seed=0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    dev_b = [tuple(t.to(dev) for t in fj_batch(rank, s)) for s in range(8)]
+    host_b = [fj_batch(rank, s, pin=True) for s in range(8)]
+    snap = model.snapshot()
+    for s in range(max(args.warmup, 3)):
+        out = model.update(*dev_b[s % 8])
+    torch.cuda.synchronize()
+    model.restore(snap)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches, nfe_total, iters = 0, 0.0, []
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        evs[s][0].record()
+        out = model.update(*dev_b[s % 8])
+        evs[s][1].record()
+        nfe_total += float(out["nfe"])
+        iters.append((out["fwd_stats"]["n_iters"], out["bwd_stats"][0]["n_iters"]))
+        launches += model.kernel_launches(out)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    ms_per_step = dev_ms / args.steps
+    loss_dev = float(out["loss"])
+
+    model.restore(snap)
+    def step_e2e(s):
+        x, eps = host_b[s % 8]
+        o = model.update(x.to(dev, non_blocking=True), eps.to(dev, non_blocking=True))
+        return float(o["loss"])
+    for s in range(2):
+        step_e2e(s)
+    model.restore(snap)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_e2e(s)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # roofline of the dominant kernel: the tcgen05 GEMM launches of the solves, CUDA events on the launch stream
+    L = _cabi.lib()
+    h = _cabi.ctx(dev.index)
+    model.restore(snap)
+    L.eno_profile_enable(h, 1)
+    n_prof = min(args.steps, 3)
+    for s in range(n_prof):
+        model.update(*dev_b[s % 8])
+    torch.cuda.synchronize()
+    L.eno_profile_enable(h, 0)
+    gms, gfl, gcnt = C.c_double(), C.c_double(), C.c_int64()
+    L.eno_profile_read_gemm(h, C.byref(gms), C.byref(gfl), C.byref(gcnt))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = float(peaks.get("bf16_tflops", 1590.0))
+    achieved = gfl.value / (gms.value * 1e-3) / 1e12 if gms.value > 0 else 0.0
+    roofline = {"kernel": "k_gemm_tf32x3<BN, Epi> (tcgen05.mma kind::tf32, 3-pass split, TMA operands, TMEM accumulators; all "
+                          "stage contractions of the forward and adjoint solves)",
+                "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                "traffic": traffic_from_profiles("k_gemm_tf32x3"),
+                "peak_source": ("measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback 1.59 PFLOP/s") +
+                               "; fp32-exact work runs 3 tf32 passes at half the bf16 rate, so 1/6 of this peak is the ceiling "
+                               "of the algorithmic rate",
+                "avg_launch_ms": gms.value / max(gcnt.value, 1), "launches_timed": int(gcnt.value),
+                "algorithmic_flop_per_launch_avg": gfl.value / max(gcnt.value, 1),
+                "frac_of_3xtf32_ceiling": achieved / (tensor_peak / 6.0),
+                "gemm_share_of_step": (gms.value / n_prof) / ms_per_step}
+    line = {"metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (tcgen05 3xTF32 contractions, fp32 accumulate)", "data": "synthetic",
+            "config": fj_config(world), "samples_per_s": FJ["B"] * 1e3 / ms_per_step, "clocks": clocks,
+            "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host_b[0]),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "nfe_per_s": nfe_total / (dev_ms * 1e-3),
+            "solver": {"iters_fwd_bwd_per_step": iters, "loss_last": loss_dev},
+            "launch_mode": "polled solves; one loop iteration (6 right-hand sides + controller) replayed as a CUDA graph",
+            "roofline": roofline}
+    if not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        sec, info = fj_cpu_steps(min(args.steps, 3), 1, threads, budget_s=40.0)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"train steps 0..{info['steps_timed'] - 1} of the same trajectory, oracle port, torch CPU "
+                                          f"fp32, {threads} threads; last step nfe {info['nfe']}, adjoint iterations "
+                                          f"{info['bwd_iters']}, loss {info['loss']:.6f}"}
+    print(json.dumps(line), file=result_out, flush=True)
 
 
 def main():
@@ -148,11 +337,16 @@ def main():
     ap.add_argument("--reg-type", default="our", choices=["our", "fin"],
                     help="development only: 'fin' times the --reg_type fin arm (odeint_sepaux, lam_fro = lam_kin = 1e-2); "
                          "the headline metric is the default 'our' (--reg r3)")
+    ap.add_argument("--workload", default="mnist", choices=["mnist", "ffjord_tabular"],
+                    help="mnist = BASELINE configs[0], the configuration the metric is quoted on (default); "
+                         "ffjord_tabular = configs[1] (single GPU)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
+        if args.workload == "ffjord_tabular":
+            return fj_reference(args) if rank == 0 else None
         return run_reference(args, rank, world)
     # stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr, so
     # that banners printed by native libraries (NCCL prints its version on communicator creation) cannot
@@ -166,6 +360,10 @@ def main():
     import easy_neural_ode_b200 as eno
     from easy_neural_ode_b200 import mnist_step, _cabi
 
+    if args.workload == "ffjord_tabular":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+        return fj_main(args, result_out, rank, local_rank, world) if rank == 0 else None
     B = args.batch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
@@ -294,7 +492,7 @@ def main():
     achieved = flop_rows / (rows_ms * 1e-3) / 1e12 if rows_ms > 0 else 0.0
     roofline = {"kernel": "k_cl_adj_rows<STEP> (adjoint dopri5 iteration, per-sample blocks; k_adj_rows on the streamed path)", "bound": "tensor",
                 "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                "traffic": 2.02e6,   # dram__bytes_read + write per launch, ncu --set full (profiles/r1_ncu_v4_kernels.txt)
+                "traffic": traffic_from_profiles("k_cl_adj_rows_step"),   # ncu --set full, per launch (profiles/roofline_traffic.json)
                 "peak_source": peak_src, "avg_launch_ms": rows_ms, "launches_timed": int(cnt[1]),
                 "fp32_ffma_peak_tflops": ffma.value, "frac_of_fp32_ffma": achieved / ffma.value if ffma.value else None,
                 "other_kernels_ms": {"k_fwd_step": ms[0] / max(cnt[0], 1), "k_adj_pgrad<STEP>": ms[2] / max(cnt[2], 1),
@@ -306,18 +504,14 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD if args.reg_type == "our" else
-                   "mnist.py Neural ODE classifier, dopri5, --reg_type fin --lam_fro 1e-2 --lam_kin 1e-2, batch 100 synthetic 28x28 "
-                   "(development run, not the headline config)",
-                   "global_batch": B * world, "per_gpu_batch": B, "rtol": TOL, "atol": TOL,
-                   "parallelism": (f"dp{world}: batch sharded {B}/GPU, ONE global adaptive step sequence (per-iteration NCCL "
-                                   "all-gather of error-norm partials + all-reduce of the params_bar stage sums)")
-                   if world > 1 else "single GPU",
-                   "l2": "flushed between steps (256 MiB device write, outside the per-step events)"},
+        "config": bench_config(world, None if args.reg_type == "our" else
+                               "mnist.py Neural ODE classifier, dopri5, --reg_type fin --lam_fro 1e-2 --lam_kin 1e-2, batch 100 "
+                               "synthetic 28x28 (development run, not the headline config)"),
+        "global_steps_per_s": 1e3 / ms_per_step, "samples_per_s": B * world * 1e3 / ms_per_step,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
-        "nfe_per_s": nfe_total * B * world / (dev_ms * 1e-3),
+        "nfe_per_s": nfe_total / (dev_ms * 1e-3), "sample_nfe_per_s": nfe_total * B * world / (dev_ms * 1e-3),
         "solver": ({"fwd_iters": out["fwd_iters"], "bwd_iters": out["bwd_iters"], "graph_redone": out["redone"]}
                    if not args.no_graph else {"fwd": out["fwd_stats"], "bwd": out["bwd_stats"][0]}),
         "launch_mode": "whole update() replayed as one CUDA graph (deferred-mode solves)" if not args.no_graph

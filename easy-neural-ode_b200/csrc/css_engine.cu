@@ -190,11 +190,40 @@ int pick_bn(int M, int N) {
   return tiles < 100 ? 64 : 128;
 }
 
+// bench.py's roofline leg: CUDA-event pairs around every GEMM launch of a profiled solve (direct launches, one
+// iteration per poll so that no launch runs past the end of the solve), with the ALGORITHMIC flops 2 M N K of each.
+struct GemmProf {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<double> flop;
+  size_t n = 0;
+  double ms = 0.0, flops = 0.0;
+  long long count = 0;
+  void begin(cudaStream_t st, double f) {
+    if (ev.size() < 2 * (n + 1)) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ev.push_back(a); ev.push_back(b); }
+    if (flop.size() < n + 1) flop.push_back(f); else flop[n] = f;
+    cudaEventRecord(ev[2 * n], st);
+  }
+  void end(cudaStream_t st) { cudaEventRecord(ev[2 * n + 1], st); ++n; }
+  void resolve() {   // after the stream has been synchronised
+    for (size_t i = 0; i < n; ++i) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]) == cudaSuccess) { ms += t; flops += flop[i]; ++count; }
+    }
+    n = 0;
+  }
+};
+thread_local GemmProf* g_prof = nullptr;
+
 template <class Epi>
 cudaError_t gemm(const tc::GemmOperand& A, const tc::GemmOperand& Bm, int M, int N, int splits, const int* done, const Epi& epi,
                  cudaStream_t st, std::string* err) {
-  return pick_bn(M, N) == 128 ? tc::launch_gemm<128>(A, Bm, M, N, splits, done, epi, st, err)
-                              : tc::launch_gemm<64>(A, Bm, M, N, splits, done, epi, st, err);
+  const bool prof = g_prof && g_prof->on;
+  if (prof) g_prof->begin(st, 2.0 * M * N * (double)A.k);
+  cudaError_t e = pick_bn(M, N) == 128 ? tc::launch_gemm<128>(A, Bm, M, N, splits, done, epi, st, err)
+                                       : tc::launch_gemm<64>(A, Bm, M, N, splits, done, epi, st, err);
+  if (prof) g_prof->end(st);
+  return e;
 }
 
 #define CSS_G(expr)                                                                   \
@@ -289,6 +318,7 @@ struct CssState {
   std::map<GraphKey, cudaGraphExec_t> graphs;
   int use_graph = 1;
   int hint[2] = {8, 8};
+  GemmProf prof;
 };
 
 CssState* state_of(eno_ctx* ctx) {
@@ -324,7 +354,10 @@ int run_loop(eno_ctx* ctx, const Plan& p, const GraphKey& key, int which, eno_st
   if ((rc = css_rhs_launch(p, 0, css::ST_INIT1, nullptr, sms, st, &err))) return css_fail(ctx, rc, err);
   css::k_flat_init<<<igrid, 256, 0, st>>>(p.flat, 1);
   cudaGraphExec_t exec = nullptr;
-  if (S->use_graph) {
+  const bool profiling = ctx->prof.enabled;
+  S->prof.on = false;
+  if (profiling) { S->prof.on = true; g_prof = &S->prof; }   // the initial-step evaluations above are not timed
+  if (S->use_graph && !profiling) {
     auto it = S->graphs.find(key);
     if (it != S->graphs.end()) exec = it->second;
     else {
@@ -338,7 +371,7 @@ int run_loop(eno_ctx* ctx, const Plan& p, const GraphKey& key, int which, eno_st
       } else cudaGetLastError();
     }
   }
-  int chunk = S->hint[which];
+  int chunk = profiling ? 1 : S->hint[which];
   int n_launched_iters = 0;
   for (;;) {
     for (int k = 0; k < chunk; ++k) {
@@ -349,8 +382,9 @@ int run_loop(eno_ctx* ctx, const Plan& p, const GraphKey& key, int which, eno_st
     CSS_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, p.flat.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
     CSS_CUDA(ctx, cudaStreamSynchronize(st));
     if (ctx->mailbox->done) break;
-    chunk = 2;
+    chunk = profiling ? 1 : 2;
   }
+  if (profiling) { S->prof.resolve(); S->prof.on = false; }
   const Ctrl& c = *ctx->mailbox;
   S->hint[which] = std::min(64, c.n_iters + 1);
   if (stats) {
@@ -541,7 +575,42 @@ void destroy(eno_ctx* ctx) {
 }  // namespace css
 }  // namespace eno
 
+namespace {
+// jax.experimental.optimizers.adam (ffjord_tabular.py:527-529) with the weight-decay term of loss_fn (lam_w * 0.5 |theta|^2,
+// ffjord_tabular.py:417-432) folded into the gradient.
+__global__ void k_adam(float* __restrict__ x, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g, size_t n,
+                       float lr, float b1, float b2, float eps, float c1, float c2, float lam_w) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] + lam_w * x[i];
+    const float mi = (1.f - b1) * gi + b1 * m[i];
+    const float vi = (1.f - b2) * gi * gi + b2 * v[i];
+    m[i] = mi;
+    v[i] = vi;
+    x[i] = x[i] - lr * (mi / c1) / (sqrtf(vi / c2) + eps);
+  }
+}
+}  // namespace
+
 extern "C" {
+
+int32_t eno_profile_read_gemm(eno_ctx* ctx, double* ms_out, double* flop_out, int64_t* count_out) {
+  if (!ctx || !ms_out || !flop_out || !count_out) return ENO_E_ARG;
+  CssState* S = state_of(ctx);
+  *ms_out = S->prof.ms; *flop_out = S->prof.flops; *count_out = S->prof.count;
+  S->prof.ms = S->prof.flops = 0.0; S->prof.count = 0;
+  return ENO_OK;
+}
+
+int32_t eno_adam_update(eno_ctx* ctx, float* params, float* m, float* v, const float* grads, int64_t n, float lr, float b1,
+                        float b2, float eps, int32_t step, float lam_w, void* stream) {
+  if (!ctx || !params || !m || !v || !grads || n <= 0 || step < 0) return css_fail(ctx, ENO_E_ARG, "eno_adam_update: bad argument");
+  CSS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const float c1 = 1.f - powf(b1, (float)(step + 1)), c2 = 1.f - powf(b2, (float)(step + 1));
+  k_adam<<<(int)std::min<int64_t>((n + 255) / 256, 2048), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      params, m, v, grads, (size_t)n, lr, b1, b2, eps, c1, c2, lam_w);
+  CSS_CUDA(ctx, cudaGetLastError());
+  return ENO_OK;
+}
 
 // Unit-test hook of the tensor-core contraction (declared in include/eno.h).
 int32_t eno_gemm_tf32x3(eno_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B,

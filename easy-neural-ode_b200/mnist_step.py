@@ -23,7 +23,10 @@ class MnistNode:
         self.spec = MLPDynamics(dim, hidden, reg=reg, reg_type=reg_type)
         self.lam, self.rtol, self.atol = lam, rtol, atol
         self.reg_type, self.lam_fro, self.lam_kin = reg_type, lam_fro, lam_kin
-        self.device = torch.device(device)
+        self.device = ode._norm_device(device)        # 'cuda' -> the current device, with an index
+        # the solves of THIS model run in workspaces nobody else touches: the captured whole-step graphs hold raw
+        # pointers into them (controller words, rings), so they must not be handed out or re-allocated behind them
+        self._wsown = ode.WorkspaceOwner(self.device)
         self.lr, self.mass = lr, mass
         self.dim, self.n_cls = dim, n_cls
         self.world = world   # data-parallel ranks: the loss is the mean over the GLOBAL batch
@@ -90,7 +93,8 @@ class MnistNode:
         h = _cabi.ctx(self.device.index)
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         x0 = (images_u8.to(torch.float32) / 255.).reshape(B, -1)
-        ys, st_f, _ = ode._fwd_call(self.spec, "dopri5", x0, self.ts, self.p_ode, self.rtol, self.atol, float("inf"))
+        ys, st_f, _ = ode._fwd_call(self.spec, "dopri5", x0, self.ts, self.p_ode, self.rtol, self.atol, float("inf"),
+                                    owner=self._wsown)
         gw, gb = buf["gwb"][:D * Cn].view(D, Cn), buf["gwb"][D * Cn:]
         with torch.cuda.device(self.device):
             rc = L.eno_mnist_head(h, B, D, Cn, ode._ptr(ys[1]), ode._ptr(labels), ode._ptr(self.post_w), ode._ptr(self.post_b),
@@ -104,7 +108,8 @@ class MnistNode:
             dist.all_reduce(buf["gwb"])
         fin = self.reg_type == "fin"
         out = ode._bwd_call(self.spec, _cabi.AUG_FIN if fin else _cabi.AUG_REG, True, ys, self.ts, self.p_ode, buf["g_y"],
-                            buf["g_r"], self.rtol, self.atol, float("inf"), eps=eps.contiguous() if fin else None)
+                            buf["g_r"], self.rtol, self.atol, float("inf"), eps=eps.contiguous() if fin else None,
+                            owner=self._wsown)
         p_bar, st_b = out[3], out[4]
         ode.last_stats["fwd"], ode.last_stats["bwd"] = st_f, st_b
         if ode._deferred["on"]:
@@ -189,6 +194,7 @@ class MnistNode:
         if not hasattr(self, "_graphs"):
             out = self.update(images_u8, labels, eps)        # polled step: learns the iteration counts
             self._graphs, self._last = {}, (out["fwd_stats"]["n_iters"], out["bwd_stats"][0]["n_iters"])
+            self._graph_gen = (self._wsown.gen, images_u8.shape[0])
             self._g_in = tuple(t.clone() for t in (images_u8, labels, eps))
             try:
                 lf, lb = self._level(self._last[0]), self._level(self._last[1])
@@ -198,6 +204,10 @@ class MnistNode:
                 self._graph_off, self._graph_error = True, repr(e)
             return dict(loss=float(out["loss"]), redone=False, fwd_iters=self._last[0], bwd_iters=self._last[1],
                         nfe=out["fwd_stats"]["nfe"])
+        if self._graph_gen != (self._wsown.gen, images_u8.shape[0]):
+            # a workspace was re-allocated (or the batch size changed): every captured pointer is stale
+            self._graphs = {}
+            self._g_in = tuple(t.clone() for t in (images_u8, labels, eps))
         key = (self._level(self._last[0]), self._level(self._last[1]))
         if key not in self._graphs:
             self._capture(key)
@@ -244,14 +254,15 @@ class MnistNode:
                 info = self._graph_body()
             launches = ode.last_stats["fwd"]["n_launches"] + sum(b["n_launches"] for b in ode.last_stats["bwd"])
             self._graphs[key] = (g, info, launches)
+            self._graph_gen = (self._wsown.gen, self._g_in[0].shape[0])
         finally:
             ode.set_deferred(False, device=self.device)
         self.restore(snap)
 
     def _graph_body(self):
         out = self.loss_and_grads(*self._g_in)
-        wf = ode.workspace_tensor("fwd", self.device).view(torch.int32)
-        wb = ode.workspace_tensor("bwd", self.device).view(torch.int32)
+        wf = self._wsown.ws["fwd"].view(torch.int32)
+        wb = self._wsown.ws["bwd"].view(torch.int32)
         g = out["grads"]
         # guarded on the device by the two `done` words: garbage gradients never reach the parameters
         self._momentum(g["ode"], g["post_w"], g["post_b"],

@@ -94,11 +94,17 @@ def set_deferred(on, fwd_iters=0, bwd_iters=0, device=None):
     _deferred["on"] = bool(on)
 
 
+def _norm_device(device):
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
 def workspace_tensor(kind, device=None):
     """The cached workspace ("fwd" or "bwd") of the most recent solves on the device (uint8 tensor whose
     first bytes are the device-side controller block)."""
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    return _workspaces.get((dev.index, kind))
+    return _workspaces.get((_norm_device(device).index, kind))
 
 
 def read_deferred_stats(kind, device=None):
@@ -125,6 +131,24 @@ def _workspace(device, nbytes, kind="fwd"):
     return ws
 
 
+class WorkspaceOwner:
+    """Dedicated solve workspaces for a caller that keeps raw pointers into them alive - a captured CUDA graph
+    (mnist_step.MnistNode).  The process-wide cache above hands its tensors to whoever asks next and replaces them
+    when a later solve needs more bytes; an owner's workspaces are only ever touched through the owner, and ``gen``
+    moves whenever one had to be re-allocated, so that the holder knows its captured pointers are stale."""
+
+    def __init__(self, device):
+        self.device, self.ws, self.gen = device, {}, 0
+
+    def get(self, kind, nbytes):
+        ws = self.ws.get(kind)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self.ws[kind] = ws
+            self.gen += 1
+        return ws
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -145,7 +169,16 @@ def _f32c(t, device):
     return t.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
 
 
-def _fwd_call(spec, solver, y0, ts, pflat, rtol, atol, mxstep, trace_cap=0):
+def _warn_status(what, status):
+    """The reference has no error channel (lib/ode.py:829-831: the loop just ends); the library reports why."""
+    if status > 0:
+        import warnings
+        why = {1: "mxstep reached", 2: "step size underflow (dt <= 0 or NaN)", 3: "non-finite error ratio"}.get(status, str(status))
+        warnings.warn(f"{what}: the adaptive loop ended early ({why}); results are what the reference would return "
+                      "(last interpolant extrapolated / NaNs)", RuntimeWarning, stacklevel=3)
+
+
+def _fwd_call(spec, solver, y0, ts, pflat, rtol, atol, mxstep, trace_cap=0, owner=None):
     """eno_odeint_fwd on device tensors. -> (ys [T,B,D], stats dict, trace or None)."""
     L = _cabi.lib()
     device = y0.device
@@ -154,7 +187,7 @@ def _fwd_call(spec, solver, y0, ts, pflat, rtol, atol, mxstep, trace_cap=0):
     T = ts.numel()
     desc = spec.desc(_cabi.AUG_NONE)
     nbytes = L.eno_workspace_bytes(C.byref(desc), B, T, _cabi.TABLEAUX[solver], 0)
-    ws = _workspace(device, nbytes)
+    ws = owner.get("fwd", nbytes) if owner is not None else _workspace(device, nbytes)
     ys = torch.empty((T, B, D), dtype=torch.float32, device=device)
     trace = torch.zeros((trace_cap, 4), dtype=torch.float32, device=device) if trace_cap else None
     st = _cabi.Stats()
@@ -164,10 +197,11 @@ def _fwd_call(spec, solver, y0, ts, pflat, rtol, atol, mxstep, trace_cap=0):
                               float(rtol), float(atol), _mx(mxstep), _ptr(ws), ws.numel(), _ptr(ys), None,
                               C.byref(st), _ptr(trace), trace_cap, stream)
     _cabi.check(rc, h, "eno_odeint_fwd")
+    _warn_status("odeint (forward solve)", rc)
     return ys, st.as_dict(), trace
 
 
-def _bwd_call(spec, aug, eps_in_args, ys, ts, pflat, g_y, g_r, rtol, atol, mxstep, trace_cap=0, eps=None):
+def _bwd_call(spec, aug, eps_in_args, ys, ts, pflat, g_y, g_r, rtol, atol, mxstep, trace_cap=0, eps=None, owner=None):
     """eno_odeint_bwd (aug NONE / REG) or eno_odeint_bwd_sepaux (aug FIN: g_r is [T, 2, B] and eps is read).
     -> (y0_bar, r0_bar [B] or [2, B], ts_bar, params_bar, stats, trace, eps_bar or None)."""
     L = _cabi.lib()
@@ -177,7 +211,7 @@ def _bwd_call(spec, aug, eps_in_args, ys, ts, pflat, g_y, g_r, rtol, atol, mxste
     fin = aug == _cabi.AUG_FIN
     desc = spec.desc(aug, eps_in_args, reg_order=spec.reg_order if aug == _cabi.AUG_REG else 0)
     nbytes = L.eno_workspace_bytes(C.byref(desc), B, T, 0, 1)
-    ws = _workspace(device, nbytes, "bwd")
+    ws = owner.get("bwd", nbytes) if owner is not None else _workspace(device, nbytes, "bwd")
     y0_bar = torch.empty((B, D), dtype=torch.float32, device=device)
     r0_bar = torch.empty((2, B) if fin else (B,), dtype=torch.float32, device=device)
     ts_bar = torch.empty((T,), dtype=torch.float32, device=device)
@@ -197,6 +231,7 @@ def _bwd_call(spec, aug, eps_in_args, ys, ts, pflat, g_y, g_r, rtol, atol, mxste
                                   float(rtol), float(atol), _mx(mxstep), _ptr(ws), ws.numel(), _ptr(y0_bar), _ptr(r0_bar),
                                   _ptr(ts_bar), _ptr(p_bar), st, _ptr(trace), trace_cap, stream)
     _cabi.check(rc, h, "eno_odeint_bwd")
+    _warn_status("odeint (adjoint solve)", rc)
     return y0_bar, r0_bar, ts_bar, p_bar, [s.as_dict() for s in st][:max(T - 1, 0)], trace, eps_bar
 
 

@@ -268,6 +268,20 @@ int32_t eno_comm_destroy(eno_ctx* ctx);
 int32_t eno_profile_enable(eno_ctx* ctx, int32_t on);
 int32_t eno_profile_read(eno_ctx* ctx, double* ms_out /*[4]*/, int64_t* count_out /*[4]*/);
 int32_t eno_ffma_peak(eno_ctx* ctx, double* tflops_out, void* stream);
+/* With profiling on, solves of ENO_ARCH_CONCATSQUASH dynamics bracket every tensor-core GEMM launch of their loop
+ * iterations with CUDA events (direct launches instead of the iteration graph).  Returns and clears the accumulated
+ * milliseconds, ALGORITHMIC flops (2 M N K per contraction, not the three tf32 passes, not the tile padding) and launches. */
+int32_t eno_profile_read_gemm(eno_ctx* ctx, double* ms_out, double* flop_out, int64_t* count_out);
+
+/*
+ * Optimiser step of the FFJORD scripts, one launch (only enqueues work).  Replaces
+ *   optimizers.adam(step_size=lr_schedule) + the lam_w * 0.5 |theta|^2 term of loss_fn     ffjord_tabular.py:417-432, 527-529
+ *   g <- g + lam_w * x;  m <- (1-b1) g + b1 m;  v <- (1-b2) g^2 + b2 v;
+ *   x <- x - lr * (m / (1 - b1^(step+1))) / (sqrt(v / (1 - b2^(step+1))) + eps)            (jax.experimental.optimizers.adam)
+ * `lr` is the schedule's value at `step` (piecewise_constant, ffjord_tabular.py:525-526; evaluated by the host).
+ */
+int32_t eno_adam_update(eno_ctx* ctx, float* params, float* m, float* v, const float* grads, int64_t n, float lr, float b1,
+                        float b2, float eps, int32_t step, float lam_w, void* stream);
 
 /*
  * Unit-test hook of the tensor-core contraction used by the wide-network path (no reference counterpart; the

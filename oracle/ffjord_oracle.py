@@ -125,3 +125,51 @@ def make_ffjord_closures(reg="r2", reg_type="our"):
     fwd = lambda y, t, eps, params: dynamics_wrap(y, t, params)
     return dict(dynamics_wrap=dynamics_wrap, reg_dynamics=reg_dynamics, ffjord_dynamics=ffjord_dynamics,
                 ffjord2_dynamics=ffjord2_dynamics, aug_dynamics=aug_dynamics, all_aug_dynamics=all_aug_dynamics, fwd=fwd)
+
+
+# ---- one update() of ffjord_tabular.py (the CPU arm of bench.py --workload ffjord_tabular) ----------------------------
+def standard_normal_logprob(z):
+    """ffjord_tabular.py:402-407."""
+    return -0.5 * math.log(2 * math.pi) - torch.square(z) / 2
+
+
+def train_step_grads(params, x, eps, lam=1e-2, lam_w=1e-6, reg="r2", rtol=1.4e-8, atol=1.4e-8):
+    """jax.grad(loss_fn) of ffjord_tabular.py:417-432, 521 for reg_type 'our': forward_aux = odeint_sepaux (forward solves y
+    only; delta_logp and r come back as zeros, lib/ode.py:1006-1018), loss = -mean(logpz - delta_logp) + lam mean(r) +
+    lam_w 0.5 |theta|^2; the backward is the adjoint of aug_dynamics (lib/ode.py:1686-1693)."""
+    from . import ode_oracle as oo
+    cl = make_ffjord_closures(reg, "our")
+    B = x.shape[0]
+    ts = torch.tensor([0., 1.], dtype=x.dtype)
+    z0 = torch.zeros(B, 1, dtype=x.dtype)
+    res, nfe, fst = oo.odeint_split_fwd(cl["fwd"], (x, z0, z0), ts, eps, params, n_aux=2, rtol=rtol, atol=atol, return_stats=True)
+    z = res[0][-1]
+    logpz = torch.sum(standard_normal_logprob(z).reshape(B, -1), dim=1, keepdim=True)
+    loss = -torch.mean(logpz - res[1][-1])
+    gg = tuple(torch.zeros_like(r) for r in res)
+    gg[0][-1], gg[1][-1], gg[2][-1] = z / B, 1.0 / B, lam / B
+    bst = []
+    out = oo.odeint_split_rev(cl["aug_dynamics"], rtol, atol, math.inf, res, ts, (eps, params), gg, bst)
+    grads = {n: {k: out[3][n][k] + lam_w * params[n][k] for k in params[n]} for n in params}
+    return dict(loss=loss, nfe=nfe, grads=grads, fwd_stats=fst, bwd_stats=bst, z=z)
+
+
+def adam_init(params):
+    zeros = lambda: {n: {k: torch.zeros_like(v) for k, v in p.items()} for n, p in params.items()}
+    return zeros(), zeros()
+
+
+def adam_update(params, m, v, grads, step, lr, b1=0.9, b2=0.999, eps=1e-8):
+    """jax.experimental.optimizers.adam (ffjord_tabular.py:527)."""
+    new_p, new_m, new_v = {}, {}, {}
+    for n in params:
+        new_p[n], new_m[n], new_v[n] = {}, {}, {}
+        for k in params[n]:
+            g = grads[n][k]
+            mi = (1 - b1) * g + b1 * m[n][k]
+            vi = (1 - b2) * g * g + b2 * v[n][k]
+            mhat = mi / (1 - b1 ** (step + 1))
+            vhat = vi / (1 - b2 ** (step + 1))
+            new_p[n][k] = params[n][k] - lr * mhat / (torch.sqrt(vhat) + eps)
+            new_m[n][k], new_v[n][k] = mi, vi
+    return new_p, new_m, new_v

@@ -93,7 +93,12 @@ def css_case(ref):
     """ffjord_tabular.py's odeint_sepaux call (reg_type 'our': state (y, logp, r)) with ConcatSquash dynamics on
     small dims: groundwork for BASELINE config C2 (oracle/ffjord_oracle.py)."""
     from oracle import ffjord_oracle as fo
-    B, D, H, seed, scale, tol = 5, 6, 12, 3, 1.5, 1e-5
+    B, D, H, seed, scale = 5, 6, 12, 3, 1.5
+    for tol, name in ((1e-5, "css_sepaux.npz"), (1.4e-8, "css_sepaux_default.npz")):   # 1.4e-8: the script default (ffjord_tabular.py:34-35)
+        _css_case(ref, fo, B, D, H, seed, scale, tol, name)
+
+
+def _css_case(ref, fo, B, D, H, seed, scale, tol, name):
     params = fo.init_css_params(D, H, seed=seed, scale=scale)
     g = torch.Generator().manual_seed(9)
     x0 = torch.randn((B, D), generator=g)
@@ -108,7 +113,7 @@ def css_case(ref):
     gg = tuple(torch.zeros_like(r) for r in res)
     gg[0][-1], gg[1][-1], gg[2][-1] = gy, 1.0 / B, 0.01 / B
     out = ref._odeint_sepaux_rev(fwd_w, rev_w, tol, tol, math.inf, saved, (gg, None))
-    np.savez(os.path.join(OUT, "css_sepaux.npz"), B=B, D=D, H=H, seed=seed, scale=scale, tol=tol, x0=x0.numpy(),
+    np.savez(os.path.join(OUT, name), B=B, D=D, H=H, seed=seed, scale=scale, tol=tol, x0=x0.numpy(),
              eps=eps.numpy(), gy=gy.numpy(), y=res[0].numpy(), nfe=float(nfe), x0_bar=out[0][0].numpy(),
              ts_bar=out[1].numpy(), eps_bar=out[2].numpy(), params_bar=flat_params(out[3]))
 
