@@ -369,8 +369,18 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    single = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        if args.reg_type == "our":
+            # parity evidence for the sharded solve, untimed: every rank first solves the CONCATENATED global batch of
+            # train step 0 on its own GPU, non-collectively (the library is not in collective mode yet) ...
+            ref_model = mnist_step.MnistNode(reg="r3", lam=LAM, rtol=TOL, atol=TOL, device=dev, dim=D, hidden=H, world=1)
+            parts = [synth_batch(r, 0) for r in range(world)]
+            o = ref_model.loss_and_grads(*(torch.cat([q[k] for q in parts]).to(dev) for k in range(3)))
+            single = dict(y1=o["y1"][rank * B:(rank + 1) * B].clone(), g=o["grads"]["ode"].clone(), loss=float(o["loss"]),
+                          fwd=o["fwd_stats"]["n_iters"], bwd=o["bwd_stats"][0]["n_iters"])
+            del ref_model, o
         eno.init_distributed()   # solves become collective: one global adaptive step sequence
 
     if args.reg_type == "fin":
@@ -381,6 +391,23 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     dev_batches = [tuple(t.to(dev) for t in synth_batch(rank, s)) for s in range(8)]
     host_batches = [synth_batch(rank, s, pin=True) for s in range(8)]
+
+    parity = None
+    if single is not None:
+        # ... then the same step as a collective solve over the shards; compared block by block
+        o = model.loss_and_grads(*dev_batches[0])
+        rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
+        errs = torch.tensor([rel(o["y1"], single["y1"]), rel(o["grads"]["ode"], single["g"]),
+                             abs(float(o["loss"]) - single["loss"]) / abs(single["loss"]),
+                             float(o["fwd_stats"]["n_iters"] != single["fwd"]), float(o["bwd_stats"][0]["n_iters"] != single["bwd"])],
+                            device=dev, dtype=torch.float64)
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        parity = {"against": f"single-GPU solve of the concatenated batch ({B * world} rows) of train step 0, same process, before "
+                             "the library entered collective mode; max over ranks",
+                  "fwd_iters": [o["fwd_stats"]["n_iters"], single["fwd"]], "bwd_iters": [o["bwd_stats"][0]["n_iters"], single["bwd"]],
+                  "iteration_counts_identical_on_all_ranks": bool(errs[3] == 0 and errs[4] == 0),
+                  "y1_rel": float(errs[0]), "grad_rel": float(errs[1]), "loss_rel": float(errs[2])}
+        single = None
 
     use_graph = not args.no_graph
 
@@ -519,6 +546,8 @@ def main():
         "roofline": roofline,
         "wall_s": wall,
     }
+    if parity is not None:
+        line["parity"] = parity
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = len(os.sched_getaffinity(0))
         n_cpu = min(args.steps, 8)

@@ -82,7 +82,7 @@ def lib():
     L.eno_mnist_head.restype = i32
     L.eno_mnist_head.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp]
     L.eno_momentum_update.restype = i32
-    L.eno_momentum_update.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), f32, f32, vp, vp, vp]
+    L.eno_momentum_update.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), f32, f32, f32, vp, vp, vp, vp]
     L.eno_profile_enable.restype = i32
     L.eno_profile_enable.argtypes = [vp, i32]
     L.eno_profile_read.restype = i32

@@ -159,7 +159,7 @@ void plan_build(const eno_dynamics_desc* d, int B, int T, int mode, void* ws, Pl
       n.WP[l] = cv.take<float>(3 * (size_t)n.din[l] * n.dout[l]);
     }
   }
-  n.cr_chunks = 16;
+  n.cr_chunks = css::kCrChunks;
   if (adj) {
     n.CR = cv.take<float>((size_t)L * n.cr_chunks * 4 * n.hmax);
     n.TC = cv.take<float>((size_t)L * n.hmax);
@@ -282,7 +282,7 @@ int css_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
       CSS_G(gemm(A, Bt, n.din[l], n.dout[l], 1 + n.nq, done, css::EpiWgrad{n.WP[l], n.din[l], n.dout[l]}, st, err));
     }
     css::k_css_colred<<<dim3((n.hmax + 31) / 32, n.cr_chunks, L), dim3(32, 8), 0, st>>>(f, n);
-    css::k_css_colfin<<<(n.hmax + 127) / 128, 128, 0, st>>>(f, n, stage, init_mode, k_override ? k_override + f.oPR : nullptr);
+    css::k_css_colfin<<<dim3((n.hmax + 63) / 64, L), 64, 0, st>>>(f, n, stage, init_mode, k_override ? k_override + f.oPR : nullptr);
   }
   const size_t work = std::max((size_t)B * n.D, n.mode == css::MODE_ADJ ? (size_t)n.H * n.H : (size_t)1);
   css::k_css_assemble<<<std::min((int)((work + 255) / 256), 8 * sms), 256, 0, st>>>(f, n, stage, init_mode, k_override);
@@ -592,6 +592,16 @@ __global__ void k_adam(float* __restrict__ x, float* __restrict__ m, float* __re
 }  // namespace
 
 extern "C" {
+
+#ifdef ENO_PHASES
+// development aid: the clock stamps of the last `n` (<= 64) GEMM launches, 8 words each (gemm_tc.cuh)
+int32_t eno_debug_gemm_stamps(long long* out, unsigned int* n_launches) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, tc::g_gemm_stamp, sizeof(long long) * 64 * 8);
+  cudaMemcpyFromSymbol(n_launches, tc::g_gemm_launch, sizeof(unsigned int));
+  return 0;
+}
+#endif
 
 int32_t eno_profile_read_gemm(eno_ctx* ctx, double* ms_out, double* flop_out, int64_t* count_out) {
   if (!ctx || !ms_out || !flop_out || !count_out) return ENO_E_ARG;

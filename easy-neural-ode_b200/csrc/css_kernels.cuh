@@ -245,28 +245,35 @@ __global__ void k_css_colred(Flat a, Net n) {
 }
 
 // gate / bias gradients of every layer into the stage derivative's params block; per-column t_bar pieces
+constexpr int kCrChunks = 16;   // row chunks of k_css_colred (Net::cr_chunks)
+
 __global__ void k_css_colfin(Flat a, Net n, int stage, int init_mode, float* pr_override) {
   if (init_mode == ST_STAGE && a.ctrl->done) return;
   float* pr = pr_override ? pr_override : k_slot(a, stage, init_mode) + a.oPR;
   const float t = *n.tval;
-  for (int l = 0; l < n.L; ++l) {
-    for (int col = blockIdx.x * blockDim.x + threadIdx.x; col < n.dout[l]; col += gridDim.x * blockDim.x) {
-      float q[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int ch = 0; ch < n.cr_chunks; ++ch)
+  const int l = blockIdx.y;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= n.dout[l]) return;
+  float q[4] = {0.f, 0.f, 0.f, 0.f};
+  float v[kCrChunks][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) q[k] += n.CR[(((size_t)l * n.cr_chunks + ch) * 4 + k) * n.hmax + col];
-      const float G = n.G[l][col], wg = n.wg[l][col], wb = n.wb[l][col];
-      const float dG = G * (1.f - G);
-      const float gbar = q[0] * dG + q[1] * dG * (1.f - 2.f * G) * wg;   // cotangent of the gate pre-activation
-      float* p = pr + n.poff[l];
-      const size_t din_dout = (size_t)n.din[l] * n.dout[l];
-      p[col] = G * q[2] + n.G1[l][col] * q[3];                                  // b_bar = column sum of lin_bar
-      p[(size_t)n.dout[l] + din_dout + col] = t * q[2] + q[3];                  // w_bias_bar
-      p[(size_t)2 * n.dout[l] + din_dout + col] = gbar;                          // b_gate_bar
-      p[(size_t)3 * n.dout[l] + din_dout + col] = gbar * t + q[1] * dG;          // w_gate_bar
-      n.TC[(size_t)l * n.hmax + col] = gbar * wg + wb * q[2];
-    }
-  }
+  for (int ch = 0; ch < kCrChunks; ++ch)     // all loads in flight before the first add
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[ch][k] = n.CR[(((size_t)l * kCrChunks + ch) * 4 + k) * n.hmax + col];
+#pragma unroll
+  for (int ch = 0; ch < kCrChunks; ++ch)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] += v[ch][k];
+  const float G = n.G[l][col], wg = n.wg[l][col], wb = n.wb[l][col];
+  const float dG = G * (1.f - G);
+  const float gbar = q[0] * dG + q[1] * dG * (1.f - 2.f * G) * wg;   // cotangent of the gate pre-activation
+  float* p = pr + n.poff[l];
+  const size_t din_dout = (size_t)n.din[l] * n.dout[l];
+  p[col] = G * q[2] + n.G1[l][col] * q[3];                                  // b_bar = column sum of lin_bar
+  p[(size_t)n.dout[l] + din_dout + col] = t * q[2] + q[3];                  // w_bias_bar
+  p[(size_t)2 * n.dout[l] + din_dout + col] = gbar;                          // b_gate_bar
+  p[(size_t)3 * n.dout[l] + din_dout + col] = gbar * t + q[1] * dG;          // w_gate_bar
+  n.TC[(size_t)l * n.hmax + col] = gbar * wg + wb * q[2];
 }
 
 // ---- stage derivative of every block --------------------------------------------------------------------------

@@ -66,21 +66,33 @@ struct Net {
   __host__ __device__ size_t abtplane(int l) const { return (size_t)dout[l] * 3 * Bp; }
 };
 
+constexpr int kW = tc::kEpiW;   // columns one epilogue call covers
+
 __device__ __forceinline__ void softplus_sigmoid(float u, float& sp, float& sg) {
-  // _logaddexp(u, 0) = max(u, 0) + log1p(exp(-|u|))  (ffjord_tabular.py:92-103); sigmoid from the same exponential
+  // _logaddexp(u, 0) = max(u, 0) + log1p(exp(-|u|))  (ffjord_tabular.py:92-103); sigmoid from the same exponential.
+  // The epilogues are instruction-issue bound, so the transcendental part uses the SFU approximations: exp(-|u|) in
+  // (0, 1] to ~2 ulp, log(1 + e) in (0, log 2] to 2^-22 absolute, the reciprocal to 1 ulp - all at the level of the fp32
+  // round-off of the surrounding arithmetic (single evaluations are checked to 3e-6 against fp64 in
+  // tests/test_gpu_ffjord.py).  -DENO_CSS_ACCURATE_MATH restores expf / log1pf / IEEE division.
+#ifdef ENO_CSS_ACCURATE_MATH
   const float e = expf(-fabsf(u));
   sp = fmaxf(u, 0.f) + log1pf(e);
   const float r = 1.0f / (1.0f + e);
+#else
+  const float e = __expf(-fabsf(u));
+  sp = fmaxf(u, 0.f) + __logf(1.0f + e);
+  const float r = __fdividef(1.0f, 1.0f + e);
+#endif
   sg = (u >= 0.f) ? r : e * r;
 }
 
-// row-major hi / lo planes: 32 consecutive elements of one row
-__device__ __forceinline__ void put_split_row(float* base, size_t plane, size_t row_off, int n0, int ncols, const float (&x)[32]) {
+// row-major hi / lo planes: kW consecutive elements of one row
+__device__ __forceinline__ void put_split_row(float* base, size_t plane, size_t row_off, int n0, int ncols, const float (&x)[kW]) {
   float* hi = base + row_off + n0;
   float* lo = hi + plane;
-  if (n0 + 32 <= ncols) {
+  if (n0 + kW <= ncols) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < kW; j += 4) {
       float4 h, l;
       tc::split_tf32(x[j], h.x, l.x); tc::split_tf32(x[j + 1], h.y, l.y);
       tc::split_tf32(x[j + 2], h.z, l.z); tc::split_tf32(x[j + 3], h.w, l.w);
@@ -89,14 +101,14 @@ __device__ __forceinline__ void put_split_row(float* base, size_t plane, size_t 
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < kW; ++j)
       if (n0 + j < ncols) { float h, l; tc::split_tf32(x[j], h, l); hi[j] = h; lo[j] = l; }
   }
 }
 // transposed hi / lo planes [ncols][ldt]: element (n0 + j, col); the lanes of a warp hold consecutive `col`
-__device__ __forceinline__ void put_split_col(float* base, size_t plane, int ldt, int col, int n0, int ncols, const float (&x)[32]) {
+__device__ __forceinline__ void put_split_col(float* base, size_t plane, int ldt, int col, int n0, int ncols, const float (&x)[kW]) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j)
+  for (int j = 0; j < kW; ++j)
     if (n0 + j < ncols) {
       float h, l;
       tc::split_tf32(x[j], h, l);
@@ -105,26 +117,26 @@ __device__ __forceinline__ void put_split_col(float* base, size_t plane, int ldt
       base[plane + o] = l;
     }
 }
-__device__ __forceinline__ void put_row(float* row, int n0, int ncols, const float (&x)[32]) {
-  if (n0 + 32 <= ncols) {
+__device__ __forceinline__ void put_row(float* row, int n0, int ncols, const float (&x)[kW]) {
+  if (n0 + kW <= ncols) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(row + n0 + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+    for (int j = 0; j < kW; j += 4) *reinterpret_cast<float4*>(row + n0 + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < kW; ++j)
       if (n0 + j < ncols) row[n0 + j] = x[j];
   }
 }
-__device__ __forceinline__ void get_row(const float* row, int n0, int ncols, float (&x)[32]) {
-  if (n0 + 32 <= ncols) {
+__device__ __forceinline__ void get_row(const float* row, int n0, int ncols, float (&x)[kW]) {
+  if (n0 + kW <= ncols) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < kW; j += 4) {
       const float4 t = *reinterpret_cast<const float4*>(row + n0 + j);
       x[j] = t.x; x[j + 1] = t.y; x[j + 2] = t.z; x[j + 3] = t.w;
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) x[j] = (n0 + j < ncols) ? row[n0 + j] : 0.f;
+    for (int j = 0; j < kW; ++j) x[j] = (n0 + j < ncols) ? row[n0 + j] : 0.f;
   }
 }
 
@@ -132,13 +144,13 @@ __device__ __forceinline__ void get_row(const float* row, int n0, int ncols, flo
 struct EpiPrimal {
   Net n;
   int l;
-  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[32], int) const {
+  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[kW], int) const {
     const int dout = n.dout[l], ldo = n.ldo[l];
     if (m >= n.B || n0 >= dout) return;
     const bool last = (l == n.L - 1);
-    float lin[32], s[32], x[32];
+    float lin[kW], s[kW], x[kW];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < kW; ++j) {
       const int c = min(n0 + j, dout - 1);
       lin[j] = v[j] + n.b[l][c];
       const float u = lin[j] * n.G[l][c] + n.CC[l][c];
@@ -164,30 +176,30 @@ struct EpiPrimal {
 struct EpiTangent {
   Net n;
   int l;
-  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[32], int) const {
+  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[kW], int) const {
     const int dout = n.dout[l], ldo = n.ldo[l];
     const int q = m / n.Bp, bm = m - q * n.Bp;
     if (q >= n.nq || bm >= n.B || n0 >= dout) return;
     const bool last = (l == n.L - 1);
-    float u1[32];
+    float u1[kW];
     if (q == 1) {
-      float lin[32];
+      float lin[kW];
       get_row(n.LIN[l] + (size_t)bm * ldo, n0, dout, lin);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < kW; ++j) {
         const int c = min(n0 + j, dout - 1);
         u1[j] = v[j] * n.G[l][c] + (lin[j] * n.G1[l][c] + n.wb[l][c]);
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) u1[j] = v[j] * n.G[l][min(n0 + j, dout - 1)];
+      for (int j = 0; j < kW; ++j) u1[j] = v[j] * n.G[l][min(n0 + j, dout - 1)];
     }
     if (n.mode == MODE_ADJ) put_row(n.A1[l] + ((size_t)q * n.B + bm) * ldo, n0, dout, v);
     if (!last) {
-      float s[32];
+      float s[kW];
       get_row(n.S[l] + (size_t)bm * ldo, n0, dout, s);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) u1[j] *= s[j];
+      for (int j = 0; j < kW; ++j) u1[j] *= s[j];
       put_split_row(n.X2[l + 1], n.xplane(l + 1), (size_t)((1 + q) * n.Bp + bm) * n.ldi[l + 1], n0, dout, u1);
       if (n.mode == MODE_ADJ) put_split_col(n.XT2[l + 1], n.xtplane(l + 1), 3 * n.Bp, (1 + q) * n.Bp + bm, n0, dout, u1);
     } else {
@@ -200,28 +212,28 @@ struct EpiTangent {
 struct EpiTanRev {
   Net n;
   int l;   // >= 1
-  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[32], int) const {
+  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[kW], int) const {
     const int lm = l - 1;
     const int dout = n.dout[lm], ldo = n.ldo[lm];
     const int q = m / n.Bp, bm = m - q * n.Bp;
     if (q >= n.nq || bm >= n.B || n0 >= dout) return;
-    float s[32], a1[32], ab[32], wq[32], vv[32];
+    float s[kW], a1[kW], ab[kW], wq[kW], vv[kW];
     get_row(n.S[lm] + (size_t)bm * ldo, n0, dout, s);
     get_row(n.A1[lm] + ((size_t)q * n.B + bm) * ldo, n0, dout, a1);
     if (q == 1) {
-      float lin[32];
+      float lin[kW];
       get_row(n.LIN[lm] + (size_t)bm * ldo, n0, dout, lin);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < kW; ++j) {
         const int c = min(n0 + j, dout - 1);
         a1[j] = a1[j] * n.G[lm][c] + (lin[j] * n.G1[lm][c] + n.wb[lm][c]);   // u1_{l-1}
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a1[j] *= n.G[lm][min(n0 + j, dout - 1)];
+      for (int j = 0; j < kW; ++j) a1[j] *= n.G[lm][min(n0 + j, dout - 1)];
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < kW; ++j) {
       vv[j] = v[j] * s[j];                              // cotangent of u1_{l-1}
       wq[j] = v[j] * a1[j] * s[j] * (1.f - s[j]);       // -> cotangent of u_{l-1} through softplus''
       ab[j] = vv[j] * n.G[lm][min(n0 + j, dout - 1)];   // cotangent of a1_{l-1}
@@ -236,7 +248,7 @@ struct EpiTanRev {
 
 struct EpiTanRev0 {   // layer 0: cotangent of the stream inputs e_0 = eps, d_0 = f
   Net n;
-  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[32], int) const {
+  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[kW], int) const {
     const int q = m / n.Bp, bm = m - q * n.Bp;
     if (q >= n.nq || bm >= n.B || n0 >= n.D) return;
     put_row(n.XB1 + ((size_t)q * n.B + bm) * n.ldD, n0, n.D, v);
@@ -247,27 +259,27 @@ struct EpiTanRev0 {   // layer 0: cotangent of the stream inputs e_0 = eps, d_0 
 struct EpiPrimRev {
   Net n;
   int l;   // >= 1: x_bar_l arrives, fold layer l-1
-  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[32], int) const {
+  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[kW], int) const {
     const int lm = l - 1;
     const int dout = n.dout[lm], ldo = n.ldo[lm];
     if (m >= n.B || n0 >= dout) return;
-    float s[32], w[32], lb[32], t[32];
+    float s[kW], w[kW], lb[kW], t[kW];
     get_row(n.S[lm] + (size_t)m * ldo, n0, dout, s);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) w[j] = v[j] * s[j];
+    for (int j = 0; j < kW; ++j) w[j] = v[j] * s[j];
     if (n.nq >= 1) {
       get_row(n.WQ[lm] + (size_t)m * ldo, n0, dout, t);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) w[j] += t[j];
+      for (int j = 0; j < kW; ++j) w[j] += t[j];
     }
     if (n.nq == 2) {
       get_row(n.WQ[lm] + ((size_t)n.B + m) * ldo, n0, dout, t);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) w[j] += t[j];
+      for (int j = 0; j < kW; ++j) w[j] += t[j];
       get_row(n.V[lm] + ((size_t)n.B + m) * ldo, n0, dout, t);
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < kW; ++j) {
       const int c = min(n0 + j, dout - 1);
       lb[j] = w[j] * n.G[lm][c] + (n.nq == 2 ? t[j] * n.G1[lm][c] : 0.f);
     }
@@ -279,7 +291,7 @@ struct EpiPrimRev {
 
 struct EpiPrimRev0 {
   Net n;
-  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[32], int) const {
+  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[kW], int) const {
     if (m >= n.B || n0 >= n.D) return;
     put_row(n.YBDOT + (size_t)m * n.ldD, n0, n.D, v);
   }
@@ -289,11 +301,11 @@ struct EpiPrimRev0 {
 struct EpiWgrad {
   float* WP;
   int din, dout;
-  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[32], int split) const {
+  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[kW], int split) const {
     if (m >= din || n0 >= dout) return;
     float* row = WP + ((size_t)split * din + m) * dout;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < kW; ++j)
       if (n0 + j < dout) row[n0 + j] = v[j];
   }
 };

@@ -469,8 +469,8 @@ int32_t eno_mnist_head(eno_ctx* ctx, int32_t B, int32_t D, int32_t C, const floa
 }
 
 int32_t eno_momentum_update(eno_ctx* ctx, int32_t n_blocks, float* const* params, float* const* velocity,
-                            const float* const* grads, const int64_t* sizes, float lr, float mass, const int32_t* ok_a,
-                            const int32_t* ok_b, void* stream_) {
+                            const float* const* grads, const int64_t* sizes, float lr, float mass, float lam_w,
+                            const float* lr_dev, const int32_t* ok_a, const int32_t* ok_b, void* stream_) {
   if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_momentum_update: ctx is null");
   if (n_blocks < 1 || n_blocks > 3 || !params || !velocity || !grads || !sizes)
     return fail(ctx, ENO_E_ARG, "eno_momentum_update: 1..3 parameter blocks");
@@ -483,7 +483,7 @@ int32_t eno_momentum_update(eno_ctx* ctx, int32_t n_blocks, float* const* params
     total = sizes[k] > total ? sizes[k] : total;
   }
   const int grid = (int)((total + 255) / 256 < 4LL * ctx->sm_count ? (total + 255) / 256 : 4LL * ctx->sm_count);
-  k_momentum<<<grid > 0 ? grid : 1, 256, 0, stream>>>(m, lr, mass, ok_a, ok_b);
+  k_momentum<<<grid > 0 ? grid : 1, 256, 0, stream>>>(m, lr, mass, lam_w, lr_dev, ok_a, ok_b);
   ENO_CUDA(ctx, cudaGetLastError());
   return ENO_OK;
 }

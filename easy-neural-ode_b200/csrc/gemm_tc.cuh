@@ -22,7 +22,11 @@ constexpr int kBM = 128;        // rows of the accumulator tile = TMEM lanes
 constexpr int kBK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 8;       // K of one tcgen05.mma kind::tf32
 constexpr int kAccs = 4;        // TMEM accumulators per tile: 3 x (hi*hi by k-block) + 1 x cross terms
-constexpr int kGemmThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kEpiWarps = 16;   // epilogue warps: 4 per TMEM lane quadrant, each owns BN / 4 columns of its 32 rows
+constexpr int kEpiChunk = 16;   // columns drained from TMEM per step (per warp: 32 rows x 16 columns)
+constexpr int kEpiW = 4;        // columns per epilogue-functor call (one float4 of one row)
+constexpr int kEpiPitch = kEpiChunk + 1;   // padded row pitch of the per-warp transposition tile
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2..: epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -99,6 +103,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 16 consecutive columns, no wait: the caller batches loads and waits once
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // Shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes, 128-byte swizzled (what TMA
 // wrote): 8-row groups 1024 bytes apart; version 1 (sm_100); layout type 2 = SWIZZLE_128B.
 __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
@@ -116,6 +133,16 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
 
+#ifdef ENO_PHASES
+// development aid (libeno_phases.so): clock stamps of CTA (0,0,0) of the most recent launches, 8 per launch:
+// entry, set-up done, first operand stage landed, last MMA issued, accumulators complete, epilogue done, exit
+__device__ long long g_gemm_stamp[64 * 8];
+__device__ unsigned int g_gemm_launch;
+#define GEMM_STAMP(slot) do { if (stamp) stamp[slot] = clock64(); } while (0)
+#else
+#define GEMM_STAMP(slot) do { } while (0)
+#endif
+
 template <int BN>
 struct GemmCfg {
   static constexpr int kStages = (BN >= 128) ? 3 : 4;
@@ -125,8 +152,8 @@ struct GemmCfg {
   static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-// Epi: struct with  __device__ void operator()(int m, int n0, float (&v)[32], int split) const
-// called once per (row, 32-column chunk) of the tile by the thread that owns TMEM lane (m % 128); the functor
+// Epi: struct with  __device__ void operator()(int m, int n0, float (&v)[kEpiW], int split) const
+// called once per (row, 4-column piece) of the tile; the functor
 // masks rows / columns outside its matrices itself.  `done` (may be null): device word; non-zero = the solve has
 // finished, the launch exits at once (iterations enqueued past the end of an adaptive solve).
 template <int BN, class Epi>
@@ -134,6 +161,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int a_row0, int b_row0,
               int kb_per_split, int kb_total, const int* __restrict__ done, Epi epi) {
   if (done && *done) return;
+#ifdef ENO_PHASES
+  __shared__ long long* stamp_s;
+  if (threadIdx.x == 0) {
+    stamp_s = nullptr;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      const unsigned int id = atomicAdd(&g_gemm_launch, 1u);
+      stamp_s = g_gemm_stamp + (id % 64) * 8;
+      stamp_s[0] = clock64();
+      stamp_s[7] = ((long long)BN << 40) | ((long long)kb_total << 24) | ((long long)gridDim.x << 12) | gridDim.y;
+    }
+  }
+  __syncthreads();
+  long long* stamp = stamp_s;
+#endif
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -160,6 +201,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) GEMM_STAMP(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -185,6 +227,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t ph = (uint32_t)(i / Cfg::kStages) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after();
+        if (i == 0) GEMM_STAMP(2);
         const uint32_t sa = smem_u32(smem + (size_t)s * Cfg::kStageBytes);
         const uint64_t a_hi = smem_desc_k_sw128(sa), a_lo = smem_desc_k_sw128(sa + Cfg::kABytes);
         const uint64_t b_hi = smem_desc_k_sw128(sa + 2 * Cfg::kABytes);
@@ -205,41 +248,74 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
       }
       umma_commit(tmem_full);
+      GEMM_STAMP(3);
     }
     __syncwarp();
   } else {
-    const int q = warp & 3;   // TMEM lane quadrant this warp may read
+    // Epilogue: 16 warps so that the element-wise work of the fused functors (exponentials, tf32 splits, several
+    // output streams) has four warps per scheduler to hide its latencies behind - with four warps in all it took
+    // longer than the main loop (tools/gemm_stamps.py).
+    const int q = warp & 3;                // TMEM lane quadrant this warp may read
+    const int cg = (warp - 2) >> 2;        // column group: BN / 4 columns
+    constexpr int kCols = BN / 4;
     if (nkb > 0) {
-      mbar_wait(tmem_full, 0);
+      while (!mbar_try_wait(tmem_full, 0)) __nanosleep(128);
       tc_fence_after();
     }
-    const int m = m0 + q * 32 + lane;
+    if (threadIdx.x == 64) GEMM_STAMP(4);
+    const int used = min(nkb, kAccs - 1);
+    // TMEM hands every thread one ROW of the tile.  Global accesses in that shape touch 32 different lines per
+    // instruction and the epilogue became L1-wavefront bound; so the chunk is transposed through shared memory (the
+    // operand stages are free once tmem_full has fired) into a quad layout: a thread owns 4 consecutive columns of 4
+    // rows, 4 lanes cover the 16 columns of a row, a warp instruction touches 8 rows.
+    float* tile = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kEpiPitch);
+    const int cq = (lane & 3) * kEpiW, r0 = lane >> 2;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
+    for (int c = cg * kCols; c < (cg + 1) * kCols; c += kEpiChunk) {
+      float v[kEpiChunk];
       if (nkb > 0) {
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
-        tmem_ld32(lane_base, v);
-        float w[32];
-        const int used = min(nkb, kAccs - 1);
-        for (int j = 1; j < used; ++j) {
-          tmem_ld32(lane_base + (uint32_t)(j * BN), w);
+        float w[kEpiChunk];
+        tmem_ld16_nowait(lane_base, v);
+        tmem_ld16_nowait(lane_base + (uint32_t)((kAccs - 1) * BN), w);
+        tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] += w[e];
+        for (int e = 0; e < kEpiChunk; ++e) v[e] += w[e];
+        if (used > 1) {   // accumulators the MMA warp never wrote hold garbage: they are not read
+          float w2[kEpiChunk];
+          tmem_ld16_nowait(lane_base + (uint32_t)BN, w);
+          if (used > 2) tmem_ld16_nowait(lane_base + (uint32_t)(2 * BN), w2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < kEpiChunk; ++e) v[e] += w[e];
+          if (used > 2) {
+#pragma unroll
+            for (int e = 0; e < kEpiChunk; ++e) v[e] += w2[e];
+          }
         }
-        tmem_ld32(lane_base + (uint32_t)((kAccs - 1) * BN), w);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] += w[e];
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        for (int j = 0; j < kEpiChunk; ++j) v[j] = 0.f;
       }
-      epi(m, n0 + c, v, split);
+#pragma unroll
+      for (int j = 0; j < kEpiChunk; ++j) tile[lane * kEpiPitch + j] = v[j];
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = r0 + 8 * it;
+        float x[kEpiW];
+#pragma unroll
+        for (int j = 0; j < kEpiW; ++j) x[j] = tile[row * kEpiPitch + cq + j];
+        epi(m0 + q * 32 + row, n0 + c + cq, x, split);
+      }
+      __syncwarp();
     }
   }
+  if (threadIdx.x == 64) GEMM_STAMP(5);
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kAccs * BN);
+  if (threadIdx.x == 64) GEMM_STAMP(6);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
@@ -332,11 +408,11 @@ struct EpiStore {
   float* C;
   int M, N, ld;
   size_t split_stride;
-  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[32], int split) const {
+  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[kEpiW], int split) const {
     if (m >= M) return;
     float* row = C + (size_t)split * split_stride + (size_t)m * ld;
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < kEpiW; ++j)
       if (n0 + j < N) row[n0 + j] = v[j];
   }
 };

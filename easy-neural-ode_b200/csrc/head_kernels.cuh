@@ -98,14 +98,16 @@ struct MomentumBlocks {
   long long n[3];
 };
 
-__global__ void __launch_bounds__(256) k_momentum(MomentumBlocks m, float lr, float mass, const int* ok_a, const int* ok_b) {
+__global__ void __launch_bounds__(256) k_momentum(MomentumBlocks m, float lr, float mass, float lam_w, const float* lr_dev,
+                                                  const int* ok_a, const int* ok_b) {
   const bool ok = (!ok_a || *ok_a != 0) && (!ok_b || *ok_b != 0);
   if (!ok) return;
+  if (lr_dev) lr = *lr_dev;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
 #pragma unroll
   for (int k = 0; k < 3; ++k)
     for (long long i = tid; i < m.n[k]; i += nth) {
-      const float vn = mass * m.v[k][i] + m.g[k][i];
+      const float vn = mass * m.v[k][i] + (m.g[k][i] + lam_w * m.p[k][i]);
       m.v[k][i] = vn;
       m.p[k][i] = m.p[k][i] - lr * vn;
     }

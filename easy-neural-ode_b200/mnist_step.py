@@ -17,9 +17,18 @@ from .dynamics import MLPDynamics
 from . import ode, _cabi
 
 
+def mnist_lr_schedule(num_batches=600):
+    """lr_schedule of mnist.py:530-538: 1e-1 for epochs < 60, 1e-2 < 100, 1e-3 < 140, then 1e-4 (num_batches = 60000 /
+    batch_size iterations per epoch)."""
+    def lr(train_itr):
+        epoch = train_itr // num_batches
+        return 1e-1 if epoch < 60 else 1e-2 if epoch < 100 else 1e-3 if epoch < 140 else 1e-4
+    return lr
+
+
 class MnistNode:
     def __init__(self, reg="r3", lam=6e-5, rtol=1.4e-8, atol=1.4e-8, device="cuda", dim=784, hidden=100,
-                 lr=1e-1, mass=0.9, n_cls=10, world=1, reg_type="our", lam_fro=0.0, lam_kin=0.0):
+                 lr=1e-1, mass=0.9, n_cls=10, world=1, reg_type="our", lam_fro=0.0, lam_kin=0.0, lam_w=0.0):
         self.spec = MLPDynamics(dim, hidden, reg=reg, reg_type=reg_type)
         self.lam, self.rtol, self.atol = lam, rtol, atol
         self.reg_type, self.lam_fro, self.lam_kin = reg_type, lam_fro, lam_kin
@@ -28,6 +37,12 @@ class MnistNode:
         # pointers into them (controller words, rings), so they must not be handed out or re-allocated behind them
         self._wsown = ode.WorkspaceOwner(self.device)
         self.lr, self.mass = lr, mass
+        # lr: a number, or the script's schedule as a callable of the training iteration (mnist.py:530-538:
+        # mnist_lr_schedule(num_batches)).  The kernel reads the step size from a device word, so the captured whole-step
+        # graphs stay valid when the schedule moves.  lam_w: the weight-decay term of loss_fn (mnist.py:456-470).
+        self.lam_w, self.itr = lam_w, 0
+        self._lr_dev = torch.zeros(1, device=self.device)
+        self._lr_val = None
         self.dim, self.n_cls = dim, n_cls
         self.world = world   # data-parallel ranks: the loss is the mean over the GLOBAL batch
         self.ts = torch.tensor([0., 1.], device=self.device)
@@ -51,12 +66,13 @@ class MnistNode:
         self._reset_velocity()
 
     def snapshot(self):
-        """Copy of the trainable state (params + momentum)."""
-        return [t.clone() for t in (self.p_ode, self.post_w, self.post_b, self.v_ode, self.v_w, self.v_b)]
+        """Copy of the trainable state (params + momentum + iteration counter)."""
+        return [t.clone() for t in (self.p_ode, self.post_w, self.post_b, self.v_ode, self.v_w, self.v_b)] + [self.itr]
 
     def restore(self, snap):
         for dst, src in zip((self.p_ode, self.post_w, self.post_b, self.v_ode, self.v_w, self.v_b), snap):
             dst.copy_(src)
+        self.itr = snap[6]
 
     def _reset_velocity(self):
         self.v_ode = torch.zeros_like(self.p_ode)
@@ -130,7 +146,8 @@ class MnistNode:
         ns = (C.c_int64 * 3)(self.p_ode.numel(), self.post_w.numel(), self.post_b.numel())
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         with torch.cuda.device(self.device):
-            rc = L.eno_momentum_update(h, 3, ps, vs, gs, ns, float(self.lr), float(self.mass), ok_a, ok_b, stream)
+            rc = L.eno_momentum_update(h, 3, ps, vs, gs, ns, 0.0, float(self.mass), float(self.lam_w),
+                                       C.c_void_p(self._lr_dev.data_ptr()), ok_a, ok_b, stream)
         _cabi.check(rc, h, "eno_momentum_update")
 
     # ---- torch.autograd formulation over the public solver surface -----------------------------------
@@ -168,8 +185,20 @@ class MnistNode:
         return dict(loss=ce.detach(), y1=y1.detach(), nfe=nfe, grads={"ode": g_ode, "post_w": g_w, "post_b": g_b},
                     fwd_stats=ode.last_stats["fwd"], bwd_stats=ode.last_stats["bwd"])
 
+    def current_lr(self):
+        return float(self.lr(self.itr)) if callable(self.lr) else float(self.lr)
+
+    def _stage_lr(self):
+        """Put the schedule's value for this iteration into the device word the update kernel reads."""
+        lr = self.current_lr()
+        if lr != self._lr_val:
+            self._lr_dev.fill_(lr)
+            self._lr_val = lr
+
     def update(self, images_u8, labels, eps):
         """One training step; returns the (device) loss tensor."""
+        self._stage_lr()
+        self.itr += 1
         out = self.loss_and_grads(images_u8, labels, eps)
         g = out["grads"]
         self.apply_grads(g["ode"], g["post_w"], g["post_b"])
@@ -212,6 +241,7 @@ class MnistNode:
         if key not in self._graphs:
             self._capture(key)
         graph, info, self._launches = self._graphs[key]
+        self._stage_lr()
         for dst, src in zip(self._g_in, (images_u8, labels, eps)):
             dst.copy_(src, non_blocking=True)
         graph.replay()
@@ -222,11 +252,12 @@ class MnistNode:
         if not (ok_f and ok_b):
             # an iteration budget was too small: the guarded update left the parameters untouched; redo the
             # step in polled mode and move to the level it needs
-            out = self.update(images_u8, labels, eps)
+            out = self.update(images_u8, labels, eps)        # (advances self.itr)
             self._last = (out["fwd_stats"]["n_iters"], out["bwd_stats"][0]["n_iters"])
             return dict(loss=float(out["loss"]), redone=True, fwd_iters=self._last[0], bwd_iters=self._last[1],
                         nfe=out["fwd_stats"]["nfe"])
         self._last = (int(n_f), int(n_b))
+        self.itr += 1
         return dict(loss=loss, redone=False, fwd_iters=self._last[0], bwd_iters=self._last[1], nfe=2.0 + 6.0 * n_f)
 
     @staticmethod
@@ -273,4 +304,5 @@ class MnistNode:
 
     def apply_grads(self, g_ode, g_w, g_b):
         """jax.experimental.optimizers.momentum: v <- mass*v + g ; x <- x - lr*v."""
+        self._stage_lr()
         self._momentum(g_ode.contiguous(), g_w.contiguous(), g_b.contiguous())

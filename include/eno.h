@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ENO_ABI_VERSION 3
+#define ENO_ABI_VERSION 4
 
 /* status codes */
 #define ENO_OK 0
@@ -218,17 +218,21 @@ int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32
  *   y1 [B, D]  labels [B] int64  W [D, C]  b [C]  scratch [B*D + B*C + B] floats
  *   -> loss_out [1] (mean over this call's B rows), gy_out [B, D] = d(sum_r loss_r * inv_count)/dy1,
  *      gW_out [D, C], gb_out [C] (sums over this call's rows; all-reduce them across ranks)
- * eno_momentum_update replaces optimizers.momentum (mnist.py:530-540) for up to three parameter blocks in one
- * launch: v <- mass * v + g; x <- x - lr * v, applied only if both guard words (device int32, may be NULL)
- * are non-zero - in deferred mode they are the solves' `done` flags (first word pairs of the workspaces).
+ * eno_momentum_update replaces optimizers.momentum (mnist.py:530-540) and the lam_w * 0.5 |theta|^2 term of loss_fn
+ * (mnist.py:456-470) for up to three parameter blocks in one launch:
+ *   g <- g + lam_w * x;  v <- mass * v + g;  x <- x - lr * v
+ * applied only if both guard words (device int32, may be NULL) are non-zero - in deferred mode they are the solves'
+ * `done` flags (first word pairs of the workspaces).  The step size is the value of the script's lr_schedule
+ * (mnist.py:530-538) at this iteration, evaluated by the host: `lr`, or - when `lr_dev` is not NULL - the device float
+ * it points to (a captured CUDA graph keeps working when the schedule moves).
  * Both calls only enqueue work (CUDA-graph capturable).
  */
 int32_t eno_mnist_head(eno_ctx* ctx, int32_t B, int32_t D, int32_t C, const float* y1, const int64_t* labels, const float* W,
                        const float* b, float inv_count, float* scratch, float* loss_out, float* gy_out, float* gW_out,
                        float* gb_out, void* stream);
 int32_t eno_momentum_update(eno_ctx* ctx, int32_t n_blocks, float* const* params, float* const* velocity,
-                            const float* const* grads, const int64_t* sizes, float lr, float mass, const int32_t* ok_a,
-                            const int32_t* ok_b, void* stream);
+                            const float* const* grads, const int64_t* sizes, float lr, float mass, float lam_w,
+                            const float* lr_dev, const int32_t* ok_a, const int32_t* ok_b, void* stream);
 
 /*
  * Deferred launch mode (no reference counterpart).  By default a solve polls its device-side controller

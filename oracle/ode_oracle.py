@@ -264,11 +264,12 @@ def odeint_rev(func, rtol, atol, mxstep, ys, ts, args, g, stats=None):
     for i in range(len(ts) - 1, 0, -1):
         t_bar = torch.dot(func(ys[i], ts[i], *args), g[i])
         t0_bar = t0_bar - t_bar
-        st = {}
+        tr = [] if stats is not None else None
         out, _, st = odeint(aug, (ys[i], y_bar, t0_bar, args_bar),
                             torch.stack([-ts[i], -ts[i - 1]]), *args,
-                            rtol=rtol, atol=atol, mxstep=mxstep, return_stats=True)
+                            rtol=rtol, atol=atol, mxstep=mxstep, return_stats=True, trace=tr)
         if stats is not None:
+            st = dict(st, trace=tr)     # controller trajectory [(t, dt, ratio, accepted)] of this segment
             stats.append(st)
         _, y_bar, t0_bar, args_bar = out
         y_bar, t0_bar, args_bar = tree_map(lambda x: x[1], (y_bar, t0_bar, args_bar))

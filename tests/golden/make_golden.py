@@ -132,9 +132,54 @@ def latent_case(ref):
              z0=z0.numpy(), ts=ts.numpy(), zs=zs.numpy(), rs=rs.numpy(), nfe=float(nfe))
 
 
+def stiff_case(ref):
+    """dopri5 forward and adjoint solves that contain REJECTED steps (weights scaled 8x: the controller overshoots
+    repeatedly).  Pins the reject branch of the no-clip flavour (lib/ode.py:843-848: old y / f / interpolant kept, dt
+    shrunk) on the forward, the dense output after rejections (three output times), and the same for every block of the
+    adjoint state including params_bar - for odeint_aux_one (R3) and odeint_sepaux ('fin')."""
+    B, D, H, scale = 6, 16, 8, 8.0
+    params, x0, eps, gy = mlp_case(B, D, H, seed=0, scale=scale)
+    rec = dict(B=B, D=D, H=H, scale=scale, seed=0, x0=x0.numpy(), params=flat_params(params), eps=eps.numpy(), gy=gy.numpy(),
+               g_r=0.01, g_fro=0.01, g_kin=0.02)
+    cl = do.make_mnist_closures("r3")
+    ts3 = torch.tensor([0., 0.35, 1.0])
+    ys, nfe = ref.odeint(cl["dynamics_wrap"], x0, ts3, params, rtol=1e-6, atol=1e-6)
+    rec["fwd3_ts"], rec["fwd3_y"], rec["fwd3_nfe"], rec["fwd3_tol"] = ts3.numpy(), ys.numpy(), float(nfe), 1e-6
+    ts = torch.tensor([0., 1.])
+    y0 = (x0, torch.zeros(B))
+    fwd_w = ref.ravel_first_arg(cl["fwd"], ravel_pytree(y0[0])[1])
+    rev_w = ref.ravel_first_arg(cl["aug_dynamics"], ravel_pytree(y0)[1])
+    for tag, tol in [("5", 1e-5), ("6", 1e-6)]:
+        (res, nfe), saved = ref._odeint_aux_one_fwd(fwd_w, rev_w, tol, tol, math.inf, y0, ts, eps, params)
+        g = (torch.zeros_like(res[0]), torch.zeros_like(res[1]))
+        g[0][-1] = gy
+        g[1][-1] = 0.01
+        out = ref._odeint_aux_one_rev(fwd_w, rev_w, tol, tol, math.inf, saved, (g, None))
+        k = f"r3_{tag}"
+        rec[f"{k}_tol"], rec[f"{k}_y1"], rec[f"{k}_nfe"] = tol, res[0][-1].numpy(), float(nfe)
+        rec[f"{k}_x0_bar"], rec[f"{k}_r0_bar"] = out[0][0].numpy(), out[0][1].numpy()
+        rec[f"{k}_ts_bar"], rec[f"{k}_params_bar"] = out[1].numpy(), flat_params(out[3])
+    clf = do.make_mnist_closures("none", reg_type="fin")
+    y0f = (x0, torch.zeros(B), torch.zeros(B))
+    fwd_w = ref.ravel_first_arg(clf["fwd"], ravel_pytree(y0f[0])[1])
+    rev_w = ref.ravel_first_arg(clf["aug_dynamics"], ravel_pytree(y0f)[1])
+    tol = 1e-5
+    (res, nfe), saved = ref._odeint_sepaux_fwd(fwd_w, rev_w, tol, tol, math.inf, y0f, ts, eps, params)
+    g = tuple(torch.zeros_like(r) for r in res)
+    g[0][-1], g[1][-1], g[2][-1] = gy, 0.01, 0.02
+    out = ref._odeint_sepaux_rev(fwd_w, rev_w, tol, tol, math.inf, saved, (g, None))
+    rec["fin_tol"], rec["fin_y1"], rec["fin_nfe"] = tol, res[0][-1].numpy(), float(nfe)
+    rec["fin_x0_bar"], rec["fin_ts_bar"], rec["fin_eps_bar"] = out[0][0].numpy(), out[1].numpy(), out[2].numpy()
+    rec["fin_params_bar"] = flat_params(out[3])
+    np.savez(os.path.join(OUT, "mlp_stiff.npz"), **rec)
+
+
 def main():
     ref = load_reference_ode()
     torch.set_num_threads(8)
+    if "--only-stiff" in sys.argv:
+        stiff_case(ref)
+        return
 
     # ---- KAT: y' = a + (y - (a t + b))^5, exact y = a t + b (lib/ode.py:1782-1797)
     a, b = 0.2, 3.0
@@ -208,6 +253,7 @@ def main():
     vmap_case(ref, do, B, D, H, params, x0)
     css_case(ref)
     latent_case(ref)
+    stiff_case(ref)
 
     # ---- plain adjoint on the pendulum (lib/ode.py:1720-1722, 1765-1774), multi-output
     def pend(y, t, m, g):

@@ -90,4 +90,4 @@ def test_null_arguments_are_usage_errors():
                                    None, None, None, None, None, 0, None) == -1
     assert L.eno_odeint_fwd_vmap(None, None, 1, None, None, 2, None, 1e-5, 1e-5, 0, None, None, None, None, None) == -1
     assert L.eno_mnist_head(None, 1, 4, 2, None, None, None, None, 1.0, None, None, None, None, None, None) == -1
-    assert L.eno_momentum_update(None, 1, None, None, None, None, 0.1, 0.9, None, None, None) == -1
+    assert L.eno_momentum_update(None, 1, None, None, None, None, 0.1, 0.9, 0.0, None, None, None, None) == -1

@@ -325,3 +325,168 @@ def test_plain_odeint_adjoint_multiple_output_times(cuda):
     assert rel_err(xg.grad, want[0].reshape(Bn, D)) < RTOL
     assert rel_err(tg.grad, want[1]) < 2e-5
     assert rel_err(pflat.grad, flat_from_params(want[2])) < RTOL
+
+
+def _stiff_truth(g, B, D, H, cl, n_aux, weights):
+    """fp64 oracle at 1e-10 for the stiff case: the exact solution both fp32 solves approximate."""
+    from oracle import ode_oracle as oo
+    d = torch.float64
+    p64 = params_from_flat(g["params"], D, H, dtype=d)
+    x0, eps, gy = (torch.as_tensor(g[k]).to(d) for k in ("x0", "eps", "gy"))
+    ts = torch.tensor([0., 1.], dtype=d)
+    res, _ = oo.odeint_split_fwd(cl["fwd"], (x0,) + (torch.zeros(B, dtype=d),) * n_aux, ts, eps, p64, n_aux=n_aux,
+                                 rtol=1e-10, atol=1e-10)
+    gg = tuple(torch.zeros_like(r) for r in res)
+    gg[0][-1] = gy
+    for q, w in enumerate(weights):
+        gg[1 + q][-1] = w
+    out = oo.odeint_split_rev(cl["aug_dynamics"], 1e-10, 1e-10, math.inf, res, ts, (eps, p64), gg)
+    return dict(y1=res[0][-1], x0_bar=out[0][0], ts_bar=out[1], eps_bar=out[2], p_bar=flat_from_params(out[3]))
+
+
+@pytest.mark.parametrize("tag", ["5", "6"])
+def test_rejected_steps_aux_one_golden(cuda, tag):
+    """tests/golden/mlp_stiff.npz: forward and adjoint dopri5 loops WITH rejected steps (the reject branch of the no-clip
+    flavour, lib/ode.py:843-848) against the unmodified reference solver: NFE / iteration counts exact and n_accepted <
+    n_iters on both solves, values per tests/util.py:assert_agree with the fp64 oracle at 1e-10 as third party."""
+    import easy_neural_ode_b200 as eno
+    from oracle import dynamics_oracle as do
+    from tests.util import assert_agree
+    g = load("mlp_stiff.npz")
+    B, D, H = int(g["B"]), int(g["D"]), int(g["H"])
+    k, tol = f"r3_{tag}", float(g[f"r3_{tag}_tol"])
+    spec = eno.MLPDynamics(D, H, reg="r3")
+    x0 = torch.as_tensor(g["x0"], device=cuda).requires_grad_(True)
+    eps = torch.as_tensor(g["eps"], device=cuda)
+    pflat = torch.as_tensor(g["params"], device=cuda).requires_grad_(True)
+    ts = torch.tensor([0., 1.], device=cuda, requires_grad=True)
+    (ys, rs), nfe = eno.odeint_aux_one(spec.fwd, spec.aug_dynamics, (x0, torch.zeros(B, device=cuda)), ts, eps, pflat,
+                                        rtol=tol, atol=tol)
+    loss = (ys[-1] * torch.as_tensor(g["gy"], device=cuda)).sum() + float(g["g_r"]) * rs[-1].sum()
+    loss.backward()
+    fst, bst = eno.last_stats["fwd"], eno.last_stats["bwd"][0]
+    assert float(nfe) == float(g[f"{k}_nfe"])
+    assert fst["n_accepted"] < fst["n_iters"] and bst["n_accepted"] < bst["n_iters"], (fst, bst)
+    tr = _stiff_truth(g, B, D, H, do.make_mnist_closures("r3"), 1, [float(g["g_r"])])
+    assert_agree(ys[-1], g[f"{k}_y1"], tr["y1"], "y1")
+    assert_agree(x0.grad, g[f"{k}_x0_bar"], tr["x0_bar"], "x0_bar")
+    assert_agree(ts.grad, g[f"{k}_ts_bar"], tr["ts_bar"], "ts_bar")
+    assert_agree(pflat.grad, g[f"{k}_params_bar"], tr["p_bar"], "params_bar")
+
+
+def test_rejected_steps_forward_dense_output_golden(cuda):
+    """Three output times on the stiff case: the dense-output quartic is formed lazily from the previous ACCEPTED step, also
+    after rejected ones (the 3-deep rings exist for this)."""
+    import easy_neural_ode_b200 as eno
+    g = load("mlp_stiff.npz")
+    B, D, H = int(g["B"]), int(g["D"]), int(g["H"])
+    spec = eno.MLPDynamics(D, H)
+    ys, nfe = eno.odeint(spec.dynamics_wrap, torch.as_tensor(g["x0"], device=cuda), torch.as_tensor(g["fwd3_ts"], device=cuda),
+                         torch.as_tensor(g["params"], device=cuda), rtol=1e-6, atol=1e-6)
+    st = eno.last_stats["fwd"]
+    assert float(nfe) == float(g["fwd3_nfe"]) and st["n_accepted"] < st["n_iters"]
+    assert rel_err(ys, g["fwd3_y"]) < RTOL
+
+
+def test_rejected_steps_sepaux_fin_golden(cuda):
+    """The same for odeint_sepaux with the 'fin' dynamics (live eps_bar block)."""
+    _needs_cluster_path()
+    import easy_neural_ode_b200 as eno
+    from oracle import dynamics_oracle as do
+    from tests.util import assert_agree
+    g = load("mlp_stiff.npz")
+    B, D, H = int(g["B"]), int(g["D"]), int(g["H"])
+    tol = float(g["fin_tol"])
+    spec = eno.MLPDynamics(D, H, reg_type="fin")
+    x0 = torch.as_tensor(g["x0"], device=cuda).requires_grad_(True)
+    eps = torch.as_tensor(g["eps"], device=cuda).requires_grad_(True)
+    pflat = torch.as_tensor(g["params"], device=cuda).requires_grad_(True)
+    ts = torch.tensor([0., 1.], device=cuda, requires_grad=True)
+    z = torch.zeros(B, device=cuda)
+    (ys, fro, kin), nfe = eno.odeint_sepaux(spec.fwd, spec.aug_dynamics, (x0, z, z), ts, eps, pflat, rtol=tol, atol=tol)
+    loss = (ys[-1] * torch.as_tensor(g["gy"], device=cuda)).sum() + float(g["g_fro"]) * fro[-1].sum() + float(g["g_kin"]) * kin[-1].sum()
+    loss.backward()
+    fst, bst = eno.last_stats["fwd"], eno.last_stats["bwd"][0]
+    assert float(nfe) == float(g["fin_nfe"])
+    assert fst["n_accepted"] < fst["n_iters"] and bst["n_accepted"] < bst["n_iters"], (fst, bst)
+    tr = _stiff_truth(g, B, D, H, do.make_mnist_closures("none", reg_type="fin"), 2, [float(g["g_fro"]), float(g["g_kin"])])
+    assert_agree(ys[-1], g["fin_y1"], tr["y1"], "y1")
+    assert_agree(x0.grad, g["fin_x0_bar"], tr["x0_bar"], "x0_bar")
+    assert_agree(eps.grad, g["fin_eps_bar"], tr["eps_bar"], "eps_bar")
+    assert_agree(pflat.grad, g["fin_params_bar"], tr["p_bar"], "params_bar")
+
+
+def test_trained_parameters_step(cuda):
+    """C1 at TRAINED parameters: the weights after 19 momentum updates of the oracle trajectory bench.py times
+    (tests/golden/mnist_trained_step19.npz, generator tests/golden/make_trained.py) and the step-19 batch.  The dynamics
+    are stiffer than at initialisation (11 forward iterations, one rejected, against 7).  At the script-default tolerance
+    the counts sit on arithmetic noise (tests/util.py:exact_arith): they must lie in the band spanned by the fp32 oracle and
+    the exact-arithmetic oracle; values 1e-5."""
+    import bench
+    from easy_neural_ode_b200 import mnist_step
+    from oracle import dynamics_oracle as do
+    from tests.util import assert_count, exact_arith
+    g = load("mnist_trained_step19.npz")
+    B, D, H = 100, 784, 100
+    p_ode = params_from_flat(g["p_ode"], D, H)
+    p_post = {"w": torch.as_tensor(g["post_w"]), "b": torch.as_tensor(g["post_b"])}
+    images, labels, eps = bench.synth_batch(0, int(g["step"]))
+    tol, lam = bench.TOL, bench.LAM
+    want = do.train_step_grads(p_ode, p_post, do.pre_ode(images), labels, eps, lam, reg="r3", rtol=tol, atol=tol)
+    # the fixture's own record of the oracle (same machine class): the restatement is deterministic
+    assert want["fwd_stats"]["n_iters"] == int(g["fwd_iters"]) and want["bwd_stats"][0]["n_iters"] == int(g["bwd_iters"])
+    # exact-arithmetic end of the band: same closures evaluated in fp64, solver arithmetic fp32
+    import oracle.dynamics_oracle as mod
+    real = mod.make_mnist_closures
+    try:
+        mod.make_mnist_closures = lambda *a, **k: {n: exact_arith(f) for n, f in real(*a, **k).items()}
+        exact = do.train_step_grads(p_ode, p_post, do.pre_ode(images), labels, eps, lam, reg="r3", rtol=tol, atol=tol)
+    finally:
+        mod.make_mnist_closures = real
+    model = mnist_step.MnistNode(reg="r3", lam=lam, rtol=tol, atol=tol, device=cuda)
+    model.load_params(p_ode, p_post)
+    out = model.loss_and_grads(images.to(cuda), labels.to(cuda), eps.to(cuda))
+    print(f"trained step: fwd iterations gpu {out['fwd_stats']['n_iters']} oracle {want['fwd_stats']['n_iters']} exact-arithmetic "
+          f"{exact['fwd_stats']['n_iters']}; adjoint gpu {out['bwd_stats'][0]['n_iters']} oracle {want['bwd_stats'][0]['n_iters']} "
+          f"exact-arithmetic {exact['bwd_stats'][0]['n_iters']}")
+    assert_count(out["fwd_stats"]["n_iters"], want["fwd_stats"]["n_iters"], exact["fwd_stats"]["n_iters"], "forward iterations", slack=1)
+    assert_count(out["bwd_stats"][0]["n_iters"], want["bwd_stats"][0]["n_iters"], exact["bwd_stats"][0]["n_iters"], "adjoint iterations",
+                 slack=1)
+    assert rel_err(out["y1"], want["y1"]) < RTOL
+    assert rel_err(out["loss"], want["loss"]) < RTOL
+    assert rel_err(out["grads"]["ode"], flat_from_params(want["grads"]["ode"])) < RTOL
+    assert rel_err(out["grads"]["post_w"], want["grads"]["post"]["w"]) < RTOL
+
+
+def test_update_lr_schedule_and_weight_decay(cuda):
+    """update() details of mnist.py: the piecewise learning-rate schedule (530-538) and the lam_w * 0.5 |theta|^2 term of
+    loss_fn (456-470) - two steps, the second at a different step size, polled and whole-step-graph paths, against the
+    oracle's gradients + momentum."""
+    from easy_neural_ode_b200 import mnist_step
+    from oracle import dynamics_oracle as do
+    assert [mnist_step.mnist_lr_schedule(600)(i) for i in (0, 35999, 36000, 59999, 60000, 83999, 84000)] == \
+        [1e-1, 1e-1, 1e-2, 1e-2, 1e-3, 1e-3, 1e-4]
+    B, D, H, lam, lam_w, tol = 8, 784, 100, 6e-5, 1e-3, 1e-6
+    sched = lambda i: 1e-1 if i < 1 else 1e-2
+    gen = torch.Generator().manual_seed(5)
+    batches = [(torch.randint(0, 256, (B, 28, 28, 1), generator=gen, dtype=torch.uint8), torch.randint(0, 10, (B,), generator=gen),
+                torch.randint(0, 2, (B, D), generator=gen).float() * 2 - 1) for _ in range(2)]
+    p_ode, p_post = do.init_mlp_params(D, H, seed=0), do.init_post_params(D, seed=1)
+    params, vel = {"ode": p_ode, "post": p_post}, None
+    for i, (im, lb, ep) in enumerate(batches):
+        w = do.train_step_grads(params["ode"], params["post"], do.pre_ode(im), lb, ep, lam, reg="r3", rtol=tol, atol=tol)
+        grads = {"ode": {n: {k: w["grads"]["ode"][n][k] + lam_w * params["ode"][n][k] for k in params["ode"][n]} for n in params["ode"]},
+                 "post": {k: w["grads"]["post"][k] + lam_w * params["post"][k] for k in params["post"]}}
+        vel = vel or do.ode_oracle_tree_zeros(params)
+        params, vel = do.momentum_update(params, vel, grads, sched(i))
+    want = flat_from_params(params["ode"])
+    for graphed in (False, True):
+        model = mnist_step.MnistNode(reg="r3", lam=lam, rtol=tol, atol=tol, device=cuda, lr=sched, lam_w=lam_w)
+        model.load_params(p_ode, p_post)
+        for im, lb, ep in batches:
+            (model.update_graphed if graphed else model.update)(im.to(cuda), lb.to(cuda), ep.to(cuda))
+        assert model.itr == 2
+        # the update moved the parameters by ~1e-2 of their size: compare the MOVE, not the parameters
+        move_w, move = want - flat_from_params(p_ode), model.p_ode.cpu() - flat_from_params(p_ode)
+        assert rel_err(move, move_w) < 1e-4, graphed
+        assert rel_err(model.post_w, params["post"]["w"]) < RTOL, graphed

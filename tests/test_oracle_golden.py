@@ -152,3 +152,44 @@ def test_pendulum_adjoint_multi_segment():
     np.testing.assert_allclose(out[0].numpy(), g["y0_bar"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(out[1].numpy(), g["ts_bar"], rtol=1e-5, atol=1e-6)
     assert abs(float(out[2]) - float(g["m_bar"])) < 1e-4 and abs(float(out[3]) - float(g["g_bar"])) < 1e-4
+
+
+def test_stiff_case_has_rejected_steps_and_matches_reference():
+    """tests/golden/mlp_stiff.npz: solves whose dopri5 loops REJECT steps, forward and adjoint (lib/ode.py:843-848).
+    The oracle reproduces the unmodified reference on them and its statistics prove the rejections are there."""
+    g = load("mlp_stiff.npz")
+    B, D, H = int(g["B"]), int(g["D"]), int(g["H"])
+    params = params_from_flat(g["params"], D, H)
+    x0, eps, gy = (torch.as_tensor(g[k]) for k in ("x0", "eps", "gy"))
+    ys, nfe, st = oo.solve(lambda y, t: do.mlp_dynamics(params, y.reshape(B, D), t).reshape(-1), x0.reshape(-1),
+                           torch.as_tensor(g["fwd3_ts"]), 1e-6, 1e-6)
+    assert nfe == float(g["fwd3_nfe"]) and st["n_accepted"] < st["n_iters"]
+    np.testing.assert_allclose(ys.reshape(-1, B, D).numpy(), g["fwd3_y"], **TIGHT)
+    ts = torch.tensor([0., 1.])
+    cl = do.make_mnist_closures("r3")
+    for tag in ("5", "6"):
+        k, tol = f"r3_{tag}", float(g[f"r3_{tag}_tol"])
+        res, nfe, fst = oo.odeint_split_fwd(cl["fwd"], (x0, torch.zeros(B)), ts, eps, params, n_aux=1, rtol=tol, atol=tol,
+                                            return_stats=True)
+        assert nfe == float(g[f"{k}_nfe"]) and fst["n_accepted"] < fst["n_iters"]
+        np.testing.assert_allclose(res[0][-1].numpy(), g[f"{k}_y1"], **TIGHT)
+        gg = (torch.zeros_like(res[0]), torch.zeros_like(res[1]))
+        gg[0][-1], gg[1][-1] = gy, float(g["g_r"])
+        bst = []
+        out = oo.odeint_split_rev(cl["aug_dynamics"], tol, tol, math.inf, res, ts, (eps, params), gg, bst)
+        assert bst[0]["n_accepted"] < bst[0]["n_iters"]
+        np.testing.assert_allclose(out[0][0].numpy(), g[f"{k}_x0_bar"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(out[1].numpy(), g[f"{k}_ts_bar"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(flat_from_params(out[3]).numpy(), g[f"{k}_params_bar"], rtol=1e-5, atol=1e-6)
+    clf = do.make_mnist_closures("none", reg_type="fin")
+    tol = float(g["fin_tol"])
+    res, nfe, fst = oo.odeint_split_fwd(clf["fwd"], (x0, torch.zeros(B), torch.zeros(B)), ts, eps, params, n_aux=2, rtol=tol,
+                                        atol=tol, return_stats=True)
+    assert nfe == float(g["fin_nfe"]) and fst["n_accepted"] < fst["n_iters"]
+    gg = tuple(torch.zeros_like(r) for r in res)
+    gg[0][-1], gg[1][-1], gg[2][-1] = gy, float(g["g_fro"]), float(g["g_kin"])
+    bst = []
+    out = oo.odeint_split_rev(clf["aug_dynamics"], tol, tol, math.inf, res, ts, (eps, params), gg, bst)
+    assert bst[0]["n_accepted"] < bst[0]["n_iters"]
+    np.testing.assert_allclose(out[2].numpy(), g["fin_eps_bar"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(flat_from_params(out[3]).numpy(), g["fin_params_bar"], rtol=1e-5, atol=1e-6)
