@@ -397,8 +397,10 @@ def main():
         # ... then the same step as a collective solve over the shards; compared block by block
         o = model.loss_and_grads(*dev_batches[0])
         rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
+        loss_g = o["loss"].detach().double().reshape(1).clone()      # mean over this rank's rows -> mean over the global batch
+        dist.all_reduce(loss_g)
         errs = torch.tensor([rel(o["y1"], single["y1"]), rel(o["grads"]["ode"], single["g"]),
-                             abs(float(o["loss"]) - single["loss"]) / abs(single["loss"]),
+                             abs(float(loss_g) / world - single["loss"]) / abs(single["loss"]),
                              float(o["fwd_stats"]["n_iters"] != single["fwd"]), float(o["bwd_stats"][0]["n_iters"] != single["bwd"])],
                             device=dev, dtype=torch.float64)
         dist.all_reduce(errs, op=dist.ReduceOp.MAX)
@@ -523,7 +525,7 @@ def main():
                 "peak_source": peak_src, "avg_launch_ms": rows_ms, "launches_timed": int(cnt[1]),
                 "fp32_ffma_peak_tflops": ffma.value, "frac_of_fp32_ffma": achieved / ffma.value if ffma.value else None,
                 "other_kernels_ms": {"k_fwd_step": ms[0] / max(cnt[0], 1), "k_adj_pgrad<STEP>": ms[2] / max(cnt[2], 1),
-                                     **({"exchange (NCCL group + replicated finish kernel), per iteration, fwd and adjoint":
+                                     **({"exchange (finish kernel incl. the peer-memory or NCCL exchange and the wait for the slowest rank), per iteration, fwd and adjoint":
                                          ms[3] / max(cnt[3], 1)} if world > 1 else {})},
                 "note": "fp32 FFMA kernel; the tensor pipe is the contract's denominator, the fp32 pipe is the one it uses"}
 

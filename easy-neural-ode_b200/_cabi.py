@@ -19,7 +19,7 @@ TABLEAUX = {"dopri5": 0, "heun": 1, "fehlberg": 2, "bosh": 3, "rk_fehlberg": 4, 
 SYMBOLS = ["eno_abi_version", "eno_last_error_string", "eno_create", "eno_destroy", "eno_param_count",
            "eno_adjoint_state_size", "eno_workspace_bytes", "eno_odeint_fwd", "eno_odeint_fwd_vmap", "eno_odeint_bwd", "eno_odeint_bwd_sepaux", "eno_rhs",
            "eno_mnist_head", "eno_momentum_update", "eno_profile_enable", "eno_profile_read", "eno_ffma_peak", "eno_comm_unique_id", "eno_comm_init",
-           "eno_comm_destroy", "eno_set_deferred", "eno_read_stats", "eno_gemm_tf32x3", "eno_adam_update", "eno_profile_read_gemm"]
+           "eno_comm_destroy", "eno_set_deferred", "eno_read_stats", "eno_gemm_tf32x3", "eno_adam_update", "eno_profile_read_gemm", "eno_peer_export", "eno_peer_attach"]
 
 
 class Desc(C.Structure):
@@ -99,6 +99,10 @@ def lib():
     L.eno_set_deferred.argtypes = [vp, i32, i32, i32]
     L.eno_read_stats.restype = i32
     L.eno_read_stats.argtypes = [vp, vp, C.POINTER(Stats), vp]
+    L.eno_peer_export.restype = i32
+    L.eno_peer_export.argtypes = [vp, C.c_uint64, vp]
+    L.eno_peer_attach.restype = i32
+    L.eno_peer_attach.argtypes = [vp, vp]
     L.eno_profile_read_gemm.restype = i32
     L.eno_profile_read_gemm.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.eno_adam_update.restype = i32

@@ -7,6 +7,8 @@
 
 #include "adj_kernels.cuh"
 #include "cl_kernels.cuh"
+#include <cstdlib>
+
 #include "dist.cuh"
 #include "tableaux.cuh"
 
@@ -31,7 +33,7 @@ inline size_t adj_ws_bytes(int B, int D, int H, int world = 1, bool fin = false)
   s += kSlots * (2 * adj_align(3 * N * 4) + 2 * adj_align(3 * (size_t)B * H * 4));
   s += adj_align((size_t)6 * kC * B * world * 8) + 2 * adj_align(npp * 8);   // xrec (one record per rank), ppart0/1
   if (world > 1) s += adj_align(4 * P * 4);          // pcomb
-  s += adj_align(N * 4) + adj_align(P * 4);         // YBAR, POUT
+  s += adj_align(N * 4) + adj_align((P + 256 * (size_t)(world + 1)) * 4);   // YBAR, POUT (padded to world equal 256-multiples)
   s += 2 * adj_align((size_t)D * H * 4);            // transposes
   return s + 4096;
 }
@@ -78,8 +80,9 @@ inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArg
   a->ppart0 = cv.take<double>(npp); a->ppart1 = cv.take<double>(npp);
   a->pcomb = (world > 1) ? cv.take<float>(4 * P) : nullptr;
   a->dist = 0;
+  a->peer = 0;
   a->YBAR = cv.take<float>(N);
-  a->POUT = cv.take<float>(P);
+  a->POUT = cv.take<float>(P + 256 * (size_t)(world + 1));
   float* W1xT = cv.take<float>((size_t)D * H);
   float* W2xT = cv.take<float>((size_t)D * H);
   a->w = mlp_weights_from_flat(params, D, H, W1xT, W2xT);
@@ -258,8 +261,27 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
   const size_t n_loc = (size_t)(plan.cluster ? kC : 1) * B;
   const int pf_grid = (a.P + 255) / 256;
   // multi-GPU continuation of one pgrad launch: exchange, then the replicated finish kernel
+  // peer-memory exchange (dist.cuh) when the ranks have mapped each other's exchange buffers
+  const int slice = (int)((((size_t)a.P + world - 1) / world + 255) / 256 * 256);   // params_bar entries per rank
+  const size_t peer_xrec_bytes = (size_t)2 * world * 6 * n_loc * 8;
+  const bool peer = dist && dc->peer_ready() && !getenv("ENO_EXCHANGE_NCCL") &&
+                    kPeerOffAdj + peer_xrec_bytes + 256 + (size_t)2 * 4 * a.P * 4 <= dc->peer.bytes;
+  if (peer) {
+    a.peer = 1;
+    a.pv = dc->peer;
+    a.peer_pcomb_off = kPeerOffAdj + ((peer_xrec_bytes + 255) / 256) * 256;
+    a.p_lo = rank * slice;
+    a.p_cnt = slice;
+  }
   auto exchange = [&](int mode) -> int {
     if (!dist) return 0;
+    if (peer) {
+      const int g = slice / 256;
+      if (mode == ADJ_STEP) k_adj_pfinish_peer<ADJ_STEP><<<g, 256, 0, st>>>(a);
+      else if (mode == ADJ_INIT0) k_adj_pfinish_peer<ADJ_INIT0><<<g, 256, 0, st>>>(a);
+      else k_adj_pfinish_peer<ADJ_INIT1><<<g, 256, 0, st>>>(a);
+      return 0;
+    }
     int rc = dc->api.GroupStart();
     rc |= dc->allreduce(a.pcomb, (mode == ADJ_STEP ? 4 : 1) * (size_t)a.P, st);
     rc |= dc->gather(a.xrec, 6 * n_loc, st);   // every rank's record: norm partials + t_bar pieces
@@ -318,10 +340,17 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
       // launch per chunk (a no-op unless the segment finished) is therefore enough.
       k_adj_out<<<egrid, 256, 0, st>>>(a);
       ++launches;
-      if (deferred) break;   // no host round-trip: the caller checks Ctrl.done later (eno_read_stats)
+      if (deferred) {   // no host round-trip: the caller checks Ctrl.done later (eno_read_stats)
+        if (peer && dc->gather(a.POUT, (size_t)slice, st)) { if (err) *err = "eno_odeint_bwd: NCCL all-gather of params_bar failed"; return ENO_E_CUDA; }
+        break;
+      }
       ENO_ADJ_CHECK(cudaMemcpyAsync(mailbox, a.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
       ENO_ADJ_CHECK(cudaStreamSynchronize(st));
-      if (mailbox->done) break;
+      if (mailbox->done) {
+        // peer mode: every rank holds its own slice of params_bar; gather them once per segment
+        if (peer && dc->gather(a.POUT, (size_t)slice, st)) { if (err) *err = "eno_odeint_bwd: NCCL all-gather of params_bar failed"; return ENO_E_CUDA; }
+        break;
+      }
       chunk = 4;
     }
     if (deferred) {

@@ -12,6 +12,7 @@
 //                 reduces the error norm over ALL blocks and runs the controller.
 // The shared blocks never feed back into the RHS, so no stage buffers are kept for them.
 #pragma once
+#include "dist.cuh"
 #include <cuda_pipeline.h>
 
 #include <string>
@@ -75,7 +76,11 @@ struct AdjArgs {
   const float* tbar_all[kSlots];           // same for the per-sample t_bar pieces of every slot (12*n_loc floats per rank)
   double *ppart0, *ppart1;                 // [pgrad grid]
   float* pcomb;                            // [4][P] multi-GPU: this rank's share of the stage combinations
-  int dist;                                // 1: multi-GPU split (local contraction | NCCL | finish)
+  int dist;                                // 1: multi-GPU split (local contraction | exchange | finish)
+  int peer;                                // 1: the exchange runs inside k_adj_pfinish_peer over NVLink peer memory (dist.cuh)
+  PeerView pv;
+  size_t peer_pcomb_off;                   // byte offset of pcomb [2 parities][4 P] inside every rank's exchange buffer
+  int p_lo, p_cnt;                         // params_bar slice this rank owns in peer mode
   // segment inputs / outputs
   const float* g_y;        // [N]   g[i] (for t_bar)
   const float* g_r;        // [na][B]
@@ -652,6 +657,10 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
     // stage derivatives, so ship the four stage combinations (without the replicated k0 term) and let
     // k_adj_pfinish continue after the all-reduce.
     const size_t P = (size_t)a.P;
+    if (a.peer) {   // the slot of the exchange that the finish kernel after this launch will run
+      const unsigned long long seq = *reinterpret_cast<const unsigned long long*>(a.pv.base[a.pv.rank] + kPeerOffSeq) + 1;
+      a.pcomb = reinterpret_cast<float*>(a.pv.base[a.pv.rank] + a.peer_pcomb_off) + (size_t)(seq & 1) * 4 * P;
+    }
     for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
       const int p = pidx[e];
       if (p < 0) continue;
@@ -827,6 +836,140 @@ __global__ void __launch_bounds__(256) k_adj_pfinish(AdjArgs a) {
   }
   if (!elect_last_block(&c->ticket)) return;
   adj_finalize<MODE>(a, c, dred, (int)gridDim.x, dt, nullptr);
+}
+
+// Peer-memory variant of k_adj_pfinish (dist.cuh): no NCCL call.  Round 1: CTA 0 pushes this rank's record (norm
+// partials + t_bar pieces, 6 n_loc doubles) into every rank's gathered array and signals; every CTA waits for all ranks,
+// then PULLS, for the params_bar slice this rank owns, the stage combinations of every rank in rank order and forms
+// candidate / error / mid-point and the slice's norm partial.  Round 2 (last CTA): the per-rank norm partials are
+// exchanged, summed in rank order, and the usual finaliser runs on identical inputs on every rank.  The params_bar
+// rings therefore hold valid data for the owned slice only; the host gathers POUT once per segment.
+#ifdef ENO_PHASES
+// development aid: clock stamps of the peer exchange (CTA 0: entry, pushed, all ranks arrived, slice done; last CTA:
+// elected, round 2 done, finalised), most recent ADJ_STEP launch
+__device__ long long g_peer_stamp[8];
+#define PEER_STAMP(cond, slot) do { if ((cond) && threadIdx.x == 0 && MODE == ADJ_STEP) g_peer_stamp[slot] = clock64(); } while (0)
+#else
+#define PEER_STAMP(cond, slot) do { } while (0)
+#endif
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_adj_pfinish_peer(AdjArgs a) {
+  Ctrl* c = a.ctrl;
+  if (MODE == ADJ_STEP && c->done) return;
+  __shared__ double dred[256];
+  PEER_STAMP(blockIdx.x == 0, 0);
+  const PeerView& pv = a.pv;
+  unsigned long long* seqp = reinterpret_cast<unsigned long long*>(pv.base[pv.rank] + kPeerOffSeq);
+  const unsigned long long seq = *seqp + 1;
+  const int par = (int)(seq & 1);
+  const size_t P = (size_t)a.P;
+  const size_t rec = (size_t)6 * a.n_loc;                       // doubles per rank record
+  const size_t xoff = kPeerOffAdj + (size_t)par * pv.world * rec * 8;
+  if (blockIdx.x == 0) {
+    const double* mine = a.xrec + (size_t)pv.rank * rec;
+    for (int r = 0; r < pv.world; ++r) {
+      double* dst = reinterpret_cast<double*>(pv.base[r] + xoff) + (size_t)pv.rank * rec;
+      for (int i = threadIdx.x; i < (int)rec; i += blockDim.x) dst[i] = mine[i];
+    }
+    __syncthreads();
+    peer_signal(pv, 0, seq);
+    PEER_STAMP(true, 1);
+  }
+  peer_wait(pv, 0, seq);
+  PEER_STAMP(blockIdx.x == 0, 2);
+  const int p = a.p_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  const float rtol = c->rtol, atol = c->atol;
+  const float dt = (MODE == ADJ_STEP) ? c->dt : 0.f;
+  double part0 = 0.0, part1 = 0.0;
+  if (p < a.p_lo + a.p_cnt && p < a.P) {
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+    for (int r = 0; r < pv.world; ++r) {
+      const float* pc = reinterpret_cast<const float*>(pv.base[r] + a.peer_pcomb_off) + (size_t)par * 4 * P;
+      v0 += __ldcv(pc + p);
+      if (MODE == ADJ_STEP) { v1 += __ldcv(pc + P + p); v2 += __ldcv(pc + 2 * P + p); v3 += __ldcv(pc + 3 * P + p); }
+    }
+    if (MODE == ADJ_STEP) {
+      const int cur = c->cur, cand = c->cand, midw = c->mid_acc ^ 1;
+      const float k0 = a.FP[(size_t)cur * P + p];
+      const float s = fmaf(c_tab.c_sol[0], k0, v0);
+      const float er = fmaf(c_tab.c_err[0], k0, v1);
+      const float md = fmaf(c_tab.c_mid[0], k0, v2);
+      const float p0 = a.PB[(size_t)cur * P + p];
+      const float p1 = fmaf(dt, s, p0);
+      const float tol = atol + rtol * fmaxf(fabsf(p0), fabsf(p1));
+      const float q = dt * er / tol;
+      part0 = (double)(q * q);
+      a.PB[(size_t)cand * P + p] = p1;
+      a.FP[(size_t)cand * P + p] = v3;
+      a.MIDP[(size_t)midw * P + p] = fmaf(dt, md, p0);
+    } else if (MODE == ADJ_INIT0) {
+      const float f0 = v0;
+      const float p0 = a.PB[p];
+      const float sc = atol + fabsf(p0) * rtol;
+      const float q0 = p0 / sc, q1 = f0 / sc;
+      part0 = (double)(q0 * q0);
+      part1 = (double)(q1 * q1);
+      a.FP[p] = f0;
+    } else if (MODE == ADJ_INIT1) {
+      const float sc = atol + fabsf(a.PB[p]) * rtol;
+      const float q = (v0 - a.FP[p]) / sc;
+      part0 = (double)(q * q);
+    }
+  }
+  dred[threadIdx.x] = part0;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a.ppart0[blockIdx.x] = dred[0];
+  __syncthreads();
+  if (MODE == ADJ_INIT0) {
+    dred[threadIdx.x] = part1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) a.ppart1[blockIdx.x] = dred[0];
+    __syncthreads();
+  }
+  PEER_STAMP(blockIdx.x == 0, 3);
+  if (!elect_last_block(&c->ticket)) return;
+  PEER_STAMP(true, 4);
+  // ---- round 2: this rank's norm partial(s) to every rank, all ranks' summed in rank order
+  const double my0 = block_sum_global(a.ppart0, (int)gridDim.x, dred);
+  __syncthreads();
+  double my1 = 0.0;
+  if (MODE == ADJ_INIT0) { my1 = block_sum_global(a.ppart1, (int)gridDim.x, dred); __syncthreads(); }
+  if ((int)threadIdx.x < pv.world) {
+    double* dst = reinterpret_cast<double*>(pv.base[threadIdx.x] + kPeerOffPart) + ((size_t)par * kPeerMax + pv.rank) * 2;
+    dst[0] = my0;
+    dst[1] = my1;
+  }
+  __syncthreads();
+  peer_signal(pv, 1, seq);
+  peer_wait(pv, 1, seq);
+  PEER_STAMP(true, 5);
+  if (threadIdx.x == 0) {
+    const volatile double* src = reinterpret_cast<const volatile double*>(pv.base[pv.rank] + kPeerOffPart) + (size_t)par * kPeerMax * 2;
+    double t0 = 0.0, t1 = 0.0;
+    for (int r = 0; r < pv.world; ++r) { t0 += src[2 * r]; t1 += src[2 * r + 1]; }
+    a.ppart0[0] = t0;
+    a.ppart1[0] = t1;
+  }
+  __syncthreads();
+  // the finaliser reads every rank's record from the gathered array in this rank's exchange buffer
+  const double* gx = reinterpret_cast<const double*>(pv.base[pv.rank] + xoff);
+  a.rp0_all = gx;
+  a.rp1_all = gx + 4 * a.n_loc;
+  a.rp2_all = gx + 5 * a.n_loc;
+  const float* f0 = reinterpret_cast<const float*>(gx) + 2 * a.n_loc;
+  for (int j = 0; j < kSlots; ++j) a.tbar_all[j] = f0 + (size_t)j * a.n_loc;
+  if (threadIdx.x == 0) *seqp = seq;   // (thread 0 is the one that survives the finaliser's early return)
+  adj_finalize<MODE>(a, c, dred, 1, dt, nullptr);
+  PEER_STAMP(true, 6);
 }
 
 // ---- segment set-up: state rings at index 0 (lib/ode.py:1516-1518) -------------------------

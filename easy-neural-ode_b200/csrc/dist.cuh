@@ -57,11 +57,72 @@ struct NcclApi {
   }
 };
 
+// ---- exchange over NVLink peer memory (no NCCL call per solver iteration) -----------------------------------------
+// Every rank owns one "symmetric" buffer (cudaMalloc, exported with cudaIpcGetMemHandle, mapped by every peer), laid out
+// identically on all ranks:
+//   [ flags: 2 kinds x 8 ranks, u64 | seq (local) | timeout word | part[2 parities][8 ranks][2] doubles | data ... ]
+// A rank SIGNALS by storing a monotonically increasing sequence number into slot [kind][its rank] of EVERY peer's buffer
+// (st.release.sys after a system fence) and WAITS by spinning on its own, local, slots - so polling never crosses
+// NVLink.  Small payloads (per-sample norm partials, the 24 KB adjoint record, the per-rank norm scalar) are PUSHED
+// into the peers' buffers before the signal; the large one (the params_bar stage combinations, 4 P floats) stays
+// where it was produced and every rank PULLS only the 1/world slice it owns (ld.global.cv), in rank order, so sums are
+// deterministic.  Payload areas are double-buffered by the parity of the sequence number: a rank can be at most one
+// exchange ahead of the slowest peer.
+constexpr int kPeerMax = 8;
+constexpr size_t kPeerOffFlags = 0;            // u64 [2][8]
+constexpr size_t kPeerOffSeq = 128;            // u64, local use
+constexpr size_t kPeerOffTimeout = 136;        // int, local use: a wait gave up (peer lost)
+constexpr size_t kPeerOffPart = 256;           // double [2][8][2]
+constexpr size_t kPeerOffFwd = 1024;           // forward: double [2 parities][2 arrays][n_rp]
+constexpr size_t kPeerOffAdj = (size_t)1 << 20;  // adjoint: xrec [2][world][6 n_loc] doubles, then pcomb [2][4 P] floats
+
+struct PeerView {
+  int world = 1, rank = 0;
+  unsigned char* base[kPeerMax] = {nullptr};   // base[r]: rank r's symmetric buffer as mapped in THIS process
+  size_t bytes = 0;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// threads 0..world-1 of the calling CTA; the CTA's earlier writes (any thread) must be ordered before by __syncthreads
+__device__ __forceinline__ void peer_signal(const PeerView& pv, int kind, unsigned long long seq) {
+  if ((int)threadIdx.x < pv.world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned long long*>(pv.base[threadIdx.x] + kPeerOffFlags) + kind * kPeerMax + pv.rank, seq);
+  }
+}
+// every thread of the CTA returns once all ranks have signalled `seq` (or a ~10 s timeout has been recorded)
+__device__ __forceinline__ void peer_wait(const PeerView& pv, int kind, unsigned long long seq) {
+  if ((int)threadIdx.x < pv.world) {
+    const unsigned long long* f =
+        reinterpret_cast<const unsigned long long*>(pv.base[pv.rank] + kPeerOffFlags) + kind * kPeerMax + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < seq) {
+      if (clock64() - t0 > 20000000000LL) {   // a peer is gone: record it and stop waiting rather than hang the GPU
+        *reinterpret_cast<volatile int*>(pv.base[pv.rank] + kPeerOffTimeout) = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+#endif
+
 struct DistCtx {
   int world = 1, rank = 0;
   NcclComm comm = nullptr;
   NcclApi api;
+  PeerView peer;            // mapped when eno_peer_attach has run; peer.base[rank] == nullptr otherwise
+  void* peer_mine = nullptr;
   bool active() const { return world > 1 && comm != nullptr; }
+  bool peer_ready() const { return active() && peer.base[rank] != nullptr; }
 
   // in-place all-gather of equal per-rank chunks: buf holds world * count elements, this rank's at rank * count
   template <typename T>

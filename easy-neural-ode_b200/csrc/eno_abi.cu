@@ -296,8 +296,14 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
     return fwd_stream_launch<4>(mode, a, grid, smem, stream);
   };
   // multi-GPU: gather every rank's per-sample partials, then one CTA per rank runs the controller
+  const bool peer = dist && dc.peer_ready() && (size_t)4 * a.n_rp * 8 <= kPeerOffAdj - kPeerOffFwd;
   auto finish = [&](int mode) -> int {
     if (!dist) return 0;
+    if (peer) {   // exchange inside the finish kernel, over NVLink peer memory (dist.cuh)
+      k_fwd_finish_peer<<<1, kThreads, 0, stream>>>(a, mode, dc.peer, (int)n_loc);
+      ++launches;
+      return 0;
+    }
     if (dc.api.GroupStart()) return 1;
     int rc = dc.gather(rp0, n_loc, stream);
     if (mode == 1) rc |= dc.gather(rp1, n_loc, stream);
@@ -537,10 +543,54 @@ int32_t eno_comm_init(eno_ctx* ctx, const uint8_t* id, int32_t rank, int32_t wor
   return ENO_OK;
 }
 
+// Exchange over NVLink peer memory (dist.cuh): every rank allocates its symmetric buffer and exports it ...
+int32_t eno_peer_export(eno_ctx* ctx, uint64_t bytes, uint8_t* handle_out /*[64]*/) {
+  if (!ctx || !handle_out || bytes < (kPeerOffAdj << 1)) return fail(ctx, ENO_E_ARG, "eno_peer_export: bad arguments");
+  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->dist.peer_mine) return fail(ctx, ENO_E_ARG, "eno_peer_export: already exported");
+  void* p = nullptr;
+  ENO_CUDA(ctx, cudaMalloc(&p, bytes));
+  ENO_CUDA(ctx, cudaMemset(p, 0, bytes));
+  ENO_CUDA(ctx, cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return fail(ctx, ENO_E_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, 64);
+  ctx->dist.peer_mine = p;
+  ctx->dist.peer.bytes = bytes;
+  return ENO_OK;
+}
+
+// ... and maps every peer's (handles of all ranks in rank order, gathered by the host side).
+int32_t eno_peer_attach(eno_ctx* ctx, const uint8_t* handles /*[world][64]*/) {
+  if (!ctx || !handles || !ctx->dist.active() || !ctx->dist.peer_mine) return fail(ctx, ENO_E_ARG, "eno_peer_attach: call eno_comm_init and eno_peer_export first");
+  if (ctx->dist.world > kPeerMax) return fail(ctx, ENO_E_UNSUPPORTED, "eno_peer_attach: at most 8 ranks");
+  ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+  PeerView pv;
+  pv.world = ctx->dist.world; pv.rank = ctx->dist.rank; pv.bytes = ctx->dist.peer.bytes;
+  for (int r = 0; r < pv.world; ++r) {
+    if (r == pv.rank) { pv.base[r] = static_cast<unsigned char*>(ctx->dist.peer_mine); continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(ctx, ENO_E_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+    pv.base[r] = static_cast<unsigned char*>(p);
+  }
+  ctx->dist.peer = pv;
+  return ENO_OK;
+}
+
 int32_t eno_comm_destroy(eno_ctx* ctx) {
   if (!ctx) return ENO_E_ARG;
   if (ctx->dist.comm) ctx->dist.api.CommDestroy(ctx->dist.comm);
   ctx->dist.comm = nullptr;
+  for (int r = 0; r < ctx->dist.peer.world; ++r)
+    if (r != ctx->dist.peer.rank && ctx->dist.peer.base[r]) cudaIpcCloseMemHandle(ctx->dist.peer.base[r]);
+  if (ctx->dist.peer_mine) cudaFree(ctx->dist.peer_mine);
+  ctx->dist.peer_mine = nullptr;
+  ctx->dist.peer = PeerView();
   ctx->dist.world = 1;
   ctx->dist.rank = 0;
   g_world = 1;
@@ -594,6 +644,11 @@ int32_t eno_ffma_peak(eno_ctx* ctx, double* tflops_out, void* stream_) {
 }
 
 #ifdef ENO_PHASES
+int32_t eno_debug_peer_stamps(long long* out /*[8]*/) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_peer_stamp, sizeof(long long) * 8);
+  return 0;
+}
 // development aid: read and clear the phase clocks of the cluster kernels
 int32_t eno_debug_phases(long long* cycles, long long* counts) {
   long long zero[32] = {0};

@@ -10,6 +10,7 @@
 // 1048-1390 (clip-flavour loops), 86-104 (initial step), 518-538 (norm, controller),
 // 56-84 + 849-850 (dense output).
 #pragma once
+#include "dist.cuh"
 #include "mlp_device.cuh"
 
 namespace eno {
@@ -275,10 +276,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_fwd_step(FwdArgs a) {
 // Multi-GPU: reduction + controller as a separate one-CTA launch, after the per-sample partials of
 // every rank have been all-gathered.  mode 0 iteration, 1 / 2 initial-step phases.  Every rank runs it on
 // identical inputs and therefore takes identical decisions.
-__global__ void __launch_bounds__(kThreads) k_fwd_finish(FwdArgs a, int mode) {
-  __shared__ double dred[kThreads];
+__device__ __forceinline__ void fwd_finish_body(FwdArgs& a, int mode, double* dred) {
   Ctrl* c = a.ctrl;
-  if (mode == 0 && c->done) return;
   const double s0 = block_sum_global(a.rp0_all, a.n_rp, dred);
   __syncthreads();
   double s1 = 0.0;
@@ -313,6 +312,37 @@ __global__ void __launch_bounds__(kThreads) k_fwd_finish(FwdArgs a, int mode) {
     const float ratio = (float)(s0 / (double)c->n_state);
     finish_iteration(c, a.ts, ratio, dt, c_tab, a.trace);
   }
+}
+
+__global__ void __launch_bounds__(kThreads) k_fwd_finish(FwdArgs a, int mode) {
+  __shared__ double dred[kThreads];
+  if (mode == 0 && a.ctrl->done) return;
+  fwd_finish_body(a, mode, dred);
+}
+
+// The same with the exchange inside the kernel (dist.cuh): push this rank's per-sample partials into every rank's
+// gathered array over NVLink, signal, wait for all ranks, then reduce + run the controller.  No NCCL call.
+__global__ void __launch_bounds__(kThreads) k_fwd_finish_peer(FwdArgs a, int mode, PeerView pv, int n_loc) {
+  __shared__ double dred[kThreads];
+  if (mode == 0 && a.ctrl->done) return;
+  unsigned long long* seqp = reinterpret_cast<unsigned long long*>(pv.base[pv.rank] + kPeerOffSeq);
+  const unsigned long long seq = *seqp + 1;
+  const size_t par_off = (size_t)(seq & 1) * 2 * a.n_rp;      // doubles
+  for (int r = 0; r < pv.world; ++r) {
+    double* dst = reinterpret_cast<double*>(pv.base[r] + kPeerOffFwd) + par_off + (size_t)pv.rank * n_loc;
+    for (int i = threadIdx.x; i < n_loc; i += blockDim.x) {
+      dst[i] = a.rowpart0[i];
+      if (mode == 1) dst[a.n_rp + i] = a.rowpart1[i];
+    }
+  }
+  __syncthreads();
+  peer_signal(pv, 0, seq);
+  peer_wait(pv, 0, seq);
+  const double* mine = reinterpret_cast<const double*>(pv.base[pv.rank] + kPeerOffFwd) + par_off;
+  a.rp0_all = mine;
+  a.rp1_all = mine + a.n_rp;
+  fwd_finish_body(a, mode, dred);
+  if (threadIdx.x == 0) *seqp = seq;
 }
 
 // ---- dense output for the targets the last iteration left behind ----------------------

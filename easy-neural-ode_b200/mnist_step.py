@@ -197,11 +197,10 @@ class MnistNode:
 
     def update(self, images_u8, labels, eps):
         """One training step; returns the (device) loss tensor."""
-        self._stage_lr()
-        self.itr += 1
         out = self.loss_and_grads(images_u8, labels, eps)
         g = out["grads"]
-        self.apply_grads(g["ode"], g["post_w"], g["post_b"])
+        self.apply_grads(g["ode"], g["post_w"], g["post_b"])      # stages the schedule's value at self.itr
+        self.itr += 1
         return out
 
     # ---- whole-step CUDA graph ------------------------------------------------------------------

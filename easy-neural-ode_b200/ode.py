@@ -17,6 +17,7 @@ and the results are returned on the input's device.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -64,6 +65,29 @@ def init_distributed(device=None):
     with torch.cuda.device(dev):
         _cabi.check(L.eno_comm_init(h, idb, rank, world, path), h, "eno_comm_init")
     _dist["world"], _dist["rank"] = world, rank
+    _dist["peer"] = False
+    if world > 1 and world <= 8 and os.environ.get("ENO_EXCHANGE", "peer") != "nccl":
+        # move the per-iteration exchange into the solver's finish kernels, over NVLink peer memory (include/eno.h):
+        # every rank exports its exchange buffer as a CUDA IPC handle, the handles are gathered, every rank maps its peers
+        nbytes = int(os.environ.get("ENO_PEER_BYTES", str(64 << 20)))
+        mine = (C.c_uint8 * 64)()
+        with torch.cuda.device(dev):
+            rc = L.eno_peer_export(h, nbytes, mine)
+        ok = [rc == 0]
+        handles = [None] * world
+        dist.all_gather_object(handles, (rc, bytes(mine)))
+        if all(r == 0 for r, _ in handles):
+            blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(b for _, b in handles))
+            with torch.cuda.device(dev):
+                rc = L.eno_peer_attach(h, blob)
+            flags = [None] * world
+            dist.all_gather_object(flags, rc)
+            if all(f == 0 for f in flags):
+                _dist["peer"] = True
+            elif rc == 0:
+                raise RuntimeError("init_distributed: a rank could not map its peers' exchange buffers; set ENO_EXCHANGE=nccl")
+            else:
+                _cabi.check(rc, h, "eno_peer_attach")
     _workspaces.clear()
     return world, rank
 

@@ -261,6 +261,18 @@ int32_t eno_read_stats(eno_ctx* ctx, const void* workspace, eno_stats* out, void
 int32_t eno_comm_unique_id(eno_ctx* ctx, uint8_t* id_out /*[128]*/, const char* nccl_path);
 int32_t eno_comm_init(eno_ctx* ctx, const uint8_t* id /*[128]*/, int32_t rank, int32_t world, const char* nccl_path);
 int32_t eno_comm_destroy(eno_ctx* ctx);
+/*
+ * Optional, after eno_comm_init: move the per-iteration exchange of the collective solves from NCCL calls into the
+ * solver's own finish kernels, over NVLink peer memory (one node, at most 8 ranks).  Every rank calls eno_peer_export
+ * (allocates its exchange buffer of `bytes` >= 2 MiB + what the solves need - 64 MiB is plenty for the MNIST size - and
+ * returns its 64-byte CUDA IPC handle), the host side gathers the handles of all ranks in rank order, and every rank
+ * calls eno_peer_attach with them.  What travels: the per-sample norm partials are pushed to every rank (forward and
+ * adjoint); of the four params_bar stage combinations every rank pulls only the 1/world slice it owns, forms candidate
+ * / error / norm partial for that slice, and one more scalar per rank is exchanged; params_bar is gathered once per
+ * segment.  Without these calls the solves use the NCCL exchange.
+ */
+int32_t eno_peer_export(eno_ctx* ctx, uint64_t bytes, uint8_t* handle_out /*[64]*/);
+int32_t eno_peer_attach(eno_ctx* ctx, const uint8_t* handles /*[world][64], rank order*/);
 
 /*
  * Measurement hooks used by bench.py (no reference counterpart; the reference only wall-clocks the
