@@ -80,7 +80,7 @@ inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArg
   a->ppart0 = cv.take<double>(npp); a->ppart1 = cv.take<double>(npp);
   a->pcomb = (world > 1) ? cv.take<float>(4 * P) : nullptr;
   a->dist = 0;
-  a->peer = 0;
+  a->peer_base = nullptr;
   a->YBAR = cv.take<float>(N);
   a->POUT = cv.take<float>(P + 256 * (size_t)(world + 1));
   float* W1xT = cv.take<float>((size_t)D * H);
@@ -267,8 +267,7 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
   const bool peer = dist && dc->peer_ready() && !getenv("ENO_EXCHANGE_NCCL") &&
                     kPeerOffAdj + peer_xrec_bytes + 256 + (size_t)2 * 4 * a.P * 4 <= dc->peer.bytes;
   if (peer) {
-    a.peer = 1;
-    a.pv = dc->peer;
+    a.peer_base = dc->peer.base[rank];
     a.peer_pcomb_off = kPeerOffAdj + ((peer_xrec_bytes + 255) / 256) * 256;
     a.p_lo = rank * slice;
     a.p_cnt = slice;

@@ -77,8 +77,8 @@ struct AdjArgs {
   double *ppart0, *ppart1;                 // [pgrad grid]
   float* pcomb;                            // [4][P] multi-GPU: this rank's share of the stage combinations
   int dist;                                // 1: multi-GPU split (local contraction | exchange | finish)
-  int peer;                                // 1: the exchange runs inside k_adj_pfinish_peer over NVLink peer memory (dist.cuh)
-  PeerView pv;
+  unsigned char* peer_base;                // non-null: the exchange runs inside k_adj_pfinish_peer over NVLink peer memory
+                                           // (dist.cuh); this rank's exchange buffer (its PeerView lives at kPeerOffView)
   size_t peer_pcomb_off;                   // byte offset of pcomb [2 parities][4 P] inside every rank's exchange buffer
   int p_lo, p_cnt;                         // params_bar slice this rank owns in peer mode
   // segment inputs / outputs
@@ -385,7 +385,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_adj_rows(AdjArgs a, float rhs_t
 // (rowpart*, slot[].tbar: n_rp entries each, already gathered from every rank in the multi-GPU case).
 template <int MODE>
 __device__ __forceinline__ void adj_finalize(AdjArgs& a, Ctrl* c, double* dred, int n_pp, float dt,
-                                             float* rhs_tbar) {
+                                             float* rhs_tbar, const double* gx = nullptr) {
+  // gx: every rank's record in one gathered array somewhere else than a.xrec (peer-memory exchange)
+  const double* rp0_all = gx ? gx : a.rp0_all;
+  const double* rp1_all = gx ? gx + 4 * a.n_loc : a.rp1_all;
+  const double* rp2_all = gx ? gx + 5 * a.n_loc : a.rp2_all;
   constexpr bool SPLITK = (MODE != ADJ_STEP);
   constexpr int NS = kSlots;
   const int B = a.B;
@@ -395,16 +399,16 @@ __device__ __forceinline__ void adj_finalize(AdjArgs& a, Ctrl* c, double* dred, 
   __shared__ double fin[12];
   {
     double v;
-    v = block_sum_records(a.rp0_all, a.n_rp, a.n_loc, 6 * a.n_loc, dred); if (threadIdx.x == 0) fin[0] = v; __syncthreads();
+    v = block_sum_records(rp0_all, a.n_rp, a.n_loc, 6 * a.n_loc, dred); if (threadIdx.x == 0) fin[0] = v; __syncthreads();
     v = block_sum_global(a.ppart0, n_pp, dred); if (threadIdx.x == 0) fin[1] = v; __syncthreads();
     if (MODE == ADJ_INIT0) {
-      v = block_sum_records(a.rp1_all, a.n_rp, a.n_loc, 6 * a.n_loc, dred); if (threadIdx.x == 0) fin[2] = v; __syncthreads();
+      v = block_sum_records(rp1_all, a.n_rp, a.n_loc, 6 * a.n_loc, dred); if (threadIdx.x == 0) fin[2] = v; __syncthreads();
       v = block_sum_global(a.ppart1, n_pp, dred); if (threadIdx.x == 0) fin[3] = v; __syncthreads();
-      v = block_sum_records(a.rp2_all, a.n_rp, a.n_loc, 6 * a.n_loc, dred); if (threadIdx.x == 0) fin[4] = v; __syncthreads();
+      v = block_sum_records(rp2_all, a.n_rp, a.n_loc, 6 * a.n_loc, dred); if (threadIdx.x == 0) fin[4] = v; __syncthreads();
     }
     // stage derivatives of t0_bar: sums of the per-sample t_bar contributions
     for (int j = 0; j < (SPLITK ? 1 : NS); ++j) {
-      const float* tb = a.tbar_all[j];
+      const float* tb = gx ? reinterpret_cast<const float*>(gx) + 2 * a.n_loc + (size_t)j * a.n_loc : a.tbar_all[j];
       const int per = (a.n_rp + blockDim.x - 1) / blockDim.x;
       const int b0 = threadIdx.x * per, b1 = min(a.n_rp, b0 + per);
       double acc = 0.0;
@@ -657,9 +661,10 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
     // stage derivatives, so ship the four stage combinations (without the replicated k0 term) and let
     // k_adj_pfinish continue after the all-reduce.
     const size_t P = (size_t)a.P;
-    if (a.peer) {   // the slot of the exchange that the finish kernel after this launch will run
-      const unsigned long long seq = *reinterpret_cast<const unsigned long long*>(a.pv.base[a.pv.rank] + kPeerOffSeq) + 1;
-      a.pcomb = reinterpret_cast<float*>(a.pv.base[a.pv.rank] + a.peer_pcomb_off) + (size_t)(seq & 1) * 4 * P;
+    float* pcomb = a.pcomb;
+    if (a.peer_base) {   // the slot of the exchange that the finish kernel after this launch will run
+      const unsigned long long seq = *reinterpret_cast<const unsigned long long*>(a.peer_base + kPeerOffSeq) + 1;
+      pcomb = reinterpret_cast<float*>(a.peer_base + a.peer_pcomb_off) + (size_t)(seq & 1) * 4 * P;
     }
     for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
       const int p = pidx[e];
@@ -673,12 +678,12 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
           er = fmaf(c_tab.c_err[j + 1], kj, er);
           md = fmaf(c_tab.c_mid[j + 1], kj, md);
         }
-        a.pcomb[p] = s;
-        a.pcomb[P + p] = er;
-        a.pcomb[2 * P + p] = md;
-        a.pcomb[3 * P + p] = tile[kSlots - 1][e];
+        pcomb[p] = s;
+        pcomb[P + p] = er;
+        pcomb[2 * P + p] = md;
+        pcomb[3 * P + p] = tile[kSlots - 1][e];
       } else {
-        a.pcomb[p] = ((((tile[0][e] + tile[1][e]) + tile[2][e]) + tile[3][e]) + tile[4][e]) + tile[5][e];
+        pcomb[p] = ((((tile[0][e] + tile[1][e]) + tile[2][e]) + tile[3][e]) + tile[4][e]) + tile[5][e];
       }
     }
     return;
@@ -859,8 +864,8 @@ __global__ void __launch_bounds__(256) k_adj_pfinish_peer(AdjArgs a) {
   if (MODE == ADJ_STEP && c->done) return;
   __shared__ double dred[256];
   PEER_STAMP(blockIdx.x == 0, 0);
-  const PeerView& pv = a.pv;
-  unsigned long long* seqp = reinterpret_cast<unsigned long long*>(pv.base[pv.rank] + kPeerOffSeq);
+  const PeerView pv = *reinterpret_cast<const PeerView*>(a.peer_base + kPeerOffView);
+  unsigned long long* seqp = reinterpret_cast<unsigned long long*>(a.peer_base + kPeerOffSeq);
   const unsigned long long seq = *seqp + 1;
   const int par = (int)(seq & 1);
   const size_t P = (size_t)a.P;
@@ -868,9 +873,23 @@ __global__ void __launch_bounds__(256) k_adj_pfinish_peer(AdjArgs a) {
   const size_t xoff = kPeerOffAdj + (size_t)par * pv.world * rec * 8;
   if (blockIdx.x == 0) {
     const double* mine = a.xrec + (size_t)pv.rank * rec;
-    for (int r = 0; r < pv.world; ++r) {
-      double* dst = reinterpret_cast<double*>(pv.base[r] + xoff) + (size_t)pv.rank * rec;
-      for (int i = threadIdx.x; i < (int)rec; i += blockDim.x) dst[i] = mine[i];
+    // all loads in flight before the first remote store (a load -> store chain per element cost 15 us here)
+    constexpr int kPer = 16;
+    for (int base = 0; base < (int)rec; base += kPer * blockDim.x) {
+      double v[kPer];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        const int i = base + k * blockDim.x + threadIdx.x;
+        v[k] = (i < (int)rec) ? mine[i] : 0.0;
+      }
+      for (int r = 0; r < pv.world; ++r) {
+        double* dst = reinterpret_cast<double*>(pv.base[r] + xoff) + (size_t)pv.rank * rec;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+          const int i = base + k * blockDim.x + threadIdx.x;
+          if (i < (int)rec) dst[i] = v[k];
+        }
+      }
     }
     __syncthreads();
     peer_signal(pv, 0, seq);
@@ -961,14 +980,9 @@ __global__ void __launch_bounds__(256) k_adj_pfinish_peer(AdjArgs a) {
   }
   __syncthreads();
   // the finaliser reads every rank's record from the gathered array in this rank's exchange buffer
-  const double* gx = reinterpret_cast<const double*>(pv.base[pv.rank] + xoff);
-  a.rp0_all = gx;
-  a.rp1_all = gx + 4 * a.n_loc;
-  a.rp2_all = gx + 5 * a.n_loc;
-  const float* f0 = reinterpret_cast<const float*>(gx) + 2 * a.n_loc;
-  for (int j = 0; j < kSlots; ++j) a.tbar_all[j] = f0 + (size_t)j * a.n_loc;
+  const double* gx = reinterpret_cast<const double*>(a.peer_base + xoff);
   if (threadIdx.x == 0) *seqp = seq;   // (thread 0 is the one that survives the finaliser's early return)
-  adj_finalize<MODE>(a, c, dred, 1, dt, nullptr);
+  adj_finalize<MODE>(a, c, dred, 1, dt, nullptr, gx);
   PEER_STAMP(true, 6);
 }
 

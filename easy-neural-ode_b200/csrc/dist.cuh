@@ -60,7 +60,7 @@ struct NcclApi {
 // ---- exchange over NVLink peer memory (no NCCL call per solver iteration) -----------------------------------------
 // Every rank owns one "symmetric" buffer (cudaMalloc, exported with cudaIpcGetMemHandle, mapped by every peer), laid out
 // identically on all ranks:
-//   [ flags: 2 kinds x 8 ranks, u64 | seq (local) | timeout word | part[2 parities][8 ranks][2] doubles | data ... ]
+//   [ flags: 2 kinds x 8 ranks, u64 | seq (local) | timeout word | part[2 parities][8 ranks][2] doubles | PeerView | data ... ]
 // A rank SIGNALS by storing a monotonically increasing sequence number into slot [kind][its rank] of EVERY peer's buffer
 // (st.release.sys after a system fence) and WAITS by spinning on its own, local, slots - so polling never crosses
 // NVLink.  Small payloads (per-sample norm partials, the 24 KB adjoint record, the per-rank norm scalar) are PUSHED
@@ -73,6 +73,7 @@ constexpr size_t kPeerOffFlags = 0;            // u64 [2][8]
 constexpr size_t kPeerOffSeq = 128;            // u64, local use
 constexpr size_t kPeerOffTimeout = 136;        // int, local use: a wait gave up (peer lost)
 constexpr size_t kPeerOffPart = 256;           // double [2][8][2]
+constexpr size_t kPeerOffView = 512;           // this rank's PeerView (device-resident copy read by the kernels)
 constexpr size_t kPeerOffFwd = 1024;           // forward: double [2 parities][2 arrays][n_rp]
 constexpr size_t kPeerOffAdj = (size_t)1 << 20;  // adjoint: xrec [2][world][6 n_loc] doubles, then pcomb [2][4 P] floats
 

@@ -300,7 +300,7 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   auto finish = [&](int mode) -> int {
     if (!dist) return 0;
     if (peer) {   // exchange inside the finish kernel, over NVLink peer memory (dist.cuh)
-      k_fwd_finish_peer<<<1, kThreads, 0, stream>>>(a, mode, dc.peer, (int)n_loc);
+      k_fwd_finish_peer<<<1, kThreads, 0, stream>>>(a, mode, dc.peer.base[dc.rank], (int)n_loc);
       ++launches;
       return 0;
     }
@@ -579,6 +579,8 @@ int32_t eno_peer_attach(eno_ctx* ctx, const uint8_t* handles /*[world][64]*/) {
     pv.base[r] = static_cast<unsigned char*>(p);
   }
   ctx->dist.peer = pv;
+  // the kernels read the view from the buffer itself (keeps their parameter blocks small)
+  ENO_CUDA(ctx, cudaMemcpy(pv.base[pv.rank] + kPeerOffView, &pv, sizeof(PeerView), cudaMemcpyHostToDevice));
   return ENO_OK;
 }
 

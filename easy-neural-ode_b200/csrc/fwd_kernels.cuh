@@ -276,12 +276,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_fwd_step(FwdArgs a) {
 // Multi-GPU: reduction + controller as a separate one-CTA launch, after the per-sample partials of
 // every rank have been all-gathered.  mode 0 iteration, 1 / 2 initial-step phases.  Every rank runs it on
 // identical inputs and therefore takes identical decisions.
-__device__ __forceinline__ void fwd_finish_body(FwdArgs& a, int mode, double* dred) {
+__device__ __forceinline__ void fwd_finish_body(const FwdArgs& a, int mode, double* dred, const double* rp0_all, const double* rp1_all) {
   Ctrl* c = a.ctrl;
-  const double s0 = block_sum_global(a.rp0_all, a.n_rp, dred);
+  const double s0 = block_sum_global(rp0_all, a.n_rp, dred);
   __syncthreads();
   double s1 = 0.0;
-  if (mode == 1) s1 = block_sum_global(a.rp1_all, a.n_rp, dred);
+  if (mode == 1) s1 = block_sum_global(rp1_all, a.n_rp, dred);
   if (threadIdx.x != 0) return;
   if (mode == 1) {
     const float d0 = sqrtf((float)s0), d1 = sqrtf((float)s1);
@@ -317,31 +317,31 @@ __device__ __forceinline__ void fwd_finish_body(FwdArgs& a, int mode, double* dr
 __global__ void __launch_bounds__(kThreads) k_fwd_finish(FwdArgs a, int mode) {
   __shared__ double dred[kThreads];
   if (mode == 0 && a.ctrl->done) return;
-  fwd_finish_body(a, mode, dred);
+  fwd_finish_body(a, mode, dred, a.rp0_all, a.rp1_all);
 }
 
 // The same with the exchange inside the kernel (dist.cuh): push this rank's per-sample partials into every rank's
 // gathered array over NVLink, signal, wait for all ranks, then reduce + run the controller.  No NCCL call.
-__global__ void __launch_bounds__(kThreads) k_fwd_finish_peer(FwdArgs a, int mode, PeerView pv, int n_loc) {
+__global__ void __launch_bounds__(kThreads) k_fwd_finish_peer(FwdArgs a, int mode, unsigned char* peer_base, int n_loc) {
   __shared__ double dred[kThreads];
   if (mode == 0 && a.ctrl->done) return;
-  unsigned long long* seqp = reinterpret_cast<unsigned long long*>(pv.base[pv.rank] + kPeerOffSeq);
+  const PeerView pv = *reinterpret_cast<const PeerView*>(peer_base + kPeerOffView);
+  unsigned long long* seqp = reinterpret_cast<unsigned long long*>(peer_base + kPeerOffSeq);
   const unsigned long long seq = *seqp + 1;
   const size_t par_off = (size_t)(seq & 1) * 2 * a.n_rp;      // doubles
-  for (int r = 0; r < pv.world; ++r) {
-    double* dst = reinterpret_cast<double*>(pv.base[r] + kPeerOffFwd) + par_off + (size_t)pv.rank * n_loc;
-    for (int i = threadIdx.x; i < n_loc; i += blockDim.x) {
-      dst[i] = a.rowpart0[i];
-      if (mode == 1) dst[a.n_rp + i] = a.rowpart1[i];
+  for (int i = threadIdx.x; i < n_loc; i += blockDim.x) {
+    const double v0 = a.rowpart0[i], v1 = (mode == 1) ? a.rowpart1[i] : 0.0;
+    for (int r = 0; r < pv.world; ++r) {
+      double* dst = reinterpret_cast<double*>(pv.base[r] + kPeerOffFwd) + par_off + (size_t)pv.rank * n_loc;
+      dst[i] = v0;
+      if (mode == 1) dst[a.n_rp + i] = v1;
     }
   }
   __syncthreads();
   peer_signal(pv, 0, seq);
   peer_wait(pv, 0, seq);
-  const double* mine = reinterpret_cast<const double*>(pv.base[pv.rank] + kPeerOffFwd) + par_off;
-  a.rp0_all = mine;
-  a.rp1_all = mine + a.n_rp;
-  fwd_finish_body(a, mode, dred);
+  const double* mine = reinterpret_cast<const double*>(peer_base + kPeerOffFwd) + par_off;
+  fwd_finish_body(a, mode, dred, mine, mine + a.n_rp);
   if (threadIdx.x == 0) *seqp = seq;
 }
 
