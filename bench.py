@@ -324,6 +324,201 @@ def fj_main(args, result_out, rank, local_rank, world):
     print(json.dumps(line), file=result_out, flush=True)
 
 
+# ---- BASELINE configs[2]: latent_ode.py generative ODE, per-trajectory solves (development workload, single GPU) --------
+LT = dict(S=3, B=50, D=20, U=50, LAYERS=3, T=49, DATA=37, LAM=1e-2, TOL=1.4e-8)
+LT_WORKLOAD = ("latent_ode.py generative ODE, synthetic Physionet-shaped series (37 features, 49 time points on [0, 1]), "
+               "GenDynamics 20-50x4-20 tanh, dopri5, --reg r3 --lam 1e-2, 3 samples x batch 50 = 150 per-trajectory solves "
+               "with 49 output times each, float64 (configs[2])")
+
+
+def lt_batch(step, pin=False):
+    import torch
+    g = torch.Generator().manual_seed(977 + (step % 8))
+    z0 = 0.1 * torch.randn((LT["S"], LT["B"], LT["D"]), generator=g, dtype=torch.float64)
+    data = torch.randn((LT["B"], LT["T"], LT["DATA"]), generator=g, dtype=torch.float64)
+    mask = (torch.rand((LT["B"], LT["T"], LT["DATA"]), generator=g) < 0.1).double()
+    if pin:
+        z0, data, mask = z0.pin_memory(), data.pin_memory(), mask.pin_memory()
+    return z0, data, mask
+
+
+def lt_config():
+    return {"workload": LT_WORKLOAD, "global_batch": LT["S"] * LT["B"], "per_gpu_batch": LT["S"] * LT["B"], "rtol": LT["TOL"],
+            "atol": LT["TOL"], "parallelism": "single GPU (trajectories are independent: replicas only, no exchange)",
+            "l2": "flushed between steps (256 MiB device write, outside the per-step events)",
+            "trajectory": "train steps 0..K-1 from the initial parameters (seeded), identical in every leg and arm"}
+
+
+def lt_cpu_sample(n_traj, threads):
+    """Oracle port on host cores: forward solve + complete adjoint of `n_traj` of the 150 trajectories of train step 0
+    (float64, nested-jvp Taylor closure), -> seconds per trajectory and the iteration counts."""
+    import math
+    import torch
+    from oracle import latent_oracle as lo, ode_oracle as oo
+    torch.set_num_threads(threads)
+    p = lo.init_gen_params(LT["D"], LT["U"], LT["LAYERS"], seed=0, dtype=torch.float64)
+    cl = lo.make_latent_closures("r3")
+    z0, _, _ = lt_batch(0)
+    z0 = z0.reshape(-1, LT["D"])
+    ts = torch.linspace(0., 1., LT["T"], dtype=torch.float64)
+    g = torch.Generator().manual_seed(5)
+    t0 = time.perf_counter()
+    nfe, bwd_iters = [], []
+    for k in range(n_traj):
+        y0 = (z0[k:k + 1], torch.zeros((), dtype=torch.float64))
+        flat0, unravel = oo.ravel(y0)
+        func = lambda yf, t, params: oo.ravel(cl["aug_dynamics"](unravel(yf), t, params))[0]
+        ys, n, _ = oo.odeint(func, flat0, ts, p, rtol=LT["TOL"], atol=LT["TOL"], return_stats=True)
+        gflat = torch.randn(ys.shape, generator=g, dtype=torch.float64)
+        st = []
+        oo.odeint_rev(func, LT["TOL"], LT["TOL"], math.inf, ys, ts, (p,), gflat, st)
+        nfe.append(n)
+        bwd_iters.append(sum(x["n_iters"] for x in st))
+    return (time.perf_counter() - t0) / n_traj, nfe, bwd_iters
+
+
+def lt_reference(args):
+    threads = len(os.sched_getaffinity(0))
+    n = 2
+    sec, nfe, bwd = lt_cpu_sample(n, threads)
+    n_all = LT["S"] * LT["B"]
+    val = 1.0 / (sec * n_all)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * n_all * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": lt_config(),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{n} of the {n_all} trajectories of train step 0 (forward solve + complete adjoint, oracle "
+                                       f"port, torch CPU float64, {threads} threads), scaled to {n_all}; NFE {nfe}, adjoint "
+                                       f"iterations {bwd}"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def lt_main(args, result_out, local_rank):
+    """`--workload latent_ode`: the generative half of one update() of latent_ode.py per step - 150 per-trajectory forward
+    solves (one launch), decoder + likelihood, 150 complete adjoints of 48 segments each (one launch), Adam."""
+    import torch
+    from easy_neural_ode_b200 import latent_step, latent
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    model = latent_step.LatentGen(LT["D"], LT["LAYERS"], LT["U"], LT["DATA"], reg="r3", lam=LT["LAM"], rtol=LT["TOL"], atol=LT["TOL"],
+                                  device=dev, seed=0)
+    ts = torch.linspace(0., 1., LT["T"], dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    dev_b = [tuple(t.to(dev) for t in lt_batch(s)) for s in range(8)]
+    host_b = [lt_batch(s, pin=True) for s in range(8)]
+    snap = model.snapshot()
+    for s in range(max(args.warmup, 3)):
+        out = model.update(dev_b[s % 8][0], ts, *dev_b[s % 8][1:])
+    torch.cuda.synchronize()
+    model.restore(snap)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    nfe_total, rhs_f, rhs_b, it_b = 0.0, 0, 0, 0
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        evs[s][0].record()
+        out = model.update(dev_b[s % 8][0], ts, *dev_b[s % 8][1:])
+        evs[s][1].record()
+        nfe_total += float(out["nfe"].sum())
+        rhs_f += int(2 * out["nfe"].numel() + 6 * out["fwd_iters"][:, 0].sum())
+        it_b += int(out["bwd_iters"][..., 0].sum())
+        rhs_b += int(2 * out["bwd_iters"][..., 0].numel() + 6 * out["bwd_iters"][..., 0].sum())
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    ms_per_step = dev_ms / args.steps
+    loss_dev = float(out["loss"])
+
+    model.restore(snap)
+    def step_e2e(s):
+        z0, data, mask = host_b[s % 8]
+        o = model.update(z0.to(dev, non_blocking=True), ts, data.to(dev, non_blocking=True), mask.to(dev, non_blocking=True))
+        return float(o["loss"])
+    for s in range(2):
+        step_e2e(s)
+    model.restore(snap)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_e2e(s)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # the dominant kernel (the adjoint of all trajectories, one launch) timed alone on the training state of step 0
+    model.restore(snap)
+    z0, data, mask = dev_b[0]
+    spec, p = model.spec, model.params
+    zs, rs, _, it_f, _ = latent.traj_fwd(spec, True, z0.reshape(-1, LT["D"]).contiguous(), ts, p, LT["TOL"], LT["TOL"], 0)
+    g_z = torch.randn_like(zs)
+    g_r = torch.zeros_like(rs)
+    g_r[:, -1] = LT["LAM"] / rs.shape[0]
+    reps, kms, fms = 5, 0.0, 0.0
+    for i in range(reps + 1):
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        flush.fill_(i)
+        a.record()
+        latent.traj_fwd(spec, True, z0.reshape(-1, LT["D"]).contiguous(), ts, p, LT["TOL"], LT["TOL"], 0)
+        b.record()
+        res = latent.traj_bwd(spec, True, zs, rs, ts, p, g_z, g_r, LT["TOL"], LT["TOL"], 0)
+        c.record()
+        torch.cuda.synchronize()
+        if i:
+            fms += a.elapsed_time(b)
+            kms += b.elapsed_time(c)
+    it1 = int(res[5][..., 0].sum())
+    segs = res[5][..., 0].numel()
+    P, nst = spec.n_params, 2 * 21 + 1 + spec.n_params
+    mv = 2 * sum(a * b for a, b in zip(spec.dims[:-1], spec.dims[1:]))      # flops of one pass through the stack
+    rhs1 = 2 * segs + 6 * it1
+    # algorithmic work of the adjoint launch: per right-hand side 3 Taylor streams forward, their reverse sweep (again 3
+    # transposed products) and 3 outer products per layer for the parameter cotangent; per iteration ~70 flops per state
+    # element for the RK combination, error estimate and norm (SURVEY.md section 8d's count)
+    flop = rhs1 * 9 * mv + it1 * 70 * nst
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = float(peaks.get("bf16_tflops", 1590.0))
+    achieved = flop / (kms / reps * 1e-3) / 1e12
+    fp64_peak = 37.0
+    roofline = {"kernel": "k_traj_bwd<double> (the complete adjoint of all 150 trajectories, 48 segments each, in ONE launch: "
+                          "one CTA per trajectory, weights resident in shared memory, float64 FMA)",
+                "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                "traffic": None, "peak_source": ("measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback 1.59 PFLOP/s"),
+                "avg_launch_ms": kms / reps, "launches_timed": reps, "algorithmic_flop_per_launch": flop,
+                "fp64_fma_peak_tflops": fp64_peak, "frac_of_fp64_fma": achieved / fp64_peak,
+                "forward_launch_ms": fms / reps, "adjoint_iterations_per_launch": it1, "adjoint_rhs_per_launch": rhs1,
+                "note": "float64 work on the non-tensor pipe (the script runs with jax_enable_x64); the tensor pipe is the contract's "
+                        "denominator, 37 TFLOP/s is B200's nominal float64 vector peak (not in MEASURED_PEAKS.json).  150 sequential "
+                        "per-trajectory solves of 2,500-FMA products are latency bound: one trajectory cannot fill an SM"}
+    line = {"metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": lt_config(),
+            "samples_per_s": LT["S"] * LT["B"] * 1e3 / ms_per_step, "clocks": clocks,
+            "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host_b[0]),
+                    "d2h_bytes_per_step": 8},
+            "gpu_launches": 3 * args.steps, "nfe_per_s": nfe_total / (dev_ms * 1e-3),
+            "adjoint_rhs_per_s": rhs_b / (dev_ms * 1e-3),
+            "solver": {"mean_nfe_per_trajectory": nfe_total / args.steps / (LT["S"] * LT["B"]),
+                       "adjoint_iterations_per_step": it_b / args.steps, "forward_rhs_per_step": rhs_f / args.steps, "loss_last": loss_dev},
+            "launch_mode": "two solver launches per step (all forward solves; all adjoints) + the per-trajectory sum; decoder, "
+                           "likelihood and Adam are float64 torch ops",
+            "roofline": roofline}
+    if not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        n = 2
+        sec, nfe, bwd = lt_cpu_sample(n, threads)
+        n_all = LT["S"] * LT["B"]
+        line["cpu_baseline"] = {"value": 1.0 / (sec * n_all), "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{n} of the {n_all} trajectories of train step 0 (forward solve + complete adjoint, oracle "
+                                          f"port, torch CPU float64, {threads} threads), scaled to {n_all}; NFE {nfe}, adjoint "
+                                          f"iterations {bwd}"}
+    print(json.dumps(line), file=result_out, flush=True)
+
+
 def main():
     global B
     ap = argparse.ArgumentParser()
@@ -337,9 +532,9 @@ def main():
     ap.add_argument("--reg-type", default="our", choices=["our", "fin"],
                     help="development only: 'fin' times the --reg_type fin arm (odeint_sepaux, lam_fro = lam_kin = 1e-2); "
                          "the headline metric is the default 'our' (--reg r3)")
-    ap.add_argument("--workload", default="mnist", choices=["mnist", "ffjord_tabular"],
+    ap.add_argument("--workload", default="mnist", choices=["mnist", "ffjord_tabular", "latent_ode"],
                     help="mnist = BASELINE configs[0], the configuration the metric is quoted on (default); "
-                         "ffjord_tabular = configs[1] (single GPU)")
+                         "ffjord_tabular = configs[1] (single GPU); latent_ode = configs[2] (single GPU)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -347,6 +542,8 @@ def main():
     if args.impl == "reference":
         if args.workload == "ffjord_tabular":
             return fj_reference(args) if rank == 0 else None
+        if args.workload == "latent_ode":
+            return lt_reference(args) if rank == 0 else None
         return run_reference(args, rank, world)
     # stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr, so
     # that banners printed by native libraries (NCCL prints its version on communicator creation) cannot
@@ -364,6 +561,10 @@ def main():
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
         return fj_main(args, result_out, rank, local_rank, world) if rank == 0 else None
+    if args.workload == "latent_ode":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+        return lt_main(args, result_out, local_rank) if rank == 0 else None
     B = args.batch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")

@@ -10,7 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ENO_LIB") or os.path.join(_HERE, "libeno.so")   # ENO_LIB: development variants only
 
 ENO_OK, ENO_MXSTEP, ENO_DT_UNDERFLOW, ENO_NONFINITE = 0, 1, 2, 3
-ARCH_MLP_SIGMOID, ARCH_CONCATSQUASH = 0, 1
+ARCH_MLP_SIGMOID, ARCH_CONCATSQUASH, ARCH_TANH_STACK = 0, 1, 2
+F32, F64 = 0, 1
 AUG_NONE, AUG_REG, AUG_ALL, AUG_FIN, AUG_FFJORD = 0, 1, 2, 3, 4
 TABLEAUX = {"dopri5": 0, "heun": 1, "fehlberg": 2, "bosh": 3, "rk_fehlberg": 4, "cash_karp": 5,
             "owrenzen": 6, "owrenzen5": 7, "tanyam": 8}
@@ -19,7 +20,8 @@ TABLEAUX = {"dopri5": 0, "heun": 1, "fehlberg": 2, "bosh": 3, "rk_fehlberg": 4, 
 SYMBOLS = ["eno_abi_version", "eno_last_error_string", "eno_create", "eno_destroy", "eno_param_count",
            "eno_adjoint_state_size", "eno_workspace_bytes", "eno_odeint_fwd", "eno_odeint_fwd_vmap", "eno_odeint_bwd", "eno_odeint_bwd_sepaux", "eno_rhs",
            "eno_mnist_head", "eno_momentum_update", "eno_profile_enable", "eno_profile_read", "eno_ffma_peak", "eno_comm_unique_id", "eno_comm_init",
-           "eno_comm_destroy", "eno_set_deferred", "eno_read_stats", "eno_gemm_tf32x3", "eno_adam_update", "eno_profile_read_gemm", "eno_peer_export", "eno_peer_attach"]
+           "eno_comm_destroy", "eno_set_deferred", "eno_read_stats", "eno_gemm_tf32x3", "eno_adam_update", "eno_profile_read_gemm", "eno_peer_export", "eno_peer_attach",
+           "eno_traj_param_count", "eno_traj_workspace_bytes", "eno_traj_fwd", "eno_traj_bwd", "eno_traj_rhs"]
 
 
 class Desc(C.Structure):
@@ -109,6 +111,18 @@ def lib():
     L.eno_adam_update.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, f32, vp]
     L.eno_gemm_tf32x3.restype = i32
     L.eno_gemm_tf32x3.argtypes = [vp, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, i32, vp]
+    f64 = C.c_double
+    L.eno_traj_param_count.restype = i64
+    L.eno_traj_param_count.argtypes = [C.POINTER(Desc)]
+    L.eno_traj_workspace_bytes.restype = sz
+    L.eno_traj_workspace_bytes.argtypes = [C.POINTER(Desc), i32, i32]
+    L.eno_traj_fwd.restype = i32
+    L.eno_traj_fwd.argtypes = [vp, C.POINTER(Desc), i32, i32, vp, vp, i32, vp, f64, f64, i32, vp, vp, vp, vp, vp, vp]
+    L.eno_traj_bwd.restype = i32
+    L.eno_traj_bwd.argtypes = [vp, C.POINTER(Desc), i32, i32, vp, vp, vp, i32, vp, vp, vp, f64, f64, i32, vp, sz, vp, vp, vp,
+                               vp, vp, vp, vp, vp]
+    L.eno_traj_rhs.restype = i32
+    L.eno_traj_rhs.argtypes = [vp, C.POINTER(Desc), i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

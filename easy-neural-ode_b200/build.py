@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libeno.so")
-SOURCES = [os.path.join(CSRC, "eno_abi.cu"), os.path.join(CSRC, "css_engine.cu")]
+SOURCES = [os.path.join(CSRC, "eno_abi.cu"), os.path.join(CSRC, "css_engine.cu"), os.path.join(CSRC, "lat_engine.cu")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--expt-relaxed-constexpr", "--extended-lambda",

@@ -195,3 +195,77 @@ class ConcatSquashDynamics:
             wg = flat[o:o + d_out].reshape(1, d_out); o += d_out
             out[n] = {"w": w, "b": b, "w_gate": wg, "b_gate": bg, "w_bias": wb}
         return out
+
+
+class GenDynamics:
+    """GenDynamics of latent_ode.py:191-208: ``[tanh, Linear(units)] x (layers + 1)`` then ``[tanh, Linear(latent_dim)]``,
+    time-independent.  ``reg`` is the script flag ``--reg`` (latent_ode.py:40): 'none', 'r2' or 'r3' (the order of the
+    total derivative whose mean square ``augment_dynamics`` integrates, latent_ode.py:82-108, 238-256).
+    Closures, named as in init_model:
+      gen_dynamics_wrap(x, t, params)            latent_ode.py:297   the count_nfe dynamics
+      aug_dynamics((z, r), t, params)            augment_dynamics(gen_dynamics_wrap), latent_ode.py:238-256
+    They are solved per trajectory (``jax.vmap(odeint)``, latent_ode.py:344-350) by ``easy_neural_ode_b200.odeint_vmap``;
+    the element type of the state (float64 like the script, or float32) selects the kernel instantiation.
+    Parameters: the Haiku dict {"gen_dynamics/linear[_i]": {"w", "b"}} or one flat vector in ravel order, per layer
+    [b | W]."""
+
+    def __init__(self, latent_dim, layers, units, reg="none"):
+        if reg not in ["none"] + REGS:
+            raise ValueError(f"--reg must be one of {['none'] + REGS}")
+        if reg in REGS[2:]:
+            raise NotImplementedError("Taylor orders above r3 are not built (BASELINE configs use r2/r3)")
+        if not (1 <= latent_dim <= 64 and 1 <= units <= 64):
+            raise ValueError("GenDynamics kernels hold widths up to 64")
+        if not 0 <= layers <= 5:
+            raise ValueError("GenDynamics supports gen_layers in 0..5")
+        self.latent_dim, self.layers, self.units, self.reg = latent_dim, layers, units, reg
+        self.dim = latent_dim
+        self.reg_order = 0 if reg == "none" else REGS.index(reg) + 2
+        self.dims = [latent_dim] + [units] * (layers + 1) + [latent_dim]
+        self.gen_dynamics_wrap = EnoFunc(self, "plain", ("params",))
+        self.dynamics_wrap = self.gen_dynamics_wrap
+        self.aug_dynamics = EnoFunc(self, "aug", ("params",))
+
+    def __repr__(self):
+        return f"GenDynamics(latent_dim={self.latent_dim}, layers={self.layers}, units={self.units}, reg={self.reg!r})"
+
+    @property
+    def layer_names(self):
+        return ["gen_dynamics/linear" + ("" if i == 0 else f"_{i}") for i in range(len(self.dims) - 1)]
+
+    @property
+    def n_params(self):
+        return sum(i * o + o for i, o in zip(self.dims[:-1], self.dims[1:]))
+
+    def desc(self, aug=_cabi.AUG_NONE, eps_in_args=False, reg_order=None):
+        return _cabi.Desc(_cabi.ARCH_TANH_STACK, self.latent_dim, self.units,
+                          self.reg_order if reg_order is None else reg_order, aug, 0, self.layers + 1)
+
+    def init_params(self, seed=0, device="cpu", scale=1.0, dtype=torch.float64):
+        """Haiku default init (GenDynamics is built without init_kwargs, latent_ode.py:293-296)."""
+        g = torch.Generator().manual_seed(seed)
+
+        def tn(shape, fan_in):
+            w = torch.empty(shape, dtype=torch.float64)
+            torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=g)
+            return (w * (scale / math.sqrt(fan_in))).to(dtype).to(device)
+
+        return {n: {"w": tn((a, b), a), "b": torch.zeros(b, dtype=dtype, device=device)}
+                for n, a, b in zip(self.layer_names, self.dims[:-1], self.dims[1:])}
+
+    def flatten_params(self, params):
+        if isinstance(params, torch.Tensor):
+            if params.numel() != self.n_params:
+                raise ValueError(f"flat params must have {self.n_params} elements")
+            return params.reshape(-1)
+        parts = []
+        for n in self.layer_names:
+            parts += [params[n]["b"].reshape(-1), params[n]["w"].reshape(-1)]
+        return torch.cat(parts)
+
+    def unflatten_params(self, flat):
+        out, o = {}, 0
+        for n, a, b in zip(self.layer_names, self.dims[:-1], self.dims[1:]):
+            out[n] = {"b": flat[o:o + b], "w": flat[o + b:o + b + a * b].reshape(a, b)}
+            o += b + a * b
+        return out

@@ -22,7 +22,8 @@ import os
 import torch
 
 from . import _cabi
-from .dynamics import EnoFunc
+from . import latent as _latent
+from .dynamics import EnoFunc, GenDynamics
 
 last_stats = {"fwd": None, "bwd": None}   # controller statistics of the most recent solves
 _workspaces = {}
@@ -563,8 +564,17 @@ def odeint_vmap(func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=math.inf):
     """``jax.vmap(lambda y0, t, *args: odeint(func, y0, t, *args), (0, None, None))`` - the per-example solves of
     mnist.py:350-353 (``--vmap`` NFE count): every row of ``y0`` is integrated as its own problem, with its own
     initial step, accept / reject sequence and NFE.  One kernel launch runs all of them to completion.
-    Forward only (the script never differentiates it).  -> (ys [T=2, B, D], nfe [B])."""
+    Forward only (the script never differentiates it).  -> (ys [T=2, B, D], nfe [B]).
+
+    For ``GenDynamics`` closures it is the per-trajectory solve of latent_ode.py:337-350,
+    ``jax.vmap(lambda z_, t_: odeint(dynamics, init_fn(z_), t_, params), in_axes=(0, None))`` (any number of leading
+    batch axes = nested vmaps): ``y0`` = z [..., D] or (z, r) for ``aug_dynamics``, ``t`` any number of output times,
+    differentiable wrt z, t and params -> (zs [..., T, D], nfe [...]) or ((zs, rs [..., T]), nfe [...])."""
     _require_spec(func, "odeint_vmap")
+    if isinstance(func.spec, GenDynamics):
+        # latent_ode.py:337-350: every trajectory its own differentiable multi-output solve (latent.py)
+        _, params = _split_args(func, args)
+        return _latent.odeint_traj(func, y0, t, params, rtol, atol, mxstep)
     if func.kind != "plain":
         raise TypeError("odeint_vmap: only the plain dynamics are vmapped by the reference (mnist.py:351)")
     spec = func.spec

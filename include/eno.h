@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ENO_ABI_VERSION 4
+#define ENO_ABI_VERSION 5
 
 /* status codes */
 #define ENO_OK 0
@@ -60,6 +60,14 @@ extern "C" {
 #define ENO_ARCH_CONCATSQUASH 1 /* NN_Dynamics of ConcatSquashLinear layers, softplus, ffjord_tabular.py:140-193:
                                    D -> H (x n_hidden) -> D; flat parameters per layer in Haiku ravel order
                                    [ b (out) | W (in x out) | w_hyper_bias (out) | b_gate (out) | w_gate (out) ] */
+
+#define ENO_ARCH_TANH_STACK 2   /* GenDynamics, latent_ode.py:191-208: x <- tanh(x) W_l + b_l for n_hidden layers of width H,
+                                   then tanh and Linear(D); no time input; flat parameters per layer in Haiku ravel order
+                                   [ b (out) | W (in x out) ]; served by the eno_traj_* entry points only */
+
+/* element type of the eno_traj_* entry points */
+#define ENO_F32 0
+#define ENO_F64 1
 
 /* what the integrated function returns besides dy/dt (the reference's closures) */
 #define ENO_AUG_NONE 0 /* dynamics_wrap            mnist.py:285            */
@@ -308,6 +316,48 @@ int32_t eno_adam_update(eno_ctx* ctx, float* params, float* m, float* v, const f
  */
 int32_t eno_gemm_tf32x3(eno_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B,
                         int32_t ldb, float* C, int32_t ldc, int32_t bn, int32_t splits, void* stream);
+
+/*
+ * Per-trajectory differentiable solves (BASELINE config C3, latent_ode.py).  Replace
+ *   jax.vmap(lambda z_, t_: odeint(dynamics, init_fn(z_), t_, params["gen_dynamics"], **gen_ode_kwargs),
+ *            in_axes=(0, None))(z0_, timesteps)                                       latent_ode.py:337-350
+ * (itself under a second vmap over the 3 latent samples) and its reverse pass: under vmap every trajectory is its own
+ * odeint problem - own dopri5 step sequence over all T output times (lib/ode.py:823-862), own adjoint over T-1
+ * segments whose state (y, y_bar, t0_bar, params_bar) carries a full params_bar block per trajectory
+ * (lib/ode.py:1494-1529); vmap's transpose then sums the per-trajectory params_bar.
+ * desc: arch ENO_ARCH_TANH_STACK, D latent width, H hidden width, n_hidden hidden layers (the script's
+ * gen_layers + 1), reg_order 0 / 2 / 3 (sol_recursive latent_ode.py:82-108), aug ENO_AUG_REG for
+ * dynamics = augment_dynamics(gen_dynamics_wrap) with state (z, r) (latent_ode.py:238-256, 352-355: dr/dt =
+ * mean(r_K^2)), ENO_AUG_NONE for the plain count_nfe dynamics.  dtype ENO_F64 is the script's precision
+ * (jax_enable_x64, latent_ode.py:23); every array below has that element type.
+ * One launch runs ALL trajectories to completion (one CTA per trajectory, weights resident in shared memory);
+ * the calls only enqueue work on `stream` (CUDA-graph capturable) and never synchronise.
+ *
+ * eno_traj_fwd:   z0 [n_traj, D]   ts [T] strictly increasing   params [P]
+ *   -> zs_out [n_traj, T, D]   rs_out [n_traj, T] (ENO_AUG_REG; r starts at 0)   nfe_out [n_traj] (2 + 6 iterations)
+ *      iters_out [n_traj, 2] or NULL (iterations, accepted)   status_out [n_traj] or NULL (ENO_OK / ENO_MXSTEP / ...)
+ * eno_traj_bwd:   zs, rs as produced by the forward call;  g_z [n_traj, T, D], g_r [n_traj, T] cotangents of the outputs
+ *   -> z0_bar_out [n_traj, D]   r0_bar_out [n_traj] or NULL   ts_bar_out [n_traj, T]
+ *      params_bar_out [P] or NULL: sum over the trajectories in index order
+ *      params_bar_traj_out [n_traj, P] or NULL: the per-trajectory blocks
+ *      iters_out [n_traj, T-1, 2] or NULL: iterations / accepted steps of the segments in the order they run (i = T-1 .. 1)
+ *   workspace: eno_traj_workspace_bytes(desc, dtype, n_traj) device bytes.
+ * eno_traj_rhs (unit-test hook): one evaluation of the dynamics per trajectory, f_out [n_traj, D], rdot_out [n_traj] or
+ *   NULL (mean(r_K^2)), and - when z_bar, zbdot_out and params_bar_traj_out are given - the vjp of (f, rdot) with
+ *   cotangents (z_bar [n_traj, D], r_bar [n_traj] or NULL = 0) wrt z and the parameters (lib/ode.py:1498-1504).
+ */
+int64_t eno_traj_param_count(const eno_dynamics_desc* desc);
+size_t eno_traj_workspace_bytes(const eno_dynamics_desc* desc, int32_t dtype, int32_t n_traj);
+int32_t eno_traj_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t dtype, int32_t n_traj, const void* z0, const void* ts,
+                     int32_t T, const void* params, double rtol, double atol, int32_t mxstep, void* zs_out, void* rs_out,
+                     void* nfe_out, int32_t* iters_out, int32_t* status_out, void* stream);
+int32_t eno_traj_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t dtype, int32_t n_traj, const void* zs, const void* rs,
+                     const void* ts, int32_t T, const void* params, const void* g_z, const void* g_r, double rtol, double atol,
+                     int32_t mxstep, void* workspace, size_t workspace_bytes, void* z0_bar_out, void* r0_bar_out, void* ts_bar_out,
+                     void* params_bar_out, void* params_bar_traj_out, int32_t* iters_out, int32_t* status_out, void* stream);
+int32_t eno_traj_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t dtype, int32_t n_traj, const void* z, const void* params,
+                     const void* z_bar, const void* r_bar, void* f_out, void* rdot_out, void* zbdot_out, void* params_bar_traj_out,
+                     void* stream);
 
 #ifdef __cplusplus
 }
