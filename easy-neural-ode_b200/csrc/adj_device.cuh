@@ -26,6 +26,43 @@ struct FactorSlot {
   float* tbar;  // [B]
 };
 
+// Tensor-core sinks (cluster path, ADJ_STEP): the same factors written TRANSPOSED and pre-split into tf32 hi / lo
+// planes, i.e. directly as the K-major operands of the batched tcgen05 contraction (k_gemm_tf32x3, gemm_tc.cuh):
+//   X [2 planes][6 stages][2][dpad][ldk] : which 0 = S^T,  which 1 = G^T      (rows = state columns d)
+//   Y [2 planes][6 stages][2][hpad][ldk] : which 0 = A^T,  which 1 = Hh^T     (rows = hidden columns h)
+// with the contraction index k = pass * Bk + sample along the row (Bk = B rounded up to 4; the padding holds zeros).
+struct FactorTc {
+  float* X;     // null: the ADJ_STEP launches use the row-major sinks (streamed path)
+  float* Y;
+  unsigned xplane, yplane;   // elements between the hi and the lo plane
+  int ldk, dpad, hpad, Bk;
+};
+
+// What the cluster kernels write one stage's factors through: the row-major sinks (TC = false; the set-up modes and
+// eno_rhs, contracted by k_adj_pgrad) or the tensor-core sinks (TC = true; ADJ_STEP).  `rm` and `tc` point into the
+// kernel's parameter block (constant bank: their fields cost no registers).
+template <bool TC>
+struct FactorDstT;
+template <>
+struct FactorDstT<false> {
+  static constexpr bool kTc = false;
+  const FactorSlot* rm;
+  __device__ __forceinline__ FactorDstT(const FactorSlot& s, const FactorTc&, int) : rm(&s) {}
+};
+template <>
+struct FactorDstT<true> {
+  static constexpr bool kTc = true;
+  const FactorSlot* rm;      // only for the per-sample t_bar pieces
+  const FactorTc* tc;
+  float *tX, *tY;            // this stage's [2][dpad][ldk] / [2][hpad][ldk] hi-plane blocks
+  __device__ __forceinline__ FactorDstT(const FactorSlot& s, const FactorTc& t, int stage) : rm(&s), tc(&t) {
+    tX = t.X + (size_t)stage * 2 * t.dpad * t.ldk;
+    tY = t.Y + (size_t)stage * 2 * t.hpad * t.ldk;
+  }
+};
+
+enum FactorMat { FM_S = 0, FM_G = 1, FM_A = 0, FM_HH = 1 };   // `which` index of the D-type / H-type factor
+
 struct AdjScratch {
   MlpScratch sc;   // s, u, h, a1, h1, a2, h2, red
   float *f, *y1, *y2;      // [R][D]

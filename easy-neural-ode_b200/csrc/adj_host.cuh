@@ -19,6 +19,24 @@ namespace eno {
 // ======================================================================================
 inline size_t adj_align(size_t x) { return (x + 255) / 256 * 256; }
 
+// geometry of the tensor-core factor sinks (FactorTc, adj_device.cuh)
+struct PgradTcGeom {
+  int ldk, dpad, hpad, Bk;
+  size_t xplane, yplane, x_elems, y_elems;
+};
+inline PgradTcGeom pgrad_tc_geom(int B, int D, int H) {
+  PgradTcGeom g;
+  g.Bk = (B + 3) / 4 * 4;
+  g.ldk = 3 * g.Bk;
+  g.dpad = (D + tc::kBM - 1) / tc::kBM * tc::kBM;
+  g.hpad = (H + 127) / 128 * 128;
+  g.xplane = (size_t)kSlots * 2 * g.dpad * g.ldk;
+  g.yplane = (size_t)kSlots * 2 * g.hpad * g.ldk;
+  g.x_elems = 2 * g.xplane;
+  g.y_elems = 2 * g.yplane;
+  return g;
+}
+
 inline size_t adj_ws_bytes(int B, int D, int H, int world = 1, bool fin = false) {
   const size_t N = (size_t)B * D, P = (size_t)(D + 1) * H + H + (size_t)(H + 1) * D + D;
   const PgradGeom g = pgrad_geom(D, H);
@@ -29,12 +47,14 @@ inline size_t adj_ws_bytes(int B, int D, int H, int world = 1, bool fin = false)
   if (fin) s += 2 * adj_align(3 * N * 4) + adj_align(2 * N * 4) + adj_align(N * 4);   // ZE, FZE, MIDZE, EBAR
   s += adj_align(2 * N * 4);                        // MIDZB
   s += 2 * adj_align(3 * P * 4) + adj_align(2 * P * 4);             // PB, FP, MIDP
-  const size_t npp = std::max((size_t)g.grid, (P + 255) / 256);
+  const size_t npp = std::max(std::max((size_t)g.grid, (P + 255) / 256), (size_t)kPcGrid);
   s += kSlots * (2 * adj_align(3 * N * 4) + 2 * adj_align(3 * (size_t)B * H * 4));
   s += adj_align((size_t)6 * kC * B * world * 8) + 2 * adj_align(npp * 8);   // xrec (one record per rank), ppart0/1
   if (world > 1) s += adj_align(4 * P * 4);          // pcomb
   s += adj_align(N * 4) + adj_align((P + 256 * (size_t)(world + 1)) * 4);   // YBAR, POUT (padded to world equal 256-multiples)
   s += 2 * adj_align((size_t)D * H * 4);            // transposes
+  const PgradTcGeom tg = pgrad_tc_geom(B, D, H);   // tensor-core factor sinks + stage products
+  s += adj_align(tg.x_elems * 4) + adj_align(tg.y_elems * 4) + adj_align((size_t)kSlots * P * 4);
   return s + 4096;
 }
 
@@ -76,7 +96,7 @@ inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArg
   a->xrec = cv.take<double>((size_t)6 * kC * B * world);
   a->rowpart0 = a->rowpart1 = a->rowpart2 = nullptr;
   a->n_rp = a->n_loc = B;
-  const size_t npp = std::max((size_t)g.grid, (P + 255) / 256);
+  const size_t npp = std::max(std::max((size_t)g.grid, (P + 255) / 256), (size_t)kPcGrid);
   a->ppart0 = cv.take<double>(npp); a->ppart1 = cv.take<double>(npp);
   a->pcomb = (world > 1) ? cv.take<float>(4 * P) : nullptr;
   a->dist = 0;
@@ -86,6 +106,16 @@ inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArg
   float* W1xT = cv.take<float>((size_t)D * H);
   float* W2xT = cv.take<float>((size_t)D * H);
   a->w = mlp_weights_from_flat(params, D, H, W1xT, W2xT);
+  {
+    const PgradTcGeom tg = pgrad_tc_geom(B, D, H);
+    a->tc.X = nullptr;   // adj_solve switches the sinks on when the path and the shape allow it
+    a->tc.Y = nullptr;
+    a->tc.xplane = (unsigned)tg.xplane; a->tc.yplane = (unsigned)tg.yplane;
+    a->tc.ldk = tg.ldk; a->tc.dpad = tg.dpad; a->tc.hpad = tg.hpad; a->tc.Bk = tg.Bk;
+    a->tcX_ws = cv.take<float>(tg.x_elems);
+    a->tcY_ws = cv.take<float>(tg.y_elems);
+    a->KP = cv.take<float>((size_t)kSlots * P);
+  }
   a->B = B; a->P = (int)P; a->N = N;
   a->n_state = (float)(2 * (N + (size_t)B) + 1 + N + P);
 }
@@ -258,6 +288,25 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
   if (!plan.cluster) adj_transposes(a, st);
   adj_set_views(&a, plan.cluster ? kC : 1, rank, world);
   const PgradGeom geo = pgrad_geom(D, H);
+  // ADJ_STEP parameter gradients of the cluster path run on the tensor cores (batched tcgen05 3xTF32 GEMM +
+  // k_adj_pcombine): k_cl_adj_rows<ADJ_STEP> writes its factors as K-major hi / lo planes
+  const bool pg_tc = plan.cluster;
+  if (pg_tc && (size_t)kSlots * 2 * a.tc.dpad * a.tc.ldk >= (1ull << 31)) {
+    if (err) *err = "eno_odeint_bwd: batch too large for the tensor-core factor planes";
+    return ENO_E_UNSUPPORTED;
+  }
+  CUtensorMap tmX, tmY;
+  if (pg_tc) {
+    a.tc.X = a.tcX_ws;
+    a.tc.Y = a.tcY_ws;
+    std::string terr;
+    if (!tc::make_operand_map(&tmX, a.tc.X, kSlots * 2 * a.tc.dpad, a.np * a.tc.Bk, a.tc.ldk, a.tc.xplane, tc::kBM, &terr) ||
+        !tc::make_operand_map(&tmY, a.tc.Y, kSlots * 2 * a.tc.hpad, a.np * a.tc.Bk, a.tc.ldk, a.tc.yplane, 128, &terr)) {
+      if (err) *err = "eno_odeint_bwd: " + terr;
+      return ENO_E_CUDA;
+    }
+  }
+  const EpiPgradStage pg_epi{a.KP, D, H, a.P, 2 * H, H * (D + 2) + 2 * D};
   const size_t n_loc = (size_t)(plan.cluster ? kC : 1) * B;
   const int pf_grid = (a.P + 255) / 256;
   // multi-GPU continuation of one pgrad launch: exchange, then the replicated finish kernel
@@ -327,7 +376,14 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
         if ((rc = adj_rows_any(plan, K, ADJ_STEP, a, 0.f, st, err))) return rc;
         prof->end(ps, st);
         ps = prof->begin(PROF_ADJ_PGRAD, st);
-        k_adj_pgrad<ADJ_STEP><<<geo.grid, kSlots * kGroup, kPgradSmem, st>>>(a, 0.f, nullptr, nullptr);
+        if (pg_tc) {
+          ENO_ADJ_CHECK(tc::launch_gemm_batched<128>(tmX, tmY, D, H, a.np * a.tc.Bk, kSlots * 2, a.tc.dpad, a.tc.hpad, &a.ctrl->done,
+                                                     pg_epi, st));
+          k_adj_pcombine<<<kPcGrid, 256, 0, st>>>(a);
+          ++launches;
+        } else {
+          k_adj_pgrad<ADJ_STEP><<<geo.grid, kSlots * kGroup, kPgradSmem, st>>>(a, 0.f, nullptr, nullptr);
+        }
         prof->end(ps, st);
         ps = dist ? prof->begin(PROF_EXCHANGE, st) : -1;
         if ((rc = exchange(ADJ_STEP))) return rc;

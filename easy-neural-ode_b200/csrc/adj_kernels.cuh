@@ -18,6 +18,7 @@
 #include <string>
 
 #include "adj_device.cuh"
+#include "gemm_tc.cuh"
 #include "tableaux.cuh"
 #include "fwd_kernels.cuh"
 
@@ -70,6 +71,9 @@ struct AdjArgs {
   float* MIDP;             // [2][P]
   // factors
   FactorSlot slot[kSlots];
+  FactorTc tc;             // tc.X non-null: ADJ_STEP factors go to the tensor-core sinks (adj_device.cuh), the stage
+  float* KP;               // contractions [kSlots][P] come from the batched tcgen05 GEMM and k_adj_pcombine finishes
+  float *tcX_ws, *tcY_ws;  // workspace blocks behind tc.X / tc.Y (host side bookkeeping)
   // partial sums
   double *rowpart0, *rowpart1, *rowpart2;  // per-sample partials of THIS rank's rows (views into rp*_all)
   const double *rp0_all, *rp1_all, *rp2_all;   // rank 0's entries; rank r's are 6*n_loc doubles further (block_sum_records)
@@ -397,7 +401,20 @@ __device__ __forceinline__ void adj_finalize(AdjArgs& a, Ctrl* c, double* dred, 
   const float rtol = c->rtol, atol = c->atol;
   const float h0 = c->h0;
   __shared__ double fin[12];
-  {
+  if (MODE == ADJ_STEP) {
+    // the eight sums of an iteration, one warp each (the CTA has at least eight warps)
+    const int w = threadIdx.x >> 5;
+    double v = 0.0;
+    if (w == 0) v = warp_sum_records(rp0_all, a.n_rp, a.n_loc, 6 * a.n_loc);
+    else if (w == 1) v = warp_sum_records(a.ppart0, n_pp, n_pp, 0);
+    else if (w < 2 + NS) {
+      const int j = w - 2;
+      const float* tb = gx ? reinterpret_cast<const float*>(gx) + 2 * a.n_loc + (size_t)j * a.n_loc : a.tbar_all[j];
+      v = warp_sum_records(tb, a.n_rp, a.n_loc, 12 * a.n_loc);
+    }
+    if ((threadIdx.x & 31) == 0 && w < 2 + NS) fin[w < 2 ? w : 3 + w] = v;   // tbar_j -> fin[5 + j]
+    __syncthreads();
+  } else {
     double v;
     v = block_sum_records(rp0_all, a.n_rp, a.n_loc, 6 * a.n_loc, dred); if (threadIdx.x == 0) fin[0] = v; __syncthreads();
     v = block_sum_global(a.ppart0, n_pp, dred); if (threadIdx.x == 0) fin[1] = v; __syncthreads();
@@ -776,6 +793,173 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
   // ---- last CTA: norm over all blocks, t0_bar element, controller -----------------------
   if (!elect_last_block(&c->ticket)) return;
   adj_finalize<MODE>(a, c, dred, geo.grid, dt, rhs_tbar);
+}
+
+// --------------------------------------------------------------------------------------
+// Tensor-core formulation of the ADJ_STEP parameter-gradient contraction (cluster path).  k_cl_adj_rows leaves
+// the factors of its six stages as K-major tf32 hi / lo planes (FactorTc); ONE batched launch of the tcgen05
+// 3xTF32 GEMM (gemm_tc.cuh, grid.z = stage x {dW1x, dW2x^T}, K = np * B) writes the twelve products into
+// KP [kSlots][P] through EpiPgradStage; k_adj_pcombine adds the bias / time-column sums, combines the stages
+// into candidate / error / mid-point of params_bar and runs the finaliser - the second half of k_adj_pgrad.
+// --------------------------------------------------------------------------------------
+struct EpiPgradStage {
+  float* KP;
+  int D, H, P, offW1, offW2;
+  // tile row m = state column d, tile columns n0.. = hidden columns; z = 2 * stage + which
+  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[tc::kEpiW], int z) const {
+    if (m >= D || n0 >= H) return;
+    float* kp = KP + (size_t)(z >> 1) * P;
+    if ((z & 1) == 0) {            // dW1x[d][h]
+      float* row = kp + offW1 + (size_t)m * H + n0;
+      if (n0 + tc::kEpiW <= H && ((offW1 + (size_t)m * H + n0) & 3) == 0) {
+        *reinterpret_cast<float4*>(row) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < tc::kEpiW; ++j)
+          if (n0 + j < H) row[j] = v[j];
+      }
+    } else {                        // dW2x[h][d] (the GEMM produced its transpose)
+#pragma unroll
+      for (int j = 0; j < tc::kEpiW; ++j)
+        if (n0 + j < H) kp[offW2 + (size_t)(n0 + j) * D + m] = v[j];
+    }
+  }
+};
+
+constexpr int kPcGrid = 256;   // fixed grid: the order of the norm partials does not depend on the device
+
+__global__ void __launch_bounds__(256, 2) k_adj_pcombine(AdjArgs a) {
+  Ctrl* c = a.ctrl;
+  if (c->done) return;
+  __shared__ double dred[256];
+  const int D = a.w.D, H = a.w.H;
+  const size_t P = (size_t)a.P;
+  const float tau = c->t, dt = c->dt;
+  const float rtol = c->rtol, atol = c->atol;
+  const int offW1 = 2 * H, offb2 = H * (D + 2), offW2 = H * (D + 2) + 2 * D;
+  const int cur = c->cur, cand = c->cand, midw = c->mid_acc ^ 1;
+  const float* PBc = a.PB + (size_t)cur * P;
+  const float* FPc = a.FP + (size_t)cur * P;
+  float* PBn = a.PB + (size_t)cand * P;
+  float* FPn = a.FP + (size_t)cand * P;
+  float* Mn = a.MIDP + (size_t)midw * P;
+  float* pcomb = a.pcomb;
+  if (a.dist && a.peer_base) {   // the slot of the exchange that the finish kernel after this launch will run
+    const unsigned long long seq = *reinterpret_cast<const unsigned long long*>(a.peer_base + kPeerOffSeq) + 1;
+    pcomb = reinterpret_cast<float*>(a.peer_base + a.peer_pcomb_off) + (size_t)(seq & 1) * 4 * P;
+  }
+  double part0 = 0.0;
+  auto combine = [&](int p, const float (&kj)[kSlots]) {
+    if (a.dist) {   // this rank's share of the four stage combinations (k_adj_pfinish* continue after the exchange)
+      float s = 0.f, er = 0.f, md = 0.f;
+#pragma unroll
+      for (int j = 0; j < kSlots; ++j) {
+        s = fmaf(c_tab.c_sol[j + 1], kj[j], s);
+        er = fmaf(c_tab.c_err[j + 1], kj[j], er);
+        md = fmaf(c_tab.c_mid[j + 1], kj[j], md);
+      }
+      pcomb[p] = s;
+      pcomb[P + p] = er;
+      pcomb[2 * P + p] = md;
+      pcomb[3 * P + p] = kj[kSlots - 1];
+      return;
+    }
+    const float k0 = FPc[p];
+    float s = c_tab.c_sol[0] * k0, er = c_tab.c_err[0] * k0, md = c_tab.c_mid[0] * k0;
+#pragma unroll
+    for (int j = 0; j < kSlots; ++j) {
+      s = fmaf(c_tab.c_sol[j + 1], kj[j], s);
+      er = fmaf(c_tab.c_err[j + 1], kj[j], er);
+      md = fmaf(c_tab.c_mid[j + 1], kj[j], md);
+    }
+    const float p0 = PBc[p];
+    const float p1 = fmaf(dt, s, p0);
+    const float tol = atol + rtol * fmaxf(fabsf(p0), fabsf(p1));
+    const float q = dt * er / tol;
+    part0 += (double)(q * q);
+    PBn[p] = p1;
+    FPn[p] = kj[kSlots - 1];
+    Mn[p] = fmaf(dt, md, p0);
+  };
+  // bias / time-column blocks: b1 = sum a_bar, w1t = sum (t a_bar + a1_bar), b2 = sum f_bar, w2t = sum (t f_bar + y1_bar)
+  // - row sums of the transposed factor planes (hi + lo restores the value exactly); one warp per output
+  {
+    const FactorTc& t = a.tc;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nvec = 2 * H + 2 * D;
+    const bool two = a.np >= 2 && !a.fin;   // the jvp of the fin dynamics has no time tangent
+    const int Bk = t.Bk;                    // samples per pass along a row, padding (zeros) included
+    for (int e = blockIdx.x * 8 + warp; e < nvec; e += gridDim.x * 8) {
+      const bool first = e < 2 * H;
+      const int W = first ? H : D;
+      const int o = first ? e : e - 2 * H;
+      const int col = o < W ? o : o - W;
+      const unsigned plane = first ? t.yplane : t.xplane;
+      const float* row0p = first ? t.Y + (size_t)col * t.ldk : t.X + ((size_t)t.dpad + col) * t.ldk;
+      const size_t sstride = (size_t)2 * (first ? t.hpad : t.dpad) * t.ldk;   // stage to stage
+      const bool second_pass = (o >= W) && two;
+      float kj[kSlots];
+#pragma unroll
+      for (int j = 0; j < kSlots; ++j) kj[j] = 0.f;
+      // a lane owns 4 consecutive samples; the loads of all six stages are issued before the first use
+      for (int k0 = 4 * lane; k0 < Bk; k0 += 128) {
+        float4 h0[kSlots], l0[kSlots], h1[kSlots], l1[kSlots];
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) {
+          const float* hp = row0p + (size_t)j * sstride + k0;
+          h0[j] = *reinterpret_cast<const float4*>(hp);
+          l0[j] = *reinterpret_cast<const float4*>(hp + plane);
+          if (second_pass) {
+            h1[j] = *reinterpret_cast<const float4*>(hp + Bk);
+            l1[j] = *reinterpret_cast<const float4*>(hp + Bk + plane);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kSlots; ++j) {
+          const float f0[4] = {h0[j].x + l0[j].x, h0[j].y + l0[j].y, h0[j].z + l0[j].z, h0[j].w + l0[j].w};
+          if (o < W) {
+            kj[j] += (f0[0] + f0[1]) + (f0[2] + f0[3]);
+          } else {
+            const float t_stage = -(tau + dt * c_tab.alpha[j]);
+            if (second_pass) {
+              const float f1[4] = {h1[j].x + l1[j].x, h1[j].y + l1[j].y, h1[j].z + l1[j].z, h1[j].w + l1[j].w};
+              kj[j] += (fmaf(t_stage, f0[0], f1[0]) + fmaf(t_stage, f0[1], f1[1])) +
+                       (fmaf(t_stage, f0[2], f1[2]) + fmaf(t_stage, f0[3], f1[3]));
+            } else {
+              kj[j] += t_stage * ((f0[0] + f0[1]) + (f0[2] + f0[3]));
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kSlots; ++j)
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) kj[j] += __shfl_xor_sync(0xffffffffu, kj[j], sft);
+      if (lane == 0) combine((first ? 0 : offb2) + o, kj);
+    }
+  }
+  // weight blocks: the GEMM's stage products
+  {
+    const int DH = D * H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * DH; i += gridDim.x * blockDim.x) {
+      const int p = i < DH ? offW1 + i : offW2 + (i - DH);
+      float kj[kSlots];
+#pragma unroll
+      for (int j = 0; j < kSlots; ++j) kj[j] = a.KP[(size_t)j * P + p];
+      combine(p, kj);
+    }
+  }
+  if (a.dist) return;
+  dred[threadIdx.x] = part0;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) a.ppart0[blockIdx.x] = dred[0];
+  __syncthreads();
+  if (!elect_last_block(&c->ticket)) return;
+  adj_finalize<ADJ_STEP>(a, c, dred, (int)gridDim.x, dt, nullptr);
 }
 
 // Multi-GPU continuation of k_adj_pgrad: pcomb now holds the all-reduced stage combinations of the

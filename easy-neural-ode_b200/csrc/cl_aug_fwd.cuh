@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_aug_fwd(AugFwdArgs A) {
         }
       }
       __syncthreads();
-      cl_aug_forward<R, K>(cluster, S.cm, g, w, tev, S.xz, S.m, nullptr, row0, a.B);   // scal[.][0] = sum_d yK^2
+      cl_aug_forward<R, K>(cluster, S.cm, g, w, tev, S.xz, S.m, (const FactorDstT<false>*)nullptr, row0, a.B);   // scal[.][0] = sum_d yK^2
       if (AUG == ENO_AUG_ALL) {
         // forward-mode pass with tangent eps: eps_dy = J_f eps  (fin_dynamics, mnist.py:294-300)
         for (int i = threadIdx.x; i < RD; i += blockDim.x) {

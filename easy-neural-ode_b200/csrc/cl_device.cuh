@@ -14,6 +14,7 @@
 //
 // Reference arithmetic: mnist.py:195-222 (MLPDynamics), 105-131 (sol_recursive), lib/ode.py:1498-1504.
 #pragma once
+#include "gemm_tc.cuh"
 #include <cooperative_groups.h>
 
 #include "adj_device.cuh"
@@ -375,21 +376,65 @@ __device__ __forceinline__ void cl_primal(cg::cluster_group& cluster, ClComm& cm
 
 namespace eno {
 
-// store this CTA's column slice of R distributed rows into a global [B][D] block
-template <int R>
-__device__ __forceinline__ void cl_store_D(float* dst, const float* src, const ClGeom& g, int D, int row0, int B) {
-  for (int i = threadIdx.x; i < R * g.Dlp; i += blockDim.x) {
-    const int r = i / g.Dlp, d = i - r * g.Dlp;
-    if (d < g.Dl && row0 + r < B) dst[(size_t)(row0 + r) * D + g.d0 + d] = src[i];
+// tf32 split of gemm_tc.cuh (round-to-nearest pieces)
+__device__ __forceinline__ void cl_split_tf32(float x, float& hi, float& lo) { tc::split_tf32(x, hi, lo); }
+
+// store this CTA's column slice of R distributed rows of factor `which` (FM_S / FM_G), Taylor pass `pass`:
+// row-major into the global [3][B][D] block, or - tensor-core sinks - transposed and hi / lo split: the R samples of
+// the tile are R consecutive k of row (d0 + d), one 16-byte store per plane (R == 4; rows past B store zeros)
+template <int R, class FD>
+__device__ __forceinline__ void cl_store_D(const FD& sl, int which, int pass, const float* src, const ClGeom& g, int D,
+                                           int row0, int B) {
+  if constexpr (FD::kTc) {
+    static_assert(R == 4, "tensor-core factor sinks store one float4 of samples per row");
+    const int ldk = sl.tc->ldk;
+    const unsigned xplane = sl.tc->xplane;
+    float* base = sl.tX + ((size_t)which * sl.tc->dpad + g.d0) * ldk + pass * sl.tc->Bk + row0;
+    const int nv = B - row0;   // valid rows of this tile
+    for (int d = threadIdx.x; d < g.Dl; d += blockDim.x) {
+      float4 h, l;
+      cl_split_tf32(src[d], h.x, l.x);
+      cl_split_tf32(nv > 1 ? src[g.Dlp + d] : 0.f, h.y, l.y);
+      cl_split_tf32(nv > 2 ? src[2 * g.Dlp + d] : 0.f, h.z, l.z);
+      cl_split_tf32(nv > 3 ? src[3 * g.Dlp + d] : 0.f, h.w, l.w);
+      float* dst = base + (size_t)d * ldk;
+      *reinterpret_cast<float4*>(dst) = h;
+      *reinterpret_cast<float4*>(dst + xplane) = l;
+    }
+  } else {
+    float* dst = (which == FM_S ? sl.rm->S : sl.rm->G) + (size_t)pass * B * D;
+    for (int i = threadIdx.x; i < R * g.Dlp; i += blockDim.x) {
+      const int r = i / g.Dlp, d = i - r * g.Dlp;
+      if (d < g.Dl && row0 + r < B) dst[(size_t)(row0 + r) * D + g.d0 + d] = src[i];
+    }
   }
 }
 
-// store replicated H-rows (rank 0 only)
-template <int R>
-__device__ __forceinline__ void cl_store_H(float* dst, const float* src, const ClGeom& g, int H, int row0, int B) {
+// store replicated H-rows of factor `which` (FM_A / FM_HH) (rank 0 only)
+template <int R, class FD>
+__device__ __forceinline__ void cl_store_H(const FD& sl, int which, int pass, const float* src, const ClGeom& g, int H,
+                                           int row0, int B) {
   if (g.rank != 0) return;
-  for (int i = threadIdx.x; i < R * H; i += blockDim.x)
-    if (row0 + i / H < B) dst[(size_t)row0 * H + i] = src[i];
+  if constexpr (FD::kTc) {
+    const int ldk = sl.tc->ldk;
+    const unsigned yplane = sl.tc->yplane;
+    float* base = sl.tY + (size_t)which * sl.tc->hpad * ldk + pass * sl.tc->Bk + row0;
+    const int nv = B - row0;
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+      float4 hi, lo;
+      cl_split_tf32(src[h], hi.x, lo.x);
+      cl_split_tf32(nv > 1 ? src[H + h] : 0.f, hi.y, lo.y);
+      cl_split_tf32(nv > 2 ? src[2 * H + h] : 0.f, hi.z, lo.z);
+      cl_split_tf32(nv > 3 ? src[3 * H + h] : 0.f, hi.w, lo.w);
+      float* dst = base + (size_t)h * ldk;
+      *reinterpret_cast<float4*>(dst) = hi;
+      *reinterpret_cast<float4*>(dst + yplane) = lo;
+    }
+  } else {
+    float* dst = (which == FM_A ? sl.rm->A : sl.rm->Hh) + (size_t)pass * B * H;
+    for (int i = threadIdx.x; i < R * H; i += blockDim.x)
+      if (row0 + i / H < B) dst[(size_t)row0 * H + i] = src[i];
+  }
 }
 
 // per-sample partial of sum_d v[d]^2 over the local slice -> scal[r*4 + slot]
@@ -409,17 +454,17 @@ __device__ __forceinline__ void cl_sumsq_local(const float* v, const ClGeom& g, 
 
 // Forward Taylor passes (aug_forward of adj_device.cuh, distributed).  On return: f, y1, y2 local slices,
 // h, a1, h1, a2, h2 replicated, scal[r*4+0] = local partial of sum_d yK^2 (K >= 2).
-template <int R, int K>
+template <int R, int K, class FD>
 __device__ __forceinline__ void cl_aug_forward(cg::cluster_group& cluster, ClComm& cm, const ClGeom& g,
                                                const ClWeights& w, float t, const float* z, const ClScratch& m,
-                                               const FactorSlot* slot, int row0, int B) {
+                                               const FD* slot, int row0, int B) {
   const int D = w.D, H = w.H, Dl = g.Dl, Dlp = g.Dlp;
   const size_t BD = (size_t)B * D, BH = (size_t)B * H;
   cl_primal<R>(cluster, cm, g, w, t, z, m.f, m);
   if (slot) {
-    cl_store_D<R>(slot->S, m.s, g, D, row0, B);
+    cl_store_D<R>(*slot, FM_S, 0, m.s, g, D, row0, B);
     ENO_TICK(PH_STORE);
-    cl_store_H<R>(slot->Hh, m.h, g, H, row0, B);
+    cl_store_H<R>(*slot, FM_HH, 0, m.h, g, H, row0, B);
     ENO_TICK(PH_STORE);
   }
   if (K >= 2) {
@@ -428,7 +473,7 @@ __device__ __forceinline__ void cl_aug_forward(cg::cluster_group& cluster, ClCom
       m.u[i] = ((i % Dlp) < Dl) ? s * (1.f - s) * m.f[i] : 0.f;
     }
     __syncthreads();
-    if (slot) cl_store_D<R>(slot->S + BD, m.u, g, D, row0, B);
+    if (slot) cl_store_D<R>(*slot, FM_S, 1, m.u, g, D, row0, B);
     ENO_TICK(PH_STORE);
     mv_n<R>(w.W1, g.ldw1, Dl, H, m.u, Dlp, m.red, kKG);
     ENO_TICK(PH_MV_DL);
@@ -440,7 +485,7 @@ __device__ __forceinline__ void cl_aug_forward(cg::cluster_group& cluster, ClCom
                      m.h1[r * H + n] = h * (1.f - h) * a1;
                    },
                    [&](int, int, float) {});
-    if (slot) cl_store_H<R>(slot->Hh + BH, m.h1, g, H, row0, B);
+    if (slot) cl_store_H<R>(*slot, FM_HH, 1, m.h1, g, H, row0, B);
     ENO_TICK(PH_STORE);
     mv_n<R>(w.W2, Dlp, H, Dl, m.h1, H, m.red, kKGw);
     ENO_TICK(PH_MV_H);
@@ -454,7 +499,7 @@ __device__ __forceinline__ void cl_aug_forward(cg::cluster_group& cluster, ClCom
       m.u[i] = ((i % Dlp) < Dl) ? sp * (1.f - 2.f * s) * fi * fi + sp * m.y1[i] : 0.f;
     }
     __syncthreads();
-    if (slot) cl_store_D<R>(slot->S + 2 * BD, m.u, g, D, row0, B);
+    if (slot) cl_store_D<R>(*slot, FM_S, 2, m.u, g, D, row0, B);
     ENO_TICK(PH_STORE);
     mv_n<R>(w.W1, g.ldw1, Dl, H, m.u, Dlp, m.red, kKG);
     ENO_TICK(PH_MV_DL);
@@ -467,7 +512,7 @@ __device__ __forceinline__ void cl_aug_forward(cg::cluster_group& cluster, ClCom
                      m.h2[r * H + n] = hp * (1.f - 2.f * h) * a1 * a1 + hp * sum;
                    },
                    [&](int, int, float) {});
-    if (slot) cl_store_H<R>(slot->Hh + 2 * BH, m.h2, g, H, row0, B);
+    if (slot) cl_store_H<R>(*slot, FM_HH, 2, m.h2, g, H, row0, B);
     ENO_TICK(PH_STORE);
     mv_n<R>(w.W2, Dlp, H, Dl, m.h2, H, m.red, kKGw);
     ENO_TICK(PH_MV_H);
@@ -481,10 +526,10 @@ __device__ __forceinline__ void cl_aug_forward(cg::cluster_group& cluster, ClCom
 
 // Reverse sweep (aug_reverse, distributed).  zb: cotangent of f (local slice), rb[r]: cotangent of r_dot.
 // On return: zacc = vjp wrt z (local slice), rdot[r] = r_dot (all ranks), factors + per-CTA t_bar pieces stored.
-template <int R, int K>
+template <int R, int K, class FD>
 __device__ __forceinline__ void cl_aug_reverse(cg::cluster_group& cluster, ClComm& cm, const ClGeom& g,
                                                const ClWeights& w, const float* zb, const float* rb,
-                                               const ClScratch& m, const FactorSlot& slot, int row0, int B) {
+                                               const ClScratch& m, const FD& slot, int row0, int B) {
   const int D = w.D, H = w.H, Dl = g.Dl, Dlp = g.Dlp;
   const size_t BD = (size_t)B * D, BH = (size_t)B * H;
   const float invD2 = 2.0f / (float)D;
@@ -494,7 +539,7 @@ __device__ __forceinline__ void cl_aug_reverse(cg::cluster_group& cluster, ClCom
   if (K >= 3) {
     for (int i = threadIdx.x; i < R * Dlp; i += blockDim.x) m.u[i] = rb[i / Dlp] * invD2 * m.y2[i];
     __syncthreads();
-    cl_store_D<R>(slot.G + 2 * BD, m.u, g, D, row0, B);
+    cl_store_D<R>(slot, FM_G, 2, m.u, g, D, row0, B);
     ENO_TICK(PH_STORE);
     mv_k<R>(w.W2, Dlp, H, Dl, m.u, Dlp, m.red, kKG);
     ENO_TICK(PH_MV_DL);
@@ -510,7 +555,7 @@ __device__ __forceinline__ void cl_aug_reverse(cg::cluster_group& cluster, ClCom
                      m.ga[r * H + n] = hb2 * (hppp * a1 * a1 + hpp * a2);
                    },
                    take_rdot);
-    cl_store_H<R>(slot.A + 2 * BH, m.ga2, g, H, row0, B);
+    cl_store_H<R>(slot, FM_A, 2, m.ga2, g, H, row0, B);
     ENO_TICK(PH_STORE);
     mv_k<R>(w.W1, g.ldw1, Dl, H, m.ga2, H, m.red, kKGw);
     ENO_TICK(PH_MV_H);
@@ -535,7 +580,7 @@ __device__ __forceinline__ void cl_aug_reverse(cg::cluster_group& cluster, ClCom
     __syncthreads();
   }
   if (K >= 2) {
-    cl_store_D<R>(slot.G + BD, m.gy1, g, D, row0, B);
+    cl_store_D<R>(slot, FM_G, 1, m.gy1, g, D, row0, B);
     ENO_TICK(PH_STORE);
     mv_k<R>(w.W2, Dlp, H, Dl, m.gy1, Dlp, m.red, kKG);
     ENO_TICK(PH_MV_DL);
@@ -548,7 +593,7 @@ __device__ __forceinline__ void cl_aug_reverse(cg::cluster_group& cluster, ClCom
                      m.ga1[r * H + n] += hb1 * hp;
                    },
                    take_rdot);
-    cl_store_H<R>(slot.A + BH, m.ga1, g, H, row0, B);
+    cl_store_H<R>(slot, FM_A, 1, m.ga1, g, H, row0, B);
     ENO_TICK(PH_STORE);
     mv_k<R>(w.W1, g.ldw1, Dl, H, m.ga1, H, m.red, kKGw);
     ENO_TICK(PH_MV_H);
@@ -566,7 +611,7 @@ __device__ __forceinline__ void cl_aug_reverse(cg::cluster_group& cluster, ClCom
     if (threadIdx.x < R) m.rdot[threadIdx.x] = 0.f;
     __syncthreads();
   }
-  cl_store_D<R>(slot.G, m.gf, g, D, row0, B);
+  cl_store_D<R>(slot, FM_G, 0, m.gf, g, D, row0, B);
     ENO_TICK(PH_STORE);
   mv_k<R>(w.W2, Dlp, H, Dl, m.gf, Dlp, m.red, kKG);
     ENO_TICK(PH_MV_DL);
@@ -576,7 +621,7 @@ __device__ __forceinline__ void cl_aug_reverse(cg::cluster_group& cluster, ClCom
                    m.ga[r * H + n] += hb * h * (1.f - h);
                  },
                  [&](int, int, float) {});
-  cl_store_H<R>(slot.A, m.ga, g, H, row0, B);
+  cl_store_H<R>(slot, FM_A, 0, m.ga, g, H, row0, B);
     ENO_TICK(PH_STORE);
   mv_k<R>(w.W1, g.ldw1, Dl, H, m.ga, H, m.red, kKGw);
     ENO_TICK(PH_MV_H);
@@ -594,7 +639,7 @@ __device__ __forceinline__ void cl_aug_reverse(cg::cluster_group& cluster, ClCom
       if (g.rank == 0)
         for (int n = lane; n < H; n += 32) acc += (double)(m.ga[r * H + n] * w.w1t[n]);
       acc = warp_sum(acc);
-      if (lane == 0 && row0 + r < B) slot.tbar[(size_t)(row0 + r) * kC + g.rank] = (float)acc;
+      if (lane == 0 && row0 + r < B) slot.rm->tbar[(size_t)(row0 + r) * kC + g.rank] = (float)acc;
     }
   }
   __syncthreads();
@@ -612,16 +657,16 @@ __device__ __forceinline__ void cl_aug_reverse(cg::cluster_group& cluster, ClCom
 // eps, which is a block of the adjoint state (lib/ode.py:1498-1504 differentiates wrt every arg).
 // On return of cl_fin_forward: f, y1 = J eps (local slices), h, a1, h1 replicated,
 // scal[r*4+0] = local partial of sum_d (J eps)^2, scal[r*4+1] = of sum_d f^2.
-template <int R>
+template <int R, class FD>
 __device__ __forceinline__ void cl_fin_forward(cg::cluster_group& cluster, ClComm& cm, const ClGeom& g,
                                                const ClWeights& w, float t, const float* z, const float* eps_g,
-                                               const ClScratch& m, const FactorSlot* slot, int row0, int B) {
+                                               const ClScratch& m, const FD* slot, int row0, int B) {
   const int D = w.D, H = w.H, Dl = g.Dl, Dlp = g.Dlp;
   const size_t BD = (size_t)B * D, BH = (size_t)B * H;
   cl_primal<R>(cluster, cm, g, w, t, z, m.f, m);
   if (slot) {
-    cl_store_D<R>(slot->S, m.s, g, D, row0, B);
-    cl_store_H<R>(slot->Hh, m.h, g, H, row0, B);
+    cl_store_D<R>(*slot, FM_S, 0, m.s, g, D, row0, B);
+    cl_store_H<R>(*slot, FM_HH, 0, m.h, g, H, row0, B);
   }
   for (int i = threadIdx.x; i < R * Dlp; i += blockDim.x) {
     const int r = i / Dlp, d = i - r * Dlp;
@@ -630,7 +675,7 @@ __device__ __forceinline__ void cl_fin_forward(cg::cluster_group& cluster, ClCom
     m.u[i] = ok ? s * (1.f - s) * __ldg(eps_g + (size_t)(row0 + r) * D + g.d0 + d) : 0.f;
   }
   __syncthreads();
-  if (slot) cl_store_D<R>(slot->S + BD, m.u, g, D, row0, B);
+  if (slot) cl_store_D<R>(*slot, FM_S, 1, m.u, g, D, row0, B);
   mv_n<R>(w.W1, g.ldw1, Dl, H, m.u, Dlp, m.red, kKG);
   allreduce_H<R>(cluster, cm, g, m.red, kKG, H, nullptr, 0,
                  [&](int r, int n, float sum) {
@@ -639,7 +684,7 @@ __device__ __forceinline__ void cl_fin_forward(cg::cluster_group& cluster, ClCom
                    m.h1[r * H + n] = h * (1.f - h) * sum;
                  },
                  [&](int, int, float) {});
-  if (slot) cl_store_H<R>(slot->Hh + BH, m.h1, g, H, row0, B);
+  if (slot) cl_store_H<R>(*slot, FM_HH, 1, m.h1, g, H, row0, B);
   mv_n<R>(w.W2, Dlp, H, Dl, m.h1, H, m.red, kKGw);
   reduce_local<R>(m.red, kKGw, Dl, [&](int r, int d, float sum) { m.y1[r * Dlp + d] = sum; });
   cl_sumsq_local<R>(m.y1, g, m.scal, 0);
@@ -650,11 +695,11 @@ __device__ __forceinline__ void cl_fin_forward(cg::cluster_group& cluster, ClCom
 // Reverse sweep of the fin dynamics.  zb: cotangent of f (local slice); rb2[r], rb2[R + r]: cotangents of
 // dfro, dkin.  On return: zacc = vjp wrt z, ebar = vjp wrt eps (local slices; ebar aliases u),
 // rdot2[r] = dfro, rdot2[R + r] = dkin (all ranks), factors + per-CTA t_bar pieces stored.
-template <int R>
+template <int R, class FD>
 __device__ __forceinline__ void cl_fin_reverse(cg::cluster_group& cluster, ClComm& cm, const ClGeom& g,
                                                const ClWeights& w, const float* zb, const float* rb2,
                                                const float* eps_g, const ClScratch& m, float* rdot2,
-                                               const FactorSlot& slot, int row0, int B) {
+                                               const FD& slot, int row0, int B) {
   const int D = w.D, H = w.H, Dl = g.Dl, Dlp = g.Dlp;
   const size_t BD = (size_t)B * D, BH = (size_t)B * H;
   const float invD2 = 2.0f / (float)D;
@@ -666,7 +711,7 @@ __device__ __forceinline__ void cl_fin_reverse(cg::cluster_group& cluster, ClCom
     m.gf[i] = zb[i] + rb2[R + r] * invD2 * m.f[i];
   }
   __syncthreads();
-  cl_store_D<R>(slot.G + BD, m.gy1, g, D, row0, B);
+  cl_store_D<R>(slot, FM_G, 1, m.gy1, g, D, row0, B);
   mv_k<R>(w.W2, Dlp, H, Dl, m.gy1, Dlp, m.red, kKG);
   allreduce_H<R>(cluster, cm, g, m.red, kKG, H, m.scal, 2,
                  [&](int r, int n, float hb1) {
@@ -676,7 +721,7 @@ __device__ __forceinline__ void cl_fin_reverse(cg::cluster_group& cluster, ClCom
                    m.ga1[r * H + n] = hb1 * hp;
                  },
                  [&](int r, int j, float v) { rdot2[j * R + r] = v * invD; });
-  cl_store_H<R>(slot.A + BH, m.ga1, g, H, row0, B);
+  cl_store_H<R>(slot, FM_A, 1, m.ga1, g, H, row0, B);
   mv_k<R>(w.W1, g.ldw1, Dl, H, m.ga1, H, m.red, kKGw);
   // gy1 (= u) is dead once its product and factor store are done: its storage takes eps_bar
   float* ebar = m.gy1;
@@ -688,7 +733,7 @@ __device__ __forceinline__ void cl_fin_reverse(cg::cluster_group& cluster, ClCom
     m.zacc[i] = sb1 * sp * (1.f - 2.f * s) * ev;
     ebar[i] = sb1 * sp;
   });
-  cl_store_D<R>(slot.G, m.gf, g, D, row0, B);
+  cl_store_D<R>(slot, FM_G, 0, m.gf, g, D, row0, B);
   mv_k<R>(w.W2, Dlp, H, Dl, m.gf, Dlp, m.red, kKG);
   allreduce_H<R>(cluster, cm, g, m.red, kKG, H, nullptr, 0,
                  [&](int r, int n, float hb) {
@@ -696,7 +741,7 @@ __device__ __forceinline__ void cl_fin_reverse(cg::cluster_group& cluster, ClCom
                    m.ga[r * H + n] += hb * h * (1.f - h);
                  },
                  [&](int, int, float) {});
-  cl_store_H<R>(slot.A, m.ga, g, H, row0, B);
+  cl_store_H<R>(slot, FM_A, 0, m.ga, g, H, row0, B);
   mv_k<R>(w.W1, g.ldw1, Dl, H, m.ga, H, m.red, kKGw);
   reduce_local<R>(m.red, kKGw, Dl, [&](int r, int d, float sb) {
     const int i = r * Dlp + d;
@@ -711,7 +756,7 @@ __device__ __forceinline__ void cl_fin_reverse(cg::cluster_group& cluster, ClCom
       if (g.rank == 0)
         for (int n = lane; n < H; n += 32) acc += (double)(m.ga[r * H + n] * w.w1t[n]);
       acc = warp_sum(acc);
-      if (lane == 0 && row0 + r < B) slot.tbar[(size_t)(row0 + r) * kC + g.rank] = (float)acc;
+      if (lane == 0 && row0 + r < B) slot.rm->tbar[(size_t)(row0 + r) * kC + g.rank] = (float)acc;
     }
   }
   __syncthreads();

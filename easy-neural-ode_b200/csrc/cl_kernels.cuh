@@ -388,7 +388,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
       }
       __syncthreads();
       ENO_TICK(PH_ELEM);
-      const FactorSlot& slot = a.slot[(MODE == ADJ_STEP) ? ev - 1 : 0];
+      // the ADJ_STEP factors feed the tensor-core contraction (transposed hi / lo planes), the others k_adj_pgrad
+      const FactorDstT<MODE == ADJ_STEP> slot(a.slot[(MODE == ADJ_STEP) ? ev - 1 : 0], a.tc, (MODE == ADJ_STEP) ? ev - 1 : 0);
       if (FIN) {
         cl_fin_forward<R>(cluster, S.cm, g, w, -tev, S.xz, a.eps, S.m, &slot, row0, a.B);
         cl_fin_reverse<R>(cluster, S.cm, g, w, S.xzb, srb, a.eps, S.m, srd, slot, row0, a.B);

@@ -1,6 +1,6 @@
 // fp32-accurate GEMM on the 5th-generation tensor cores (sm_100a): tcgen05.mma kind::tf32 with the
-// 3-pass split  a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi,  x_hi = x with the 13 low mantissa bits cleared
-// (exactly representable in tf32), x_lo = x - x_hi (exact in fp32).  Accumulators live in TMEM, operand
+// 3-pass split  a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi,  x_hi = x rounded to the nearest tf32, x_lo = the
+// remainder rounded to the nearest tf32 (split_tf32 below).  Accumulators live in TMEM, operand
 // tiles are staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through a ring of shared-memory stages,
 // one elected thread issues the MMAs, four warps drain TMEM with tcgen05.ld and run a fused epilogue functor.
 //
@@ -136,8 +136,8 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int bn) {
 #ifdef ENO_PHASES
 // development aid (libeno_phases.so): clock stamps of CTA (0,0,0) of the most recent launches, 8 per launch:
 // entry, set-up done, first operand stage landed, last MMA issued, accumulators complete, epilogue done, exit
-__device__ long long g_gemm_stamp[64 * 8];
-__device__ unsigned int g_gemm_launch;
+static __device__ long long g_gemm_stamp[64 * 8];
+static __device__ unsigned int g_gemm_launch;
 #define GEMM_STAMP(slot) do { if (stamp) stamp[slot] = clock64(); } while (0)
 #else
 #define GEMM_STAMP(slot) do { } while (0)
@@ -156,10 +156,12 @@ struct GemmCfg {
 // called once per (row, 4-column piece) of the tile; the functor
 // masks rows / columns outside its matrices itself.  `done` (may be null): device word; non-zero = the solve has
 // finished, the launch exits at once (iterations enqueued past the end of an adaptive solve).
+// blockIdx.z is a K-split (a_zrows == 0: z takes k-blocks [z * kb_per_split, ...)) or a BATCH index (a_zrows != 0:
+// problem z reads operand rows a_row0 + z * a_zrows / b_row0 + z * b_zrows over the whole K; the functor gets z).
 template <int BN, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int a_row0, int b_row0,
-              int kb_per_split, int kb_total, const int* __restrict__ done, Epi epi) {
+              int kb_per_split, int kb_total, const int* __restrict__ done, Epi epi, int a_zrows = 0, int b_zrows = 0) {
   if (done && *done) return;
 #ifdef ENO_PHASES
   __shared__ long long* stamp_s;
@@ -185,9 +187,12 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kBM, split = blockIdx.z;
-  const int kb0 = split * kb_per_split;
-  const int kb1 = min(kb_total, kb0 + kb_per_split);
+  const bool batched = a_zrows != 0;
+  const int kb0 = batched ? 0 : split * kb_per_split;
+  const int kb1 = batched ? kb_total : min(kb_total, kb0 + kb_per_split);
   const int nkb = kb1 - kb0;
+  a_row0 += split * a_zrows;
+  b_row0 += split * b_zrows;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -380,14 +385,34 @@ inline cudaError_t launch_gemm(const GemmOperand& A, const GemmOperand& Bm, int 
   return cudaGetLastError();
 }
 
+// Batched launch over prebuilt tensor maps: grid.z problems, problem z at operand rows row0 + z * zrows (all K).
+template <int BN, class Epi>
+inline cudaError_t launch_gemm_batched(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int batch, int a_zrows,
+                                       int b_zrows, const int* done, const Epi& epi, cudaStream_t st) {
+  const int kb_total = (K + kBK - 1) / kBK;
+  cudaError_t e = cudaFuncSetAttribute(k_gemm_tf32x3<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<BN>::kSmem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM, batch);
+  k_gemm_tf32x3<BN, Epi><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, st>>>(ta, tb, 0, 0, kb_total, kb_total, done, epi, a_zrows, b_zrows);
+  return cudaGetLastError();
+}
+
 // ---- operand preparation ----------------------------------------------------------------------------------
+// hi = x rounded to NEAREST tf32, lo = (x - hi) rounded to nearest tf32: both pieces are exactly what the tensor core
+// reads (it would otherwise TRUNCATE the 13-bit remainder to 11 bits: a one-sided error of up to 2^-20 |x| per operand;
+// this way |x - hi - lo| <= 2^-22 |x|, unbiased, and every product hi*hi, hi*lo, lo*hi is exact in fp32)
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = x - hi;
+  hi = rn_tf32(x);
+  lo = rn_tf32(x - hi);
 }
 
 // src [rows][cols] (ld_src) -> dst planes [2][rows_alloc][ld_dst] (optionally transposed: dst row = src col)
-__global__ void k_split_planes(const float* __restrict__ src, int rows, int cols, int ld_src, float* __restrict__ dst, int ld_dst,
+static __global__ void k_split_planes(const float* __restrict__ src, int rows, int cols, int ld_src, float* __restrict__ dst, int ld_dst,
                                size_t plane_stride, int transpose) {
   const size_t n = (size_t)rows * cols;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -418,7 +443,7 @@ struct EpiStore {
 };
 
 // C[r, c] = sum_s part[s][r * n_cols + c], fixed order (deterministic split-K)
-__global__ void k_sum_splits(const float* __restrict__ part, int splits, size_t n, int n_cols, float* __restrict__ C, int ldc) {
+static __global__ void k_sum_splits(const float* __restrict__ part, int splits, size_t n, int n_cols, float* __restrict__ C, int ldc) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float acc = 0.f;
     for (int s = 0; s < splits; ++s) acc += part[(size_t)s * n + i];

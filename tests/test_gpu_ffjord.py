@@ -194,8 +194,17 @@ def test_split_solves_match_oracle(cuda, reg_type, tol):
     outs, nfe = fn(spec.fwd, spec.aug_dynamics, (xg,) + (zc,) * n_aux, ts, eg, pflat, rtol=tol, atol=tol)
     loss = (outs[0][-1] * gy.to(cuda)).sum() + sum(w[q] * outs[1 + q][-1].sum() for q in range(n_aux))
     loss.backward()
-    assert float(nfe) == float(nfe_w)
-    assert eno.last_stats["bwd"][0]["n_iters"] == bst[0]["n_iters"]
+    if tol < 1e-7:
+        # below fp32 epsilon the counts are a property of the arithmetic noise (tests/util.py:exact_arith): the band spanned
+        # by the fp32 oracle and the exact-arithmetic oracle (here 50 / 44 NFE and 11 / 9 adjoint iterations)
+        resx, nfe_x = oo.odeint_split_fwd(exact_arith(cl["fwd"]), (x,) + (z,) * n_aux, ts, eps, p, n_aux=n_aux, rtol=tol, atol=tol)
+        bsx = []
+        oo.odeint_split_rev(exact_arith(cl["aug_dynamics"]), tol, tol, math.inf, resx, ts, (eps, p), gg, bsx)
+        assert_count(float(nfe), float(nfe_w), float(nfe_x), "nfe")
+        assert_count(eno.last_stats["bwd"][0]["n_iters"], bst[0]["n_iters"], bsx[0]["n_iters"], "adjoint iterations")
+    else:
+        assert float(nfe) == float(nfe_w)
+        assert eno.last_stats["bwd"][0]["n_iters"] == bst[0]["n_iters"]
     tr = None
     if tol > 1e-7:
         t = _truth_split(p, x, eps, gy, w, reg, reg_type)
