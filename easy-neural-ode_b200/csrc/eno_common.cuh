@@ -184,49 +184,59 @@ __device__ __forceinline__ float next_dt(float last, float ratio, int order) {
 
 // Loop bookkeeping after an iteration (or after init): leave every target whose
 // while-condition (lib/ode.py:829-831) is false, queueing its dense output.
-__device__ __forceinline__ void advance_targets(Ctrl* c, const float* __restrict__ ts) {
-  while (c->tgt < c->T) {
-    const bool go = (c->t < ts[c->tgt]) && (c->iters_tgt < c->mxstep) && (c->dt > 0.0f);
+// Works on a register copy of the controller: through the pointer every field access is a dependent global round trip
+// (the compiler must assume ts / trace alias it), which made this single-thread tail ~20 k cycles per iteration.
+__device__ __forceinline__ void advance_targets_local(Ctrl& c, const float* __restrict__ ts) {
+  while (c.tgt < c.T) {
+    const float target = ts[c.tgt];
+    const bool go = (c.t < target) && (c.iters_tgt < c.mxstep) && (c.dt > 0.0f);
     if (go) break;
-    if (c->t < ts[c->tgt]) {  // left early: record why (first cause wins)
-      if (c->status == ENO_OK) c->status = (c->iters_tgt >= c->mxstep) ? ENO_MXSTEP : ENO_DT_UNDERFLOW;
+    if (c.t < target) {  // left early: record why (first cause wins)
+      if (c.status == ENO_OK) c.status = (c.iters_tgt >= c.mxstep) ? ENO_MXSTEP : ENO_DT_UNDERFLOW;
     }
-    c->out_end = c->tgt + 1;
-    c->tgt += 1;
-    c->iters_tgt = 0;
+    c.out_end = c.tgt + 1;
+    c.tgt += 1;
+    c.iters_tgt = 0;
   }
-  if (c->tgt >= c->T) c->done = 1;
+  if (c.tgt >= c.T) c.done = 1;
+}
+__device__ __forceinline__ void advance_targets(Ctrl* cp, const float* __restrict__ ts) {
+  Ctrl c = *cp;
+  advance_targets_local(c, ts);
+  *cp = c;
 }
 
 // Controller update of one iteration (lib/ode.py:836-847).  Single thread.
-__device__ __forceinline__ void finish_iteration(Ctrl* c, const float* __restrict__ ts, float ratio, float dt_used,
+__device__ __forceinline__ void finish_iteration(Ctrl* cp, const float* __restrict__ ts, float ratio, float dt_used,
                                                  const Tableau& tab, eno_trace_row* trace) {
+  Ctrl c = *cp;
   const bool ok = (ratio <= 1.0f);
-  if (trace && c->n_iters < c->trace_cap) {
+  if (trace && c.n_iters < c.trace_cap) {
     eno_trace_row r;
-    r.t = c->t; r.dt = dt_used; r.ratio = ratio; r.accepted = ok ? 1.0f : 0.0f;
-    trace[c->n_iters] = r;
+    r.t = c.t; r.dt = dt_used; r.ratio = ratio; r.accepted = ok ? 1.0f : 0.0f;
+    trace[c.n_iters] = r;
   }
-  if (!(ratio == ratio) || isinf(ratio)) { if (c->status == ENO_OK) c->status = ENO_NONFINITE; }
+  if (!(ratio == ratio) || isinf(ratio)) { if (c.status == ENO_OK) c.status = ENO_NONFINITE; }
   const float dtn = next_dt(dt_used, ratio, tab.order);
-  c->ratio = ratio;
-  c->out_begin = c->out_end;
+  c.ratio = ratio;
+  c.out_begin = c.out_end;
   if (ok) {
-    const int old_prev = c->prev;
-    c->prev = c->cur;
-    c->cur = c->cand;
-    c->cand = old_prev;
-    c->mid_acc ^= 1;
-    c->last_t = c->t;
-    c->t = c->t + dt_used;
-    c->step_dt = dt_used;
-    c->n_accepted += 1;
+    const int old_prev = c.prev;
+    c.prev = c.cur;
+    c.cur = c.cand;
+    c.cand = old_prev;
+    c.mid_acc ^= 1;
+    c.last_t = c.t;
+    c.t = c.t + dt_used;
+    c.step_dt = dt_used;
+    c.n_accepted += 1;
   }
-  c->dt = dtn;
-  c->iters_tgt += 1;
-  c->n_iters += 1;
-  c->nfe += tab.nfe_per_iter;
-  advance_targets(c, ts);
+  c.dt = dtn;
+  c.iters_tgt += 1;
+  c.n_iters += 1;
+  c.nfe += tab.nfe_per_iter;
+  advance_targets_local(c, ts);
+  *cp = c;
 }
 
 }  // namespace eno

@@ -211,7 +211,12 @@ def test_ragged_batches_cluster_path_equals_streamed_path(cuda, Bn):
         assert res.returncode == 0, res.stderr[-2000:]
         outs[path] = json.loads(res.stdout.strip().splitlines()[-1])
     a, b = outs["cluster"], outs["stream"]
-    assert a["nfe"] == b["nfe"] and a["bwd"] == b["bwd"]
+    assert a["nfe"] == b["nfe"]
+    # The adjoint iteration count of this problem is set by arithmetic noise even at 1e-6 (its first error ratios are
+    # ~1e-6 in fp32 and ~2e-7 with exact dynamics: the oracle takes 8 iterations in fp32 and 7 with exact arithmetic at
+    # B = 130, tests/util.py:exact_arith).  The two formulations contract the parameter gradients differently (tcgen05
+    # 3xTF32 on the cluster path, FFMA on the streamed path), so they may sit at different ends of that band.
+    assert abs(a["bwd"] - b["bwd"]) <= 1
     for k in ("y", "ya", "g"):
         assert abs(a[k] - b[k]) <= 2e-5 * abs(b[k]) + 1e-9, (k, a[k], b[k])
 
