@@ -791,6 +791,8 @@ __global__ void __launch_bounds__(kSlots * kGroup) k_adj_pgrad(AdjArgs a, float 
   }
 
   // ---- last CTA: norm over all blocks, t0_bar element, controller -----------------------
+  // the next per-sample kernel may run its weight prologue under the finaliser (cl_kernels.cuh: pdl_wait)
+  if (MODE == ADJ_STEP || MODE == ADJ_INIT1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (!elect_last_block(&c->ticket)) return;
   adj_finalize<MODE>(a, c, dred, geo.grid, dt, rhs_tbar);
 }
@@ -958,6 +960,8 @@ __global__ void __launch_bounds__(256, 2) k_adj_pcombine(AdjArgs a) {
   }
   if (threadIdx.x == 0) a.ppart0[blockIdx.x] = dred[0];
   __syncthreads();
+  // the next per-sample kernel may run its weight prologue under the finaliser (cl_kernels.cuh: pdl_wait)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (!elect_last_block(&c->ticket)) return;
   adj_finalize<ADJ_STEP>(a, c, dred, (int)gridDim.x, dt, nullptr);
 }

@@ -3,6 +3,8 @@
 // 5-CTA cluster owns a tile of R samples, keeps its weight slices in shared memory for the whole
 // launch, loops persistently over tiles, and exchanges only R x H partial sums over DSMEM.
 #pragma once
+#include <cstdlib>
+
 #include "adj_kernels.cuh"
 #include "cl_device.cuh"
 
@@ -103,13 +105,22 @@ __device__ __forceinline__ void cl_row_sums(const float* q, const ClGeom& g, int
   }
 }
 
+// Programmatic dependent launch (single-GPU iteration kernels): the weight prologue of an iteration kernel does
+// not depend on the kernel before it, so it may run while that kernel's one-CTA finaliser is still busy.
+// Producers call pdl_trigger() when their per-CTA work is done (just before the ticket election); a consumer
+// launched with the programmatic-serialization attribute calls pdl_wait() after its prologue and only then reads
+// anything the producer wrote.  `done` goes 0 -> 1 once per solve and is reset kernels earlier, so a (possibly
+// stale) read of 1 BEFORE the wait is always true.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------
 // forward: MODE 0 = iteration, 1 = initial-step phase 0, 2 = initial-step phase 1
 // ------------------------------------------------------------------------------------------
 template <int R, int MODE, int DT, int HT>
 __global__ void __launch_bounds__(kThreads, 1) k_cl_fwd(FwdArgs a) {
   Ctrl* c = a.ctrl;
-  if (MODE == 0 && c->done) return;
+  if (MODE == 0 && *reinterpret_cast<volatile int*>(&c->done)) return;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ float4 smem4[];
   const int D = DT > 0 ? DT : a.w.D, H = HT > 0 ? HT : a.w.H;   // compile-time sizes in the specialised build
@@ -117,6 +128,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_fwd(FwdArgs a) {
   const ClGeom g = cl_geom(D, H, (int)cluster.block_rank());
   ClSmem S = cl_carve<R>(reinterpret_cast<float*>(smem4), D, H, g, s, false);
   cl_load_weights(a.w, g, S.W1, S.W2, S.vec);
+  if (MODE == 0) {
+    pdl_wait();
+    if (*reinterpret_cast<volatile int*>(&c->done)) return;   // uniform over the grid
+  }
   ClWeights w{S.W1, S.W2, S.vec, S.vec + H, S.vec + 2 * H, S.vec + 2 * H + g.Dlp, D, H};
   const int Dl = g.Dl, Dlp = g.Dlp, RD = R * Dlp;
   const float rtol = c->rtol, atol = c->atol;
@@ -245,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_fwd(FwdArgs a) {
   cluster.sync();   // no CTA may exit while a peer can still read its shared memory
 
   if (a.dist) return;
+  if (MODE == 0) pdl_trigger();   // the next iteration's launch may run its prologue under the finaliser below
   if (!elect_last_block(&c->ticket)) return;
   const int nrp = a.n_rp;
   const double s0 = block_sum_global(a.rp0_all, nrp, S.dred);
@@ -291,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_fwd(FwdArgs a) {
 template <int R, int K, int MODE, int DT, int HT, bool FIN = false>
 __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rhs_tau) {
   Ctrl* c = a.ctrl;
-  if (MODE == ADJ_STEP && c->done) return;
+  if (MODE == ADJ_STEP && *reinterpret_cast<volatile int*>(&c->done)) return;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ float4 smem4[];
   const int D = DT > 0 ? DT : a.w.D, H = HT > 0 ? HT : a.w.H;
@@ -299,6 +315,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
   ClSmem S = cl_carve<R>(reinterpret_cast<float*>(smem4), D, H, g, 0, true);
   ENO_TICK_START();
   cl_load_weights(a.w, g, S.W1, S.W2, S.vec);
+  if (MODE == ADJ_STEP) {
+    pdl_wait();   // the prologue above overlapped the parameter-gradient kernel's finaliser
+    if (*reinterpret_cast<volatile int*>(&c->done)) return;   // uniform over the grid
+  }
   ClWeights w{S.W1, S.W2, S.vec, S.vec + H, S.vec + 2 * H, S.vec + 2 * H + g.Dlp, D, H};
   const int Dl = g.Dl, Dlp = g.Dlp, RD = R * Dlp;
   constexpr int EPT = 2;   // elements per thread: R * Dlp <= 2 * kThreads (checked on the host)
@@ -615,7 +635,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
   cluster.sync();
 }
 
-template <typename... KArgs, typename... Args>
+template <bool PDL = false, typename... KArgs, typename... Args>
 inline cudaError_t launch_cluster(void (*kernel)(KArgs...), int grid, size_t smem, cudaStream_t st, Args... args) {
   static thread_local const void* s_last = nullptr;   // per kernel instantiation: set the attribute once
   static thread_local size_t s_smem = 0;
@@ -630,14 +650,22 @@ inline cudaError_t launch_cluster(void (*kernel)(KArgs...), int grid, size_t sme
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kC;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = PDL ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ENO_PDL=0 switches the programmatic dependent launches off (A/B measurements)
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("ENO_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 constexpr int kClRows = 4;           // samples per cluster tile
@@ -655,7 +683,9 @@ inline bool cl_is_mnist(int D, int H) { return D == 784 && H == 100; }
 template <int K, int DT, int HT, bool FIN = false>
 inline cudaError_t cl_adj_rows_launch(int mode, const AdjArgs& a, int grid, size_t smem, float rhs_tau, cudaStream_t st) {
   switch (mode) {
-    case ADJ_STEP: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_STEP, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
+    case ADJ_STEP:
+      if (!a.dist && pdl_enabled()) return launch_cluster<true>(k_cl_adj_rows<kClRows, K, ADJ_STEP, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
+      return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_STEP, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
     case ADJ_INIT0: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_INIT0, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
     case ADJ_INIT1: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_INIT1, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
     default: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_RHS, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
@@ -679,11 +709,14 @@ inline cudaError_t cl_adj_rows(int K, int mode, const AdjArgs& a, int grid, size
 
 // forward: mode 0 iteration, 1 / 2 initial-step phases
 inline cudaError_t cl_fwd_launch(int mode, const FwdArgs& a, int grid, size_t smem, cudaStream_t st) {
+  const bool pdl = !a.dist && pdl_enabled();
   if (cl_is_mnist(a.w.D, a.w.H)) {
+    if (mode == 0 && pdl) return launch_cluster<true>(k_cl_fwd<kClRows, 0, 784, 100>, grid, smem, st, a);
     if (mode == 0) return launch_cluster(k_cl_fwd<kClRows, 0, 784, 100>, grid, smem, st, a);
     if (mode == 1) return launch_cluster(k_cl_fwd<kClRows, 1, 784, 100>, grid, smem, st, a);
     return launch_cluster(k_cl_fwd<kClRows, 2, 784, 100>, grid, smem, st, a);
   }
+  if (mode == 0 && pdl) return launch_cluster<true>(k_cl_fwd<kClRows, 0, 0, 0>, grid, smem, st, a);
   if (mode == 0) return launch_cluster(k_cl_fwd<kClRows, 0, 0, 0>, grid, smem, st, a);
   if (mode == 1) return launch_cluster(k_cl_fwd<kClRows, 1, 0, 0>, grid, smem, st, a);
   return launch_cluster(k_cl_fwd<kClRows, 2, 0, 0>, grid, smem, st, a);
