@@ -705,8 +705,8 @@ def main():
         step(s)
     torch.cuda.synchronize()
     L.eno_profile_enable(h, 0)
-    ms = (C.c_double * 4)()
-    cnt = (C.c_int64 * 4)()
+    ms = (C.c_double * 5)()
+    cnt = (C.c_int64 * 5)()
     L.eno_profile_read(h, ms, cnt)
     peaks = {}
     try:
@@ -718,6 +718,7 @@ def main():
     ffma = C.c_double()
     L.eno_ffma_peak(h, C.byref(ffma), None)
     rows_ms = ms[1] / max(cnt[1], 1)
+    pgemm_ms = ms[4] / max(cnt[4], 1)
     flop_rows = 6.0 * B * 12 * 2 * D * H + 70.0 * 2 * B * D   # DESIGN.md "Algorithmic work"
     achieved = flop_rows / (rows_ms * 1e-3) / 1e12 if rows_ms > 0 else 0.0
     roofline = {"kernel": "k_cl_adj_rows<STEP> (adjoint dopri5 iteration, per-sample blocks; k_adj_rows on the streamed path)", "bound": "tensor",
@@ -725,10 +726,24 @@ def main():
                 "traffic": traffic_from_profiles("k_cl_adj_rows_step"),   # ncu --set full, per launch (profiles/roofline_traffic.json)
                 "peak_source": peak_src, "avg_launch_ms": rows_ms, "launches_timed": int(cnt[1]),
                 "fp32_ffma_peak_tflops": ffma.value, "frac_of_fp32_ffma": achieved / ffma.value if ffma.value else None,
-                "other_kernels_ms": {"k_fwd_step": ms[0] / max(cnt[0], 1), "k_adj_pgrad<STEP>": ms[2] / max(cnt[2], 1),
+                "other_kernels_ms": {"k_fwd_step": ms[0] / max(cnt[0], 1),
+                                     "adjoint parameter gradients per iteration (batched tcgen05 3xTF32 GEMM + k_adj_pcombine; "
+                                     "k_adj_pgrad on the streamed path)": ms[2] / max(cnt[2], 1),
+                                     **({"k_gemm_tf32x3<128, EpiPgradStage> alone": pgemm_ms} if cnt[4] else {}),
                                      **({"exchange (finish kernel incl. the peer-memory or NCCL exchange and the wait for the slowest rank), per iteration, fwd and adjoint":
                                          ms[3] / max(cnt[3], 1)} if world > 1 else {})},
                 "note": "fp32 FFMA kernel; the tensor pipe is the contract's denominator, the fp32 pipe is the one it uses"}
+    if cnt[4]:
+        # the tensor-core kernel of the step: 12 contractions [D x K] x [K x H], K = 3 B, per launch (algorithmic 2 M N K flops)
+        flop_pg = 12.0 * 2 * D * H * 3 * B
+        roofline["tensor_kernel"] = {
+            "kernel": "k_gemm_tf32x3<128, EpiPgradStage> (adjoint parameter-gradient contraction: tcgen05.mma kind::tf32, 3-pass "
+                      "split, TMA operands, TMEM accumulators; one batched launch per adjoint iteration)",
+            "avg_launch_ms": pgemm_ms, "launches_timed": int(cnt[4]), "algorithmic_flop_per_launch": flop_pg,
+            "achieved": flop_pg / (pgemm_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+            "frac_of_3xtf32_ceiling": flop_pg / (pgemm_ms * 1e-3) / 1e12 / (tensor_peak / 6.0),
+            "note": "fp32-exact work runs 3 tf32 passes at half the bf16 rate: 1/6 of the bf16 peak is the ceiling; at B = 100 the "
+                    "launch is 84 tiles of 128 x 128 x 300 - latency bound, not throughput bound"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

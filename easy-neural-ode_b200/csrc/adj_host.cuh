@@ -377,8 +377,10 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
         prof->end(ps, st);
         ps = prof->begin(PROF_ADJ_PGRAD, st);
         if (pg_tc) {
+          const int pg = prof->begin(PROF_ADJ_PGEMM, st);
           ENO_ADJ_CHECK(tc::launch_gemm_batched<128>(tmX, tmY, D, H, a.np * a.tc.Bk, kSlots * 2, a.tc.dpad, a.tc.hpad, &a.ctrl->done,
                                                      pg_epi, st));
+          prof->end(pg, st);
           k_adj_pcombine<<<kPcGrid, 256, 0, st>>>(a);
           ++launches;
         } else {
@@ -413,7 +415,7 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
       continue;
     }
     {
-      int valid[PROF_KINDS] = {0, mailbox->n_iters, mailbox->n_iters, dist ? mailbox->n_iters : 0};
+      int valid[PROF_KINDS] = {0, mailbox->n_iters, mailbox->n_iters, dist ? mailbox->n_iters : 0, pg_tc ? mailbox->n_iters : 0};
       prof->resolve(valid);
     }
     *hint = mailbox->n_iters + 1 > 64 ? 64 : mailbox->n_iters + 1;

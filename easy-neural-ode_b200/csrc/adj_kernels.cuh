@@ -974,6 +974,9 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_adj_pfinish(AdjArgs a) {
   Ctrl* c = a.ctrl;
   if (MODE == ADJ_STEP && c->done) return;
+  // every CTA of this grid is resident by the time all have passed this point: the next per-sample kernel
+  // (programmatic serialization) may load its weights while the exchange below runs
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __shared__ double dred[256];
   const size_t P = (size_t)a.P;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1050,6 +1053,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_adj_pfinish_peer(AdjArgs a) {
   Ctrl* c = a.ctrl;
   if (MODE == ADJ_STEP && c->done) return;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // as in k_adj_pfinish
   __shared__ double dred[256];
   PEER_STAMP(blockIdx.x == 0, 0);
   const PeerView pv = *reinterpret_cast<const PeerView*>(a.peer_base + kPeerOffView);

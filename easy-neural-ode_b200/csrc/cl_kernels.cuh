@@ -709,7 +709,7 @@ inline cudaError_t cl_adj_rows(int K, int mode, const AdjArgs& a, int grid, size
 
 // forward: mode 0 iteration, 1 / 2 initial-step phases
 inline cudaError_t cl_fwd_launch(int mode, const FwdArgs& a, int grid, size_t smem, cudaStream_t st) {
-  const bool pdl = !a.dist && pdl_enabled();
+  const bool pdl = !a.dist && pdl_enabled();   // multi-GPU: measured slower with it (875 vs 944 steps/s at N = 2)
   if (cl_is_mnist(a.w.D, a.w.H)) {
     if (mode == 0 && pdl) return launch_cluster<true>(k_cl_fwd<kClRows, 0, 784, 100>, grid, smem, st, a);
     if (mode == 0) return launch_cluster(k_cl_fwd<kClRows, 0, 784, 100>, grid, smem, st, a);

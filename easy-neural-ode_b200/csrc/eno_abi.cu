@@ -354,7 +354,7 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   }
   const Ctrl& c = *ctx->mailbox;
   {
-    int valid[PROF_KINDS] = {c.n_iters, 0, 0, dist ? c.n_iters : 0};
+    int valid[PROF_KINDS] = {c.n_iters, 0, 0, dist ? c.n_iters : 0, 0};
     ctx->prof.resolve(valid);
   }
   ctx->hint_fwd = c.n_iters + 1 > 64 ? 64 : c.n_iters + 1;

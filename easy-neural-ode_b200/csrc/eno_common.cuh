@@ -59,7 +59,7 @@ static_assert(offsetof(Ctrl, done) == 72 && offsetof(Ctrl, n_iters) == 80, "Ctrl
 
 // Optional per-kernel device timing (bench.py's roofline leg): event pairs around the launches of
 // one kernel kind, resolved after the solve's final synchronize.
-enum ProfKind { PROF_FWD_STEP = 0, PROF_ADJ_ROWS = 1, PROF_ADJ_PGRAD = 2, PROF_EXCHANGE = 3, PROF_KINDS = 4 };
+enum ProfKind { PROF_FWD_STEP = 0, PROF_ADJ_ROWS = 1, PROF_ADJ_PGRAD = 2, PROF_EXCHANGE = 3, PROF_ADJ_PGEMM = 4, PROF_KINDS = 5 };
 struct Profiler {
   bool enabled = false;
   static constexpr int kMax = 512;
@@ -67,8 +67,8 @@ struct Profiler {
   int kind[kMax];
   int n = 0;
   bool created = false;
-  double ms[PROF_KINDS] = {0, 0, 0, 0};
-  long long count[PROF_KINDS] = {0, 0, 0, 0};
+  double ms[PROF_KINDS] = {0, 0, 0, 0, 0};
+  long long count[PROF_KINDS] = {0, 0, 0, 0, 0};
   int begin(int k, cudaStream_t st) {
     if (!enabled || n >= kMax) return -1;
     if (!created) {
@@ -82,7 +82,7 @@ struct Profiler {
   void end(int slot, cudaStream_t st) { if (slot >= 0) cudaEventRecord(ev[slot][1], st); }
   // call after the stream has been synchronized; drops launches that exited early (done flag)
   void resolve(int valid_per_kind[PROF_KINDS]) {
-    int seen[PROF_KINDS] = {0, 0, 0, 0};
+    int seen[PROF_KINDS] = {0, 0, 0, 0, 0};
     for (int i = 0; i < n; ++i) {
       const int k = kind[i];
       if (seen[k]++ < valid_per_kind[k]) {

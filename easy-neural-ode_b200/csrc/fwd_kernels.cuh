@@ -317,6 +317,8 @@ __device__ __forceinline__ void fwd_finish_body(const FwdArgs& a, int mode, doub
 __global__ void __launch_bounds__(kThreads) k_fwd_finish(FwdArgs a, int mode) {
   __shared__ double dred[kThreads];
   if (mode == 0 && a.ctrl->done) return;
+  // the next iteration kernel (launched with programmatic serialization) may load its weights under this exchange
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   fwd_finish_body(a, mode, dred, a.rp0_all, a.rp1_all);
 }
 
@@ -325,6 +327,7 @@ __global__ void __launch_bounds__(kThreads) k_fwd_finish(FwdArgs a, int mode) {
 __global__ void __launch_bounds__(kThreads) k_fwd_finish_peer(FwdArgs a, int mode, unsigned char* peer_base, int n_loc) {
   __shared__ double dred[kThreads];
   if (mode == 0 && a.ctrl->done) return;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // as in k_fwd_finish
   const PeerView pv = *reinterpret_cast<const PeerView*>(peer_base + kPeerOffView);
   unsigned long long* seqp = reinterpret_cast<unsigned long long*>(peer_base + kPeerOffSeq);
   const unsigned long long seq = *seqp + 1;

@@ -287,10 +287,12 @@ int32_t eno_peer_attach(eno_ctx* ctx, const uint8_t* handles /*[world][64], rank
  * whole jitted update, mnist.py:632-640).  With profiling on, the step kernels are bracketed by CUDA
  * events on the launch stream; eno_profile_read returns and clears the accumulated milliseconds and
  * launch counts per kernel kind: [0] forward step, [1] adjoint per-sample step, [2] adjoint
- * parameter-gradient step, [3] multi-GPU exchange (NCCL group + replicated finish kernel).  eno_ffma_peak measures the non-tensor fp32 FMA peak (TFLOP/s).
+ * parameter-gradient step (cluster path: the batched tcgen05 contraction + k_adj_pcombine), [3] multi-GPU exchange
+ * (finish kernel incl. the peer-memory or NCCL exchange), [4] the batched tcgen05 contraction of [2] alone.
+ * eno_ffma_peak measures the non-tensor fp32 FMA peak (TFLOP/s).
  */
 int32_t eno_profile_enable(eno_ctx* ctx, int32_t on);
-int32_t eno_profile_read(eno_ctx* ctx, double* ms_out /*[4]*/, int64_t* count_out /*[4]*/);
+int32_t eno_profile_read(eno_ctx* ctx, double* ms_out /*[5]*/, int64_t* count_out /*[5]*/);
 int32_t eno_ffma_peak(eno_ctx* ctx, double* tflops_out, void* stream);
 /* With profiling on, solves of ENO_ARCH_CONCATSQUASH dynamics bracket every tensor-core GEMM launch of their loop
  * iterations with CUDA events (direct launches instead of the iteration graph).  Returns and clears the accumulated

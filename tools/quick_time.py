@@ -42,7 +42,7 @@ for _ in range(5):
     m.loss_and_grads(images, labels, eps)
 torch.cuda.synchronize()
 L.eno_profile_enable(h, 0)
-ms = (C.c_double * 4)(); cnt = (C.c_int64 * 4)()
+ms = (C.c_double * 5)(); cnt = (C.c_int64 * 5)()
 L.eno_profile_read(h, ms, cnt)
 for name, a, b in zip(["fwd_step", "adj_rows", "adj_pgrad"], ms, cnt):
     print(f"{name}: {1e3*a/max(b,1):.1f} us avg over {b} launches")
