@@ -192,15 +192,13 @@ inline void adj_set_views(AdjArgs* a, int stride, int rank, int world) {
 
 constexpr size_t kPgradSmem = (size_t)kSlots * kPStages * kPRows * 64 * sizeof(float);   // operand rings of k_adj_pgrad
 
+// The opt-in is a per-DEVICE attribute: set it on every solve (four cheap calls) rather than once per thread.
 inline cudaError_t pgrad_prepare() {
-  static thread_local bool done = false;
-  if (done) return cudaSuccess;
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(k_adj_pgrad<ADJ_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPgradSmem))) return e;
   if ((e = cudaFuncSetAttribute(k_adj_pgrad<ADJ_INIT0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPgradSmem))) return e;
   if ((e = cudaFuncSetAttribute(k_adj_pgrad<ADJ_INIT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPgradSmem))) return e;
   if ((e = cudaFuncSetAttribute(k_adj_pgrad<ADJ_RHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPgradSmem))) return e;
-  done = true;
   return cudaSuccess;
 }
 

@@ -637,13 +637,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
 
 template <bool PDL = false, typename... KArgs, typename... Args>
 inline cudaError_t launch_cluster(void (*kernel)(KArgs...), int grid, size_t smem, cudaStream_t st, Args... args) {
-  static thread_local const void* s_last = nullptr;   // per kernel instantiation: set the attribute once
+  static thread_local const void* s_last = nullptr;   // per kernel instantiation and device: set the attribute once
   static thread_local size_t s_smem = 0;
-  if (s_last != (const void*)kernel || s_smem < smem) {
+  static thread_local int s_dev = -1;
+  int dev = -1;
+  cudaGetDevice(&dev);
+  if (s_last != (const void*)kernel || s_smem < smem || s_dev != dev) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     s_last = (const void*)kernel;
     s_smem = smem;
+    s_dev = dev;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, 1, 1);
