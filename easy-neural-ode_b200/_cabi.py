@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ENO_LIB") or os.path.join(_HERE, "libeno.so")   # ENO_LIB: development variants only
 
 ENO_OK, ENO_MXSTEP, ENO_DT_UNDERFLOW, ENO_NONFINITE = 0, 1, 2, 3
-ARCH_MLP_SIGMOID, ARCH_CONCATSQUASH, ARCH_TANH_STACK = 0, 1, 2
+ARCH_MLP_SIGMOID, ARCH_CONCATSQUASH, ARCH_TANH_STACK, ARCH_CONCATCONV = 0, 1, 2, 3
 F32, F64 = 0, 1
 AUG_NONE, AUG_REG, AUG_ALL, AUG_FIN, AUG_FFJORD = 0, 1, 2, 3, 4
 TABLEAUX = {"dopri5": 0, "heun": 1, "fehlberg": 2, "bosh": 3, "rk_fehlberg": 4, "cash_karp": 5,
@@ -26,7 +26,8 @@ SYMBOLS = ["eno_abi_version", "eno_last_error_string", "eno_create", "eno_destro
 
 class Desc(C.Structure):
     _fields_ = [("arch", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("reg_order", C.c_int32),
-                ("aug", C.c_int32), ("eps_in_args", C.c_int32), ("n_hidden", C.c_int32)]
+                ("aug", C.c_int32), ("eps_in_args", C.c_int32), ("n_hidden", C.c_int32), ("img_h", C.c_int32),
+                ("img_w", C.c_int32)]
 
 
 class Stats(C.Structure):

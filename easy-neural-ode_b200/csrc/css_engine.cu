@@ -16,6 +16,7 @@
 
 #include "css_api.h"
 #include "css_kernels.cuh"
+#include "ccv_kernels.cuh"
 #include "eno_ctx.cuh"
 #include "tableaux.cuh"
 
@@ -54,6 +55,8 @@ struct Carver {
 struct Plan {
   css::Net net;
   css::Flat flat;
+  bool conv = false;         // ENO_ARCH_CONCATCONV: the right-hand side is the convolutional pipeline of ccv_kernels.cuh
+  ccv::CNet cnet;
   size_t P = 0;
   float* params = nullptr;   // copies inside the workspace, so that a captured iteration graph only names the workspace
   float* eps = nullptr;
@@ -73,8 +76,81 @@ int aux_count(int aug) {
   return -1;
 }
 
+// ConcatConv2D dynamics (forward closures only): the flat driver's buffers + the padded-grid activations
+void plan_build_conv(const eno_dynamics_desc* d, int B, int T, void* ws, Plan* p) {
+  p->conv = true;
+  ccv::CNet& c = p->cnet;
+  css::Net& n = p->net;
+  css::Flat& f = p->flat;
+  memset(&c, 0, sizeof(c));
+  memset(&n, 0, sizeof(n));
+  memset(&f, 0, sizeof(f));
+  const int C = d->H, D = d->D;
+  c.B = B; c.Hh = d->img_h; c.Ww = d->img_w; c.C = C;
+  c.HP = c.Hh + 2; c.WP = c.Ww + 2; c.PP = c.HP * c.WP;
+  c.R = B * c.PP; c.Rp = (c.R + 127) / 128 * 128;
+  c.D = D; c.ldD = ld4(D);
+  switch (d->aug) {
+    case ENO_AUG_NONE: c.nq = 0; break;
+    case ENO_AUG_FFJORD: case ENO_AUG_FIN: c.nq = 1; break;
+    default: c.nq = d->reg_order ? 2 : 1;
+  }
+  c.mode = d->aug == ENO_AUG_NONE ? css::MODE_PLAIN : css::MODE_AUG;
+  // what k_css_seed / k_css_assemble read in the forward modes
+  n.B = B; n.Bp = (B + 127) / 128 * 128; n.D = D; n.H = C; n.L = 1; n.nq = c.nq; n.mode = c.mode;
+  n.fin = (d->aug == ENO_AUG_FIN); n.ldD = c.ldD;
+  size_t po = 0;
+  for (int l = 0; l < ccv::kLayers; ++l) {
+    const size_t cin = l == 0 ? 1 : C, cout = l == ccv::kLayers - 1 ? 1 : C;
+    c.poff[l] = po;
+    po += cout + 9 * (cin + 1) * cout;
+  }
+  p->P = po;
+  const size_t BD = (size_t)B * D;
+  const int na = aux_count(d->aug);
+  f.B = B; f.D = D; f.n_aux = na;
+  f.oAUX = BD;
+  f.N = BD + (size_t)na * B;
+  f.n_feed = BD;
+  f.tsign = 1.f;
+  Carver cv{static_cast<char*>(ws)};
+  f.ctrl = cv.take<Ctrl>(1);
+  f.Y = cv.take<float>(3 * f.N);
+  f.F = cv.take<float>(3 * f.N);
+  f.KS = cv.take<float>(5 * f.N);
+  f.MID = cv.take<float>(2 * f.N);
+  f.YS = cv.take<float>(f.n_feed);
+  f.n_part = 2048;
+  f.part = cv.take<double>(2 * (size_t)f.n_part);
+  f.out = cv.take<float>((size_t)std::max(T, 2) * f.N);
+  p->params = cv.take<float>(p->P);
+  p->eps = cv.take<float>(BD);
+  p->seg_ts = cv.take<float>(4);
+  n.eps = p->eps;
+  n.tval = cv.take<float>(4);
+  c.eps = p->eps; c.ys = f.YS; c.tval = n.tval;
+  for (int l = 0; l < ccv::kLayers; ++l) {
+    const size_t cout = l == ccv::kLayers - 1 ? 1 : C;
+    c.b[l] = p->params ? p->params + c.poff[l] : nullptr;
+    c.W[l] = p->params ? p->params + c.poff[l] + cout : nullptr;
+    c.TM[l] = cv.take<float>(9 * cout);
+  }
+  for (int l = 0; l < 2; ++l) c.WT2[l] = cv.take<float>((size_t)2 * C * 9 * C);
+  for (int l = 0; l < 3; ++l) c.S[l] = cv.take<float>((size_t)c.Rp * C);
+  c.F = n.F = cv.take<float>((size_t)B * c.ldD);
+  c.JE = n.JE = cv.take<float>((size_t)B * c.ldD);
+  c.Y1 = n.Y1 = cv.take<float>((size_t)B * c.ldD);
+  n.DIV = cv.take<float>(B); n.RR = cv.take<float>(B); n.FRO = cv.take<float>(B); n.KIN = cv.take<float>(B);
+  p->zero_from = cv.off;   // halo / padding rows of the activations must read as zero
+  for (int l = 0; l < 2; ++l) c.X2[l] = cv.take<float>(2 * c.xplane());
+  c.X3 = cv.take<float>((size_t)3 * c.Rp * C);
+  p->zero_bytes = cv.off - p->zero_from;
+  p->bytes = cv.off + 1024;
+}
+
 // mode: 0 forward solve, 1 adjoint solve
 void plan_build(const eno_dynamics_desc* d, int B, int T, int mode, void* ws, Plan* p) {
+  if (d->arch == ENO_ARCH_CONCATCONV) { plan_build_conv(d, B, T, ws, p); return; }
   css::Net& n = p->net;
   css::Flat& f = p->flat;
   memset(&n, 0, sizeof(n));
@@ -235,8 +311,42 @@ cudaError_t gemm(const tc::GemmOperand& A, const tc::GemmOperand& Bm, int M, int
     }                                                                                 \
   } while (0)
 
+// ConcatConv2D dynamics: direct first / last layers, the two C -> C layers as 9-tap loops of the tensor-core kernel
+int ccv_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, int sms, cudaStream_t st, std::string* err) {
+  const ccv::CNet& c = p.cnet;
+  const css::Flat& f = p.flat;
+  const int C = c.C, B = c.B;
+  const int* done = (init_mode == css::ST_STAGE) ? &f.ctrl->done : nullptr;
+  const int egrid = std::min<int>((int)((f.n_feed + 255) / 256), 4 * sms);
+  ccv::k_ccv_stage<<<egrid, 256, 0, st>>>(f, c.tval, stage, init_mode);
+  CUtensorMap ta[2], tb[2];
+  for (int l = 0; l < 2; ++l) {
+    if (!tc::make_operand_map(&ta[l], c.X2[l], 3 * c.Rp, C, C, c.xplane(), tc::kBM, err) ||
+        !tc::make_operand_map(&tb[l], c.WT2[l], C, 9 * C, 9 * C, (size_t)C * 9 * C, 64, err))
+      return ENO_E_CUDA;
+  }
+  const size_t pix = (size_t)B * c.D;
+  auto l0grid = [&](size_t streams) { return (int)std::min<size_t>((streams * pix * (C / 4) + 255) / 256, (size_t)16 * sms); };
+  auto l3grid = [&](size_t streams) { return (int)std::min<size_t>((streams * pix * 32 + 255) / 256, (size_t)16 * sms); };
+  ccv::k_ccv_l0<false><<<l0grid(1), 256, 0, st>>>(c, done);
+  CSS_G(tc::launch_conv3x3<64>(ta[0], tb[0], 0, c.R, C, C, c.WP, done, ccv::EpiConvPrimal{c, 1}, st));
+  CSS_G(tc::launch_conv3x3<64>(ta[1], tb[1], 0, c.R, C, C, c.WP, done, ccv::EpiConvPrimal{c, 2}, st));
+  ccv::k_ccv_l3<<<l3grid(1), 256, 0, st>>>(c, 0, 1, done);
+  if (c.nq > 0) {   // the tangent streams, stacked (the Taylor stream's direction is f: after the primal pass)
+    ccv::k_ccv_l0<true><<<l0grid(c.nq), 256, 0, st>>>(c, done);
+    CSS_G(tc::launch_conv3x3<64>(ta[0], tb[0], c.Rp, c.nq * c.Rp, C, C, c.WP, done, ccv::EpiConvTangent{c, 1}, st));
+    CSS_G(tc::launch_conv3x3<64>(ta[1], tb[1], c.Rp, c.nq * c.Rp, C, C, c.WP, done, ccv::EpiConvTangent{c, 2}, st));
+    ccv::k_ccv_l3<<<l3grid(c.nq), 256, 0, st>>>(c, 1, c.nq, done);
+  }
+  if (c.mode != css::MODE_PLAIN) css::k_css_seed<<<(B * 32 + 255) / 256, 256, 0, st>>>(f, p.net);
+  css::k_css_assemble<<<std::min((int)((pix + 255) / 256), 8 * sms), 256, 0, st>>>(f, p.net, stage, init_mode, k_override);
+  CSS_G(cudaGetLastError());
+  return 0;
+}
+
 // One evaluation of the integrated function into the stage slot (or k_override).
 int css_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, int sms, cudaStream_t st, std::string* err) {
+  if (p.conv) return ccv_rhs_launch(p, stage, init_mode, k_override, sms, st, err);
   const css::Net& n = p.net;
   const css::Flat& f = p.flat;
   const int L = n.L, B = n.B, Bp = n.Bp;
@@ -298,6 +408,11 @@ int css_prepare(eno_ctx* ctx, Plan& p, const float* params, const float* eps, cu
   if (eps) CSS_CUDA(ctx, cudaMemcpyAsync(p.eps, eps, (size_t)n.B * n.D * 4, cudaMemcpyDeviceToDevice, st));
   else CSS_CUDA(ctx, cudaMemsetAsync(p.eps, 0, (size_t)n.B * n.D * 4, st));
   if (p.zero_bytes) CSS_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<char*>(p.flat.ctrl) + p.zero_from, 0, p.zero_bytes, st));
+  if (p.conv) {
+    ccv::k_ccv_prepare<<<256, 256, 0, st>>>(p.cnet);
+    CSS_CUDA(ctx, cudaGetLastError());
+    return 0;
+  }
   for (int l = 0; l < n.L; ++l) {
     // forward operand: W^T [dout][din];  reverse operand: W [din][dout]
     tc::k_split_planes<<<512, 256, 0, st>>>(n.W[l], n.din[l], n.dout[l], n.dout[l], n.WT2[l], n.ldi[l], (size_t)n.dout[l] * n.ldi[l], 1);
@@ -401,13 +516,23 @@ int run_loop(eno_ctx* ctx, const Plan& p, const GraphKey& key, int which, eno_st
 namespace eno {
 namespace css {
 
+bool conv_desc_ok(const eno_dynamics_desc* d) {
+  return d && d->arch == ENO_ARCH_CONCATCONV && (d->H == 32 || d->H == 64) && d->n_hidden == 3 && d->img_h >= 2 && d->img_w >= 2 &&
+         d->D == d->img_h * d->img_w && d->D % 4 == 0 && aux_count(d->aug) >= 0 && (d->reg_order == 0 || d->reg_order == 2);
+}
+
 bool desc_ok(const eno_dynamics_desc* d) {
+  if (d && d->arch == ENO_ARCH_CONCATCONV) return conv_desc_ok(d);
   return d && d->arch == ENO_ARCH_CONCATSQUASH && d->D > 0 && d->H > 0 && d->n_hidden >= 1 && d->n_hidden + 1 <= kMaxLayers &&
          aux_count(d->aug) >= 0 && (d->reg_order == 0 || d->reg_order == 2);
 }
 
 int64_t param_count(const eno_dynamics_desc* d) {
   int64_t P = 0;
+  if (d->arch == ENO_ARCH_CONCATCONV) {   // per layer b [c_out] + w [3][3][c_in + 1][c_out]
+    const int64_t C = d->H;
+    return (C + 18 * C) + 2 * (C + 9 * (C + 1) * C) + (1 + 9 * (C + 1));
+  }
   const int L = d->n_hidden + 1;
   for (int l = 0; l < L; ++l) {
     const int64_t din = l == 0 ? d->D : d->H, dout = l == L - 1 ? d->D : d->H;
@@ -448,7 +573,9 @@ int odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* 
   if ((rc = css_prepare(ctx, p, params, eps, st))) return rc;
   const size_t N = p.flat.N, BD = (size_t)B * desc->D;
   css::k_flat_reset<<<1, 1, 0, st>>>(p.flat.ctrl, rtol, atol, T, mxstep <= 0 ? INT_MAX : mxstep, trace ? trace_cap : 0, (float)N);
-  css::k_css_fwd_begin<<<std::min<int>((int)((N + 255) / 256), 1024), 256, 0, st>>>(p.flat, y0, nullptr);
+  // the auxiliary states start from aux_out[0] (zeros from aug_init; delta_logp of the logit pre-flow in
+  // ffjord_mnist.py:409-417): their magnitude enters the error norm through tol = atol + rtol max(|y0|, |y1|)
+  css::k_css_fwd_begin<<<std::min<int>((int)((N + 255) / 256), 1024), 256, 0, st>>>(p.flat, y0, na > 0 ? aux_out : nullptr);
   int launches = 0;
   int status = ENO_OK;
   if (T > 1) {
@@ -469,6 +596,8 @@ int odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* 
                size_t ws_bytes, float* y0_bar_out, float* aux0_bar_out, float* eps_bar_out, float* ts_bar_out,
                float* params_bar_out, eno_stats* stats, eno_trace_row* trace, int trace_cap, cudaStream_t st) {
   if (!desc_ok(desc)) return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: unsupported ConcatSquash descriptor");
+  if (desc->arch == ENO_ARCH_CONCATCONV)
+    return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: the adjoint of the ConcatConv2D dynamics is not built (forward closures only)");
   const int na = aux_count(desc->aug);
   if (desc->aug != ENO_AUG_REG && desc->aug != ENO_AUG_FIN)
     return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: the FFJORD adjoint integrates aug_dynamics ('our' or 'fin')");
@@ -529,6 +658,8 @@ int rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int mode, int B, const floa
   if (mode > 0 && (!eps || !aux_out)) return css_fail(ctx, ENO_E_ARG, "eno_rhs: augmented modes need eps and aux_out");
   if (mode == 2 && (!y_bar || !aux_bar || !ybar_dot_out || !tbar_out || !params_bar_out))
     return css_fail(ctx, ENO_E_ARG, "eno_rhs: mode 2 needs y_bar, aux_bar and all outputs");
+  if (mode == 2 && desc->arch == ENO_ARCH_CONCATCONV)
+    return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_rhs: the vjp of the ConcatConv2D dynamics is not built (forward closures only)");
   Plan p;
   plan_build(&d, B, 2, mode == 2 ? 1 : 0, ws, &p);
   if (ws_bytes < p.bytes) return css_fail(ctx, ENO_E_WORKSPACE, "eno_rhs: workspace too small");

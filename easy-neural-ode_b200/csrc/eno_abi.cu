@@ -179,20 +179,20 @@ void eno_destroy(eno_ctx* ctx) {
 
 int64_t eno_param_count(const eno_dynamics_desc* d) {
   if (!d) return -1;
-  if (d->arch == ENO_ARCH_CONCATSQUASH) return css::desc_ok(d) ? css::param_count(d) : -1;
+  if ((d->arch == ENO_ARCH_CONCATSQUASH || d->arch == ENO_ARCH_CONCATCONV)) return css::desc_ok(d) ? css::param_count(d) : -1;
   return (int64_t)(d->D + 1) * d->H + d->H + (int64_t)(d->H + 1) * d->D + d->D;
 }
 
 int64_t eno_adjoint_state_size(const eno_dynamics_desc* d, int32_t B) {
   if (!d) return -1;
-  if (d->arch == ENO_ARCH_CONCATSQUASH) return css::desc_ok(d) ? css::adjoint_state_size(d, B) : -1;
+  if ((d->arch == ENO_ARCH_CONCATSQUASH || d->arch == ENO_ARCH_CONCATCONV)) return css::desc_ok(d) ? css::adjoint_state_size(d, B) : -1;
   const int64_t n_aux = (d->aug == ENO_AUG_NONE) ? 0 : (d->aug == ENO_AUG_FIN ? 2 : 1);
   return 2 * ((int64_t)B * d->D + n_aux * B) + 1 + (d->eps_in_args ? (int64_t)B * d->D : 0) + eno_param_count(d);
 }
 
 size_t eno_workspace_bytes(const eno_dynamics_desc* d, int32_t B, int32_t T, int32_t tableau, int32_t mode) {
   (void)tableau;
-  if (d && d->arch == ENO_ARCH_CONCATSQUASH) return css::workspace_bytes(d, B, T, mode);
+  if (d && (d->arch == ENO_ARCH_CONCATSQUASH || d->arch == ENO_ARCH_CONCATCONV)) return css::workspace_bytes(d, B, T, mode);
   if (!desc_ok(d) || B <= 0) return 0;
   if (mode == 0) return fwd_ws_bytes(B, d->D);
   return adj_ws_bytes(B, d->D, d->H, g_world, d->aug == ENO_AUG_FIN);
@@ -202,7 +202,7 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
                        const float* ts, int32_t T, const float* params, const float* eps, float rtol, float atol,
                        int32_t mxstep, void* workspace, size_t workspace_bytes, float* ys_out, float* aux_out,
                        eno_stats* stats_host, eno_trace_row* trace_out, int32_t trace_cap, void* stream_) {
-  if (ctx && desc && desc->arch == ENO_ARCH_CONCATSQUASH) {
+  if (ctx && desc && (desc->arch == ENO_ARCH_CONCATSQUASH || desc->arch == ENO_ARCH_CONCATCONV)) {
     if (tableau != ENO_TABLEAU_DOPRI5)
       return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd: the ConcatSquash dynamics run dopri5 only (the tableau sweep is defined on the MNIST dynamics)");
     return css::odeint_fwd(ctx, desc, B, y0, ts, T, params, eps, rtol, atol, mxstep, workspace, workspace_bytes, ys_out, aux_out,
@@ -400,7 +400,7 @@ int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32
                 size_t workspace_bytes, float* dy_out, float* aux_out, float* ybar_dot_out, float* tbar_out,
                 float* params_bar_out, float* eps_bar_dot_out, void* stream_) {
   if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_rhs: ctx is null");
-  if (desc && desc->arch == ENO_ARCH_CONCATSQUASH)
+  if (desc && (desc->arch == ENO_ARCH_CONCATSQUASH || desc->arch == ENO_ARCH_CONCATCONV))
     return css::rhs(ctx, desc, mode, B, y, t, params, eps, y_bar, r_bar, workspace, workspace_bytes, dy_out, aux_out, ybar_dot_out,
                     tbar_out, params_bar_out, eps_bar_dot_out, static_cast<cudaStream_t>(stream_));
   if (!desc_ok(desc)) return fail(ctx, ENO_E_UNSUPPORTED, "eno_rhs: unsupported dynamics desc");
@@ -427,7 +427,7 @@ int32_t eno_odeint_bwd_sepaux(eno_ctx* ctx, const eno_dynamics_desc* desc, int32
                               float* params_bar_out, eno_stats* stats_host, eno_trace_row* trace_out, int32_t trace_cap,
                               void* stream_) {
   if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_odeint_bwd: ctx is null");
-  if (desc && desc->arch == ENO_ARCH_CONCATSQUASH)
+  if (desc && (desc->arch == ENO_ARCH_CONCATSQUASH || desc->arch == ENO_ARCH_CONCATCONV))
     return css::odeint_bwd(ctx, desc, B, ys, ts, T, params, eps, g_y, g_aux, rtol, atol, mxstep, workspace, workspace_bytes,
                            y0_bar_out, aux0_bar_out, eps_bar_out, ts_bar_out, params_bar_out, stats_host, trace_out, trace_cap,
                            static_cast<cudaStream_t>(stream_));

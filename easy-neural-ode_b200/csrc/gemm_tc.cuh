@@ -158,10 +158,15 @@ struct GemmCfg {
 // finished, the launch exits at once (iterations enqueued past the end of an adaptive solve).
 // blockIdx.z is a K-split (a_zrows == 0: z takes k-blocks [z * kb_per_split, ...)) or a BATCH index (a_zrows != 0:
 // problem z reads operand rows a_row0 + z * a_zrows / b_row0 + z * b_zrows over the whole K; the functor gets z).
+// tap_kb != 0: 3x3 CONVOLUTION as a 9-tap K loop (ccv_kernels.cuh).  The A rows are the positions of a zero-padded
+// image grid with tap_w positions per grid row and tap_kb * 32 channels per position, so tap (dy, dx) of output row
+// m is input row m + dy * tap_w + dx: k-block i reads A at row shift(i / tap_kb), channel block i % tap_kb, and B (the
+// weights, [n][tap][channel]) at k-block i.  Rows shifted out of the tensor read as zero (TMA out-of-bounds fill).
 template <int BN, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int a_row0, int b_row0,
-              int kb_per_split, int kb_total, const int* __restrict__ done, Epi epi, int a_zrows = 0, int b_zrows = 0) {
+              int kb_per_split, int kb_total, const int* __restrict__ done, Epi epi, int a_zrows = 0, int b_zrows = 0,
+              int tap_kb = 0, int tap_w = 0) {
   if (done && *done) return;
 #ifdef ENO_PHASES
   __shared__ long long* stamp_s;
@@ -217,8 +222,14 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         uint8_t* st = smem + (size_t)s * Cfg::kStageBytes;
         mbar_expect_tx(&full[s], Cfg::kStageBytes);
         const int k = (kb0 + i) * kBK;
-        tma_load_3d(st, &tmA, &full[s], k, a_row0 + m0, 0);
-        tma_load_3d(st + Cfg::kABytes, &tmA, &full[s], k, a_row0 + m0, 1);
+        int ka = k, ra = a_row0 + m0;
+        if (tap_kb) {
+          const int tap = (kb0 + i) / tap_kb;
+          ka = ((kb0 + i) - tap * tap_kb) * kBK;
+          ra += (tap / 3 - 1) * tap_w + (tap % 3 - 1);
+        }
+        tma_load_3d(st, &tmA, &full[s], ka, ra, 0);
+        tma_load_3d(st + Cfg::kABytes, &tmA, &full[s], ka, ra, 1);
         tma_load_3d(st + 2 * Cfg::kABytes, &tmB, &full[s], k, b_row0 + n0, 0);
         tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full[s], k, b_row0 + n0, 1);
       }
@@ -394,6 +405,20 @@ inline cudaError_t launch_gemm_batched(const CUtensorMap& ta, const CUtensorMap&
   if (e != cudaSuccess) return e;
   dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM, batch);
   k_gemm_tf32x3<BN, Epi><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, st>>>(ta, tb, 0, 0, kb_total, kb_total, done, epi, a_zrows, b_zrows);
+  return cudaGetLastError();
+}
+
+// 3x3 convolution over a padded position grid (see k_gemm_tf32x3): M output positions starting at row a_row0 of the
+// activation planes, N output channels, `cin` input channels per position (a multiple of 32), weights [N][9 * cin].
+template <int BN, class Epi>
+inline cudaError_t launch_conv3x3(const CUtensorMap& ta, const CUtensorMap& tb, int a_row0, int M, int N, int cin, int grid_w,
+                                  const int* done, const Epi& epi, cudaStream_t st) {
+  const int tap_kb = cin / kBK;
+  const int kb_total = 9 * tap_kb;
+  cudaError_t e = cudaFuncSetAttribute(k_gemm_tf32x3<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<BN>::kSmem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM, 1);
+  k_gemm_tf32x3<BN, Epi><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, st>>>(ta, tb, a_row0, 0, kb_total, kb_total, done, epi, 0, 0, tap_kb, grid_w);
   return cudaGetLastError();
 }
 

@@ -197,6 +197,84 @@ class ConcatSquashDynamics:
         return out
 
 
+class ConcatConvDynamics:
+    """NN_Dynamics of ffjord_mnist.py:186-232: ConcatConv2D layers (123-135) 1 -> hidden -> hidden -> hidden -> 1 channels,
+    3x3, stride 1, zero padding 1, the time concatenated as input channel 0 of every layer, softplus between the layers,
+    on an ``image = (H, W)`` one-channel state (NHWC as in the script; any [B, H, W, 1] / [B, H*W] tensor).
+
+    FORWARD closures only - the evaluation / NFE path of the script: ``dynamics_wrap``, ``fwd``, ``ffjord_dynamics``
+    ((dy, -div), 291-299, the ``nfe_fn`` solve 362-385), ``aug_dynamics`` and ``all_aug_dynamics`` values (311-338, the
+    ``forward_all`` solve).  Differentiating through a solve of these closures raises: the adjoint of the convolutional
+    stack is not built.  Parameters: the Haiku dict {layer: {"w" [3, 3, c_in + 1, c_out], "b" [c_out]}} or one flat vector
+    in ravel order, per layer [b | w].
+    """
+
+    def __init__(self, image=(28, 28), hidden=64, reg="none", reg_type="our"):
+        if reg not in ["none"] + REGS:
+            raise ValueError(f"--reg must be one of {['none'] + REGS}")
+        if reg_type not in ("our", "fin"):
+            raise ValueError("--reg_type must be 'our' or 'fin' (ffjord_mnist.py:45)")
+        if hidden not in (32, 64):
+            raise ValueError("ConcatConvDynamics supports 32 or 64 hidden channels (the script uses 64)")
+        self.image, self.hidden, self.reg, self.reg_type = tuple(image), hidden, reg, reg_type
+        self.dim = image[0] * image[1]
+        if self.dim % 4:
+            raise ValueError("image height x width must be a multiple of 4")
+        self.reg_order = 0 if reg == "none" else 2
+        self.chans = [1, hidden, hidden, hidden, 1]
+        self.dynamics_wrap = EnoFunc(self, "plain", ("params",))
+        self.fwd = EnoFunc(self, "plain", ("eps", "params"))
+        self.ffjord_dynamics = EnoFunc(self, "ffjord", ("eps", "params"))
+        self.aug_dynamics = EnoFunc(self, "aug" if reg_type == "our" else "fin", ("eps", "params"))
+        self.all_aug_dynamics = EnoFunc(self, "all", ("eps", "params"))
+
+    AUG_OF_KIND = ConcatSquashDynamics.AUG_OF_KIND
+    eps_kinds = ConcatSquashDynamics.eps_kinds
+
+    def __repr__(self):
+        return f"ConcatConvDynamics(image={self.image}, hidden={self.hidden}, reg={self.reg!r}, reg_type={self.reg_type!r})"
+
+    @property
+    def layer_names(self):
+        return ["nn__dynamics/concat_conv2_d" + ("" if i == 0 else f"_{i}") + "/conv2_d" for i in range(4)]
+
+    @property
+    def n_params(self):
+        return sum(o + 9 * (i + 1) * o for i, o in zip(self.chans[:-1], self.chans[1:]))
+
+    def desc(self, aug=_cabi.AUG_NONE, eps_in_args=False, reg_order=None):
+        return _cabi.Desc(_cabi.ARCH_CONCATCONV, self.dim, self.hidden, self.reg_order if reg_order is None else reg_order,
+                          aug, int(eps_in_args), 3, self.image[0], self.image[1])
+
+    def init_params(self, seed=0, device="cpu", scale=1.0, last_scale=0.0):
+        """hk.Conv2D defaults (truncated normal, sigma = 1/sqrt(9 (c_in + 1)), zero biases); the script zero-initialises
+        the last layer's w (ffjord_mnist.py:214-215) - ``last_scale`` = 0 reproduces that."""
+        g = torch.Generator().manual_seed(seed)
+        params = {}
+        for i, (name, c_in, c_out) in enumerate(zip(self.layer_names, self.chans[:-1], self.chans[1:])):
+            w = torch.empty((3, 3, c_in + 1, c_out), dtype=torch.float64)
+            torch.nn.init.trunc_normal_(w, mean=0.0, std=1.0, a=-2.0, b=2.0, generator=g)
+            s = last_scale if i == 3 else scale
+            params[name] = {"b": torch.zeros(c_out, device=device),
+                            "w": (w * (s / math.sqrt(9 * (c_in + 1)))).float().to(device)}
+        return params
+
+    def flatten_params(self, params):
+        if isinstance(params, torch.Tensor):
+            if params.numel() != self.n_params:
+                raise ValueError(f"flat params must have {self.n_params} elements")
+            return params.reshape(-1)
+        return torch.cat([t.reshape(-1) for n in self.layer_names for t in (params[n]["b"], params[n]["w"])])
+
+    def unflatten_params(self, flat):
+        out, o = {}, 0
+        for n, c_in, c_out in zip(self.layer_names, self.chans[:-1], self.chans[1:]):
+            b = flat[o:o + c_out]; o += c_out
+            w = flat[o:o + 9 * (c_in + 1) * c_out].reshape(3, 3, c_in + 1, c_out); o += 9 * (c_in + 1) * c_out
+            out[n] = {"b": b, "w": w}
+        return out
+
+
 class GenDynamics:
     """GenDynamics of latent_ode.py:191-208: ``[tanh, Linear(units)] x (layers + 1)`` then ``[tanh, Linear(latent_dim)]``,
     time-independent.  ``reg`` is the script flag ``--reg`` (latent_ode.py:40): 'none', 'r2' or 'r3' (the order of the

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ENO_ABI_VERSION 5
+#define ENO_ABI_VERSION 6
 
 /* status codes */
 #define ENO_OK 0
@@ -65,6 +65,13 @@ extern "C" {
                                    then tanh and Linear(D); no time input; flat parameters per layer in Haiku ravel order
                                    [ b (out) | W (in x out) ]; served by the eno_traj_* entry points only */
 
+#define ENO_ARCH_CONCATCONV 3   /* NN_Dynamics of ConcatConv2D layers, softplus, ffjord_mnist.py:123-135, 186-232: four 3x3
+                                   convolutions (stride 1, zero padding 1) 1 -> H -> H -> H -> 1 channels on an img_h x img_w
+                                   image, time concatenated as input channel 0 of every layer; H = 32 or 64; flat parameters per
+                                   layer in Haiku ravel order [ b (c_out) | w (3 x 3 x (c_in + 1) x c_out) ]; state NHWC with one
+                                   channel, i.e. [B, img_h * img_w].  FORWARD closures only (eno_odeint_fwd with ENO_AUG_NONE /
+                                   FFJORD / REG / FIN / ALL values, eno_rhs modes 0 and 1): the adjoint is not built */
+
 /* element type of the eno_traj_* entry points */
 #define ENO_F32 0
 #define ENO_F64 1
@@ -94,7 +101,9 @@ typedef struct eno_dynamics_desc {
   int32_t eps_in_args; /* 1 when the reference call passes eps among *args (mnist.py:330-332):
                         its cotangent eps_bar (identically 0 for reg_type 'our') is then
                         part of the adjoint state and dilutes the error mean            */
-  int32_t n_hidden;  /* ENO_ARCH_CONCATSQUASH: hidden layers (--num_layers, ffjord_tabular.py:56); else ignored */
+  int32_t n_hidden;  /* ENO_ARCH_CONCATSQUASH: hidden layers (--num_layers, ffjord_tabular.py:56); ENO_ARCH_CONCATCONV: 3 */
+  int32_t img_h;     /* ENO_ARCH_CONCATCONV: image height and width (28 x 28, one channel: D = img_h * img_w); else ignored */
+  int32_t img_w;
 } eno_dynamics_desc;
 
 typedef struct eno_stats {
@@ -143,6 +152,8 @@ size_t eno_workspace_bytes(const eno_dynamics_desc* desc, int32_t B, int32_t T, 
  *   y0      [B, D]            ts  [T] strictly increasing (device)
  *   params  [P]               eps [B, D] or NULL (only ENO_AUG_ALL reads it)
  *   ys_out  [T, B, D]         aux_out [T, n_aux, B] or NULL (n_aux = 1 REG, 3 ALL)
+ *   ENO_ARCH_CONCATSQUASH / ENO_ARCH_CONCATCONV: aux_out[0] is READ as the initial auxiliary state (zeros after
+ *   aug_init; delta_logp of the logit pre-flow in ffjord_mnist.py:409-417) - its magnitude enters the error norm.
  *   mxstep <= 0 means unbounded (np.inf).
  *   trace_out: NULL or device array of trace_cap rows.
  */

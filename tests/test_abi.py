@@ -41,7 +41,7 @@ def test_constants_match_header_and_oracle_ids():
 
 
 def test_struct_layouts():
-    assert C.sizeof(_cabi.Desc) == 7 * 4
+    assert C.sizeof(_cabi.Desc) == 9 * 4
     assert C.sizeof(_cabi.Stats) == 8 * 4
     body = re.search(r"typedef struct eno_dynamics_desc \{(.*?)\} eno_dynamics_desc;", HEADER, re.S).group(1)
     assert len(re.findall(r"^\s*int32_t\s+\w+;", body, flags=re.M)) == len(_cabi.Desc._fields_)
