@@ -77,7 +77,7 @@ int aux_count(int aug) {
 }
 
 // ConcatConv2D dynamics (forward closures only): the flat driver's buffers + the padded-grid activations
-void plan_build_conv(const eno_dynamics_desc* d, int B, int T, void* ws, Plan* p) {
+void plan_build_conv(const eno_dynamics_desc* d, int B, int T, int mode, void* ws, Plan* p) {
   p->conv = true;
   ccv::CNet& c = p->cnet;
   css::Net& n = p->net;
@@ -95,8 +95,9 @@ void plan_build_conv(const eno_dynamics_desc* d, int B, int T, void* ws, Plan* p
     case ENO_AUG_FFJORD: case ENO_AUG_FIN: c.nq = 1; break;
     default: c.nq = d->reg_order ? 2 : 1;
   }
-  c.mode = d->aug == ENO_AUG_NONE ? css::MODE_PLAIN : css::MODE_AUG;
-  // what k_css_seed / k_css_assemble read in the forward modes
+  c.mode = mode ? css::MODE_ADJ : (d->aug == ENO_AUG_NONE ? css::MODE_PLAIN : css::MODE_AUG);
+  c.fin = (d->aug == ENO_AUG_FIN);
+  // what k_css_assemble / k_css_tbar read
   n.B = B; n.Bp = (B + 127) / 128 * 128; n.D = D; n.H = C; n.L = 1; n.nq = c.nq; n.mode = c.mode;
   n.fin = (d->aug == ENO_AUG_FIN); n.ldD = c.ldD;
   size_t po = 0;
@@ -110,9 +111,20 @@ void plan_build_conv(const eno_dynamics_desc* d, int B, int T, void* ws, Plan* p
   const int na = aux_count(d->aug);
   f.B = B; f.D = D; f.n_aux = na;
   f.oAUX = BD;
-  f.N = BD + (size_t)na * B;
-  f.n_feed = BD;
-  f.tsign = 1.f;
+  if (mode) {
+    f.oYB = BD + (size_t)na * B;
+    f.oAUXB = f.oYB + BD;
+    f.oT0 = f.oAUXB + (size_t)na * B;
+    f.oEB = f.oT0 + 1;
+    f.oPR = f.oEB + BD;
+    f.N = f.oPR + p->P;
+    f.n_feed = f.oAUXB;
+    f.tsign = -1.f;
+  } else {
+    f.N = BD + (size_t)na * B;
+    f.n_feed = BD;
+    f.tsign = 1.f;
+  }
   Carver cv{static_cast<char*>(ws)};
   f.ctrl = cv.take<Ctrl>(1);
   f.Y = cv.take<float>(3 * f.N);
@@ -141,16 +153,35 @@ void plan_build_conv(const eno_dynamics_desc* d, int B, int T, void* ws, Plan* p
   c.JE = n.JE = cv.take<float>((size_t)B * c.ldD);
   c.Y1 = n.Y1 = cv.take<float>((size_t)B * c.ldD);
   n.DIV = cv.take<float>(B); n.RR = cv.take<float>(B); n.FRO = cv.take<float>(B); n.KIN = cv.take<float>(B);
-  p->zero_from = cv.off;   // halo / padding rows of the activations must read as zero
+  if (mode) {
+    for (int l = 0; l < 3; ++l) {
+      c.A1[l] = cv.take<float>((size_t)2 * c.Rp * C);
+      c.WQ[l] = cv.take<float>((size_t)2 * c.Rp * C);
+    }
+    for (int l = 0; l < 2; ++l) c.W2F[l] = cv.take<float>((size_t)2 * C * 9 * C);
+    c.XB1 = cv.take<float>((size_t)2 * B * c.ldD);
+    c.EBD = cv.take<float>((size_t)B * c.ldD);
+    c.YBDOT = cv.take<float>((size_t)B * c.ldD);
+    c.wsplits = 32;
+    for (int l = 0; l < 2; ++l) c.WPART[l] = cv.take<float>((size_t)c.wsplits * 9 * C * C);
+    c.chunks = ccv::kRedChunks;
+    c.PART = cv.take<float>((size_t)ccv::kLayers * c.chunks * 27 * C);
+  }
+  p->zero_from = cv.off;   // halo / padding rows of the activations and of the cotangents must read as zero
   for (int l = 0; l < 2; ++l) c.X2[l] = cv.take<float>(2 * c.xplane());
   c.X3 = cv.take<float>((size_t)3 * c.Rp * C);
+  if (mode) {
+    for (int l = 0; l < 2; ++l) c.AB2[l] = cv.take<float>(2 * c.xplane());
+    c.AB0 = cv.take<float>((size_t)3 * c.Rp * C);
+    c.AB3 = cv.take<float>((size_t)3 * c.Rp);
+  }
   p->zero_bytes = cv.off - p->zero_from;
   p->bytes = cv.off + 1024;
 }
 
 // mode: 0 forward solve, 1 adjoint solve
 void plan_build(const eno_dynamics_desc* d, int B, int T, int mode, void* ws, Plan* p) {
-  if (d->arch == ENO_ARCH_CONCATCONV) { plan_build_conv(d, B, T, ws, p); return; }
+  if (d->arch == ENO_ARCH_CONCATCONV) { plan_build_conv(d, B, T, mode, ws, p); return; }
   css::Net& n = p->net;
   css::Flat& f = p->flat;
   memset(&n, 0, sizeof(n));
@@ -338,8 +369,40 @@ int ccv_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
     CSS_G(tc::launch_conv3x3<64>(ta[1], tb[1], c.Rp, c.nq * c.Rp, C, C, c.WP, done, ccv::EpiConvTangent{c, 2}, st));
     ccv::k_ccv_l3<<<l3grid(c.nq), 256, 0, st>>>(c, 1, c.nq, done);
   }
-  if (c.mode != css::MODE_PLAIN) css::k_css_seed<<<(B * 32 + 255) / 256, 256, 0, st>>>(f, p.net);
-  css::k_css_assemble<<<std::min((int)((pix + 255) / 256), 8 * sms), 256, 0, st>>>(f, p.net, stage, init_mode, k_override);
+  const css::Net& n = p.net;
+  if (c.mode != css::MODE_PLAIN) ccv::k_ccv_seed<<<(B * 32 + 255) / 256, 256, 0, st>>>(f, c, n.DIV, n.RR, n.FRO, n.KIN);
+  if (c.mode != css::MODE_ADJ) {
+    css::k_css_assemble<<<std::min((int)((pix + 255) / 256), 8 * sms), 256, 0, st>>>(f, n, stage, init_mode, k_override);
+    CSS_G(cudaGetLastError());
+    return 0;
+  }
+  // ---- reverse sweep: backward-data convolutions (taps mirrored), tangent streams first, then the primal stream
+  CUtensorMap tg[2], tw[2];
+  for (int l = 0; l < 2; ++l) {
+    if (!tc::make_operand_map(&tg[l], c.AB2[l], 3 * c.Rp, C, C, c.xplane(), tc::kBM, err) ||
+        !tc::make_operand_map(&tw[l], c.W2F[l], C, 9 * C, 9 * C, (size_t)C * 9 * C, 64, err))
+      return ENO_E_CUDA;
+  }
+  auto reverse = [&](int first, int count, int primal) -> int {
+    ccv::k_ccv_l3_bwd<<<l0grid(count), 256, 0, st>>>(c, first, count, done);
+    CSS_G(tc::launch_conv3x3<64>(tg[1], tw[1], first * c.Rp, primal ? c.R : count * c.Rp, C, C, c.WP, done,
+                                 ccv::EpiConvRev{c, 2, primal}, st));
+    CSS_G(tc::launch_conv3x3<64>(tg[0], tw[0], first * c.Rp, primal ? c.R : count * c.Rp, C, C, c.WP, done,
+                                 ccv::EpiConvRev{c, 1, primal}, st));
+    ccv::k_ccv_l0_bwd<<<l3grid(count), 256, 0, st>>>(c, first, count, done);
+    return 0;
+  };
+  int rc;
+  if (c.nq > 0 && (rc = reverse(1, c.nq, 0))) return rc;
+  ccv::k_ccv_seed2<<<std::min((int)((pix + 255) / 256), 4 * sms), 256, 0, st>>>(f, c);
+  if ((rc = reverse(0, 1, 1))) return rc;
+  // ---- weight gradients: the two C -> C layers (9 taps x position chunks, FFMA), everything else by chunked sums
+  for (int l = 0; l < 2; ++l) ccv::k_ccv_wgrad<<<dim3(9, c.wsplits), 256, 0, st>>>(c, l, done);
+  ccv::k_ccv_reduce<<<dim3(c.chunks, ccv::kLayers), 64, 0, st>>>(c, done);
+  ccv::k_ccv_reduce2<<<dim3(8, ccv::kLayers), 256, 0, st>>>(c, done);
+  const size_t work = std::max(pix, (size_t)9 * (C + 1) * C);
+  ccv::k_ccv_assemble_adj<<<std::min((int)((work + 255) / 256), 8 * sms), 256, 0, st>>>(f, c, n.DIV, n.RR, n.FRO, n.KIN, stage, init_mode,
+                                                                                        k_override);
   CSS_G(cudaGetLastError());
   return 0;
 }
@@ -596,8 +659,6 @@ int odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* 
                size_t ws_bytes, float* y0_bar_out, float* aux0_bar_out, float* eps_bar_out, float* ts_bar_out,
                float* params_bar_out, eno_stats* stats, eno_trace_row* trace, int trace_cap, cudaStream_t st) {
   if (!desc_ok(desc)) return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: unsupported ConcatSquash descriptor");
-  if (desc->arch == ENO_ARCH_CONCATCONV)
-    return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: the adjoint of the ConcatConv2D dynamics is not built (forward closures only)");
   const int na = aux_count(desc->aug);
   if (desc->aug != ENO_AUG_REG && desc->aug != ENO_AUG_FIN)
     return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: the FFJORD adjoint integrates aug_dynamics ('our' or 'fin')");
@@ -658,8 +719,6 @@ int rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int mode, int B, const floa
   if (mode > 0 && (!eps || !aux_out)) return css_fail(ctx, ENO_E_ARG, "eno_rhs: augmented modes need eps and aux_out");
   if (mode == 2 && (!y_bar || !aux_bar || !ybar_dot_out || !tbar_out || !params_bar_out))
     return css_fail(ctx, ENO_E_ARG, "eno_rhs: mode 2 needs y_bar, aux_bar and all outputs");
-  if (mode == 2 && desc->arch == ENO_ARCH_CONCATCONV)
-    return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_rhs: the vjp of the ConcatConv2D dynamics is not built (forward closures only)");
   Plan p;
   plan_build(&d, B, 2, mode == 2 ? 1 : 0, ws, &p);
   if (ws_bytes < p.bytes) return css_fail(ctx, ENO_E_WORKSPACE, "eno_rhs: workspace too small");

@@ -162,6 +162,9 @@ struct GemmCfg {
 // image grid with tap_w positions per grid row and tap_kb * 32 channels per position, so tap (dy, dx) of output row
 // m is input row m + dy * tap_w + dx: k-block i reads A at row shift(i / tap_kb), channel block i % tap_kb, and B (the
 // weights, [n][tap][channel]) at k-block i.  Rows shifted out of the tensor read as zero (TMA out-of-bounds fill).
+// (Only ROW coordinates are shifted: a shift along the contiguous dimension of a box is not a multiple of 16 bytes,
+// which TMA rejects - so the weight gradient of the convolution, whose contraction runs over the positions, cannot use
+// transposed planes this way; ccv_kernels.cuh: k_ccv_wgrad.)
 template <int BN, class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int a_row0, int b_row0,
@@ -228,10 +231,11 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           ka = ((kb0 + i) - tap * tap_kb) * kBK;
           ra += (tap / 3 - 1) * tap_w + (tap % 3 - 1);
         }
+        const int rb = b_row0 + n0;
         tma_load_3d(st, &tmA, &full[s], ka, ra, 0);
         tma_load_3d(st + Cfg::kABytes, &tmA, &full[s], ka, ra, 1);
-        tma_load_3d(st + 2 * Cfg::kABytes, &tmB, &full[s], k, b_row0 + n0, 0);
-        tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full[s], k, b_row0 + n0, 1);
+        tma_load_3d(st + 2 * Cfg::kABytes, &tmB, &full[s], k, rb, 0);
+        tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes, &tmB, &full[s], k, rb, 1);
       }
     }
     __syncwarp();

@@ -202,10 +202,10 @@ class ConcatConvDynamics:
     3x3, stride 1, zero padding 1, the time concatenated as input channel 0 of every layer, softplus between the layers,
     on an ``image = (H, W)`` one-channel state (NHWC as in the script; any [B, H, W, 1] / [B, H*W] tensor).
 
-    FORWARD closures only - the evaluation / NFE path of the script: ``dynamics_wrap``, ``fwd``, ``ffjord_dynamics``
-    ((dy, -div), 291-299, the ``nfe_fn`` solve 362-385), ``aug_dynamics`` and ``all_aug_dynamics`` values (311-338, the
-    ``forward_all`` solve).  Differentiating through a solve of these closures raises: the adjoint of the convolutional
-    stack is not built.  Parameters: the Haiku dict {layer: {"w" [3, 3, c_in + 1, c_out], "b" [c_out]}} or one flat vector
+    Closures, named as in init_model (268-338): ``dynamics_wrap``, ``fwd``, ``ffjord_dynamics`` ((dy, -div), 291-299, the
+    ``nfe_fn`` solve 362-385), ``aug_dynamics`` ((dy, -div, r) or, reg_type 'fin', (dy, -div, dfro, dkin), 311-324: the
+    rev_func of odeint_sepaux / odeint_fin_sepaux) and ``all_aug_dynamics`` (326-338, the ``forward_all`` solve).
+    Parameters: the Haiku dict {layer: {"w" [3, 3, c_in + 1, c_out], "b" [c_out]}} or one flat vector
     in ravel order, per layer [b | w].
     """
 
@@ -217,6 +217,7 @@ class ConcatConvDynamics:
         if hidden not in (32, 64):
             raise ValueError("ConcatConvDynamics supports 32 or 64 hidden channels (the script uses 64)")
         self.image, self.hidden, self.reg, self.reg_type = tuple(image), hidden, reg, reg_type
+        self.num_layers = 3          # hidden ConcatConv2D layers (marks the FFJORD closure family for the split solves)
         self.dim = image[0] * image[1]
         if self.dim % 4:
             raise ValueError("image height x width must be a multiple of 4")

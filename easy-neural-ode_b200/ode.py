@@ -23,7 +23,7 @@ import torch
 
 from . import _cabi
 from . import latent as _latent
-from .dynamics import ConcatConvDynamics, EnoFunc, GenDynamics
+from .dynamics import EnoFunc, GenDynamics
 
 last_stats = {"fwd": None, "bwd": None}   # controller statistics of the most recent solves
 _workspaces = {}
@@ -416,12 +416,6 @@ def _split_args(func, args):
     return named.get("eps"), named["params"]
 
 
-def _no_conv_adjoint(func, where):
-    if isinstance(getattr(func, "spec", None), ConcatConvDynamics):
-        raise NotImplementedError(f"{where}: the adjoint of the ConcatConv2D dynamics is not built - ConcatConvDynamics serves the "
-                                  "forward closures (odeint on dynamics_wrap / ffjord_dynamics / aug_dynamics / all_aug_dynamics)")
-
-
 def _require_spec(func, what):
     if not isinstance(func, EnoFunc):
         raise TypeError(f"{what}: func must be a dynamics-spec closure (e.g. MLPDynamics(...).dynamics_wrap); "
@@ -505,7 +499,6 @@ def odeint_aux_one(fwd_func, rev_func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, m
     returns zeros for the auxiliary state; backward runs the adjoint with ``rev_func`` on the
     augmented state.  -> ((ys [T,B,D], rs [T,B,1]), nfe)."""
     _require_spec(fwd_func, "odeint_aux_one")
-    _no_conv_adjoint(fwd_func, "odeint_aux_one")
     _require_spec(rev_func, "odeint_aux_one")
     if fwd_func.kind != "plain" or rev_func.kind != "aug" or fwd_func.spec is not rev_func.spec:
         raise TypeError("odeint_aux_one expects (spec.fwd, spec.aug_dynamics) of the same dynamics spec")
@@ -530,7 +523,6 @@ def odeint_sepaux(fwd_func, rev_func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mx
     runs the adjoint with ``rev_func`` = aug_dynamics('fin') on (y, fro, kin).
     -> ((ys [T,B,D], fro [T,B,1], kin [T,B,1]), nfe)."""
     _require_spec(fwd_func, "odeint_sepaux")
-    _no_conv_adjoint(fwd_func, "odeint_sepaux")
     _require_spec(rev_func, "odeint_sepaux")
     if getattr(fwd_func.spec, "num_layers", None) is not None:
         # FFJORD closures (ffjord_tabular.py:299-304): rev_func = aug_dynamics 'our' on (y, delta_logp, r)
@@ -566,7 +558,6 @@ def odeint_fin_sepaux(fwd_func, rev_func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8
     backward runs the adjoint with ``rev_func`` = aug_dynamics('fin') = (dy, -div, mean (J eps)^2, mean f^2).
     -> ((ys [T,B,D], delta_logp [T,B,1], fro [T,B,1], kin [T,B,1]), nfe)."""
     _require_spec(fwd_func, "odeint_fin_sepaux")
-    _no_conv_adjoint(fwd_func, "odeint_fin_sepaux")
     _require_spec(rev_func, "odeint_fin_sepaux")
     if (getattr(fwd_func.spec, "num_layers", None) is None or fwd_func.kind != "plain" or rev_func.kind != "fin"
             or fwd_func.spec is not rev_func.spec):

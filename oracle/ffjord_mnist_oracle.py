@@ -61,7 +61,7 @@ def conv_dynamics(params, x, t, image=(28, 28, 1)):
     for i, n in enumerate(names):
         p = params[n]
         ttx = torch.cat([torch.ones_like(dx[..., :1]) * t, dx], dim=-1)          # time is input channel 0
-        y = F.conv2d(ttx.permute(0, 3, 1, 2), p["w"].permute(3, 2, 0, 1), bias=p["b"], stride=1, padding=1)
+        y = F.conv2d(ttx.permute(0, 3, 1, 2).contiguous(), p["w"].permute(3, 2, 0, 1).contiguous(), bias=p["b"], stride=1, padding=1)
         dx = y.permute(0, 2, 3, 1)
         if i < len(names) - 1:
             dx = softplus(dx)
@@ -78,7 +78,7 @@ def conv_taylor_closed(params, x, t, image=(28, 28, 1)):
     t = torch.as_tensor(t, dtype=z.dtype)
     for i, n in enumerate(names):
         p = params[n]
-        w = p["w"].permute(3, 2, 0, 1)
+        w = p["w"].permute(3, 2, 0, 1).contiguous()
         ttx = torch.cat([torch.ones_like(z[..., :1]) * t, z], dim=-1).permute(0, 3, 1, 2)
         tt1 = torch.cat([torch.ones_like(z[..., :1]), z1], dim=-1).permute(0, 3, 1, 2)
         u = F.conv2d(ttx, w, bias=p["b"], padding=1).permute(0, 2, 3, 1)

@@ -162,11 +162,102 @@ def test_pre_flow_and_bits_per_dim(cuda):
     _close(out["kin"], kin[-1], tol, "kin")
 
 
-def test_adjoint_is_not_built(cuda):
+@pytest.mark.parametrize("reg_type,reg", [("our", "r2"), ("our", "none"), ("fin", "none")])
+@pytest.mark.parametrize("shape", [(3, (6, 6), 32), (2, (28, 28), 64)])
+def test_adjoint_rhs_matches_torch_func_vjp(cuda, shape, reg_type, reg):
+    """The adjoint's integrand (lib/ode.py:1498-1504): the pull-back of (y_bar, aux_bar) through aug_dynamics at (y, t)
+    wrt y, t, eps and every parameter, against torch.func.vjp of the oracle closure in float64."""
     import easy_neural_ode_b200 as eno
-    spec = eno.ConcatConvDynamics((6, 6), 32, reg="r2")
-    p = spec.flatten_params(spec.init_params(seed=0, device=cuda, last_scale=1.0))
-    x = torch.rand(2, 6, 6, 1, device=cuda)
-    z = torch.zeros(2, 1, device=cuda)
-    with pytest.raises(NotImplementedError):
-        eno.odeint_sepaux(spec.fwd, spec.aug_dynamics, (x, z, z), torch.tensor([0., 1.]), x, p)
+    from oracle import ffjord_mnist_oracle as fm
+    B, image, hidden = shape
+    p, x, eps = _case(B, image, hidden, seed=7)
+    img = image + (1,)
+    spec = eno.ConcatConvDynamics(image, hidden, reg=reg, reg_type=reg_type)
+    cl = fm.make_ffjord_mnist_closures(reg, reg_type, img)
+    n_aux = 2 if reg_type == "our" else 3
+    g = torch.Generator().manual_seed(31)
+    y_bar = torch.randn((B,) + img, generator=g)
+    aux_bar = torch.randn((n_aux, B), generator=g)
+    t = 0.41
+    p64 = {k: {kk: vv.double() for kk, vv in v.items()} for k, v in p.items()}
+    z = torch.zeros(B, 1, dtype=torch.float64)
+
+    def f(y, tt, e, pp):
+        out = cl["aug_dynamics"]((y, z) + (z,) * (n_aux - 1), tt, e, pp)
+        return (out[0],) + tuple(o.reshape(-1) for o in out[1:])
+
+    outs, vjp = torch.func.vjp(f, x.double(), torch.tensor(t, dtype=torch.float64), eps.double(), p64)
+    cot = (y_bar.double(),) + tuple(aux_bar[q].double() for q in range(n_aux))
+    wy, wt, we, wp = vjp(cot)
+    dy, aux, zb, tbar, pbar, eb = eno.rhs_closure(spec.aug_dynamics, 2, x.to(cuda), t, eps.to(cuda), _to(p, cuda), y_bar=y_bar.to(cuda),
+                                                  aux_bar=aux_bar.to(cuda))
+    assert rel_err(dy.reshape(-1), outs[0].reshape(-1)) < 1e-5
+    for q in range(n_aux):
+        assert rel_err(aux[q], outs[1 + q]) < 2e-5, ("aux", q)
+    assert rel_err(zb.reshape(-1), wy.reshape(-1)) < 2e-5
+    assert rel_err(eb.reshape(-1), we.reshape(-1)) < 2e-5
+    assert abs(float(tbar) - float(wt)) <= 2e-5 * max(1.0, abs(float(wt)))
+    want_p = spec.flatten_params(wp)
+    assert rel_err(pbar, want_p) < 2e-5
+    for name, lo, hi in _param_blocks(spec):        # every block on its own scale (the last layer's are much larger)
+        assert rel_err(pbar[lo:hi], want_p[lo:hi]) < 5e-5, name
+
+
+def _param_blocks(spec):
+    o = 0
+    for n, c_in, c_out in zip(spec.layer_names, spec.chans[:-1], spec.chans[1:]):
+        yield n + "/b", o, o + c_out
+        o += c_out
+        yield n + "/w", o, o + 9 * (c_in + 1) * c_out
+        o += 9 * (c_in + 1) * c_out
+
+
+@pytest.mark.parametrize("reg_type", ["our", "fin"])
+def test_split_solve_and_adjoint_vs_oracle(cuda, reg_type):
+    """The training call of ffjord_mnist.py (340-347: odeint_sepaux / odeint_fin_sepaux with the conv closures) on 12 x 12
+    images, 32 channels: forward NFE and adjoint iteration count in the band of the fp32 / exact-arithmetic oracles
+    (tests/util.py), gradients wrt the image, eps and every parameter against the oracle whose step counts it shares."""
+    import easy_neural_ode_b200 as eno
+    from oracle import ffjord_mnist_oracle as fm, ode_oracle as oo
+    B, image, hidden, tol = 3, (12, 12), 32, 1e-6
+    img = image + (1,)
+    p, x, eps = _case(B, image, hidden, seed=11, scale=1.3)
+    reg = "r2" if reg_type == "our" else "none"
+    spec = eno.ConcatConvDynamics(image, hidden, reg=reg, reg_type=reg_type)
+    n_aux = 2 if reg_type == "our" else 3
+    cl = fm.make_ffjord_mnist_closures(reg, reg_type, img)
+    ts = torch.tensor([0., 1.])
+    z = torch.zeros(B, 1)
+    gy = torch.randn((B,) + img, generator=torch.Generator().manual_seed(4))
+    w = [1.0 / B, 0.01 / B, 0.02 / B][:n_aux]
+
+    def oracle_run(fwd, rev):
+        res, nfe_w = oo.odeint_split_fwd(fwd, (x,) + (z,) * n_aux, ts, eps, p, n_aux=n_aux, rtol=tol, atol=tol)
+        gg = tuple(torch.zeros_like(r) for r in res)
+        gg[0][-1] = gy
+        for q in range(n_aux):
+            gg[1 + q][-1] = w[q]
+        bst = []
+        want = oo.odeint_split_rev(rev, tol, tol, math.inf, res, ts, (eps, p), gg, bst)
+        return res, float(nfe_w), bst[0]["n_iters"], want
+
+    res, nfe_w, bwd_w, want = oracle_run(cl["fwd"], cl["aug_dynamics"])
+    resx, nfe_x, bwd_x, wantx = oracle_run(exact_arith(cl["fwd"]), exact_arith(cl["aug_dynamics"]))
+    xg = x.to(cuda).requires_grad_(True)
+    eg = eps.to(cuda).requires_grad_(True)
+    pflat = spec.flatten_params(_to(p, cuda)).clone().requires_grad_(True)
+    zc = z.to(cuda)
+    fn = eno.odeint_sepaux if reg_type == "our" else eno.odeint_fin_sepaux
+    outs, nfe = fn(spec.fwd, spec.aug_dynamics, (xg,) + (zc,) * n_aux, ts, eg, pflat, rtol=tol, atol=tol)
+    loss = (outs[0][-1].reshape(gy.shape) * gy.to(cuda)).sum() + sum(w[q] * outs[1 + q][-1].sum() for q in range(n_aux))
+    loss.backward()
+    got_bwd = eno.last_stats["bwd"][0]["n_iters"]
+    print(f"C4 split solve {reg_type}: nfe cuda {float(nfe):.0f} / fp32 oracle {nfe_w:.0f} / exact {nfe_x:.0f}; adjoint iterations "
+          f"cuda {got_bwd} / {bwd_w} / {bwd_x}")
+    assert_count(float(nfe), nfe_w, nfe_x, "nfe")
+    assert_count(got_bwd, bwd_w, bwd_x, "adjoint iterations")
+    ref_res, ref = (res, want) if (float(nfe), got_bwd) == (nfe_w, bwd_w) else (resx, wantx)
+    assert rel_err(outs[0][-1].reshape(-1), ref_res[0][-1].reshape(-1)) < 1e-5
+    assert rel_err(xg.grad.reshape(-1), ref[0][0].reshape(-1)) < 3e-5
+    assert rel_err(eg.grad.reshape(-1), ref[2].reshape(-1)) < 3e-5
+    assert rel_err(pflat.grad, spec.flatten_params(ref[3])) < 3e-5
