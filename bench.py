@@ -324,6 +324,158 @@ def fj_main(args, result_out, rank, local_rank, world):
     print(json.dumps(line), file=result_out, flush=True)
 
 
+# ---- BASELINE configs[3]: ffjord_mnist.py, 28x28 images, ConcatConv2D dynamics, --reg r2 --lam 3e-4, batch 200 -----------
+FM = dict(B=200, IMG=(28, 28), C=64, LAM=3e-4, TOL=1e-5)
+FM_WORKLOAD = ("ffjord_mnist.py FFJORD on synthetic 28x28 images, ConcatConv2D 1-64-64-64-1 (3x3) softplus, logit pre-flow, dopri5, "
+               "--reg r2 --lam 3e-4, Hutchinson trace (Rademacher probe), rtol = atol = 1e-5 (script default), batch 200 (configs[3])")
+
+
+def fm_batch(rank, step, pin=False, batch=None):
+    import torch
+    b = batch or FM["B"]
+    g = torch.Generator().manual_seed(8765 + 97 * rank + (step % 8))
+    images = torch.rand((b,) + FM["IMG"] + (1,), generator=g)
+    eps = torch.randint(0, 2, (b,) + FM["IMG"] + (1,), generator=g).float() * 2 - 1
+    if pin:
+        images, eps = images.pin_memory(), eps.pin_memory()
+    return images, eps
+
+
+def fm_config(world):
+    return {"workload": FM_WORKLOAD, "global_batch": FM["B"] * world, "per_gpu_batch": FM["B"], "rtol": FM["TOL"], "atol": FM["TOL"],
+            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (development)",
+            "l2": "flushed between steps (256 MiB device write, outside the per-step events)",
+            "trajectory": "train steps 0..K-1 from the script's initial parameters (last layer zero-initialised, seeded), identical "
+                          "in every leg and arm"}
+
+
+def fm_cpu_steps(n_steps, threads, batch, budget_s=None):
+    """Oracle port of one update() of ffjord_mnist.py (570-583) on host cores, on a shard of `batch` images of the
+    same synthetic batches -> (seconds per step, info).  Adam on the host as in ffjord_oracle."""
+    import torch
+    from oracle import ffjord_mnist_oracle as fm, ffjord_oracle as fo
+    torch.set_num_threads(threads)
+    params = fm.init_conv_params(hidden=FM["C"], seed=0)
+    m, v = fo.adam_init(params)
+    times, info = [], {}
+    for s in range(n_steps):
+        if budget_s is not None and times and sum(times) > budget_s:
+            break
+        images, eps = fm_batch(0, s, batch=batch)
+        t0 = time.perf_counter()
+        out = fm.train_step_grads(params, images, eps, lam=FM["LAM"], reg="r2", rtol=FM["TOL"], atol=FM["TOL"])
+        params, m, v = fo.adam_update(params, m, v, out["grads"], s, 1e-3 * min((s + 1.0) / 1e3, 1.0))
+        times.append(time.perf_counter() - t0)
+        info = dict(nfe=float(out["nfe"]), bwd_iters=out["bwd_stats"][0]["n_iters"], steps_timed=len(times), loss=float(out["loss"]))
+    return sum(times) / len(times), info
+
+
+def fm_reference(args):
+    threads = len(os.sched_getaffinity(0))
+    shard = 8
+    sec, info = fm_cpu_steps(max(1, min(args.steps, 6)), threads, shard, budget_s=120.0)
+    val = (shard / FM["B"]) / sec          # batch-200 train steps per second, extrapolated from the shard
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": fm_config(1), "samples_per_s": shard / sec,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"train steps 0..{info['steps_timed'] - 1} on a shard of {shard} of the 200 images (the cost of a "
+                                       f"step is linear in the batch), scaled to 200; oracle port, torch CPU fp32, {threads} threads; "
+                                       f"last step nfe {info['nfe']}, adjoint iterations {info['bwd_iters']}"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "nfe_per_s": info["nfe"] * val}
+    print(json.dumps(line), flush=True)
+
+
+def fm_main(args, result_out, rank, local_rank, world):
+    """`--workload ffjord_mnist`: one update() of ffjord_mnist.py per step (logit pre-flow, forward solve of y, bits/dim head,
+    adjoint solve of aug_dynamics with the Hutchinson term and the K = 2 Taylor regulariser, clip + Adam)."""
+    import torch
+    from easy_neural_ode_b200 import ffjord_mnist_step
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    model = ffjord_mnist_step.ImageFfjord(FM["IMG"], FM["C"], reg="r2", lam=FM["LAM"], rtol=FM["TOL"], atol=FM["TOL"], device=dev, seed=0)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    dev_b = [tuple(t.to(dev) for t in fm_batch(rank, s)) for s in range(8)]
+    host_b = [fm_batch(rank, s, pin=True) for s in range(8)]
+    snap = model.snapshot()
+    for s in range(max(args.warmup, 3)):
+        out = model.update(*dev_b[s % 8])
+    torch.cuda.synchronize()
+    model.restore(snap)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    nfe_total, iters, n_rhs = 0.0, [], 0
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)
+        evs[s][0].record()
+        out = model.update(*dev_b[s % 8])
+        evs[s][1].record()
+        nfe_total += float(out["nfe"])
+        iters.append((out["fwd_stats"]["n_iters"], out["bwd_stats"][0]["n_iters"]))
+        n_rhs += 2 + 6 * out["fwd_stats"]["n_iters"] + 3 + 6 * out["bwd_stats"][0]["n_iters"]
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    ms_per_step = dev_ms / args.steps
+    loss_dev = float(out["loss"])
+    model.restore(snap)
+
+    def step_e2e(s):
+        images, eps = host_b[s % 8]
+        o = model.update(images.to(dev, non_blocking=True), eps.to(dev, non_blocking=True))
+        return float(o["loss"])
+    for s in range(2):
+        step_e2e(s)
+    model.restore(snap)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_e2e(s)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = float(peaks.get("bf16_tflops", 1590.0))
+    # algorithmic flops of the two 64 -> 64 layers per step: forward RHS 1 stream, adjoint RHS 3 streams forward + 3 reverse +
+    # weight gradients (3 streams), 2 * 784 * 64 * 576 MACs per image, stream and layer
+    per = 2.0 * 2 * FM["B"] * 784 * 64 * 576
+    fwd_rhs = sum(2 + 6 * f for f, _ in iters)
+    bwd_rhs = sum(3 + 6 * b for _, b in iters)
+    flop = per * (fwd_rhs + 9 * bwd_rhs)
+    achieved = flop / (dev_ms * 1e-3) / 1e12
+    roofline = {"kernel": "whole step against the conv contractions of the two 64 -> 64 layers (k_gemm_tf32x3 9-tap convolutions: forward "
+                          "and backward data on tcgen05 3xTF32; weight gradients k_ccv_wgrad on FFMA)",
+                "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback 1.59 PFLOP/s",
+                "note": "algorithmic conv flops of the step divided by the WHOLE step time (no per-kernel events on this path yet): a lower "
+                        "bound on the kernels' own rate", "frac_of_3xtf32_ceiling": achieved / (tensor_peak / 6.0)}
+    line = {"metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (tcgen05 3xTF32 convolutions, fp32 accumulate)", "data": "synthetic",
+            "config": fm_config(world), "samples_per_s": FM["B"] * 1e3 / ms_per_step, "clocks": clocks,
+            "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host_b[0]),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": 20 * n_rhs, "nfe_per_s": nfe_total / (dev_ms * 1e-3),
+            "solver": {"iters_fwd_bwd_per_step": iters, "loss_last": loss_dev},
+            "launch_mode": "polled solves; one loop iteration (6 right-hand sides + controller) replayed as a CUDA graph",
+            "roofline": roofline}
+    if not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        shard = 8
+        sec, info = fm_cpu_steps(min(args.steps, 3), threads, shard, budget_s=40.0)
+        line["cpu_baseline"] = {"value": (shard / FM["B"]) / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"train steps 0..{info['steps_timed'] - 1} on a shard of {shard} of the 200 images, scaled to 200; "
+                                          f"oracle port, torch CPU fp32, {threads} threads; last step nfe {info['nfe']}, adjoint iterations "
+                                          f"{info['bwd_iters']}, loss {info['loss']:.6f}"}
+    print(json.dumps(line), file=result_out, flush=True)
+
+
 # ---- BASELINE configs[2]: latent_ode.py generative ODE, per-trajectory solves (development workload, single GPU) --------
 LT = dict(S=3, B=50, D=20, U=50, LAYERS=3, T=49, DATA=37, LAM=1e-2, TOL=1.4e-8)
 LT_WORKLOAD = ("latent_ode.py generative ODE, synthetic Physionet-shaped series (37 features, 49 time points on [0, 1]), "
@@ -532,9 +684,10 @@ def main():
     ap.add_argument("--reg-type", default="our", choices=["our", "fin"],
                     help="development only: 'fin' times the --reg_type fin arm (odeint_sepaux, lam_fro = lam_kin = 1e-2); "
                          "the headline metric is the default 'our' (--reg r3)")
-    ap.add_argument("--workload", default="mnist", choices=["mnist", "ffjord_tabular", "latent_ode"],
+    ap.add_argument("--workload", default="mnist", choices=["mnist", "ffjord_tabular", "latent_ode", "ffjord_mnist"],
                     help="mnist = BASELINE configs[0], the configuration the metric is quoted on (default); "
-                         "ffjord_tabular = configs[1] (single GPU); latent_ode = configs[2] (single GPU)")
+                         "ffjord_tabular = configs[1] (single GPU); latent_ode = configs[2] (single GPU); ffjord_mnist = configs[3] "
+                         "(single GPU)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -544,6 +697,8 @@ def main():
             return fj_reference(args) if rank == 0 else None
         if args.workload == "latent_ode":
             return lt_reference(args) if rank == 0 else None
+        if args.workload == "ffjord_mnist":
+            return fm_reference(args) if rank == 0 else None
         return run_reference(args, rank, world)
     # stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr, so
     # that banners printed by native libraries (NCCL prints its version on communicator creation) cannot
@@ -565,6 +720,10 @@ def main():
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
         return lt_main(args, result_out, local_rank) if rank == 0 else None
+    if args.workload == "ffjord_mnist":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+        return fm_main(args, result_out, rank, local_rank, world) if rank == 0 else None
     B = args.batch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")

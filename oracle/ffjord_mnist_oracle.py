@@ -155,3 +155,26 @@ def bits_per_dim(z, delta_logp):
     logpx = logpz - delta_logp
     logpx_per_dim = torch.sum(logpx) / z.numel()
     return -(logpx_per_dim - math.log(256)) / math.log(2)
+
+
+# ---- one update() of ffjord_mnist.py (the CPU arm of bench.py --workload ffjord_mnist) ---------------------------------
+def train_step_grads(params, images, eps, lam=3e-4, lam_w=0.0, reg="r2", rtol=1.4e-8, atol=1.4e-8, image=(28, 28, 1)):
+    """jax.grad(loss_fn) of ffjord_mnist.py:480-497, 544 for reg_type 'our': forward_aux = pre-flow + odeint_sepaux (forward
+    solves y only; delta_logp and r come back as zeros, lib/ode.py:1006-1018), loss = bits/dim + lam mean(r) + lam_w 0.5
+    |theta|^2; the backward is the adjoint of aug_dynamics (lib/ode.py:1686-1693)."""
+    from . import ode_oracle as oo
+    cl = make_ffjord_mnist_closures(reg, "our", image)
+    B = images.shape[0]
+    ts = torch.tensor([0., 1.], dtype=images.dtype)
+    z0 = torch.zeros(B, 1, dtype=images.dtype)
+    y, logpy = forward_pre_ode(images.reshape(-1, *image), z0)
+    res, nfe, fst = oo.odeint_split_fwd(cl["fwd"], (y, logpy, z0), ts, eps, params, n_aux=2, rtol=rtol, atol=atol, return_stats=True)
+    z = res[0][-1]
+    loss = bits_per_dim(z, res[1][-1])
+    gg = tuple(torch.zeros_like(r) for r in res)
+    nd = z.numel() * math.log(2)
+    gg[0][-1], gg[1][-1], gg[2][-1] = z / nd, 1.0 / nd, lam / B
+    bst = []
+    out = oo.odeint_split_rev(cl["aug_dynamics"], rtol, atol, math.inf, res, ts, (eps, params), gg, bst)
+    grads = {n: {k: out[3][n][k] + lam_w * params[n][k] for k in params[n]} for n in params}
+    return dict(loss=loss, nfe=nfe, grads=grads, fwd_stats=fst, bwd_stats=bst, z=z)

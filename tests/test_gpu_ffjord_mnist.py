@@ -261,3 +261,22 @@ def test_split_solve_and_adjoint_vs_oracle(cuda, reg_type):
     assert rel_err(xg.grad.reshape(-1), ref[0][0].reshape(-1)) < 3e-5
     assert rel_err(eg.grad.reshape(-1), ref[2].reshape(-1)) < 3e-5
     assert rel_err(pflat.grad, spec.flatten_params(ref[3])) < 3e-5
+
+
+def test_train_step_gradients_vs_oracle(cuda):
+    """One update() of ffjord_mnist.py (pre-flow, split solve, bits/dim + lam mean(r), adjoint) on 12 x 12 images against
+    the oracle's jax.grad restatement: step counts in the noise band, parameter gradients 3e-5."""
+    from easy_neural_ode_b200 import ffjord_mnist_step as fs
+    from oracle import ffjord_mnist_oracle as fm
+    B, image, hidden, tol, lam = 3, (12, 12), 32, 1e-6, 3e-4
+    p, _, eps = _case(B, image, hidden, seed=13, scale=1.3)
+    images = torch.rand((B,) + image + (1,), generator=torch.Generator().manual_seed(3))
+    model = fs.ImageFfjord(image, hidden, reg="r2", rtol=tol, atol=tol, device=cuda, lam=lam)
+    model.params = model.spec.flatten_params(_to(p, cuda)).clone()
+    out = model.loss_and_grads(images.to(cuda), eps.to(cuda))
+    want = fm.train_step_grads(p, images, eps, lam=lam, reg="r2", rtol=tol, atol=tol, image=image + (1,))
+    assert float(out["nfe"]) == float(want["nfe"])
+    assert out["bwd_stats"][0]["n_iters"] == want["bwd_stats"][0]["n_iters"]
+    assert rel_err(out["z"].reshape(-1), want["z"].reshape(-1)) < 1e-5
+    assert abs(float(out["loss"]) - float(want["loss"])) < 1e-5 * abs(float(want["loss"]))
+    assert rel_err(out["grads"], model.spec.flatten_params(want["grads"])) < 3e-5
