@@ -59,7 +59,7 @@ struct CNet {
   __host__ __device__ size_t xplane() const { return (size_t)3 * Rp * C; }
 };
 
-constexpr int kRedChunks = 128;
+constexpr int kRedChunks = 592;   // 4 per SM; every block is 4 pixel groups x 64 channels
 
 // border class of image pixel (y, x): 3 * {0 top, 1 inside, 2 bottom} + {0 left, 1 inside, 2 right}
 __device__ __forceinline__ int border_class(int y, int x, int Hh, int Ww) {
@@ -505,18 +505,19 @@ __global__ void __launch_bounds__(256) k_ccv_wgrad(CNet n, int l, const int* __r
 //   [0, 9)   class sums of the primal cotangent ab_x          -> bias, time weights (x t), t_bar
 //   [9, 18)  class sums of the Taylor stream's cotangent ab_d -> time weights
 //   [18, 27) layer 0: dW0[tap][c_out] = sum x_s[p + shift] ab_s[p][c_out];  layer 3: dW3[tap][c_in] = sum x3_s[p + shift][c_in] ab_s[p]
-// thread = channel (c_out for layers 0..2, c_in for layer 3)
-__global__ void __launch_bounds__(64) k_ccv_reduce(CNet n, const int* __restrict__ done) {
+// thread = (pixel group g of 4, channel c): c_out for layers 0..2, c_in for layer 3; the four groups take every fourth pixel of
+// the block's chunk and are summed in order through shared memory
+__global__ void __launch_bounds__(256) k_ccv_reduce(CNet n, const int* __restrict__ done) {
   if (done && *done) return;
-  const int l = blockIdx.y, ch = blockIdx.x, c = threadIdx.x, C = n.C;
-  if (c >= C) return;
+  const int l = blockIdx.y, ch = blockIdx.x, c = threadIdx.x & 63, grp = threadIdx.x >> 6, C = n.C;
+  __shared__ float red[3][27][64];
   float acc[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) acc[k] = 0.f;
   const int total = n.B * n.D;
   const int per = (total + gridDim.x - 1) / gridDim.x;
   const int i0 = ch * per, i1 = min(total, i0 + per);
-  for (int i = i0; i < i1; ++i) {
+  for (int i = i0 + grp; i < i1 && c < C; i += 4) {
     const int b = i / n.D, pix = i - b * n.D;
     const int y = pix / n.Ww, x = pix - y * n.Ww;
     const int cls = border_class(y, x, n.Hh, n.Ww);
@@ -557,9 +558,16 @@ __global__ void __launch_bounds__(64) k_ccv_reduce(CNet n, const int* __restrict
       }
     }
   }
-  float* out = n.PART + (((size_t)l * gridDim.x + ch) * 27) * C + c;
+  if (grp > 0) {
 #pragma unroll
-  for (int k = 0; k < 27; ++k) out[(size_t)k * C] = acc[k];
+    for (int k = 0; k < 27; ++k) red[grp - 1][k][c] = acc[k];
+  }
+  __syncthreads();
+  if (grp == 0 && c < C) {
+    float* out = n.PART + (((size_t)l * gridDim.x + ch) * 27) * C + c;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) out[(size_t)k * C] = ((acc[k] + red[0][k][c]) + red[1][k][c]) + red[2][k][c];
+  }
 }
 
 // second stage of k_ccv_reduce: PART[l][chunk][k][c] summed over the chunks in order -> PART[l][0][k][c]

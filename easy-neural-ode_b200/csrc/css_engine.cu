@@ -398,7 +398,7 @@ int ccv_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
   if ((rc = reverse(0, 1, 1))) return rc;
   // ---- weight gradients: the two C -> C layers (9 taps x position chunks, FFMA), everything else by chunked sums
   for (int l = 0; l < 2; ++l) ccv::k_ccv_wgrad<<<dim3(9, c.wsplits), 256, 0, st>>>(c, l, done);
-  ccv::k_ccv_reduce<<<dim3(c.chunks, ccv::kLayers), 64, 0, st>>>(c, done);
+  ccv::k_ccv_reduce<<<dim3(c.chunks, ccv::kLayers), 256, 0, st>>>(c, done);
   ccv::k_ccv_reduce2<<<dim3(8, ccv::kLayers), 256, 0, st>>>(c, done);
   const size_t work = std::max(pix, (size_t)9 * (C + 1) * C);
   ccv::k_ccv_assemble_adj<<<std::min((int)((work + 255) / 256), 8 * sms), 256, 0, st>>>(f, c, n.DIV, n.RR, n.FRO, n.KIN, stage, init_mode,
