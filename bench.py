@@ -79,8 +79,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def bench_config(world, workload=None):
+def bench_config(world, workload=None, strong=False):
     """The `config` object of the JSON line; IDENTICAL in both arms (the reference arm runs the b200 arm's config)."""
+    if strong and world > 1:
+        per, extra = divmod(B, world)
+        return {"workload": workload or WORKLOAD, "global_batch": B, "per_gpu_batch": [per + (1 if r < extra else 0) for r in range(world)],
+                "rtol": TOL, "atol": TOL,
+                "parallelism": (f"dp{world}, STRONG scaling: the batch-{B} problem split in contiguous row blocks (uneven where {B} is not a "
+                                "multiple of the GPU count), ONE global adaptive step sequence = the single-GPU sequence"),
+                "l2": "flushed between steps (256 MiB device write, outside the per-step events)",
+                "trajectory": "train steps 0..K-1 from the initial parameters (seeded), identical in every leg and arm"}
     return {"workload": workload or WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "rtol": TOL, "atol": TOL,
             "parallelism": (f"dp{world}: batch sharded {B}/GPU, ONE global adaptive step sequence (per-iteration exchange of the "
                             "error-norm partials and of the params_bar stage sums); the reference arm solves the "
@@ -137,17 +145,18 @@ def run_reference(args, rank, world):
     threads = len(os.sched_getaffinity(0))
     steps = max(1, min(args.steps, 40))
     # same workload as the b200 arm at this N: weak scaling, the global batch is B per GPU
-    sec, info = cpu_train_steps(steps, 1, threads, shards=max(args.gpus, 1), budget_s=150.0)
+    strong = getattr(args, "scaling", "weak") == "strong"
+    shards = 1 if strong else max(args.gpus, 1)     # strong scaling: the global batch stays the batch-100 problem
+    sec, info = cpu_train_steps(steps, 1, threads, shards=shards, budget_s=150.0)
     steps = info["steps_timed"]
     # same unit as the b200 arm: per-GPU-batch (batch-100) train steps per second over the whole job - one step of
     # the concatenated global batch is `shards` of them
-    shards = max(args.gpus, 1)
     val = shards / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": bench_config(shards),
+        "config": bench_config(max(args.gpus, 1), strong=strong),
         "global_steps_per_s": 1.0 / sec, "samples_per_s": B * shards / sec,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"train steps 0..{steps - 1} from the initial parameters (forward solve + adjoint + "
@@ -684,6 +693,9 @@ def main():
     ap.add_argument("--reg-type", default="our", choices=["our", "fin"],
                     help="development only: 'fin' times the --reg_type fin arm (odeint_sepaux, lam_fro = lam_kin = 1e-2); "
                          "the headline metric is the default 'our' (--reg r3)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): batch 100 PER GPU; strong: the batch-100 problem itself split "
+                         "over the GPUs in contiguous row blocks (100 rows on 8 GPUs = 13,13,13,13,12,12,12,12: uneven shards)")
     ap.add_argument("--workload", default="mnist", choices=["mnist", "ffjord_tabular", "latent_ode", "ffjord_mnist"],
                     help="mnist = BASELINE configs[0], the configuration the metric is quoted on (default); "
                          "ffjord_tabular = configs[1] (single GPU); latent_ode = configs[2] (single GPU); ffjord_mnist = configs[3] "
@@ -730,18 +742,23 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     single = None
+    strong = args.scaling == "strong" and world > 1
+    sl = eno.shard_rows(B, world, rank) if strong else slice(0, B)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         if args.reg_type == "our":
             # parity evidence for the sharded solve, untimed: every rank first solves the CONCATENATED global batch of
             # train step 0 on its own GPU, non-collectively (the library is not in collective mode yet) ...
             ref_model = mnist_step.MnistNode(reg="r3", lam=LAM, rtol=TOL, atol=TOL, device=dev, dim=D, hidden=H, world=1)
-            parts = [synth_batch(r, 0) for r in range(world)]
+            parts = [synth_batch(r, 0) for r in range(1 if strong else world)]
             o = ref_model.loss_and_grads(*(torch.cat([q[k] for q in parts]).to(dev) for k in range(3)))
-            single = dict(y1=o["y1"][rank * B:(rank + 1) * B].clone(), g=o["grads"]["ode"].clone(), loss=float(o["loss"]),
+            mine = sl if strong else slice(rank * B, (rank + 1) * B)
+            single = dict(y1=o["y1"][mine].clone(), g=o["grads"]["ode"].clone(), loss=float(o["loss"]),
                           fwd=o["fwd_stats"]["n_iters"], bwd=o["bwd_stats"][0]["n_iters"])
             del ref_model, o
         eno.init_distributed()   # solves become collective: one global adaptive step sequence
+        if strong:
+            eno.set_shards(B)    # ranks hold different numbers of rows; the error mean runs over the B rows of the problem
 
     if args.reg_type == "fin":
         model = mnist_step.MnistNode(reg="none", rtol=TOL, atol=TOL, device=dev, dim=D, hidden=H, world=world,
@@ -749,8 +766,13 @@ def main():
     else:
         model = mnist_step.MnistNode(reg="r3", lam=LAM, rtol=TOL, atol=TOL, device=dev, dim=D, hidden=H, world=world)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    dev_batches = [tuple(t.to(dev) for t in synth_batch(rank, s)) for s in range(8)]
-    host_batches = [synth_batch(rank, s, pin=True) for s in range(8)]
+    if strong:
+        model.rows_global = B
+        dev_batches = [tuple(t[sl].contiguous().to(dev) for t in synth_batch(0, s)) for s in range(8)]
+        host_batches = [tuple(t[sl].contiguous().pin_memory() for t in synth_batch(0, s)) for s in range(8)]
+    else:
+        dev_batches = [tuple(t.to(dev) for t in synth_batch(rank, s)) for s in range(8)]
+        host_batches = [synth_batch(rank, s, pin=True) for s in range(8)]
 
     parity = None
     if single is not None:
@@ -758,13 +780,15 @@ def main():
         o = model.loss_and_grads(*dev_batches[0])
         rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
         loss_g = o["loss"].detach().double().reshape(1).clone()      # mean over this rank's rows -> mean over the global batch
+        if strong:
+            loss_g *= world * (sl.stop - sl.start) / B                # uneven shards: weight by the rows held
         dist.all_reduce(loss_g)
         errs = torch.tensor([rel(o["y1"], single["y1"]), rel(o["grads"]["ode"], single["g"]),
                              abs(float(loss_g) / world - single["loss"]) / abs(single["loss"]),
                              float(o["fwd_stats"]["n_iters"] != single["fwd"]), float(o["bwd_stats"][0]["n_iters"] != single["bwd"])],
                             device=dev, dtype=torch.float64)
         dist.all_reduce(errs, op=dist.ReduceOp.MAX)
-        parity = {"against": f"single-GPU solve of the concatenated batch ({B * world} rows) of train step 0, same process, before "
+        parity = {"against": f"single-GPU solve of the concatenated batch ({B if strong else B * world} rows) of train step 0, same process, before "
                              "the library entered collective mode; max over ranks",
                   "fwd_iters": [o["fwd_stats"]["n_iters"], single["fwd"]], "bwd_iters": [o["bwd_stats"][0]["n_iters"], single["bwd"]],
                   "iteration_counts_identical_on_all_ranks": bool(errs[3] == 0 and errs[4] == 0),
@@ -824,7 +848,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     ms_per_step = dev_ms / args.steps
-    value = world * 1e3 / ms_per_step            # batch-100 train steps per second, all ranks
+    units = 1 if strong else world                # batch-100 problems one step of the job advances
+    value = units * 1e3 / ms_per_step             # batch-100 train steps per second, all ranks
 
     # ---- e2e: host (pinned) buffers through the public API, H2D + D2H inside the timed region
     def step_e2e(s):
@@ -851,7 +876,7 @@ def main():
     t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps / float(t.item())
+    e2e_value = units * args.steps / float(t.item())
     h2d = sum(x.numel() * x.element_size() for x in host_batches[0])
 
     # ---- roofline of the dominant kernel (adjoint per-sample step kernel), separate profiled pass
@@ -906,16 +931,16 @@ def main():
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": bench_config(world, None if args.reg_type == "our" else
+        "config": bench_config(world, strong=strong, workload=None if args.reg_type == "our" else
                                "mnist.py Neural ODE classifier, dopri5, --reg_type fin --lam_fro 1e-2 --lam_kin 1e-2, batch 100 "
                                "synthetic 28x28 (development run, not the headline config)"),
-        "global_steps_per_s": 1e3 / ms_per_step, "samples_per_s": B * world * 1e3 / ms_per_step,
+        "global_steps_per_s": 1e3 / ms_per_step, "samples_per_s": B * units * 1e3 / ms_per_step,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
-        "nfe_per_s": nfe_total / (dev_ms * 1e-3), "sample_nfe_per_s": nfe_total * B * world / (dev_ms * 1e-3),
+        "nfe_per_s": nfe_total / (dev_ms * 1e-3), "sample_nfe_per_s": nfe_total * B * units / (dev_ms * 1e-3),
         "solver": ({"fwd_iters": out["fwd_iters"], "bwd_iters": out["bwd_iters"], "graph_redone": out["redone"]}
                    if not args.no_graph else {"fwd": out["fwd_stats"], "bwd": out["bwd_stats"][0]}),
         "launch_mode": "whole update() replayed as one CUDA graph (deferred-mode solves)" if not args.no_graph

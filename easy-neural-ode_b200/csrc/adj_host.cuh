@@ -37,7 +37,8 @@ inline PgradTcGeom pgrad_tc_geom(int B, int D, int H) {
   return g;
 }
 
-inline size_t adj_ws_bytes(int B, int D, int H, int world = 1, bool fin = false) {
+inline size_t adj_ws_bytes(int B, int D, int H, int world = 1, bool fin = false, int slot = 0) {
+  slot = std::max(slot, B);   // rows of the largest shard (uneven shards: every rank's record is laid out for it)
   const size_t N = (size_t)B * D, P = (size_t)(D + 1) * H + H + (size_t)(H + 1) * D + D;
   const PgradGeom g = pgrad_geom(D, H);
   size_t s = 0;
@@ -49,7 +50,7 @@ inline size_t adj_ws_bytes(int B, int D, int H, int world = 1, bool fin = false)
   s += 2 * adj_align(3 * P * 4) + adj_align(2 * P * 4);             // PB, FP, MIDP
   const size_t npp = std::max(std::max((size_t)g.grid, (P + 255) / 256), (size_t)kPcGrid);
   s += kSlots * (2 * adj_align(3 * N * 4) + 2 * adj_align(3 * (size_t)B * H * 4));
-  s += adj_align((size_t)6 * kC * B * world * 8) + 2 * adj_align(npp * 8);   // xrec (one record per rank), ppart0/1
+  s += adj_align((size_t)6 * kC * slot * world * 8) + 2 * adj_align(npp * 8);   // xrec (one record per rank), ppart0/1
   if (world > 1) s += adj_align(4 * P * 4);          // pcomb
   s += adj_align(N * 4) + adj_align((P + 256 * (size_t)(world + 1)) * 4);   // YBAR, POUT (padded to world equal 256-multiples)
   s += 2 * adj_align((size_t)D * H * 4);            // transposes
@@ -69,7 +70,8 @@ struct AdjCarver {
   }
 };
 
-inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArgs* a, int world = 1, bool fin = false) {
+inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArgs* a, int world = 1, bool fin = false, int slot = 0) {
+  slot = std::max(slot, B);
   const size_t N = (size_t)B * D, P = (size_t)(D + 1) * H + H + (size_t)(H + 1) * D + D;
   const PgradGeom g = pgrad_geom(D, H);
   AdjCarver cv{static_cast<char*>(ws)};
@@ -93,7 +95,7 @@ inline void adj_carve(void* ws, int B, int D, int H, const float* params, AdjArg
     a->slot[j].Hh = cv.take<float>(3 * (size_t)B * H);
     a->slot[j].tbar = nullptr;   // adj_set_views
   }
-  a->xrec = cv.take<double>((size_t)6 * kC * B * world);
+  a->xrec = cv.take<double>((size_t)6 * kC * slot * world);
   a->rowpart0 = a->rowpart1 = a->rowpart2 = nullptr;
   a->n_rp = a->n_loc = B;
   const size_t npp = std::max(std::max((size_t)g.grid, (P + 255) / 256), (size_t)kPcGrid);
@@ -172,8 +174,8 @@ inline int adj_rows(int R, int K, int mode, const AdjArgs& a, int grid, size_t s
 // 6 * n_loc doubles, so that the multi-GPU exchange is a single all-gather (plus the params_bar all-reduce):
 //   [ rp0: n_loc doubles | t_bar pieces of slots 0..5: 6 * n_loc floats | rp1: n_loc doubles | rp2: n_loc doubles ]
 // Point the kernels' write views at this rank's record and the readers at rank 0's (block_sum_records).
-inline void adj_set_views(AdjArgs* a, int stride, int rank, int world) {
-  const size_t n_loc = (size_t)stride * a->B;
+inline void adj_set_views(AdjArgs* a, int stride, int rank, int world, int slot = 0) {
+  const size_t n_loc = (size_t)stride * std::max(slot, a->B);   // slot rows per rank (>= this rank's B; the tail stays zero)
   a->n_loc = (int)n_loc;
   a->n_rp = (int)(n_loc * world);
   a->rp0_all = a->xrec;
@@ -258,17 +260,19 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
       !params_bar_out) { if (err) *err = "eno_odeint_bwd: null pointer or empty batch"; return ENO_E_ARG; }
   const bool dist = dc && dc->active();
   const int world = dist ? dc->world : 1, rank = dist ? dc->rank : 0;
-  if (ws_bytes < adj_ws_bytes(B, D, H, world, fin)) { if (err) *err = "eno_odeint_bwd: workspace too small"; return ENO_E_WORKSPACE; }
+  const int slot = dist ? dc->slot(B) : B;
+  if (B > slot) { if (err) *err = "eno_odeint_bwd: this rank's batch exceeds the shard slot (eno_comm_set_shards)"; return ENO_E_ARG; }
+  if (ws_bytes < adj_ws_bytes(B, D, H, world, fin, slot)) { if (err) *err = "eno_odeint_bwd: workspace too small"; return ENO_E_WORKSPACE; }
   const size_t N = (size_t)B * D;
   AdjArgs a = {};
-  adj_carve(ws, B, D, H, params, &a, world, fin);
+  adj_carve(ws, B, D, H, params, &a, world, fin, slot);
   a.eps = eps;
   const size_t na = (size_t)a.na;
   a.dist = dist ? 1 : 0;
   a.np = (K == 0) ? 1 : K;
   {
     const size_t n_aux = (desc->aug == ENO_AUG_NONE) ? 0 : na;
-    const size_t Ng = N * world, Bg = (size_t)B * world;   // the ODE state spans the GLOBAL batch
+    const size_t Bg = (size_t)(dist ? dc->rows(B) : B), Ng = Bg * D;   // the ODE state spans the GLOBAL batch
     a.n_state = (float)(2 * (Ng + n_aux * Bg) + 1 + (desc->eps_in_args ? Ng : 0) + (size_t)a.P);
   }
   a.trace = trace;
@@ -284,7 +288,7 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
   }
   ENO_ADJ_CHECK(pgrad_prepare());
   if (!plan.cluster) adj_transposes(a, st);
-  adj_set_views(&a, plan.cluster ? kC : 1, rank, world);
+  adj_set_views(&a, plan.cluster ? kC : 1, rank, world, slot);
   const PgradGeom geo = pgrad_geom(D, H);
   // ADJ_STEP parameter gradients of the cluster path run on the tensor cores (batched tcgen05 3xTF32 GEMM +
   // k_adj_pcombine): k_cl_adj_rows<ADJ_STEP> writes its factors as K-major hi / lo planes
@@ -305,7 +309,7 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
     }
   }
   const EpiPgradStage pg_epi{a.KP, D, H, a.P, 2 * H, H * (D + 2) + 2 * D};
-  const size_t n_loc = (size_t)(plan.cluster ? kC : 1) * B;
+  const size_t n_loc = (size_t)(plan.cluster ? kC : 1) * slot;
   const int pf_grid = (a.P + 255) / 256;
   // multi-GPU continuation of one pgrad launch: exchange, then the replicated finish kernel
   // peer-memory exchange (dist.cuh) when the ranks have mapped each other's exchange buffers
@@ -357,6 +361,8 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
     a.g_r = g_r + (size_t)i * na * B;
     a.g_y_prev = g_y + (size_t)(i - 1) * N;
     a.tbar_out = ts_bar_out + i;
+    if (slot != B)   // uneven shards: the tail of this rank's record (rows B .. slot) must read as zero
+      ENO_ADJ_CHECK(cudaMemsetAsync(a.xrec + (size_t)rank * 6 * n_loc, 0, 6 * n_loc * 8, st));
     k_adj_seg_begin<<<egrid, 256, 0, st>>>(a, ys + (size_t)i * N, a.g_y, a.g_r, ts, i, first, rtol, atol, mx,
                                            trace ? trace_cap : 0);
     int rc;

@@ -122,6 +122,12 @@ struct DistCtx {
   NcclApi api;
   PeerView peer;            // mapped when eno_peer_attach has run; peer.base[rank] == nullptr otherwise
   void* peer_mine = nullptr;
+  // Uneven shards (eno_comm_set_shards): every rank's records are laid out for `slot_rows` rows (the largest shard); a
+  // rank with fewer rows leaves the tail of its records zero.  rows_global = rows of the concatenated batch.
+  int slot_rows = 0;
+  long long rows_global = 0;
+  int slot(int B) const { return (active() && slot_rows > 0) ? slot_rows : B; }
+  long long rows(int B) const { return (active() && rows_global > 0) ? rows_global : (long long)B * (active() ? world : 1); }
   bool active() const { return world > 1 && comm != nullptr; }
   bool peer_ready() const { return active() && peer.base[rank] != nullptr; }
 

@@ -94,11 +94,13 @@ cudaError_t set_smem(KernelT k, size_t bytes) {
 }
 
 int g_world = 1;   // ranks of this process group (set by eno_comm_init); sizes the gathered partial-sum arrays
+int g_slot = 0;    // rows of the largest shard (eno_comm_set_shards); 0 = equal shards
+inline int slot_of(int B) { return std::max(B, g_world > 1 ? g_slot : 0); }
 
 size_t fwd_ws_bytes(int B, int D) {
   const size_t N = (size_t)B * D;
   return align_up(sizeof(Ctrl)) + align_up(3 * N * 4) * 2 + align_up(2 * N * 4) +
-         2 * align_up((size_t)kC * B * g_world * 8) + 3 * align_up((size_t)9 * B * 4) + 1024;
+         2 * align_up((size_t)kC * slot_of(B) * g_world * 8) + 3 * align_up((size_t)9 * B * 4) + 1024;
 }
 
 template <int R>
@@ -195,7 +197,7 @@ size_t eno_workspace_bytes(const eno_dynamics_desc* d, int32_t B, int32_t T, int
   if (d && (d->arch == ENO_ARCH_CONCATSQUASH || d->arch == ENO_ARCH_CONCATCONV)) return css::workspace_bytes(d, B, T, mode);
   if (!desc_ok(d) || B <= 0) return 0;
   if (mode == 0) return fwd_ws_bytes(B, d->D);
-  return adj_ws_bytes(B, d->D, d->H, g_world, d->aug == ENO_AUG_FIN);
+  return adj_ws_bytes(B, d->D, d->H, g_world, d->aug == ENO_AUG_FIN, slot_of(B));
 }
 
 int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tableau, int32_t B, const float* y0,
@@ -238,8 +240,8 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   a.Y = cv.take<float>(3 * N);
   a.F = cv.take<float>(3 * N);
   a.MID = cv.take<float>(2 * N);
-  a.rowpart0 = cv.take<double>((size_t)kC * B * g_world);
-  a.rowpart1 = cv.take<double>((size_t)kC * B * g_world);
+  a.rowpart0 = cv.take<double>((size_t)kC * slot_of(B) * g_world);
+  a.rowpart1 = cv.take<double>((size_t)kC * slot_of(B) * g_world);
   AugFwdArgs A;
   A.RSa = cv.take<float>((size_t)9 * B);
   A.FRa = cv.take<float>((size_t)9 * B);
@@ -261,13 +263,18 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   const bool use_cluster = aug != ENO_AUG_NONE ||
                            (ctx->path_mode != 1 && cl_supported(D, H, kClRows, tab.s < 2 ? 2 : tab.s, false));
   const int stride = use_cluster ? kC : 1;           // partial sums per sample
-  const size_t n_loc = (size_t)stride * B;           // this rank's partial sums
+  if (dist && B > dc.slot(B)) return fail(ctx, ENO_E_ARG, "eno_odeint_fwd: this rank's batch exceeds the shard slot (eno_comm_set_shards)");
+  const size_t n_loc = (size_t)stride * dc.slot(B);  // this rank's slot of partial sums (stride * B of them written, the rest zero)
   a.n_rp = (int)(n_loc * world);
   a.dist = dist ? 1 : 0;
   a.rp0_all = a.rowpart0;
   a.rp1_all = a.rowpart1;
   a.rowpart0 += (size_t)(dist ? dc.rank : 0) * n_loc;
   a.rowpart1 += (size_t)(dist ? dc.rank : 0) * n_loc;
+  if (dist && dc.slot(B) != B) {   // uneven shards: the unused tail of this rank's slot must read as zero
+    ENO_CUDA(ctx, cudaMemsetAsync(a.rowpart0, 0, n_loc * 8, static_cast<cudaStream_t>(stream_)));
+    ENO_CUDA(ctx, cudaMemsetAsync(a.rowpart1, 0, n_loc * 8, static_cast<cudaStream_t>(stream_)));
+  }
   double* rp0 = const_cast<double*>(a.rp0_all);
   double* rp1 = const_cast<double*>(a.rp1_all);
 
@@ -281,7 +288,7 @@ int32_t eno_odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t tabl
   ENO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tab, &ctx->tabs[tableau], sizeof(Tableau), 0, cudaMemcpyHostToDevice, stream));
   const bool deferred = ctx->deferred && ctx->spec_fwd > 0;
   k_ctrl_reset<<<1, 1, 0, stream>>>(a.ctrl, rtol, atol, T, mxstep <= 0 ? INT_MAX : mxstep, trace_out ? trace_cap : 0,
-                                    (float)((N + (size_t)n_aux * B) * world));
+                                    (float)((size_t)(D + n_aux) * (size_t)dc.rows(B)));
   ++launches;
 
   auto launch = [&](int mode) -> cudaError_t {
@@ -543,6 +550,16 @@ int32_t eno_comm_init(eno_ctx* ctx, const uint8_t* id, int32_t rank, int32_t wor
   return ENO_OK;
 }
 
+int32_t eno_comm_set_shards(eno_ctx* ctx, int32_t slot_rows, int64_t rows_global) {
+  if (!ctx || slot_rows < 0 || rows_global < 0) return fail(ctx, ENO_E_ARG, "eno_comm_set_shards: bad arguments");
+  if (slot_rows > 0 && rows_global > (int64_t)slot_rows * ctx->dist.world)
+    return fail(ctx, ENO_E_ARG, "eno_comm_set_shards: rows_global exceeds world * slot_rows");
+  ctx->dist.slot_rows = slot_rows;
+  ctx->dist.rows_global = rows_global;
+  g_slot = slot_rows;
+  return ENO_OK;
+}
+
 // Exchange over NVLink peer memory (dist.cuh): every rank allocates its symmetric buffer and exports it ...
 int32_t eno_peer_export(eno_ctx* ctx, uint64_t bytes, uint8_t* handle_out /*[64]*/) {
   if (!ctx || !handle_out || bytes < (kPeerOffAdj << 1)) return fail(ctx, ENO_E_ARG, "eno_peer_export: bad arguments");
@@ -595,7 +612,10 @@ int32_t eno_comm_destroy(eno_ctx* ctx) {
   ctx->dist.peer = PeerView();
   ctx->dist.world = 1;
   ctx->dist.rank = 0;
+  ctx->dist.slot_rows = 0;
+  ctx->dist.rows_global = 0;
   g_world = 1;
+  g_slot = 0;
   return ENO_OK;
 }
 

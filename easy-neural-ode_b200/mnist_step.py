@@ -45,6 +45,7 @@ class MnistNode:
         self._lr_val = None
         self.dim, self.n_cls = dim, n_cls
         self.world = world   # data-parallel ranks: the loss is the mean over the GLOBAL batch
+        self.rows_global = None   # uneven shards (ode.set_shards): rows of the concatenated batch; None = world * B
         self.ts = torch.tensor([0., 1.], device=self.device)
         self.init_params(0)
 
@@ -87,7 +88,7 @@ class MnistNode:
         D, Cn, dev = self.dim, self.n_cls, self.device
         fin = self.reg_type == "fin"
         g_y = torch.zeros((2, B, D), device=dev)                      # cotangent of ys: only the last time is hit
-        n = B * self.world
+        n = self.rows_global or B * self.world
         if fin:
             g_r = torch.zeros((2, 2, B), device=dev)
             g_r[1, 0], g_r[1, 1] = self.lam_fro / n, self.lam_kin / n   # d(lam * mean(reg))/d reg[b], mnist.py:462-478
@@ -114,7 +115,7 @@ class MnistNode:
         gw, gb = buf["gwb"][:D * Cn].view(D, Cn), buf["gwb"][D * Cn:]
         with torch.cuda.device(self.device):
             rc = L.eno_mnist_head(h, B, D, Cn, ode._ptr(ys[1]), ode._ptr(labels), ode._ptr(self.post_w), ode._ptr(self.post_b),
-                                  1.0 / (B * self.world), ode._ptr(buf["scratch"]), ode._ptr(buf["loss"]),
+                                  1.0 / (self.rows_global or B * self.world), ode._ptr(buf["scratch"]), ode._ptr(buf["loss"]),
                                   ode._ptr(buf["g_y"][1]), ode._ptr(gw), ode._ptr(gb), stream)
         _cabi.check(rc, h, "eno_mnist_head")
         if self.world > 1:

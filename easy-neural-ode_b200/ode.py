@@ -66,6 +66,7 @@ def init_distributed(device=None):
     with torch.cuda.device(dev):
         _cabi.check(L.eno_comm_init(h, idb, rank, world, path), h, "eno_comm_init")
     _dist["world"], _dist["rank"] = world, rank
+    _dist["rows_global"] = None
     _dist["peer"] = False
     if world > 1 and world <= 8 and os.environ.get("ENO_EXCHANGE", "peer") != "nccl":
         # move the per-iteration exchange into the solver's finish kernels, over NVLink peer memory (include/eno.h):
@@ -100,11 +101,28 @@ def shutdown_distributed(device=None):
 
 
 def shard_rows(n_rows, world, rank):
-    """Contiguous equal row blocks (the collective solves need the same B on every rank)."""
-    if n_rows % world:
-        raise ValueError(f"global batch {n_rows} is not divisible by world size {world}")
-    per = n_rows // world
-    return slice(rank * per, (rank + 1) * per)
+    """Contiguous row blocks of the global batch, the first ``n_rows % world`` ranks one row longer (SURVEY.md section 8e:
+    100 rows on 8 GPUs = 13, 13, 13, 13, 12, 12, 12, 12).  Uneven blocks need ``set_shards(n_rows)`` on every rank."""
+    if n_rows < world:
+        raise ValueError(f"global batch {n_rows} is smaller than the world size {world}")
+    per, extra = divmod(n_rows, world)
+    lo = rank * per + min(rank, extra)
+    return slice(lo, lo + per + (1 if rank < extra else 0))
+
+
+def set_shards(rows_global=None, device=None):
+    """Declare the size of the concatenated batch of the collective solves (eno_comm_set_shards): ranks may then hold
+    different numbers of rows (``shard_rows``).  ``None`` restores equal shards."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    h = _cabi.ctx(dev.index)
+    world = _dist["world"]
+    if rows_global is None:
+        slot, rows = 0, 0
+    else:
+        slot, rows = -(-int(rows_global) // world), int(rows_global)
+    _cabi.check(_cabi.lib().eno_comm_set_shards(h, slot, rows), h, "eno_comm_set_shards")
+    _dist["rows_global"] = rows or None
+    _workspaces.clear()
 
 
 _deferred = {"on": False}

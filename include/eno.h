@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ENO_ABI_VERSION 6
+#define ENO_ABI_VERSION 7
 
 /* status codes */
 #define ENO_OK 0
@@ -280,6 +280,11 @@ int32_t eno_read_stats(eno_ctx* ctx, const void* workspace, eno_stats* out, void
 int32_t eno_comm_unique_id(eno_ctx* ctx, uint8_t* id_out /*[128]*/, const char* nccl_path);
 int32_t eno_comm_init(eno_ctx* ctx, const uint8_t* id /*[128]*/, int32_t rank, int32_t world, const char* nccl_path);
 int32_t eno_comm_destroy(eno_ctx* ctx);
+/* Uneven shards (global batch 100 on 8 GPUs = 13,13,13,13,12,12,12,12 rows).  By default every rank
+ * must pass the same B.  After this call a rank may pass any B <= slot_rows; every rank's exchange records are laid out for
+ * slot_rows rows (the unused tail reads as zero, which leaves the rank-ordered sums unchanged) and the mean of the error
+ * norm runs over rows_global rows (the concatenated batch).  (0, 0) restores equal shards.  Same values on every rank. */
+int32_t eno_comm_set_shards(eno_ctx* ctx, int32_t slot_rows, int64_t rows_global);
 /*
  * Optional, after eno_comm_init: move the per-iteration exchange of the collective solves from NCCL calls into the
  * solver's own finish kernels, over NVLink peer memory (one node, at most 8 ranks).  Every rank calls eno_peer_export

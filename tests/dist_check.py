@@ -44,6 +44,9 @@ def main():
     eno.init_distributed()
     sl = eno.shard_rows(Bg, world, rank)
     model = mnist_step.MnistNode(rtol=tol, atol=tol, device=dev, world=world, **kw)
+    if Bg % world:   # uneven shards (e.g. ENO_DIST_B=100 on 8 GPUs: 13,13,13,13,12,12,12,12): declare the global batch
+        eno.set_shards(Bg)
+        model.rows_global = Bg
     got = model.loss_and_grads(images[sl], labels[sl], eps[sl])
     f, b = got["fwd_stats"], got["bwd_stats"][0]
     errs = dict(y1=rel(got["y1"], want["y1"][sl]), g_ode=rel(got["grads"]["ode"], want["grads"]["ode"]),

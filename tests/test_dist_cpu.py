@@ -19,8 +19,12 @@ def test_shard_rows_partitions_the_batch():
     idx = torch.arange(100)
     assert torch.equal(torch.cat([idx[s] for s in got]), idx)
     assert all((s.stop - s.start) == 25 for s in got)
+    # uneven shards: 100 rows on 8 ranks = 13, 13, 13, 13, 12, 12, 12, 12, contiguous and covering
+    got = [eno.shard_rows(100, 8, r) for r in range(8)]
+    assert [s.stop - s.start for s in got] == [13, 13, 13, 13, 12, 12, 12, 12]
+    assert torch.equal(torch.cat([idx[s] for s in got]), idx)
     with pytest.raises(ValueError):
-        eno.shard_rows(100, 8, 0)      # the collective solves need equal shards
+        eno.shard_rows(3, 8, 0)
 
 
 def test_init_distributed_requires_a_process_group():
