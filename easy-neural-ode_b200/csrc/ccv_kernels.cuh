@@ -438,10 +438,26 @@ __global__ void k_ccv_l0_bwd(CNet n, int first_stream, int n_streams, const int*
 }
 
 // Weight gradients of the two C -> C layers: dW[tap][c_in][c_out] = sum_p x[p + shift(tap)][c_in] ab[p][c_out] over the
-// positions of all streams.  FFMA for now: on the tensor cores the contraction index (the position) would have to be the
-// contiguous one of both operands, i.e. transposed planes, and a tap is then a shift along the CONTIGUOUS dimension of a
-// TMA box - not a multiple of 16 bytes, which TMA rejects (measured: illegal instruction).  The tensor-core formulation
-// needs MN-major operand descriptors (operands as they are, [position][channel], the shift on the row coordinate).
+// positions of all streams.  On the tensor cores the contraction index is the position, i.e. the SLOW index of both operands
+// as they lie in memory ([position][channel]): MN-major operand descriptors (gemm_tc.cuh: k_gemm_tf32x3<.., MN = true>,
+// SWIZZLE_128B_BASE32B), the tap shift on the TMA row coordinate, two taps per 128-row tile (EpiConvWgradMN).  With K-major
+// (transposed) planes a tap would be a shift along the CONTIGUOUS dimension of a TMA box - not a multiple of 16 bytes,
+// which TMA rejects (measured: illegal instruction).
+struct EpiConvWgradMN {
+  float* WP;
+  int C;
+  // tile rows: 64 input channels of tap 2 x, then of tap 2 x + 1; tile columns: x * 64 + c_out
+  __device__ __forceinline__ void operator()(int m, int n0, float (&v)[css::kW], int split) const {
+    const int pair = n0 >> 6, co = n0 & 63, tap = 2 * pair + (m >> 6), ci = m & 63;
+    if (tap > 8 || ci >= C || co >= C) return;
+    float* row = WP + (((size_t)split * 9 + tap) * C + ci) * C + co;
+#pragma unroll
+    for (int j = 0; j < css::kW; ++j)
+      if (co + j < C) row[j] = v[j];
+  }
+};
+
+// The FFMA formulation of the same contraction (ENO_CCV_WGRAD_FFMA=1; 43 TFLOP/s = 60 % of the FFMA peak at batch 200):
 // grid (9 taps, splits): one block = one tap x one chunk of positions, 64 x 64 outputs, 4 x 4 per thread.
 __global__ void __launch_bounds__(256) k_ccv_wgrad(CNet n, int l, const int* __restrict__ done) {
   if (done && *done) return;

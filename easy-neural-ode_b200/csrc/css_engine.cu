@@ -162,7 +162,7 @@ void plan_build_conv(const eno_dynamics_desc* d, int B, int T, int mode, void* w
     c.XB1 = cv.take<float>((size_t)2 * B * c.ldD);
     c.EBD = cv.take<float>((size_t)B * c.ldD);
     c.YBDOT = cv.take<float>((size_t)B * c.ldD);
-    c.wsplits = 32;
+    c.wsplits = 29;   // 5 tap pairs x 29 position chunks = 145 CTAs
     for (int l = 0; l < 2; ++l) c.WPART[l] = cv.take<float>((size_t)c.wsplits * 9 * C * C);
     c.chunks = ccv::kRedChunks;
     c.PART = cv.take<float>((size_t)ccv::kLayers * c.chunks * 27 * C);
@@ -396,8 +396,18 @@ int ccv_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
   if (c.nq > 0 && (rc = reverse(1, c.nq, 0))) return rc;
   ccv::k_ccv_seed2<<<std::min((int)((pix + 255) / 256), 4 * sms), 256, 0, st>>>(f, c);
   if ((rc = reverse(0, 1, 1))) return rc;
-  // ---- weight gradients: the two C -> C layers (9 taps x position chunks, FFMA), everything else by chunked sums
-  for (int l = 0; l < 2; ++l) ccv::k_ccv_wgrad<<<dim3(9, c.wsplits), 256, 0, st>>>(c, l, done);
+  // ---- weight gradients: the two C -> C layers on the tensor cores (MN-major operands, 5 tap pairs x position chunks),
+  // everything else by chunked sums
+  static const bool wgrad_ffma = getenv("ENO_CCV_WGRAD_FFMA") != nullptr;
+  for (int l = 0; l < 2; ++l) {
+    if (wgrad_ffma) { ccv::k_ccv_wgrad<<<dim3(9, c.wsplits), 256, 0, st>>>(c, l, done); continue; }
+    CUtensorMap txa, txb;   // the operands as they lie in memory ([position][channel] planes), MN-major
+    const int K = (1 + c.nq) * c.Rp;
+    if (!tc::make_operand_map(&txa, c.X2[l], K, C, C, c.xplane(), 32, err, true) ||
+        !tc::make_operand_map(&txb, c.AB2[l], K, C, C, c.xplane(), 32, err, true))
+      return ENO_E_CUDA;
+    CSS_G(tc::launch_gemm_mn<64>(txa, txb, 128, 64, K, c.wsplits, c.WP, done, ccv::EpiConvWgradMN{c.WPART[l], C}, st));
+  }
   ccv::k_ccv_reduce<<<dim3(c.chunks, ccv::kLayers), 256, 0, st>>>(c, done);
   ccv::k_ccv_reduce2<<<dim3(8, ccv::kLayers), 256, 0, st>>>(c, done);
   const size_t work = std::max(pix, (size_t)9 * (C + 1) * C);
@@ -846,6 +856,42 @@ int32_t eno_gemm_tf32x3(eno_ctx* ctx, int32_t M, int32_t N, int32_t K, const flo
   cudaError_t es = cudaStreamSynchronize(st);
   cudaFree(a2); cudaFree(b2); if (part) cudaFree(part);
   if (es != cudaSuccess) return css_fail(ctx, ENO_E_CUDA, std::string("eno_gemm_tf32x3: ") + cudaGetErrorString(es));
+  return ENO_OK;
+}
+
+// Unit-test hook of the MN-major operand mode: C[m, n] = sum_k A[k, m] B[k, n], A [K][lda], B [K][ldb] row-major.
+int32_t eno_gemm_tf32x3_mn(eno_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B,
+                           int32_t ldb, float* C, int32_t ldc, int32_t bn, int32_t splits, void* stream) {
+  if (!ctx || !A || !B || !C || M <= 0 || N <= 0 || K <= 0 || splits < 1 || (bn != 64 && bn != 128) || lda % 4 || ldb % 4)
+    return css_fail(ctx, ENO_E_ARG, "eno_gemm_tf32x3_mn: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CSS_CUDA(ctx, cudaSetDevice(ctx->device));
+  float *a2 = nullptr, *b2 = nullptr, *part = nullptr;
+  CSS_CUDA(ctx, cudaMalloc(&a2, (size_t)2 * K * lda * 4));
+  CSS_CUDA(ctx, cudaMalloc(&b2, (size_t)2 * K * ldb * 4));
+  tc::k_split_planes<<<1024, 256, 0, st>>>(A, K, M, lda, a2, lda, (size_t)K * lda, 0);
+  tc::k_split_planes<<<1024, 256, 0, st>>>(B, K, N, ldb, b2, ldb, (size_t)K * ldb, 0);
+  std::string err;
+  CUtensorMap ta, tb;
+  if (!tc::make_operand_map(&ta, a2, K, M, lda, (size_t)K * lda, 32, &err, true) ||
+      !tc::make_operand_map(&tb, b2, K, N, ldb, (size_t)K * ldb, 32, &err, true)) {
+    cudaFree(a2); cudaFree(b2);
+    return css_fail(ctx, ENO_E_CUDA, "eno_gemm_tf32x3_mn: " + err);
+  }
+  tc::EpiStore epi;
+  if (splits > 1) {
+    CSS_CUDA(ctx, cudaMalloc(&part, (size_t)splits * M * N * 4));
+    epi = tc::EpiStore{part, M, N, N, (size_t)M * N};
+  } else {
+    epi = tc::EpiStore{C, M, N, ldc, 0};
+  }
+  cudaError_t e = (bn == 128) ? tc::launch_gemm_mn<128>(ta, tb, M, N, K, splits, 0, nullptr, epi, st)
+                              : tc::launch_gemm_mn<64>(ta, tb, M, N, K, splits, 0, nullptr, epi, st);
+  if (e == cudaSuccess && splits > 1) tc::k_sum_splits<<<256, 256, 0, st>>>(part, splits, (size_t)M * N, N, C, ldc);
+  cudaError_t es = cudaStreamSynchronize(st);
+  cudaFree(a2); cudaFree(b2); if (part) cudaFree(part);
+  if (e != cudaSuccess || es != cudaSuccess)
+    return css_fail(ctx, ENO_E_CUDA, std::string("eno_gemm_tf32x3_mn: ") + cudaGetErrorString(e != cudaSuccess ? e : es));
   return ENO_OK;
 }
 

@@ -128,10 +128,28 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
   return d;
 }
 
+// The same for an MN-major tile (the contraction index is the SLOW one: rows = k, 32 contiguous m or n per 128-byte row,
+// 128-byte swizzled as TMA wrote it).  Canonical layout (CUTLASS make_umma_desc<Major::MN>, SWIZZLE_128B, in 16-byte
+// units): for 32-bit elements the atom is the 128-byte swizzle with 32-BYTE granularity (LayoutType SWIZZLE_128B_BASE32B,
+// Swizzle<2,5,2>: Layout_MN_SW128_32B_Atom = 128 bytes along M / N x 4 k-rows; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) -
+// with the ordinary 16-byte-granular SWIZZLE_128B the products come out wrong (measured).  Atoms along M / N (chunks of 32
+// elements) are LBO apart, groups of 4 k-rows SBO = 512 bytes apart; one tf32 MMA (K = 8) consumes two atoms per chunk.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t chunk_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((chunk_bytes >> 4) & 0x3FFFu) << 16;   // leading byte offset: next chunk of 32 elements along M / N
+  d |= (uint64_t)(512u >> 4) << 32;                      // stride byte offset: next group of 4 k-rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                                // SWIZZLE_128B_BASE32B
+  return d;
+}
+
 // instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = BN
 __host__ __device__ constexpr uint32_t idesc_tf32(int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
+// ... both operands MN-major ("transposed": bits 15, 16)
+__host__ __device__ constexpr uint32_t idesc_tf32_mn(int bn) { return idesc_tf32(bn) | (1u << 15) | (1u << 16); }
 
 #ifdef ENO_PHASES
 // development aid (libeno_phases.so): clock stamps of CTA (0,0,0) of the most recent launches, 8 per launch:
@@ -165,7 +183,11 @@ struct GemmCfg {
 // (Only ROW coordinates are shifted: a shift along the contiguous dimension of a box is not a multiple of 16 bytes,
 // which TMA rejects - so the weight gradient of the convolution, whose contraction runs over the positions, cannot use
 // transposed planes this way; ccv_kernels.cuh: k_ccv_wgrad.)
-template <int BN, class Epi>
+// MN = true: D[m, n] = sum_k A[k, m] * B[k, n], both operands MN-major ([2 planes][k rows][ld], m / n contiguous): TMA boxes
+// of 32 columns x 32 k-rows; a_row0 / b_row0 are COLUMN offsets then, and tap_w != 0 selects the convolution weight-gradient
+// mode: tile column block x = tap pair, tile rows 0..63 / 64..127 = the two taps' input channels, A read shift(tap) rows
+// further along K (a row coordinate: any shift is legal), B from column block 0.
+template <int BN, class Epi, bool MN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int a_row0, int b_row0,
               int kb_per_split, int kb_total, const int* __restrict__ done, Epi epi, int a_zrows = 0, int b_zrows = 0,
@@ -225,6 +247,27 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         uint8_t* st = smem + (size_t)s * Cfg::kStageBytes;
         mbar_expect_tx(&full[s], Cfg::kStageBytes);
         const int k = (kb0 + i) * kBK;
+        if constexpr (MN) {
+          constexpr int kChunk = kBK * 128;   // one box: 32 k-rows x 128 bytes
+#pragma unroll
+          for (int c = 0; c < kBM / 32; ++c) {
+            int col = a_row0 + m0 + 32 * c, row = k;
+            if (tap_w) {
+              const int tap = min(2 * (int)blockIdx.x + (c >> 1), 8);
+              col = a_row0 + 32 * (c & 1);
+              row += (tap / 3 - 1) * tap_w + (tap % 3 - 1);
+            }
+            tma_load_3d(st + c * kChunk, &tmA, &full[s], col, row, 0);
+            tma_load_3d(st + Cfg::kABytes + c * kChunk, &tmA, &full[s], col, row, 1);
+          }
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+            const int col = b_row0 + (tap_w ? 0 : n0) + 32 * c;
+            tma_load_3d(st + 2 * Cfg::kABytes + c * kChunk, &tmB, &full[s], col, k, 0);
+            tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes + c * kChunk, &tmB, &full[s], col, k, 1);
+          }
+          continue;
+        }
         int ka = k, ra = a_row0 + m0;
         if (tap_kb) {
           const int tap = (kb0 + i) / tap_kb;
@@ -241,7 +284,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_tf32(BN);
+      constexpr uint32_t idesc = MN ? idesc_tf32_mn(BN) : idesc_tf32(BN);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % Cfg::kStages;
         const uint32_t ph = (uint32_t)(i / Cfg::kStages) & 1u;
@@ -249,9 +292,12 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tc_fence_after();
         if (i == 0) GEMM_STAMP(2);
         const uint32_t sa = smem_u32(smem + (size_t)s * Cfg::kStageBytes);
-        const uint64_t a_hi = smem_desc_k_sw128(sa), a_lo = smem_desc_k_sw128(sa + Cfg::kABytes);
-        const uint64_t b_hi = smem_desc_k_sw128(sa + 2 * Cfg::kABytes);
-        const uint64_t b_lo = smem_desc_k_sw128(sa + 2 * Cfg::kABytes + Cfg::kBBytes);
+        constexpr uint32_t kChunk = kBK * 128;
+        const uint64_t a_hi = MN ? smem_desc_mn_sw128(sa, kChunk) : smem_desc_k_sw128(sa);
+        const uint64_t a_lo = MN ? smem_desc_mn_sw128(sa + Cfg::kABytes, kChunk) : smem_desc_k_sw128(sa + Cfg::kABytes);
+        const uint64_t b_hi = MN ? smem_desc_mn_sw128(sa + 2 * Cfg::kABytes, kChunk) : smem_desc_k_sw128(sa + 2 * Cfg::kABytes);
+        const uint64_t b_lo = MN ? smem_desc_mn_sw128(sa + 2 * Cfg::kABytes + Cfg::kBBytes, kChunk)
+                                 : smem_desc_k_sw128(sa + 2 * Cfg::kABytes + Cfg::kBBytes);
         // The tensor core adds into its fp32 accumulator with truncation; a long chain of adds into ONE
         // accumulator shows up as a bias (measured: 2.1e-6 of sum|a||b| at K = 860 against 3.3e-7 for an fp32
         // FFMA GEMM).  So the hi*hi products rotate over three accumulators by k-block and the two small cross
@@ -260,7 +306,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t acc_cross = tmem_base + (uint32_t)((kAccs - 1) * BN);
 #pragma unroll
         for (int k = 0; k < kBK / kUmmaK; ++k) {
-          const uint64_t adv = (uint64_t)((k * kUmmaK * 4) >> 4);   // start-address field counts 16-byte units
+          // start-address field counts 16-byte units: K-major: 8 elements along the 128-byte row; MN-major: 8 k-rows = 1024 B
+          const uint64_t adv = MN ? (uint64_t)((k * 1024) >> 4) : (uint64_t)((k * kUmmaK * 4) >> 4);
           umma_tf32(acc_cross, a_lo + adv, b_hi + adv, idesc, (i | k) != 0);
           umma_tf32(acc_cross, a_hi + adv, b_lo + adv, idesc, 1u);
           umma_tf32(acc_main, a_hi + adv, b_hi + adv, idesc, (i >= kAccs - 1 || k != 0) ? 1u : 0u);
@@ -357,7 +404,7 @@ inline EncodeTiledFn encode_tiled_fn() {
 // Tensor map of an operand stored as [2 planes (hi, lo)][rows][ld] fp32, K contiguous; boxes of box_rows x 32
 // elements.  Rows >= `rows` and columns >= `k` read as zero (out-of-bounds fill), so neither has to be padded.
 inline bool make_operand_map(CUtensorMap* tm, const float* base, int rows, int k, int ld, size_t plane_stride, int box_rows,
-                             std::string* err) {
+                             std::string* err, bool mn_major = false) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) { if (err) *err = "cuTensorMapEncodeTiled is not available from the driver"; return false; }
   cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, 2};
@@ -365,7 +412,8 @@ inline bool make_operand_map(CUtensorMap* tm, const float* base, int rows, int k
   cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     if (err) *err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + "): rows " + std::to_string(rows) + " k " +
@@ -423,6 +471,21 @@ inline cudaError_t launch_conv3x3(const CUtensorMap& ta, const CUtensorMap& tb, 
   if (e != cudaSuccess) return e;
   dim3 grid((N + BN - 1) / BN, (M + kBM - 1) / kBM, 1);
   k_gemm_tf32x3<BN, Epi><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, st>>>(ta, tb, a_row0, 0, kb_total, kb_total, done, epi, 0, 0, tap_kb, grid_w);
+  return cudaGetLastError();
+}
+
+// MN-major operands: D[m, n] = sum_k A[k, m] B[k, n].  Maps from make_operand_map(tm, base, K rows, columns, ld, plane, 32).
+// tap_w == 0: plain GEMM (grid = N tiles x M tiles x K-splits).  tap_w != 0: weight gradient of a 3x3 convolution over a
+// padded position grid with tap_w positions per grid row: grid.x = 5 tap pairs, 64 input channels per tap (see the kernel).
+template <int BN, class Epi>
+inline cudaError_t launch_gemm_mn(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int splits, int tap_w,
+                                  const int* done, const Epi& epi, cudaStream_t st) {
+  const int kb_total = (K + kBK - 1) / kBK;
+  const int kb_per = (kb_total + splits - 1) / splits;
+  cudaError_t e = cudaFuncSetAttribute(k_gemm_tf32x3<BN, Epi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<BN>::kSmem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(tap_w ? 5 : (N + BN - 1) / BN, tap_w ? 1 : (M + kBM - 1) / kBM, splits);
+  k_gemm_tf32x3<BN, Epi, true><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, st>>>(ta, tb, 0, 0, kb_per, kb_total, done, epi, 0, 0, 0, tap_w);
   return cudaGetLastError();
 }
 

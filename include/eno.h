@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ENO_ABI_VERSION 7
+#define ENO_ABI_VERSION 8
 
 /* status codes */
 #define ENO_OK 0
@@ -334,6 +334,10 @@ int32_t eno_adam_update(eno_ctx* ctx, float* params, float* m, float* v, const f
  */
 int32_t eno_gemm_tf32x3(eno_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B,
                         int32_t ldb, float* C, int32_t ldc, int32_t bn, int32_t splits, void* stream);
+/* The same contraction with MN-major operands (tcgen05 "transposed" operand descriptors): C[m, n] = sum_k A[k, m] B[k, n],
+ * A [K][lda], B [K][ldb] row-major, lda % 4 == ldb % 4 == 0.  Unit-test hook of the mode the convolution weight gradients use. */
+int32_t eno_gemm_tf32x3_mn(eno_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, int32_t lda, const float* B,
+                           int32_t ldb, float* C, int32_t ldc, int32_t bn, int32_t splits, void* stream);
 
 /*
  * Per-trajectory differentiable solves (BASELINE config C3, latent_ode.py).  Replace

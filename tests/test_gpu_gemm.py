@@ -68,3 +68,30 @@ def test_single_pass_tf32_would_not_be_enough(cuda):
     one = hi(A).double() @ hi(B).double().T
     scale = A.double().abs() @ B.double().abs().T
     assert ((one - want).abs() / scale).max().item() > 1e-5
+
+
+@pytest.mark.parametrize("bn", [64, 128])
+@pytest.mark.parametrize("shape", [(128, 64, 32), (64, 64, 256), (200, 150, 100), (784, 100, 300), (64, 64, 4096)])
+def test_tf32x3_gemm_mn_major_operands_match_fp64(cuda, shape, bn):
+    """MN-major operand descriptors (the contraction index is the slow one of both operands): C = A^T B with A [K, M], B [K, N]
+    as they lie in memory - no transposed copies.  Same bar as the K-major mode."""
+    import easy_neural_ode_b200 as eno
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M * 5 + N * 11 + K)
+    ma, na = (M + 3) // 4 * 4, (N + 3) // 4 * 4
+    A = torch.randn((K, ma), generator=g).to(cuda)[:, :M]       # row stride ma / na (multiples of 4 elements: TMA needs 16 bytes)
+    B = torch.randn((K, na), generator=g).to(cuda)[:, :N]
+    want = A.double().T @ B.double()
+    L = eno._cabi.lib()
+    h = eno._cabi.ctx(cuda.index)
+    for splits in (1, 3):
+        out = torch.full((M, N), float("nan"), device=cuda)
+        st = C.c_void_p(torch.cuda.current_stream(cuda).cuda_stream)
+        rc = L.eno_gemm_tf32x3_mn(h, M, N, K, C.c_void_p(A.data_ptr()), A.stride(0), C.c_void_p(B.data_ptr()), B.stride(0),
+                                  C.c_void_p(out.data_ptr()), out.stride(0), bn, splits, st)
+        eno._cabi.check(rc, h, "eno_gemm_tf32x3_mn")
+        scale = A.double().abs().T @ B.double().abs()
+        err = ((out.double() - want).abs() / scale).max().item()
+        print(f"tf32x3 MN-major {shape} bn={bn} splits={splits}: max err / sum|a||b| = {err:.3e}")
+        assert torch.isfinite(out).all()
+        assert err < 1e-6, err
