@@ -241,6 +241,9 @@ void plan_build(const eno_dynamics_desc* d, int B, int T, int mode, void* ws, Pl
   p->seg_ts = cv.take<float>(4);
   n.eps = p->eps;
   n.tval = cv.take<float>(4);
+  // adjoint: the weight-gradient GEMMs contract X2 / AB2 over their ROWS (MN-major operands): rows B .. Bp of every stream
+  // must read as zero, so everything from here on is cleared once per solve
+  const size_t zero_all_from = cv.off;
   for (int l = 0; l < L; ++l) {
     const float* base = p->params ? p->params + n.poff[l] : nullptr;
     const size_t dd = (size_t)n.din[l] * n.dout[l];
@@ -278,12 +281,7 @@ void plan_build(const eno_dynamics_desc* d, int B, int T, int mode, void* ws, Pl
   n.JE = cv.take<float>((size_t)B * n.ldD);
   n.Y1 = cv.take<float>((size_t)B * n.ldD);
   n.DIV = cv.take<float>(B); n.RR = cv.take<float>(B); n.FRO = cv.take<float>(B); n.KIN = cv.take<float>(B);
-  p->zero_from = cv.off;
-  if (adj)
-    for (int l = 0; l < L; ++l) {
-      n.XT2[l] = cv.take<float>(2 * n.xtplane(l));
-      n.ABT2[l] = cv.take<float>(2 * n.abtplane(l));
-    }
+  p->zero_from = adj ? zero_all_from : cv.off;
   p->zero_bytes = cv.off - p->zero_from;
   p->bytes = cv.off + 1024;
 }
@@ -458,11 +456,19 @@ int css_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
       else CSS_G(gemm(A, W, B, n.din[l], 1, done, css::EpiPrimRev0{n}, st, err));
     }
     // weight gradients: contraction over the batch, one K-split per row stream
+    // (MN-major operands: the activations and cotangents as they lie in memory, [row][column] planes - no transposed copies)
     for (int l = 0; l < L; ++l) {
       const int K = (1 + n.nq) * Bp;
-      tc::GemmOperand A{n.XT2[l], n.din[l], K, 3 * Bp, n.xtplane(l), 0};
-      tc::GemmOperand Bt{n.ABT2[l], n.dout[l], K, 3 * Bp, n.abtplane(l), 0};
-      CSS_G(gemm(A, Bt, n.din[l], n.dout[l], 1 + n.nq, done, css::EpiWgrad{n.WP[l], n.din[l], n.dout[l]}, st, err));
+      CUtensorMap txa, txb;
+      if (!tc::make_operand_map(&txa, n.X2[l], K, n.din[l], n.ldi[l], n.xplane(l), 32, err, true) ||
+          !tc::make_operand_map(&txb, n.AB2[l], K, n.dout[l], n.ldo[l], n.abplane(l), 32, err, true))
+        return ENO_E_CUDA;
+      const bool prof = g_prof && g_prof->on;
+      if (prof) g_prof->begin(st, 2.0 * n.din[l] * n.dout[l] * (double)((1 + n.nq) * B));
+      const css::EpiWgrad epi{n.WP[l], n.din[l], n.dout[l]};
+      if (n.dout[l] >= 128) CSS_G(tc::launch_gemm_mn<128>(txa, txb, n.din[l], n.dout[l], K, 1 + n.nq, 0, done, epi, st));
+      else CSS_G(tc::launch_gemm_mn<64>(txa, txb, n.din[l], n.dout[l], K, 1 + n.nq, 0, done, epi, st));
+      if (prof) g_prof->end(st);
     }
     css::k_css_colred<<<dim3((n.hmax + 31) / 32, n.cr_chunks, L), dim3(32, 8), 0, st>>>(f, n);
     css::k_css_colfin<<<dim3((n.hmax + 63) / 64, L), 64, 0, st>>>(f, n, stage, init_mode, k_override ? k_override + f.oPR : nullptr);

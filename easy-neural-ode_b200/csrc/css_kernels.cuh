@@ -93,11 +93,6 @@ __global__ void k_css_stage(Flat a, Net n, int stage, int init_mode) {
       const size_t o = (size_t)b * n.ldi[0] + d;
       n.X2[0][o] = hi;
       n.X2[0][n.xplane(0) + o] = lo;
-      if (n.mode == MODE_ADJ) {
-        const size_t ot = (size_t)d * 3 * n.Bp + b;
-        n.XT2[0][ot] = hi;
-        n.XT2[0][n.xtplane(0) + ot] = lo;
-      }
     }
   }
   for (int l = 0; l < n.L; ++l) {
@@ -122,11 +117,6 @@ __global__ void k_css_eps(Net n) {
     const size_t o = (size_t)(n.Bp + b) * n.ldi[0] + d;
     n.X2[0][o] = hi;
     n.X2[0][n.xplane(0) + o] = lo;
-    if (n.mode == MODE_ADJ) {
-      const size_t ot = (size_t)d * 3 * n.Bp + n.Bp + b;
-      n.XT2[0][ot] = hi;
-      n.XT2[0][n.xtplane(0) + ot] = lo;
-    }
   }
 }
 
@@ -170,17 +160,15 @@ __global__ void k_css_seed(Flat a, Net n) {
     n.EBD[(size_t)b * n.ldD + d] = -pb * je[d];
     float hi, lo;
     tc::split_tf32(ve * g, hi, lo);
-    size_t o = (size_t)(n.Bp + b) * ldo + d, ot = (size_t)d * 3 * n.Bp + n.Bp + b;
+    size_t o = (size_t)(n.Bp + b) * ldo + d;
     n.AB2[Ll][o] = hi; n.AB2[Ll][n.abplane(Ll) + o] = lo;
-    n.ABT2[Ll][ot] = hi; n.ABT2[Ll][n.abtplane(Ll) + ot] = lo;
     if (n.nq == 2) {
       const float vd = rb * 2.f * y1[d] / D;
       n.V[Ll][((size_t)n.B + b) * ldo + d] = vd;
       tc::split_tf32(vd * g, hi, lo);
-      o = (size_t)(2 * n.Bp + b) * ldo + d; ot = (size_t)d * 3 * n.Bp + 2 * n.Bp + b;
+      o = (size_t)(2 * n.Bp + b) * ldo + d;
       n.AB2[Ll][o] = hi; n.AB2[Ll][n.abplane(Ll) + o] = lo;
-      n.ABT2[Ll][ot] = hi; n.ABT2[Ll][n.abtplane(Ll) + ot] = lo;
-    }
+      }
   }
 }
 
@@ -200,9 +188,8 @@ __global__ void k_css_seed2(Flat a, Net n) {
     if (n.nq == 2) lb += n.V[Ll][((size_t)n.B + b) * ldo + d] * n.G1[Ll][d];
     float hi, lo;
     tc::split_tf32(lb, hi, lo);
-    const size_t o = (size_t)b * ldo + d, ot = (size_t)d * 3 * n.Bp + b;
+    const size_t o = (size_t)b * ldo + d;
     n.AB2[Ll][o] = hi; n.AB2[Ll][n.abplane(Ll) + o] = lo;
-    n.ABT2[Ll][ot] = hi; n.ABT2[Ll][n.abtplane(Ll) + ot] = lo;
   }
 }
 

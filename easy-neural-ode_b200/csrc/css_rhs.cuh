@@ -11,7 +11,8 @@
 // 2 = tangent with f and time tangent 1 ("d", the Taylor term).  Forward: primal GEMMs (M = B), then the two
 // tangent streams stacked (M = 2 Bp).  Reverse: tangent streams first (their cotangent reaches f through d_0 = f),
 // then the primal stream; weight gradients contract all three streams over the batch (K = 3 Bp) in one GEMM per
-// layer.  Every operand a GEMM reads is stored pre-split into tf32 hi / lo planes by the epilogue that produced it.
+// layer, reading the activations and cotangents as they lie in memory (MN-major operand descriptors, gemm_tc.cuh).
+// Every operand a GEMM reads is stored pre-split into tf32 hi / lo planes by the epilogue that produced it.
 #pragma once
 #include "eno_common.cuh"
 #include "gemm_tc.cuh"
@@ -40,7 +41,6 @@ struct Net {
   float* tval;              // [1] the time this evaluation runs at
   // activations
   float *X2[kMaxLayers];    // [2][3 Bp][ldi]    inputs of layer l: slot 0 x, 1 e, 2 d
-  float *XT2[kMaxLayers];   // [2][din][3 Bp]    the same, transposed (weight-gradient operand)
   float *LIN[kMaxLayers];   // [B][ldo]
   float *S[kMaxLayers];     // [B][ldo]          sigmoid(u_l) = softplus'(u_l)
   float *A1[kMaxLayers];    // [2][B][ldo]       x1 W per tangent stream
@@ -48,7 +48,6 @@ struct Net {
   float *WQ[kMaxLayers];    // [2][B][ldo]       tangent streams' contribution to the cotangent of u_l
   float *WW[kMaxLayers];    // [B][ldo]          cotangent of u_l
   float *AB2[kMaxLayers];   // [2][3 Bp][ldo]    slot 0 lin_bar, 1 a1_bar(e), 2 a1_bar(d)
-  float *ABT2[kMaxLayers];  // [2][dout][3 Bp]
   float *WP[kMaxLayers];    // [3][din][dout]    split-K partials of the weight gradient
   float *CR;                // [layers][chunks][4][Hmax] column partial sums
   float *TC;                // [layers][Hmax] per-column contributions to t_bar
@@ -61,9 +60,7 @@ struct Net {
   const float* eps;         // [B][D]
   int ldD;
   __host__ __device__ size_t xplane(int l) const { return (size_t)3 * Bp * ldi[l]; }
-  __host__ __device__ size_t xtplane(int l) const { return (size_t)din[l] * 3 * Bp; }
   __host__ __device__ size_t abplane(int l) const { return (size_t)3 * Bp * ldo[l]; }
-  __host__ __device__ size_t abtplane(int l) const { return (size_t)dout[l] * 3 * Bp; }
 };
 
 constexpr int kW = tc::kEpiW;   // columns one epilogue call covers
@@ -161,12 +158,10 @@ struct EpiPrimal {
     if (!last) {
       if (n.nq > 0) put_row(n.S[l] + (size_t)m * ldo, n0, dout, s);
       put_split_row(n.X2[l + 1], n.xplane(l + 1), (size_t)m * n.ldi[l + 1], n0, dout, x);
-      if (n.mode == MODE_ADJ) put_split_col(n.XT2[l + 1], n.xtplane(l + 1), 3 * n.Bp, m, n0, dout, x);
     } else {
       put_row(n.F + (size_t)m * n.ldD, n0, dout, x);
       if (n.nq == 2) {   // d_0 = f feeds the Taylor stream
         put_split_row(n.X2[0], n.xplane(0), (size_t)(2 * n.Bp + m) * n.ldi[0], n0, dout, x);
-        if (n.mode == MODE_ADJ) put_split_col(n.XT2[0], n.xtplane(0), 3 * n.Bp, 2 * n.Bp + m, n0, dout, x);
       }
     }
   }
@@ -201,7 +196,6 @@ struct EpiTangent {
 #pragma unroll
       for (int j = 0; j < kW; ++j) u1[j] *= s[j];
       put_split_row(n.X2[l + 1], n.xplane(l + 1), (size_t)((1 + q) * n.Bp + bm) * n.ldi[l + 1], n0, dout, u1);
-      if (n.mode == MODE_ADJ) put_split_col(n.XT2[l + 1], n.xtplane(l + 1), 3 * n.Bp, (1 + q) * n.Bp + bm, n0, dout, u1);
     } else {
       put_row((q == 0 ? n.JE : n.Y1) + (size_t)bm * n.ldD, n0, dout, u1);
     }
@@ -242,7 +236,6 @@ struct EpiTanRev {
     put_row(n.V[lm] + ro, n0, dout, vv);
     put_row(n.WQ[lm] + ro, n0, dout, wq);
     put_split_row(n.AB2[lm], n.abplane(lm), (size_t)((1 + q) * n.Bp + bm) * ldo, n0, dout, ab);
-    put_split_col(n.ABT2[lm], n.abtplane(lm), 3 * n.Bp, (1 + q) * n.Bp + bm, n0, dout, ab);
   }
 };
 
@@ -285,7 +278,6 @@ struct EpiPrimRev {
     }
     put_row(n.WW[lm] + (size_t)m * ldo, n0, dout, w);
     put_split_row(n.AB2[lm], n.abplane(lm), (size_t)m * ldo, n0, dout, lb);
-    put_split_col(n.ABT2[lm], n.abtplane(lm), 3 * n.Bp, m, n0, dout, lb);
   }
 };
 
