@@ -221,8 +221,9 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int kb0 = batched ? 0 : split * kb_per_split;
   const int kb1 = batched ? kb_total : min(kb_total, kb0 + kb_per_split);
   const int nkb = kb1 - kb0;
-  a_row0 += split * a_zrows;
-  b_row0 += split * b_zrows;
+  int a_krow0 = 0, b_krow0 = 0;     // MN-major batched: the problems are stacked along the ROWS (= k) of the operands
+  if (MN) { a_krow0 = split * a_zrows; b_krow0 = split * b_zrows; }
+  else { a_row0 += split * a_zrows; b_row0 += split * b_zrows; }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -251,7 +252,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           constexpr int kChunk = kBK * 128;   // one box: 32 k-rows x 128 bytes
 #pragma unroll
           for (int c = 0; c < kBM / 32; ++c) {
-            int col = a_row0 + m0 + 32 * c, row = k;
+            int col = a_row0 + m0 + 32 * c, row = a_krow0 + k;
             if (tap_w) {
               const int tap = min(2 * (int)blockIdx.x + (c >> 1), 8);
               col = a_row0 + 32 * (c & 1);
@@ -263,8 +264,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
           for (int c = 0; c < BN / 32; ++c) {
             const int col = b_row0 + (tap_w ? 0 : n0) + 32 * c;
-            tma_load_3d(st + 2 * Cfg::kABytes + c * kChunk, &tmB, &full[s], col, k, 0);
-            tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes + c * kChunk, &tmB, &full[s], col, k, 1);
+            tma_load_3d(st + 2 * Cfg::kABytes + c * kChunk, &tmB, &full[s], col, b_krow0 + k, 0);
+            tma_load_3d(st + 2 * Cfg::kABytes + Cfg::kBBytes + c * kChunk, &tmB, &full[s], col, b_krow0 + k, 1);
           }
           continue;
         }
