@@ -275,6 +275,64 @@ __global__ void k_ccv_l3(CNet n, int first_stream, int n_streams, const int* __r
   }
 }
 
+// The same layer, one warp = one image ROW of one stream (image width <= 32): the three input rows are read once each
+// (3 (W + 2) positions for W outputs instead of 9 W), a lane holds channels (lane, lane + 32) and W running outputs.
+__global__ void k_ccv_l3_rows(CNet n, int first_stream, int n_streams, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int C = n.C, lane = threadIdx.x & 31;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const size_t total = (size_t)n_streams * n.B * n.Hh;
+  const float t = *n.tval;
+  const bool two = C > 32;
+  float w0[9], w1[9];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    w0[tap] = n.W[3][(size_t)tap * (C + 1) + 1 + lane];
+    w1[tap] = two ? n.W[3][(size_t)tap * (C + 1) + 1 + lane + 32] : 0.f;
+  }
+  for (size_t i = warp; i < total; i += nwarps) {
+    const int y = (int)(i % n.Hh);
+    const size_t r = i / n.Hh;
+    const int b = (int)(r % n.B), st = first_stream + (int)(r / n.B);
+    float acc[32];
+#pragma unroll
+    for (int x = 0; x < 32; ++x) acc[x] = 0.f;
+#pragma unroll
+    for (int ry = 0; ry < 3; ++ry) {
+      const float* row = n.X3 + ((size_t)st * n.Rp + (size_t)b * n.PP + (size_t)(y + ry) * n.WP) * C;   // padded row y + ry
+#pragma unroll
+      for (int xx = 0; xx < 34; ++xx) {
+        if (xx < n.Ww + 2) {
+          const float v0 = row[(size_t)xx * C + lane];
+          const float v1 = two ? row[(size_t)xx * C + lane + 32] : 0.f;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const int x = xx - dx;   // the output column this position feeds through tap (ry, dx)
+            if (x >= 0 && x < 32) acc[x] = fmaf(v0, w0[ry * 3 + dx], fmaf(v1, w1[ry * 3 + dx], acc[x]));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < 32; ++x) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], o);
+    }
+    // lane x finishes output column x
+    float mine = 0.f;
+#pragma unroll
+    for (int x = 0; x < 32; ++x)
+      if (lane == x) mine = acc[x];
+    if (lane < n.Ww) {
+      const int pix = y * n.Ww + lane;
+      const int cls = border_class(y, lane, n.Hh, n.Ww);
+      if (st == 0) n.F[(size_t)b * n.ldD + pix] = mine + n.b[3][0] + t * n.TM[3][cls];
+      else if (st == 1) n.JE[(size_t)b * n.ldD + pix] = mine;
+      else n.Y1[(size_t)b * n.ldD + pix] = mine + n.TM[3][cls];
+    }
+  }
+}
+
 // =====================================================================================================================
 // Adjoint: the vjp of aug_dynamics (ffjord_mnist.py:311-324) wrt (y, t, eps, params), lib/ode.py:1498-1504.  Same order
 // as css_rhs.cuh: tangent streams first (their cotangent reaches f through d_0 = f), then the primal stream; weight
@@ -541,12 +599,13 @@ __global__ void __launch_bounds__(256) k_ccv_reduce(CNet n, const int* __restric
     float ab[3];
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
-      if (s > n.nq) { ab[s] = 0.f; continue; }
+      // the class sums need the primal and the Taylor stream; only layer 0's direct weight gradient reads all three
+      if (s > n.nq || (s == 1 && l != 0) || l == 3) { ab[s] = 0.f; continue; }
       const size_t row = (size_t)s * n.Rp + m;
       if (l == 0) ab[s] = n.AB0[row * C + c];
-      else if (l == 3) ab[s] = n.AB3[row];
       else ab[s] = n.AB2[l - 1][row * C + c] + n.AB2[l - 1][n.xplane() + row * C + c];
     }
+    if (l == 3 && c == 0) { ab[0] = n.AB3[m]; ab[2] = (n.nq == 2) ? n.AB3[(size_t)2 * n.Rp + m] : 0.f; }
     if (l < 3 || c == 0) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
@@ -565,12 +624,13 @@ __global__ void __launch_bounds__(256) k_ccv_reduce(CNet n, const int* __restric
         acc[18 + tap] += v;
       }
     } else if (l == 3) {
+      // dW3[tap][c_in] = sum_p x3[p + shift][c_in] ab3[p] = sum_q x3[q][c_in] ab3[q - shift]: every x3 row is read ONCE (it is
+      // zero on the halo, and so is ab3), the nine cotangents around it are scalars
+      for (int s = 0; s <= n.nq; ++s) {
+        const float xv = n.X3[((size_t)s * n.Rp + m) * C + c];
+        const float* g3 = n.AB3 + (size_t)s * n.Rp + m;
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const size_t sh = m + (tap / 3 - 1) * n.WP + (tap % 3 - 1);
-        float v = 0.f;
-        for (int s = 0; s <= n.nq; ++s) v = fmaf(n.X3[((size_t)s * n.Rp + sh) * C + c], ab[s], v);
-        acc[18 + tap] += v;
+        for (int tap = 0; tap < 9; ++tap) acc[18 + tap] = fmaf(xv, g3[-((tap / 3 - 1) * n.WP + (tap % 3 - 1))], acc[18 + tap]);
       }
     }
   }

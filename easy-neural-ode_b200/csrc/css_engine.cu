@@ -360,12 +360,16 @@ int ccv_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
   ccv::k_ccv_l0<false><<<l0grid(1), 256, 0, st>>>(c, done);
   CSS_G(tc::launch_conv3x3<64>(ta[0], tb[0], 0, c.R, C, C, c.WP, done, ccv::EpiConvPrimal{c, 1}, st));
   CSS_G(tc::launch_conv3x3<64>(ta[1], tb[1], 0, c.R, C, C, c.WP, done, ccv::EpiConvPrimal{c, 2}, st));
-  ccv::k_ccv_l3<<<l3grid(1), 256, 0, st>>>(c, 0, 1, done);
+  const bool l3rows = c.Ww <= 32;   // one warp per image row: every input row is read once
+  auto l3rgrid = [&](size_t streams) { return (int)std::min<size_t>((streams * B * c.Hh * 32 + 255) / 256, (size_t)16 * sms); };
+  if (l3rows) ccv::k_ccv_l3_rows<<<l3rgrid(1), 256, 0, st>>>(c, 0, 1, done);
+  else ccv::k_ccv_l3<<<l3grid(1), 256, 0, st>>>(c, 0, 1, done);
   if (c.nq > 0) {   // the tangent streams, stacked (the Taylor stream's direction is f: after the primal pass)
     ccv::k_ccv_l0<true><<<l0grid(c.nq), 256, 0, st>>>(c, done);
     CSS_G(tc::launch_conv3x3<64>(ta[0], tb[0], c.Rp, c.nq * c.Rp, C, C, c.WP, done, ccv::EpiConvTangent{c, 1}, st));
     CSS_G(tc::launch_conv3x3<64>(ta[1], tb[1], c.Rp, c.nq * c.Rp, C, C, c.WP, done, ccv::EpiConvTangent{c, 2}, st));
-    ccv::k_ccv_l3<<<l3grid(c.nq), 256, 0, st>>>(c, 1, c.nq, done);
+    if (l3rows) ccv::k_ccv_l3_rows<<<l3rgrid(c.nq), 256, 0, st>>>(c, 1, c.nq, done);
+    else ccv::k_ccv_l3<<<l3grid(c.nq), 256, 0, st>>>(c, 1, c.nq, done);
   }
   const css::Net& n = p.net;
   if (c.mode != css::MODE_PLAIN) ccv::k_ccv_seed<<<(B * 32 + 255) / 256, 256, 0, st>>>(f, c, n.DIV, n.RR, n.FRO, n.KIN);
