@@ -277,6 +277,9 @@ __global__ void k_ccv_l3(CNet n, int first_stream, int n_streams, const int* __r
 
 // The same layer, one warp = one image ROW of one stream (image width <= 32): the three input rows are read once each
 // (3 (W + 2) positions for W outputs instead of 9 W), a lane holds channels (lane, lane + 32) and W running outputs.
+// KIND 0: layer 3 forward (reads X3, writes F / JE / Y1); KIND 1: backward data of layer 0 (reads the cotangents AB0 with the
+// taps mirrored, writes vjp_y / the cotangents of the tangent streams' inputs) - both are C -> 1 convolutions.
+template <int KIND>
 __global__ void k_ccv_l3_rows(CNet n, int first_stream, int n_streams, const int* __restrict__ done) {
   if (done && *done) return;
   const int C = n.C, lane = threadIdx.x & 31;
@@ -287,9 +290,15 @@ __global__ void k_ccv_l3_rows(CNet n, int first_stream, int n_streams, const int
   float w0[9], w1[9];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
-    w0[tap] = n.W[3][(size_t)tap * (C + 1) + 1 + lane];
-    w1[tap] = two ? n.W[3][(size_t)tap * (C + 1) + 1 + lane + 32] : 0.f;
+    if (KIND == 0) {
+      w0[tap] = n.W[3][(size_t)tap * (C + 1) + 1 + lane];
+      w1[tap] = two ? n.W[3][(size_t)tap * (C + 1) + 1 + lane + 32] : 0.f;
+    } else {   // out[p] = sum_tap g[p - shift(tap)] w0[tap][c_out] = sum_tap' g[p + shift(tap')] w0[8 - tap'][c_out]
+      w0[tap] = n.W[0][((size_t)(8 - tap) * 2 + 1) * C + lane];
+      w1[tap] = two ? n.W[0][((size_t)(8 - tap) * 2 + 1) * C + lane + 32] : 0.f;
+    }
   }
+  const float* src = (KIND == 0) ? n.X3 : n.AB0;
   for (size_t i = warp; i < total; i += nwarps) {
     const int y = (int)(i % n.Hh);
     const size_t r = i / n.Hh;
@@ -299,7 +308,7 @@ __global__ void k_ccv_l3_rows(CNet n, int first_stream, int n_streams, const int
     for (int x = 0; x < 32; ++x) acc[x] = 0.f;
 #pragma unroll
     for (int ry = 0; ry < 3; ++ry) {
-      const float* row = n.X3 + ((size_t)st * n.Rp + (size_t)b * n.PP + (size_t)(y + ry) * n.WP) * C;   // padded row y + ry
+      const float* row = src + ((size_t)st * n.Rp + (size_t)b * n.PP + (size_t)(y + ry) * n.WP) * C;   // padded row y + ry
 #pragma unroll
       for (int xx = 0; xx < 34; ++xx) {
         if (xx < n.Ww + 2) {
@@ -325,10 +334,15 @@ __global__ void k_ccv_l3_rows(CNet n, int first_stream, int n_streams, const int
       if (lane == x) mine = acc[x];
     if (lane < n.Ww) {
       const int pix = y * n.Ww + lane;
-      const int cls = border_class(y, lane, n.Hh, n.Ww);
-      if (st == 0) n.F[(size_t)b * n.ldD + pix] = mine + n.b[3][0] + t * n.TM[3][cls];
-      else if (st == 1) n.JE[(size_t)b * n.ldD + pix] = mine;
-      else n.Y1[(size_t)b * n.ldD + pix] = mine + n.TM[3][cls];
+      if (KIND == 0) {
+        const int cls = border_class(y, lane, n.Hh, n.Ww);
+        if (st == 0) n.F[(size_t)b * n.ldD + pix] = mine + n.b[3][0] + t * n.TM[3][cls];
+        else if (st == 1) n.JE[(size_t)b * n.ldD + pix] = mine;
+        else n.Y1[(size_t)b * n.ldD + pix] = mine + n.TM[3][cls];
+      } else {
+        if (st == 0) n.YBDOT[(size_t)b * n.ldD + pix] = mine;
+        else n.XB1[((size_t)(st - 1) * n.B + b) * n.ldD + pix] = mine;
+      }
     }
   }
 }

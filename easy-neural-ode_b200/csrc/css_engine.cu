@@ -362,13 +362,13 @@ int ccv_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
   CSS_G(tc::launch_conv3x3<64>(ta[1], tb[1], 0, c.R, C, C, c.WP, done, ccv::EpiConvPrimal{c, 2}, st));
   const bool l3rows = c.Ww <= 32;   // one warp per image row: every input row is read once
   auto l3rgrid = [&](size_t streams) { return (int)std::min<size_t>((streams * B * c.Hh * 32 + 255) / 256, (size_t)16 * sms); };
-  if (l3rows) ccv::k_ccv_l3_rows<<<l3rgrid(1), 256, 0, st>>>(c, 0, 1, done);
+  if (l3rows) ccv::k_ccv_l3_rows<0><<<l3rgrid(1), 256, 0, st>>>(c, 0, 1, done);
   else ccv::k_ccv_l3<<<l3grid(1), 256, 0, st>>>(c, 0, 1, done);
   if (c.nq > 0) {   // the tangent streams, stacked (the Taylor stream's direction is f: after the primal pass)
     ccv::k_ccv_l0<true><<<l0grid(c.nq), 256, 0, st>>>(c, done);
     CSS_G(tc::launch_conv3x3<64>(ta[0], tb[0], c.Rp, c.nq * c.Rp, C, C, c.WP, done, ccv::EpiConvTangent{c, 1}, st));
     CSS_G(tc::launch_conv3x3<64>(ta[1], tb[1], c.Rp, c.nq * c.Rp, C, C, c.WP, done, ccv::EpiConvTangent{c, 2}, st));
-    if (l3rows) ccv::k_ccv_l3_rows<<<l3rgrid(c.nq), 256, 0, st>>>(c, 1, c.nq, done);
+    if (l3rows) ccv::k_ccv_l3_rows<0><<<l3rgrid(c.nq), 256, 0, st>>>(c, 1, c.nq, done);
     else ccv::k_ccv_l3<<<l3grid(c.nq), 256, 0, st>>>(c, 1, c.nq, done);
   }
   const css::Net& n = p.net;
@@ -391,7 +391,8 @@ int ccv_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
                                  ccv::EpiConvRev{c, 2, primal}, st));
     CSS_G(tc::launch_conv3x3<64>(tg[0], tw[0], first * c.Rp, primal ? c.R : count * c.Rp, C, C, c.WP, done,
                                  ccv::EpiConvRev{c, 1, primal}, st));
-    ccv::k_ccv_l0_bwd<<<l3grid(count), 256, 0, st>>>(c, first, count, done);
+    if (l3rows) ccv::k_ccv_l3_rows<1><<<l3rgrid(count), 256, 0, st>>>(c, first, count, done);
+    else ccv::k_ccv_l0_bwd<<<l3grid(count), 256, 0, st>>>(c, first, count, done);
     return 0;
   };
   int rc;
