@@ -357,17 +357,23 @@ int ccv_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
   const size_t pix = (size_t)B * c.D;
   auto l0grid = [&](size_t streams) { return (int)std::min<size_t>((streams * pix * (C / 4) + 255) / 256, (size_t)16 * sms); };
   auto l3grid = [&](size_t streams) { return (int)std::min<size_t>((streams * pix * 32 + 255) / 256, (size_t)16 * sms); };
+  // bench.py's roofline leg: CUDA-event pairs around the tensor-core launches, ALGORITHMIC flops (interior positions,
+  // 2 * C * 9 C per position and stream - not the halo rows, not the three tf32 passes)
+  const bool prof = g_prof && g_prof->on;
+  const double conv_flop = 2.0 * (double)pix * C * 9.0 * C;
+  auto pb = [&](double streams) { if (prof) g_prof->begin(st, streams * conv_flop); };
+  auto pe = [&]() { if (prof) g_prof->end(st); };
   ccv::k_ccv_l0<false><<<l0grid(1), 256, 0, st>>>(c, done);
-  CSS_G(tc::launch_conv3x3<64>(ta[0], tb[0], 0, c.R, C, C, c.WP, done, ccv::EpiConvPrimal{c, 1}, st));
-  CSS_G(tc::launch_conv3x3<64>(ta[1], tb[1], 0, c.R, C, C, c.WP, done, ccv::EpiConvPrimal{c, 2}, st));
+  pb(1); CSS_G(tc::launch_conv3x3<64>(ta[0], tb[0], 0, c.R, C, C, c.WP, done, ccv::EpiConvPrimal{c, 1}, st)); pe();
+  pb(1); CSS_G(tc::launch_conv3x3<64>(ta[1], tb[1], 0, c.R, C, C, c.WP, done, ccv::EpiConvPrimal{c, 2}, st)); pe();
   const bool l3rows = c.Ww <= 32;   // one warp per image row: every input row is read once
   auto l3rgrid = [&](size_t streams) { return (int)std::min<size_t>((streams * B * c.Hh * 32 + 255) / 256, (size_t)16 * sms); };
   if (l3rows) ccv::k_ccv_l3_rows<0><<<l3rgrid(1), 256, 0, st>>>(c, 0, 1, done);
   else ccv::k_ccv_l3<<<l3grid(1), 256, 0, st>>>(c, 0, 1, done);
   if (c.nq > 0) {   // the tangent streams, stacked (the Taylor stream's direction is f: after the primal pass)
     ccv::k_ccv_l0<true><<<l0grid(c.nq), 256, 0, st>>>(c, done);
-    CSS_G(tc::launch_conv3x3<64>(ta[0], tb[0], c.Rp, c.nq * c.Rp, C, C, c.WP, done, ccv::EpiConvTangent{c, 1}, st));
-    CSS_G(tc::launch_conv3x3<64>(ta[1], tb[1], c.Rp, c.nq * c.Rp, C, C, c.WP, done, ccv::EpiConvTangent{c, 2}, st));
+    pb(c.nq); CSS_G(tc::launch_conv3x3<64>(ta[0], tb[0], c.Rp, c.nq * c.Rp, C, C, c.WP, done, ccv::EpiConvTangent{c, 1}, st)); pe();
+    pb(c.nq); CSS_G(tc::launch_conv3x3<64>(ta[1], tb[1], c.Rp, c.nq * c.Rp, C, C, c.WP, done, ccv::EpiConvTangent{c, 2}, st)); pe();
     if (l3rows) ccv::k_ccv_l3_rows<0><<<l3rgrid(c.nq), 256, 0, st>>>(c, 1, c.nq, done);
     else ccv::k_ccv_l3<<<l3grid(c.nq), 256, 0, st>>>(c, 1, c.nq, done);
   }
@@ -387,10 +393,14 @@ int ccv_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
   }
   auto reverse = [&](int first, int count, int primal) -> int {
     ccv::k_ccv_l3_bwd<<<l0grid(count), 256, 0, st>>>(c, first, count, done);
+    pb(count);
     CSS_G(tc::launch_conv3x3<64>(tg[1], tw[1], first * c.Rp, primal ? c.R : count * c.Rp, C, C, c.WP, done,
                                  ccv::EpiConvRev{c, 2, primal}, st));
+    pe();
+    pb(count);
     CSS_G(tc::launch_conv3x3<64>(tg[0], tw[0], first * c.Rp, primal ? c.R : count * c.Rp, C, C, c.WP, done,
                                  ccv::EpiConvRev{c, 1, primal}, st));
+    pe();
     if (l3rows) ccv::k_ccv_l3_rows<1><<<l3rgrid(count), 256, 0, st>>>(c, first, count, done);
     else ccv::k_ccv_l0_bwd<<<l3grid(count), 256, 0, st>>>(c, first, count, done);
     return 0;
@@ -409,7 +419,9 @@ int ccv_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
     if (!tc::make_operand_map(&txa, c.X2[l], K, C, C, c.xplane(), 32, err, true) ||
         !tc::make_operand_map(&txb, c.AB2[l], K, C, C, c.xplane(), 32, err, true))
       return ENO_E_CUDA;
+    pb(1 + c.nq);
     CSS_G(tc::launch_gemm_mn<64>(txa, txb, 128, 64, K, c.wsplits, c.WP, done, ccv::EpiConvWgradMN{c.WPART[l], C}, st));
+    pe();
   }
   ccv::k_ccv_reduce<<<dim3(c.chunks, ccv::kLayers), 256, 0, st>>>(c, done);
   ccv::k_ccv_reduce2<<<dim3(8, ccv::kLayers), 256, 0, st>>>(c, done);
