@@ -304,7 +304,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_fwd(FwdArgs a) {
 // FIN = the "fin" augmented dynamics (cl_fin_forward / cl_fin_reverse): two scalar states per sample and
 // the eps_bar block, which never feeds back into the RHS and is therefore carried as running stage
 // combinations (solution, error, mid-point) instead of stage buffers.
-template <int R, int K, int MODE, int DT, int HT, bool FIN = false>
+// TC (ADJ_STEP only): the stage factors go to the tensor-core sinks (single GPU) instead of the row-major sinks that
+// k_adj_pgrad contracts (collective solves: one launch fewer per iteration, measured faster there).
+template <int R, int K, int MODE, int DT, int HT, bool FIN = false, bool TC = false>
 __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rhs_tau) {
   Ctrl* c = a.ctrl;
   if (MODE == ADJ_STEP && *reinterpret_cast<volatile int*>(&c->done)) return;
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cl_adj_rows(AdjArgs a, float rh
       __syncthreads();
       ENO_TICK(PH_ELEM);
       // the ADJ_STEP factors feed the tensor-core contraction (transposed hi / lo planes), the others k_adj_pgrad
-      const FactorDstT<MODE == ADJ_STEP> slot(a.slot[(MODE == ADJ_STEP) ? ev - 1 : 0], a.tc, (MODE == ADJ_STEP) ? ev - 1 : 0);
+      const FactorDstT<TC> slot(a.slot[(MODE == ADJ_STEP) ? ev - 1 : 0], a.tc, (MODE == ADJ_STEP) ? ev - 1 : 0);
       if (FIN) {
         cl_fin_forward<R>(cluster, S.cm, g, w, -tev, S.xz, a.eps, S.m, &slot, row0, a.B);
         cl_fin_reverse<R>(cluster, S.cm, g, w, S.xzb, srb, a.eps, S.m, srd, slot, row0, a.B);
@@ -688,6 +690,10 @@ template <int K, int DT, int HT, bool FIN = false>
 inline cudaError_t cl_adj_rows_launch(int mode, const AdjArgs& a, int grid, size_t smem, float rhs_tau, cudaStream_t st) {
   switch (mode) {
     case ADJ_STEP:
+      if (a.tc.X) {   // tensor-core factor sinks (adj_host.cuh decides)
+        if (!a.dist && pdl_enabled()) return launch_cluster<true>(k_cl_adj_rows<kClRows, K, ADJ_STEP, DT, HT, FIN, true>, grid, smem, st, a, rhs_tau);
+        return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_STEP, DT, HT, FIN, true>, grid, smem, st, a, rhs_tau);
+      }
       if (!a.dist && pdl_enabled()) return launch_cluster<true>(k_cl_adj_rows<kClRows, K, ADJ_STEP, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
       return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_STEP, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
     case ADJ_INIT0: return launch_cluster(k_cl_adj_rows<kClRows, K, ADJ_INIT0, DT, HT, FIN>, grid, smem, st, a, rhs_tau);
