@@ -350,9 +350,13 @@ def fm_batch(rank, step, pin=False, batch=None):
     return images, eps
 
 
-def fm_config(world):
-    return {"workload": FM_WORKLOAD, "global_batch": FM["B"] * world, "per_gpu_batch": FM["B"], "rtol": FM["TOL"], "atol": FM["TOL"],
-            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (development)",
+def fm_config(world, strong=False):
+    gb = FM["B"] if strong else FM["B"] * world
+    return {"workload": FM_WORKLOAD, "global_batch": gb, "per_gpu_batch": gb // world, "rtol": FM["TOL"], "atol": FM["TOL"],
+            "parallelism": "single GPU" if world == 1 else
+                           (f"dp{world}: {'the batch-200 problem split' if strong else 'batch sharded 200/GPU'} in contiguous row blocks, "
+                            "ONE global adaptive step sequence (per iteration: all-reduce of the stage combinations of the params_bar "
+                            "block, all-gather of the per-rank error-norm sums; NCCL, captured in the iteration graph)"),
             "l2": "flushed between steps (256 MiB device write, outside the per-step events)",
             "trajectory": "train steps 0..K-1 from the script's initial parameters (last layer zero-initialised, seeded), identical "
                           "in every leg and arm"}
@@ -403,10 +407,49 @@ def fm_main(args, result_out, rank, local_rank, world):
     from easy_neural_ode_b200 import ffjord_mnist_step
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    model = ffjord_mnist_step.ImageFfjord(FM["IMG"], FM["C"], reg="r2", lam=FM["LAM"], rtol=FM["TOL"], atol=FM["TOL"], device=dev, seed=0)
+    strong = args.scaling == "strong" and world > 1
+    parity = None
+    if world > 1:
+        # batch rows sharded over the ranks, collective solves (tests/dist_check_flat.py); strong: BASELINE's 8-GPU line is
+        # the batch-200 step itself split over the GPUs (25 images each at 8)
+        import torch.distributed as dist
+        import easy_neural_ode_b200 as eno
+        dist.init_process_group("nccl", device_id=dev)
+        if FM["B"] % world and strong:
+            raise SystemExit("bench.py: --workload ffjord_mnist --scaling strong needs a world size that divides 200")
+        sl = eno.shard_rows(FM["B"], world, rank) if strong else slice(0, FM["B"])
+        do_parity = strong or world == 2                      # weak: the concatenated batch is 200 x world images
+        if do_parity:
+            parts = [fm_batch(0 if strong else r, 0) for r in range(1 if strong else world)]
+            full = tuple(torch.cat([q[i] for q in parts]).to(dev) for i in range(2))
+            single = ffjord_mnist_step.ImageFfjord(FM["IMG"], FM["C"], reg="r2", lam=FM["LAM"], rtol=FM["TOL"], atol=FM["TOL"],
+                                                   device=dev, seed=0)
+            single.update(*full)                              # one update first: the zero-initialised last layer has f == 0
+            want = single.loss_and_grads(*full)
+            snap1 = single.snapshot()
+        eno.init_distributed()
+    else:
+        sl = slice(0, FM["B"])
+    model = ffjord_mnist_step.ImageFfjord(FM["IMG"], FM["C"], reg="r2", lam=FM["LAM"], rtol=FM["TOL"], atol=FM["TOL"], device=dev, seed=0,
+                                          world=world)
+    if world > 1 and do_parity:
+        # driver-visible parity: the collective solve of train step 1 against the single-device solve of the concatenated batch
+        model.restore(snap1)
+        mine = tuple(t[sl] if strong else t[rank * FM["B"]:(rank + 1) * FM["B"]] for t in full)
+        got = model.loss_and_grads(*mine)
+        gr = float((got["grads"] - want["grads"]).abs().max() / want["grads"].abs().max())
+        parity = {"against": f"single-GPU solve of the concatenated batch ({full[0].shape[0]} images) of train step 1, same process, "
+                             "before going collective",
+                  "fwd_iters": [got["fwd_stats"]["n_iters"], want["fwd_stats"]["n_iters"]],
+                  "bwd_iters": [got["bwd_stats"][0]["n_iters"], want["bwd_stats"][0]["n_iters"]],
+                  "loss_rel": abs(float(got["loss"]) - float(want["loss"])) / abs(float(want["loss"])), "grad_rel": gr}
+        model = ffjord_mnist_step.ImageFfjord(FM["IMG"], FM["C"], reg="r2", lam=FM["LAM"], rtol=FM["TOL"], atol=FM["TOL"], device=dev,
+                                              seed=0, world=world)
+        del single, want, full
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    dev_b = [tuple(t.to(dev) for t in fm_batch(rank, s)) for s in range(8)]
-    host_b = [fm_batch(rank, s, pin=True) for s in range(8)]
+    src = 0 if strong else rank
+    dev_b = [tuple(t[sl].to(dev) for t in fm_batch(src, s)) for s in range(8)]
+    host_b = [tuple(t[sl].contiguous().pin_memory() for t in fm_batch(src, s)) for s in range(8)]
     snap = model.snapshot()
     for s in range(max(args.warmup, 3)):
         out = model.update(*dev_b[s % 8])
@@ -415,6 +458,8 @@ def fm_main(args, result_out, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     sampler.start()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     nfe_total, iters, n_rhs = 0.0, [], 0
     for s in range(args.steps):
@@ -428,7 +473,13 @@ def fm_main(args, result_out, rank, local_rank, world):
     torch.cuda.synchronize()
     clocks = sampler.stop()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    if world > 1:                                             # device time of the slowest rank
+        t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t)
     ms_per_step = dev_ms / args.steps
+    units = 1 if (strong or world == 1) else world            # batch-200 steps one step of the job advances
     loss_dev = float(out["loss"])
     model.restore(snap)
 
@@ -440,11 +491,17 @@ def fm_main(args, result_out, rank, local_rank, world):
         step_e2e(s)
     model.restore(snap)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
         step_e2e(s)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -479,17 +536,24 @@ def fm_main(args, result_out, rank, local_rank, world):
                 "algorithmic_flop_per_launch_avg": gfl.value / max(gcnt.value, 1),
                 "frac_of_3xtf32_ceiling": achieved / (tensor_peak / 6.0),
                 "gemm_share_of_step": (gms.value / n_prof) / ms_per_step}
-    line = {"metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+    if world > 1:
+        eno.shutdown_distributed()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+    line = {"metric": METRIC, "value": units * 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32 (tcgen05 3xTF32 convolutions, fp32 accumulate)", "data": "synthetic",
-            "config": fm_config(world), "samples_per_s": FM["B"] * 1e3 / ms_per_step, "clocks": clocks,
-            "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host_b[0]),
-                    "d2h_bytes_per_step": 4},
+            "config": fm_config(world, strong), "samples_per_s": units * FM["B"] * 1e3 / ms_per_step, "clocks": clocks,
+            "e2e": {"value": units * args.steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": world * sum(x.numel() * x.element_size() for x in host_b[0]), "d2h_bytes_per_step": 4 * world},
             "gpu_launches": 20 * n_rhs, "nfe_per_s": nfe_total / (dev_ms * 1e-3),
             "solver": {"iters_fwd_bwd_per_step": iters, "loss_last": loss_dev},
             "launch_mode": "polled solves; one loop iteration (6 right-hand sides + controller) replayed as a CUDA graph",
             "roofline": roofline}
-    if not args.no_cpu_baseline:
+    if parity:
+        line["parity"] = parity
+    if not args.no_cpu_baseline and world == 1:
         threads = len(os.sched_getaffinity(0))
         shard = 8
         sec, info = fm_cpu_steps(min(args.steps, 3), threads, shard, budget_s=40.0)
@@ -714,7 +778,7 @@ def main():
     ap.add_argument("--workload", default="mnist", choices=["mnist", "ffjord_tabular", "latent_ode", "ffjord_mnist"],
                     help="mnist = BASELINE configs[0], the configuration the metric is quoted on (default); "
                          "ffjord_tabular = configs[1] (single GPU); latent_ode = configs[2] (single GPU); ffjord_mnist = configs[3] "
-                         "(single GPU)")
+                         "(--gpus N: batch rows sharded, collective solves; --scaling strong splits the batch-200 step itself)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -750,7 +814,7 @@ def main():
     if args.workload == "ffjord_mnist":
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
-        return fm_main(args, result_out, rank, local_rank, world) if rank == 0 else None
+        return fm_main(args, result_out, rank, local_rank, world)
     B = args.batch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")

@@ -292,10 +292,10 @@ inline int adj_solve(Profiler* prof, int path_mode, const DistCtx* dc, int defer
   const PgradGeom geo = pgrad_geom(D, H);
   // ADJ_STEP parameter gradients of the cluster path run on the tensor cores (batched tcgen05 3xTF32 GEMM +
   // k_adj_pcombine): k_cl_adj_rows<ADJ_STEP> writes its factors as K-major hi / lo planes
-  // (single GPU; collective solves keep the FFMA kernel k_adj_pgrad: one launch fewer per iteration means less
-  // rank-to-rank skew for the exchange to wait for - 3349 against 3152 steps/s at 8 GPUs; ENO_PGRAD_TC=1 forces it)
-  static const bool pg_force = getenv("ENO_PGRAD_TC") != nullptr;
-  const bool pg_tc = plan.cluster && (!dist || pg_force);
+  // (single GPU and collective solves alike; ENO_PGRAD_FFMA=1 keeps the FFMA kernel k_adj_pgrad for A/B runs - measured
+  // at 2 GPUs: 931 steps/s with it against 944 with the tensor-core path)
+  static const bool pg_ffma = getenv("ENO_PGRAD_FFMA") != nullptr;
+  const bool pg_tc = plan.cluster && !pg_ffma;
   if (pg_tc && (size_t)kSlots * 2 * a.tc.dpad * a.tc.ldk >= (1ull << 31)) {
     if (err) *err = "eno_odeint_bwd: batch too large for the tensor-core factor planes";
     return ENO_E_UNSUPPORTED;

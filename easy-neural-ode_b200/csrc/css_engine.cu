@@ -133,8 +133,12 @@ void plan_build_conv(const eno_dynamics_desc* d, int B, int T, int mode, void* w
   f.MID = cv.take<float>(2 * f.N);
   f.YS = cv.take<float>(f.n_feed);
   f.n_part = 2048;
-  f.part = cv.take<double>(2 * (size_t)f.n_part);
+  f.part = cv.take<double>(4 * (size_t)f.n_part);
   f.out = cv.take<float>((size_t)std::max(T, 2) * f.N);
+  f.world = 1; f.rank = 0;
+  f.gbuf = cv.take<double>(32);
+  f.n_x = mode ? 1 + p->P : 0;
+  f.xbuf = cv.take<float>(std::max<size_t>(4 * f.n_x, 4));
   p->params = cv.take<float>(p->P);
   p->eps = cv.take<float>(BD);
   p->seg_ts = cv.take<float>(4);
@@ -234,8 +238,12 @@ void plan_build(const eno_dynamics_desc* d, int B, int T, int mode, void* ws, Pl
   f.MID = cv.take<float>(2 * f.N);
   f.YS = cv.take<float>(f.n_feed);
   f.n_part = 2048;
-  f.part = cv.take<double>(2 * (size_t)f.n_part);
+  f.part = cv.take<double>(4 * (size_t)f.n_part);
   f.out = cv.take<float>((size_t)std::max(T, 2) * f.N);
+  f.world = 1; f.rank = 0;
+  f.gbuf = cv.take<double>(32);
+  f.n_x = mode ? 1 + p->P : 0;
+  f.xbuf = cv.take<float>(std::max<size_t>(4 * f.n_x, 4));
   p->params = cv.take<float>(p->P);
   p->eps = cv.take<float>(BD);
   p->seg_ts = cv.take<float>(4);
@@ -522,7 +530,7 @@ int css_prepare(eno_ctx* ctx, Plan& p, const float* params, const float* eps, cu
 
 // cached graph of one loop iteration, keyed by everything its kernel arguments depend on
 struct GraphKey {
-  void* ws; int B, D, H, L, aug, reg, mode, T;
+  void* ws; int B, D, H, L, aug, reg, mode, T, world, rank;
   bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
 };
 struct CssState {
@@ -541,13 +549,49 @@ CssState* state_of(eno_ctx* ctx) {
   return static_cast<CssState*>(ctx->css);
 }
 
-int enqueue_iteration(const Plan& p, int sms, cudaStream_t st, std::string* err) {
+// Collective solves (eno_comm_init has run): the batch rows are sharded over the ranks, the solve is ONE global solve of the
+// concatenated batch.  Returns the element count of the global state (the mean in the error norm, lib/ode.py:518-538).
+double set_collective(eno_ctx* ctx, Plan* p, int B) {
+  css::Flat& f = p->flat;
+  if (!ctx->dist.active()) return (double)f.N;
+  f.world = ctx->dist.world;
+  f.rank = ctx->dist.rank;
+  const double per_row = (double)(f.N - f.n_x) / (double)B;
+  return per_row * (double)ctx->dist.rows(B) + (double)f.n_x;
+}
+
+// NCCL calls of the collective solves (dist.cuh); every rank enqueues the same sequence
+#define CSS_NCCL(expr, what)                                                                      \
+  do {                                                                                            \
+    int n_ = (expr);                                                                              \
+    if (n_ != 0) { if (err) *err = std::string(what) + ": " + dc->api.GetErrorString(n_); return ENO_E_CUDA; } \
+  } while (0)
+
+// sums the replicated elements ([t0_bar | params_bar]) of one flat vector over the ranks, in place
+int allreduce_replicated(const Plan& p, const DistCtx* dc, float* vec, cudaStream_t st, std::string* err) {
+  if (!dc || p.flat.n_x == 0) return 0;
+  CSS_NCCL(dc->api.GroupStart(), "ncclGroupStart");
+  CSS_NCCL(dc->allreduce(vec + p.flat.oT0, 1, st), "ncclAllReduce");
+  CSS_NCCL(dc->allreduce(vec + p.flat.oPR, p.flat.n_x - 1, st), "ncclAllReduce");
+  CSS_NCCL(dc->api.GroupEnd(), "ncclGroupEnd");
+  return 0;
+}
+
+int enqueue_iteration(const Plan& p, const DistCtx* dc, int sms, cudaStream_t st, std::string* err) {
   for (int s = 1; s <= 6; ++s) {
     int rc = css_rhs_launch(p, s, css::ST_STAGE, nullptr, sms, st, err);
     if (rc) return rc;
   }
   const int fgrid = std::min<int>((int)((p.flat.N + 255) / 256), p.flat.n_part);
+  if (dc && p.flat.n_x) {
+    css::k_flat_xcomb<<<std::min<int>((int)((p.flat.n_x + 255) / 256), 4 * sms), 256, 0, st>>>(p.flat);
+    CSS_NCCL(dc->allreduce(p.flat.xbuf, 4 * p.flat.n_x, st), "ncclAllReduce");
+  }
   css::k_flat_finish<<<fgrid, 256, 0, st>>>(p.flat);
+  if (dc) {
+    CSS_NCCL(dc->gather(p.flat.gbuf, 2, st), "ncclAllGather");
+    css::k_flat_control<<<1, 1, 0, st>>>(p.flat);
+  }
   css::k_flat_out<<<std::min<int>((int)((p.flat.N + 255) / 256), 4 * sms), 256, 0, st>>>(p.flat);
   return 0;
 }
@@ -557,13 +601,21 @@ int run_loop(eno_ctx* ctx, const Plan& p, const GraphKey& key, int which, eno_st
   CssState* S = state_of(ctx);
   std::string err;
   const int sms = ctx->sm_count;
+  const DistCtx* dc = p.flat.world > 1 ? &ctx->dist : nullptr;
   int rc;
-  // initial step: f0, norms, f(y0 + h0 f0), norms
+  // initial step: f0, norms, f(y0 + h0 f0), norms.  Collective solves: the replicated elements of both derivatives are
+  // summed over the ranks (the controller ring is at slot 0 here: F[cur] = F), the norms gathered in rank order.
   if ((rc = css_rhs_launch(p, 0, css::ST_INIT0, nullptr, sms, st, &err))) return css_fail(ctx, rc, err);
   const int igrid = std::min<int>((int)((p.flat.N + 255) / 256), p.flat.n_part);
-  css::k_flat_init<<<igrid, 256, 0, st>>>(p.flat, 0);
-  if ((rc = css_rhs_launch(p, 0, css::ST_INIT1, nullptr, sms, st, &err))) return css_fail(ctx, rc, err);
-  css::k_flat_init<<<igrid, 256, 0, st>>>(p.flat, 1);
+  for (int phase = 0; phase < 2; ++phase) {
+    if (phase == 1 && (rc = css_rhs_launch(p, 0, css::ST_INIT1, nullptr, sms, st, &err))) return css_fail(ctx, rc, err);
+    if ((rc = allreduce_replicated(p, dc, phase == 0 ? p.flat.F : p.flat.KS, st, &err))) return css_fail(ctx, rc, err);
+    css::k_flat_init<<<igrid, 256, 0, st>>>(p.flat, phase);
+    if (dc) {
+      if (dc->gather(p.flat.gbuf, 2, st) != 0) return css_fail(ctx, ENO_E_CUDA, "ncclAllGather failed (initial step)");
+      css::k_flat_init_control<<<1, 1, 0, st>>>(p.flat, phase);
+    }
+  }
   cudaGraphExec_t exec = nullptr;
   const bool profiling = ctx->prof.enabled;
   S->prof.on = false;
@@ -574,7 +626,7 @@ int run_loop(eno_ctx* ctx, const Plan& p, const GraphKey& key, int which, eno_st
     else {
       cudaGraph_t g = nullptr;
       if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        rc = enqueue_iteration(p, sms, st, &err);
+        rc = enqueue_iteration(p, dc, sms, st, &err);
         cudaError_t e = cudaStreamEndCapture(st, &g);
         if (rc == 0 && e == cudaSuccess && g && cudaGraphInstantiate(&exec, g, 0) == cudaSuccess) S->graphs[key] = exec;
         else { exec = nullptr; cudaGetLastError(); }
@@ -587,7 +639,7 @@ int run_loop(eno_ctx* ctx, const Plan& p, const GraphKey& key, int which, eno_st
   for (;;) {
     for (int k = 0; k < chunk; ++k) {
       if (exec) CSS_CUDA(ctx, cudaGraphLaunch(exec, st));
-      else if ((rc = enqueue_iteration(p, sms, st, &err))) return css_fail(ctx, rc, err);
+      else if ((rc = enqueue_iteration(p, dc, sms, st, &err))) return css_fail(ctx, rc, err);
       ++n_launched_iters;
     }
     CSS_CUDA(ctx, cudaMemcpyAsync(ctx->mailbox, p.flat.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
@@ -668,14 +720,15 @@ int odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* 
   int rc;
   if ((rc = css_prepare(ctx, p, params, eps, st))) return rc;
   const size_t N = p.flat.N, BD = (size_t)B * desc->D;
-  css::k_flat_reset<<<1, 1, 0, st>>>(p.flat.ctrl, rtol, atol, T, mxstep <= 0 ? INT_MAX : mxstep, trace ? trace_cap : 0, (float)N);
+  const double n_state = set_collective(ctx, &p, B);
+  css::k_flat_reset<<<1, 1, 0, st>>>(p.flat.ctrl, rtol, atol, T, mxstep <= 0 ? INT_MAX : mxstep, trace ? trace_cap : 0, (float)n_state);
   // the auxiliary states start from aux_out[0] (zeros from aug_init; delta_logp of the logit pre-flow in
   // ffjord_mnist.py:409-417): their magnitude enters the error norm through tol = atol + rtol max(|y0|, |y1|)
   css::k_css_fwd_begin<<<std::min<int>((int)((N + 255) / 256), 1024), 256, 0, st>>>(p.flat, y0, na > 0 ? aux_out : nullptr);
   int launches = 0;
   int status = ENO_OK;
   if (T > 1) {
-    GraphKey key{ws, B, desc->D, desc->H, desc->n_hidden, desc->aug, desc->reg_order, 0, T};
+    GraphKey key{ws, B, desc->D, desc->H, desc->n_hidden, desc->aug, desc->reg_order, 0, T, p.flat.world, p.flat.rank};
     status = run_loop(ctx, p, key, 0, stats, &launches, st);
     if (status < 0) return status;
   } else if (stats) memset(stats, 0, sizeof(*stats));
@@ -716,6 +769,8 @@ int odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* 
   if ((rc = css_prepare(ctx, p, params, eps, st))) return rc;
   p.flat.ts = p.seg_ts;
   p.flat.trace = trace;
+  const double n_state = set_collective(ctx, &p, B);
+  const DistCtx* dc = p.flat.world > 1 ? &ctx->dist : nullptr;
   const int egrid = std::min<int>((int)((N + 255) / 256), 2048);
   int worst = ENO_OK, launches = 0;
   std::string err;
@@ -723,12 +778,16 @@ int odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* 
     const float* gy_i = g_y + (size_t)i * BD;
     const float* ga_i = g_aux + (size_t)i * AB;
     css::k_css_seg_ts<<<1, 1, 0, st>>>(ts, i, p.seg_ts);
-    css::k_flat_reset<<<1, 1, 0, st>>>(p.flat.ctrl, rtol, atol, 2, mxstep <= 0 ? INT_MAX : mxstep, trace ? trace_cap : 0, (float)N);
+    css::k_flat_reset<<<1, 1, 0, st>>>(p.flat.ctrl, rtol, atol, 2, mxstep <= 0 ? INT_MAX : mxstep, trace ? trace_cap : 0, (float)n_state);
     css::k_css_adj_begin<<<egrid, 256, 0, st>>>(p.flat, ys + (size_t)i * BD, nullptr, gy_i, ga_i, i == T - 1);
     // t_bar needs func(ys[i], ts[i]): the forward half of one evaluation (scratch slot: stage buffer 1)
     if ((rc = css_rhs_launch(p, 0, css::ST_PROBE, p.flat.KS + N, ctx->sm_count, st, &err))) return css_fail(ctx, rc, err);
     css::k_css_tbar<<<1, 512, 0, st>>>(p.flat, p.net, gy_i, ga_i, ts_bar_out + i);
-    GraphKey key{ws, B, desc->D, desc->H, desc->n_hidden, desc->aug, desc->reg_order, 1, 2};
+    if (dc) {   // t_bar is a sum over the rows of the concatenated batch
+      if (dc->allreduce(p.flat.xbuf, 1, st) != 0) return css_fail(ctx, ENO_E_CUDA, "ncclAllReduce failed (t_bar)");
+      css::k_css_tbar_apply<<<1, 1, 0, st>>>(p.flat, ts_bar_out + i);
+    }
+    GraphKey key{ws, B, desc->D, desc->H, desc->n_hidden, desc->aug, desc->reg_order, 1, 2, p.flat.world, p.flat.rank};
     int status = run_loop(ctx, p, key, 1, stats ? stats + (T - 1 - i) : nullptr, &launches, st);
     if (status < 0) return status;
     if (status != ENO_OK && worst == ENO_OK) worst = status;

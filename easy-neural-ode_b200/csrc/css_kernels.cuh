@@ -20,8 +20,14 @@ struct Flat {
   float *KS;            // [5][N] stage derivatives 1..5
   float *MID;           // [2][N]
   float *YS;            // [n_feed] stage input
-  double* part;         // [n_part] per-block partial sums (two lanes: part, part + n_part)
+  double* part;         // [4][n_part] per-block partial sums (lanes: part + l * n_part)
   int n_part;
+  // collective solves (batch rows sharded over `world` ranks, css_engine.cu): the [t0_bar | params_bar] elements of the
+  // adjoint state are REPLICATED (every rank holds the global value), everything else is this rank's rows
+  int world, rank;
+  double* gbuf;         // [world][2] per-rank sums of the sharded elements (all-gathered), then [2] replicated-block sums
+  float* xbuf;          // [4][n_x] stage combinations (sol, err, mid, k6) of the replicated elements, all-reduced
+  size_t n_x;           // 1 + P
   float* out;           // [T][N]
   eno_trace_row* trace;
   float tsign;          // +1 forward, -1 adjoint (RHS time = tsign * solver time)
@@ -61,6 +67,15 @@ __device__ __forceinline__ double block_reduce(double v, double* sm) {
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sm[i];
   return r;   // valid in thread 0
 }
+
+// collective adjoint solves: is state element i replicated?  *j = its index in xbuf (0: t0_bar, 1 + p: params_bar[p])
+__device__ __forceinline__ bool replicated(const Flat& a, size_t i, size_t* j) {
+  if (a.world <= 1 || a.oPR == 0) return false;
+  if (i >= a.oPR) { *j = 1 + (i - a.oPR); return true; }
+  if (i == a.oT0) { *j = 0; return true; }
+  return false;
+}
+__device__ __forceinline__ size_t replicated_at(const Flat& a, size_t j) { return j == 0 ? a.oT0 : a.oPR + (j - 1); }
 
 // ---- stage input + network input + gate vectors, one launch ---------------------------------------------------
 __global__ void k_css_stage(Flat a, Net n, int stage, int init_mode) {
@@ -311,34 +326,7 @@ __global__ void k_css_assemble(Flat a, Net n, int stage, int init_mode, float* k
 }
 
 // ---- initial step size (lib/ode.py:86-104), two phases ----------------------------------------------------------
-__global__ void k_flat_init(Flat a, int phase) {
-  __shared__ double sm[32];
-  __shared__ double dred[512];
-  Ctrl* c = a.ctrl;
-  const float rtol = c->rtol, atol = c->atol;
-  const float* y = a.Y + (size_t)c->cur * a.N;
-  const float* f0 = a.F + (size_t)c->cur * a.N;
-  double s0 = 0.0, s1 = 0.0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += (size_t)gridDim.x * blockDim.x) {
-    const float scale = atol + fabsf(y[i]) * rtol;
-    if (phase == 0) {
-      const float q0 = y[i] / scale, q1 = f0[i] / scale;
-      s0 += (double)(q0 * q0);
-      s1 += (double)(q1 * q1);
-    } else {
-      const float q = (a.KS[i] - f0[i]) / scale;
-      s0 += (double)(q * q);
-    }
-  }
-  const double b0 = block_reduce(s0, sm);
-  const double b1 = block_reduce(s1, sm);
-  if (threadIdx.x == 0) { a.part[blockIdx.x] = b0; a.part[a.n_part + blockIdx.x] = b1; }
-  if (!last_block(&c->ticket)) return;
-  const double t0s = block_sum_global(a.part, gridDim.x, dred);
-  __syncthreads();
-  const double t1s = block_sum_global(a.part + a.n_part, gridDim.x, dred);
-  if (threadIdx.x != 0) return;
-  c->ticket = 0;
+__device__ __forceinline__ void init_control(const Flat& a, Ctrl* c, int phase, double t0s, double t1s) {
   if (phase == 0) {
     const float d0 = sqrtf((float)t0s), d1 = sqrtf((float)t1s);
     c->d0 = d0; c->d1 = d1;
@@ -362,7 +350,93 @@ __global__ void k_flat_init(Flat a, int phase) {
   }
 }
 
+// sums over ranks in rank order (every rank holds the same gathered values, so every controller takes the same decision)
+__device__ __forceinline__ double gathered_sum(const Flat& a, int lane) {
+  double s = 0.0;
+  for (int r = 0; r < a.world; ++r) s += a.gbuf[2 * r + lane];
+  return s + a.gbuf[2 * a.world + lane];
+}
+
+__global__ void k_flat_init(Flat a, int phase) {
+  __shared__ double sm[32];
+  __shared__ double dred[512];
+  Ctrl* c = a.ctrl;
+  const float rtol = c->rtol, atol = c->atol;
+  const float* y = a.Y + (size_t)c->cur * a.N;
+  const float* f0 = a.F + (size_t)c->cur * a.N;
+  double s0 = 0.0, s1 = 0.0, r0 = 0.0, r1 = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += (size_t)gridDim.x * blockDim.x) {
+    const float scale = atol + fabsf(y[i]) * rtol;
+    size_t j;
+    const bool rep = replicated(a, i, &j);
+    if (phase == 0) {
+      const float q0 = y[i] / scale, q1 = f0[i] / scale;
+      if (rep) { r0 += (double)(q0 * q0); r1 += (double)(q1 * q1); }
+      else { s0 += (double)(q0 * q0); s1 += (double)(q1 * q1); }
+    } else {
+      const float q = (a.KS[i] - f0[i]) / scale;
+      if (rep) r0 += (double)(q * q);
+      else s0 += (double)(q * q);
+    }
+  }
+  const double b0 = block_reduce(s0, sm);
+  const double b1 = block_reduce(s1, sm);
+  const double b2 = block_reduce(r0, sm);
+  const double b3 = block_reduce(r1, sm);
+  if (threadIdx.x == 0) {
+    a.part[blockIdx.x] = b0; a.part[a.n_part + blockIdx.x] = b1;
+    a.part[2 * a.n_part + blockIdx.x] = b2; a.part[3 * a.n_part + blockIdx.x] = b3;
+  }
+  if (!last_block(&c->ticket)) return;
+  const double t0s = block_sum_global(a.part, gridDim.x, dred);
+  __syncthreads();
+  const double t1s = block_sum_global(a.part + a.n_part, gridDim.x, dred);
+  __syncthreads();
+  const double t2s = block_sum_global(a.part + 2 * a.n_part, gridDim.x, dred);
+  __syncthreads();
+  const double t3s = block_sum_global(a.part + 3 * a.n_part, gridDim.x, dred);
+  if (threadIdx.x != 0) return;
+  c->ticket = 0;
+  if (a.world > 1) {   // k_flat_init_control finishes after the all-gather
+    a.gbuf[2 * a.rank] = t0s; a.gbuf[2 * a.rank + 1] = t1s;
+    a.gbuf[2 * a.world] = t2s; a.gbuf[2 * a.world + 1] = t3s;
+    return;
+  }
+  init_control(a, c, phase, t0s + t2s, t1s + t3s);
+}
+
+__global__ void k_flat_init_control(Flat a, int phase) {
+  init_control(a, a.ctrl, phase, gathered_sum(a, 0), gathered_sum(a, 1));
+}
+
 // ---- end of an iteration: candidate, error estimate, mid-point, norm, controller ------------------------------
+// Collective solves: the stage derivatives of the replicated elements are per-rank PARTIAL sums over this rank's rows
+// (stages 1..6; the first stage is the global derivative the previous iteration left in the F ring), and everything
+// downstream of the batch sum is linear: k_flat_xcomb forms the three stage combinations + k6, ONE all-reduce sums
+// them, k_flat_finish completes the replicated elements from the sums and stores the global k6 into the F ring.
+__global__ void k_flat_xcomb(Flat a) {
+  const Ctrl* c = a.ctrl;
+  if (c->done) return;
+  const size_t N = a.N;
+  const float* K6 = a.F + (size_t)c->cand * N;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < a.n_x; j += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = replicated_at(a, j);
+    float as = 0.f, ae = 0.f, am = 0.f;
+#pragma unroll
+    for (int s = 1; s < 6; ++s) {
+      const float k = a.KS[(size_t)(s - 1) * N + i];
+      as = fmaf(c_tab.c_sol[s], k, as);
+      ae = fmaf(c_tab.c_err[s], k, ae);
+      am = fmaf(c_tab.c_mid[s], k, am);
+    }
+    const float k6 = K6[i];
+    a.xbuf[j] = fmaf(c_tab.c_sol[6], k6, as);
+    a.xbuf[a.n_x + j] = fmaf(c_tab.c_err[6], k6, ae);
+    a.xbuf[2 * a.n_x + j] = fmaf(c_tab.c_mid[6], k6, am);
+    a.xbuf[3 * a.n_x + j] = k6;
+  }
+}
+
 __global__ void k_flat_finish(Flat a) {
   __shared__ double sm[32];
   __shared__ double dred[512];
@@ -373,40 +447,72 @@ __global__ void k_flat_finish(Flat a) {
   const float* Yc = a.Y + (size_t)c->cur * N;
   const float* K0 = a.F + (size_t)c->cur * N;
   float* Yn = a.Y + (size_t)c->cand * N;
-  const float* K6 = a.F + (size_t)c->cand * N;
+  float* K6 = a.F + (size_t)c->cand * N;
   float* Mn = a.MID + (size_t)(c->mid_acc ^ 1) * N;
-  double acc = 0.0;
+  double acc = 0.0, accr = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x) {
-    float kk[7];
-    kk[0] = K0[i];
-#pragma unroll
-    for (int j = 1; j < 6; ++j) kk[j] = a.KS[(size_t)(j - 1) * N + i];
-    kk[6] = K6[i];
     float as = 0.f, ae = 0.f, am = 0.f;
+    size_t j;
+    const bool rep = replicated(a, i, &j);
+    if (rep) {
+      const float k0 = K0[i];
+      as = fmaf(c_tab.c_sol[0], k0, a.xbuf[j]);
+      ae = fmaf(c_tab.c_err[0], k0, a.xbuf[a.n_x + j]);
+      am = fmaf(c_tab.c_mid[0], k0, a.xbuf[2 * a.n_x + j]);
+      K6[i] = a.xbuf[3 * a.n_x + j];
+    } else {
+      float kk[7];
+      kk[0] = K0[i];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      as = fmaf(c_tab.c_sol[j], kk[j], as);
-      ae = fmaf(c_tab.c_err[j], kk[j], ae);
-      am = fmaf(c_tab.c_mid[j], kk[j], am);
+      for (int s = 1; s < 6; ++s) kk[s] = a.KS[(size_t)(s - 1) * N + i];
+      kk[6] = K6[i];
+#pragma unroll
+      for (int s = 0; s < 7; ++s) {
+        as = fmaf(c_tab.c_sol[s], kk[s], as);
+        ae = fmaf(c_tab.c_err[s], kk[s], ae);
+        am = fmaf(c_tab.c_mid[s], kk[s], am);
+      }
     }
     const float y = Yc[i];
     const float y1 = fmaf(dt, as, y);
     const float err = dt * ae;
     const float tol = atol + rtol * fmaxf(fabsf(y), fabsf(y1));
     const float q = err / tol;
-    acc += (double)(q * q);
+    if (rep) accr += (double)(q * q);
+    else acc += (double)(q * q);
     Yn[i] = y1;
     Mn[i] = fmaf(dt, am, y);
   }
   const double b0 = block_reduce(acc, sm);
   if (threadIdx.x == 0) a.part[blockIdx.x] = b0;
+  if (a.world > 1) {
+    const double b1 = block_reduce(accr, sm);
+    if (threadIdx.x == 0) a.part[a.n_part + blockIdx.x] = b1;
+  }
   if (!last_block(&c->ticket)) return;
   const double sum = block_sum_global(a.part, gridDim.x, dred);
+  if (a.world > 1) {   // k_flat_control finishes after the all-gather
+    __syncthreads();
+    const double sumr = block_sum_global(a.part + a.n_part, gridDim.x, dred);
+    if (threadIdx.x == 0) {
+      c->ticket = 0;
+      a.gbuf[2 * a.rank] = sum; a.gbuf[2 * a.rank + 1] = 0.0;
+      a.gbuf[2 * a.world] = sumr; a.gbuf[2 * a.world + 1] = 0.0;
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     c->ticket = 0;
     const float ratio = (float)(sum / (double)c->n_state);
     finish_iteration(c, a.ts, ratio, dt, c_tab, a.trace);
   }
+}
+
+__global__ void k_flat_control(Flat a) {
+  Ctrl* c = a.ctrl;
+  if (c->done) return;
+  const float ratio = (float)(gathered_sum(a, 0) / (double)c->n_state);
+  finish_iteration(c, a.ts, ratio, c->dt, c_tab, a.trace);
 }
 
 // ---- dense output for the targets the last iteration left behind (lib/ode.py:56-84, 849-850) -------------------
@@ -500,10 +606,18 @@ __global__ void k_css_tbar(Flat a, Net n, const float* gy_i, const float* gaux_i
   const double tot = block_reduce(acc, sm);
   if (threadIdx.x == 0) {
     const float tb = (float)tot;
+    if (a.world > 1) { a.xbuf[0] = tb; return; }   // this rank's rows only: all-reduced, then k_css_tbar_apply
     *tbar_out = tb;
     a.Y[a.oT0] -= tb;
     a.out[a.oT0] = a.Y[a.oT0];
   }
+}
+
+__global__ void k_css_tbar_apply(Flat a, float* tbar_out) {
+  const float tb = a.xbuf[0];
+  *tbar_out = tb;
+  a.Y[a.oT0] -= tb;
+  a.out[a.oT0] = a.Y[a.oT0];
 }
 
 // results of the whole backward pass from the last segment's final state (out row 1)

@@ -24,7 +24,10 @@ from . import ode, _cabi
 class ImageFfjord:
     def __init__(self, image=(28, 28), hidden=64, reg="r2", reg_type="our", rtol=1.4e-8, atol=1.4e-8, alpha=1e-5,
                  device="cuda", seed=0, lam=3e-4, lam_fro=0.0, lam_kin=0.0, lam_w=0.0, lr=1e-3, warmup_itrs=1e3,
-                 max_grad_norm=1e10, world=1):
+                 max_grad_norm=1e10, world=1, rows_global=None):
+        """world > 1: batch rows sharded over the ranks, ode.init_distributed() has run - the solves are ONE collective solve
+        of the concatenated batch (css_engine.cu) and the parameter gradient they return is already the global one;
+        rows_global: rows of the concatenated batch when the shards are uneven (ode.set_shards)."""
         self.spec = ConcatConvDynamics(image, hidden, reg=reg, reg_type=reg_type)
         self.image, self.rtol, self.atol, self.alpha = tuple(image), rtol, atol, alpha
         self.reg_type, self.lam, self.lam_fro, self.lam_kin, self.lam_w = reg_type, lam, lam_fro, lam_kin, lam_w
@@ -35,6 +38,7 @@ class ImageFfjord:
         self.m = torch.zeros_like(self.params)
         self.v = torch.zeros_like(self.params)
         self.itr = 0
+        self.rows_global = rows_global
 
     def snapshot(self):
         return [t.clone() for t in (self.params, self.m, self.v)] + [self.itr]
@@ -47,7 +51,7 @@ class ImageFfjord:
     def loss_and_grads(self, images, eps):
         """images in [0, 1], eps Rademacher, both [B, H, W, 1] on self.device.  Forward solve -> loss head -> adjoint."""
         B = images.shape[0]
-        n = B * self.world
+        n = self.rows_global or B * self.world
         D = self.spec.dim
         fin = self.reg_type == "fin"
         aug, n_aux = self.spec.AUG_OF_KIND["fin" if fin else "aug"]
@@ -56,6 +60,9 @@ class ImageFfjord:
         z = ys[1]
         # _loss_fn (455-470) with delta_logp = 0 (the split solve's auxiliary outputs are zeros)
         logpz = (-0.5 * math.log(2 * math.pi) - z.square() / 2).sum() / (n * D)
+        if self.world > 1:                                   # the mean runs over the rows of the concatenated batch
+            import torch.distributed as dist
+            dist.all_reduce(logpz)
         loss = -(logpz - math.log(256)) / math.log(2) + self.lam_w * 0.5 * self.params.square().sum()
         g_y = torch.zeros_like(ys)
         g_y[1] = z / (n * D * math.log(2))
@@ -76,9 +83,6 @@ class ImageFfjord:
         return self.lr * frac if itr // num_batches < 80 else self.lr / 10
 
     def apply_grads(self, g):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(g)
         g = g + self.lam_w * self.params                     # the weight term of loss_fn is inside jax.grad
         norm = g.norm()                                      # optimizers.clip_grads(grad, max_grad_norm), 574-575
         g = torch.where(norm < self.max_grad_norm, g, g * (self.max_grad_norm / norm))

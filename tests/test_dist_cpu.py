@@ -83,3 +83,18 @@ def test_two_gpu_collective_step_matches_single_device(reg_type):
            os.path.join(ROOT, "tests", "dist_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, ENO_DIST_REGTYPE=reg_type))
     assert res.returncode == 0 and "DIST PARITY OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows", [None, "7"])
+def test_two_gpu_collective_flat_engine_matches_single_device(rows):
+    """ConcatSquash / ConcatConv2D split solves sharded over 2 GPUs (even shards, then 7 rows = 4 + 3) against the
+    single-device solve of the concatenated batch (tests/dist_check_flat.py)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29538" if rows is None else "29540",
+           os.path.join(ROOT, "tests", "dist_check_flat.py")]
+    env = dict(os.environ) if rows is None else dict(os.environ, ENO_DIST_FLAT_B=rows)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0 and "FLAT DIST PARITY OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
