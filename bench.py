@@ -186,9 +186,13 @@ def fj_batch(rank, step, pin=False):
     return x, eps
 
 
-def fj_config(world):
-    return {"workload": FJ_WORKLOAD, "global_batch": FJ["B"] * world, "per_gpu_batch": FJ["B"], "rtol": FJ["TOL"], "atol": FJ["TOL"],
-            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (development)",
+def fj_config(world, strong=False):
+    gb = FJ["B"] if strong else FJ["B"] * world
+    return {"workload": FJ_WORKLOAD, "global_batch": gb, "per_gpu_batch": gb // world, "rtol": FJ["TOL"], "atol": FJ["TOL"],
+            "parallelism": "single GPU" if world == 1 else
+                           (f"dp{world}: {'the batch-1000 problem split' if strong else 'batch sharded 1000/GPU'} in contiguous row "
+                            "blocks, ONE global adaptive step sequence (per iteration: all-reduce of the stage combinations of the "
+                            "params_bar block, all-gather of the per-rank error-norm sums; NCCL, captured in the iteration graph)"),
             "l2": "flushed between steps (256 MiB device write, outside the per-step events)",
             "trajectory": "train steps 0..K-1 from the initial parameters (seeded), identical in every leg and arm"}
 
@@ -239,11 +243,39 @@ def fj_main(args, result_out, rank, local_rank, world):
     from easy_neural_ode_b200 import ffjord_step, _cabi
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    model = ffjord_step.TabularFfjord(dim=FJ["D"], hdim_factor=FJ["HF"], num_layers=FJ["LAYERS"], reg="r2", lam=FJ["LAM"],
-                                      lam_w=FJ["LAM_W"], rtol=FJ["TOL"], atol=FJ["TOL"], device=dev, seed=0)
+    def make(w):
+        return ffjord_step.TabularFfjord(dim=FJ["D"], hdim_factor=FJ["HF"], num_layers=FJ["LAYERS"], reg="r2", lam=FJ["LAM"],
+                                         lam_w=FJ["LAM_W"], rtol=FJ["TOL"], atol=FJ["TOL"], device=dev, seed=0, world=w)
+    strong = args.scaling == "strong" and world > 1
+    parity, sl = None, slice(0, FJ["B"])
+    if world > 1:
+        # batch rows sharded over the ranks, collective solves (tests/dist_check_flat.py); driver-visible parity: train step 0
+        # against the single-device solve of the concatenated batch
+        import torch.distributed as dist
+        import easy_neural_ode_b200 as eno
+        dist.init_process_group("nccl", device_id=dev)
+        if FJ["B"] % world and strong:
+            raise SystemExit("bench.py: --workload ffjord_tabular --scaling strong needs a world size that divides 1000")
+        if strong:
+            sl = eno.shard_rows(FJ["B"], world, rank)
+        parts = [fj_batch(0 if strong else r, 0) for r in range(1 if strong else world)]
+        full = tuple(torch.cat([q[i] for q in parts]).to(dev) for i in range(2))
+        want = make(1).loss_and_grads(*full)
+        eno.init_distributed()
+        mine = tuple(t[sl] if strong else t[rank * FJ["B"]:(rank + 1) * FJ["B"]] for t in full)
+        got = make(world).loss_and_grads(*mine)
+        parity = {"against": f"single-GPU solve of the concatenated batch ({full[0].shape[0]} rows) of train step 0, same process, "
+                             "before going collective",
+                  "fwd_iters": [got["fwd_stats"]["n_iters"], want["fwd_stats"]["n_iters"]],
+                  "bwd_iters": [got["bwd_stats"][0]["n_iters"], want["bwd_stats"][0]["n_iters"]],
+                  "loss_rel": abs(float(got["loss"]) - float(want["loss"])) / abs(float(want["loss"])),
+                  "grad_rel": float((got["grads"] - want["grads"]).abs().max() / want["grads"].abs().max())}
+        del want, got, full
+    model = make(world)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    dev_b = [tuple(t.to(dev) for t in fj_batch(rank, s)) for s in range(8)]
-    host_b = [fj_batch(rank, s, pin=True) for s in range(8)]
+    src = 0 if strong else rank
+    dev_b = [tuple(t[sl].to(dev) for t in fj_batch(src, s)) for s in range(8)]
+    host_b = [tuple(t[sl].contiguous().pin_memory() for t in fj_batch(src, s)) for s in range(8)]
     snap = model.snapshot()
     for s in range(max(args.warmup, 3)):
         out = model.update(*dev_b[s % 8])
@@ -252,6 +284,8 @@ def fj_main(args, result_out, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     sampler.start()
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches, nfe_total, iters = 0, 0.0, []
     for s in range(args.steps):
@@ -265,7 +299,13 @@ def fj_main(args, result_out, rank, local_rank, world):
     torch.cuda.synchronize()
     clocks = sampler.stop()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    if world > 1:                                             # device time of the slowest rank
+        t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t)
     ms_per_step = dev_ms / args.steps
+    units = 1 if (strong or world == 1) else world            # batch-1000 steps one step of the job advances
     loss_dev = float(out["loss"])
 
     model.restore(snap)
@@ -277,11 +317,17 @@ def fj_main(args, result_out, rank, local_rank, world):
         step_e2e(s)
     model.restore(snap)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
         step_e2e(s)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t)
 
     # roofline of the dominant kernel: the tcgen05 GEMM launches of the solves, CUDA events on the launch stream
     L = _cabi.lib()
@@ -313,17 +359,24 @@ def fj_main(args, result_out, rank, local_rank, world):
                 "algorithmic_flop_per_launch_avg": gfl.value / max(gcnt.value, 1),
                 "frac_of_3xtf32_ceiling": achieved / (tensor_peak / 6.0),
                 "gemm_share_of_step": (gms.value / n_prof) / ms_per_step}
-    line = {"metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+    if world > 1:
+        eno.shutdown_distributed()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+    line = {"metric": METRIC, "value": units * 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32 (tcgen05 3xTF32 contractions, fp32 accumulate)", "data": "synthetic",
-            "config": fj_config(world), "samples_per_s": FJ["B"] * 1e3 / ms_per_step, "clocks": clocks,
-            "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host_b[0]),
-                    "d2h_bytes_per_step": 4},
+            "config": fj_config(world, strong), "samples_per_s": units * FJ["B"] * 1e3 / ms_per_step, "clocks": clocks,
+            "e2e": {"value": units * args.steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": world * sum(x.numel() * x.element_size() for x in host_b[0]), "d2h_bytes_per_step": 4 * world},
             "gpu_launches": launches, "nfe_per_s": nfe_total / (dev_ms * 1e-3),
             "solver": {"iters_fwd_bwd_per_step": iters, "loss_last": loss_dev},
             "launch_mode": "polled solves; one loop iteration (6 right-hand sides + controller) replayed as a CUDA graph",
             "roofline": roofline}
-    if not args.no_cpu_baseline:
+    if parity:
+        line["parity"] = parity
+    if not args.no_cpu_baseline and world == 1:
         threads = len(os.sched_getaffinity(0))
         sec, info = fj_cpu_steps(min(args.steps, 3), 1, threads, budget_s=40.0)
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port",
@@ -777,7 +830,7 @@ def main():
                          "over the GPUs in contiguous row blocks (100 rows on 8 GPUs = 13,13,13,13,12,12,12,12: uneven shards)")
     ap.add_argument("--workload", default="mnist", choices=["mnist", "ffjord_tabular", "latent_ode", "ffjord_mnist"],
                     help="mnist = BASELINE configs[0], the configuration the metric is quoted on (default); "
-                         "ffjord_tabular = configs[1] (single GPU); latent_ode = configs[2] (single GPU); ffjord_mnist = configs[3] "
+                         "ffjord_tabular = configs[1] (--gpus N: batch rows sharded, collective solves); latent_ode = configs[2] (single GPU); ffjord_mnist = configs[3] "
                          "(--gpus N: batch rows sharded, collective solves; --scaling strong splits the batch-200 step itself)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -806,7 +859,7 @@ def main():
     if args.workload == "ffjord_tabular":
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
-        return fj_main(args, result_out, rank, local_rank, world) if rank == 0 else None
+        return fj_main(args, result_out, rank, local_rank, world)
     if args.workload == "latent_ode":
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")

@@ -32,6 +32,8 @@ class TabularFfjord:
         self.dim, self.lam, self.lam_w, self.rtol, self.atol = dim, lam, lam_w, rtol, atol
         self.reg_type, self.lam_fro, self.lam_kin = reg_type, lam_fro, lam_kin
         self.device = ode._norm_device(device)
+        # world > 1: rows sharded over the ranks and ode.init_distributed() has run - the solves are ONE collective solve of the
+        # concatenated batch (css_engine.cu) and the parameter gradient they return is already the global one
         self.world = world
         self.lr_schedule = lr_schedule
         self.ts = torch.tensor([0., 1.], device=self.device)
@@ -57,7 +59,11 @@ class TabularFfjord:
         ys, st_f, _ = ode._fwd_call(self.spec, "dopri5", x, self.ts, self.params, self.rtol, self.atol, math.inf)
         z = ys[1]
         # _loss_fn (402-407) with delta_logp = 0: -mean_b sum_d (-0.5 log 2 pi - z^2 / 2)
-        loss = 0.5 * self.dim * math.log(2 * math.pi) + 0.5 * (z * z).sum() / B
+        zz = 0.5 * (z * z).sum() / n
+        if self.world > 1:                                   # collective solves: the mean runs over the concatenated batch
+            import torch.distributed as dist
+            dist.all_reduce(zz)
+        loss = 0.5 * self.dim * math.log(2 * math.pi) + zz
         g_y = torch.zeros_like(ys)
         g_y[1] = z / n
         g_aux = torch.zeros((2, n_aux, B), device=self.device)
@@ -85,9 +91,6 @@ class TabularFfjord:
         return n + 4 * L + 3 + 1
 
     def apply_grads(self, g):
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(g)
         L = _cabi.lib()
         h = _cabi.ctx(self.device.index)
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

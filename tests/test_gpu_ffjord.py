@@ -265,8 +265,13 @@ def test_c2_shape_train_path(cuda, tol):
         return res, float(nfe_w), gg, bst[0]["n_iters"], want
 
     res, nfe_w, gg, bwd_w, want = oracle_run(cl["fwd"], cl["aug_dynamics"])
+    tr = None
     if tol < 1e-7:
-        _, nfe_x, _, bwd_x, _ = oracle_run(exact_arith(cl["fwd"]), exact_arith(cl["aug_dynamics"]))
+        # the exact-arithmetic solve at this tolerance doubles as the third party of assert_agree (error ~ 1e-8): the fp32
+        # oracle's own step sequence depends on the host's GEMM threading, and two fp32 solves that take different steps
+        # need not agree to 1e-5 in every gradient entry
+        res_x, nfe_x, _, bwd_x, want_x = oracle_run(exact_arith(cl["fwd"]), exact_arith(cl["aug_dynamics"]))
+        tr = dict(y=res_x[0], x0_bar=want_x[0][0], p_bar=spec.flatten_params(want_x[3]))
     else:
         nfe_x, bwd_x = nfe_w, bwd_w
     xg = x.to(cuda).requires_grad_(True)
@@ -277,9 +282,9 @@ def test_c2_shape_train_path(cuda, tol):
     loss.backward()
     print(f"C2 tol {tol}: nfe gpu {float(nfe)} oracle fp32 {nfe_w} exact-arithmetic {nfe_x}; adjoint iterations gpu "
           f"{eno.last_stats['bwd'][0]['n_iters']} oracle fp32 {bwd_w} exact-arithmetic {bwd_x}")
-    assert_count(float(nfe), nfe_w, nfe_x, "nfe")
-    assert_count(eno.last_stats["bwd"][0]["n_iters"], bwd_w, bwd_x, "adjoint iterations")
-    tr = None
+    slack = 1 if tol < 1e-7 else 0    # two samples of the round-off noise do not bound a third (tests/util.py:assert_count)
+    assert_count(float(nfe), nfe_w, nfe_x, "nfe", slack=6 * slack)
+    assert_count(eno.last_stats["bwd"][0]["n_iters"], bwd_w, bwd_x, "adjoint iterations", slack=slack)
     if tol > 1e-7:   # fp64 oracle at 1e-10 as third party (tests/util.py:assert_agree)
         t = _truth_split(p, x, eps, gg[0][-1], [1.0 / B, 0.01 / B], "r2", "our")
         tr = dict(y=t["y"], x0_bar=t["x0_bar"], p_bar=_oracle_flat(spec, t["p_bar"]))
