@@ -624,9 +624,9 @@ LT_WORKLOAD = ("latent_ode.py generative ODE, synthetic Physionet-shaped series 
                "with 49 output times each, float64 (configs[2])")
 
 
-def lt_batch(step, pin=False):
+def lt_batch(step, pin=False, rank=0):
     import torch
-    g = torch.Generator().manual_seed(977 + (step % 8))
+    g = torch.Generator().manual_seed(977 + 97 * rank + (step % 8))
     z0 = 0.1 * torch.randn((LT["S"], LT["B"], LT["D"]), generator=g, dtype=torch.float64)
     data = torch.randn((LT["B"], LT["T"], LT["DATA"]), generator=g, dtype=torch.float64)
     mask = (torch.rand((LT["B"], LT["T"], LT["DATA"]), generator=g) < 0.1).double()
@@ -635,9 +635,14 @@ def lt_batch(step, pin=False):
     return z0, data, mask
 
 
-def lt_config():
-    return {"workload": LT_WORKLOAD, "global_batch": LT["S"] * LT["B"], "per_gpu_batch": LT["S"] * LT["B"], "rtol": LT["TOL"],
-            "atol": LT["TOL"], "parallelism": "single GPU (trajectories are independent: replicas only, no exchange)",
+def lt_config(world=1, strong=False):
+    gb = LT["S"] * LT["B"] * (1 if strong else world)
+    return {"workload": LT_WORKLOAD, "global_batch": gb, "per_gpu_batch": gb / world, "rtol": LT["TOL"],
+            "atol": LT["TOL"],
+            "parallelism": "single GPU (trajectories are independent: replicas only, no exchange)" if world == 1 else
+                           (f"dp{world}: the batch axis {'of the 50-series problem split' if strong else 'sharded 50 series/GPU'}; "
+                            "trajectories are independent (no collective in the solves), the likelihood sums and the parameter "
+                            "gradient are all-reduced once per step"),
             "l2": "flushed between steps (256 MiB device write, outside the per-step events)",
             "trajectory": "train steps 0..K-1 from the initial parameters (seeded), identical in every leg and arm"}
 
@@ -687,19 +692,46 @@ def lt_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def lt_main(args, result_out, local_rank):
+def lt_main(args, result_out, local_rank, rank=0, world=1):
     """`--workload latent_ode`: the generative half of one update() of latent_ode.py per step - 150 per-trajectory forward
     solves (one launch), decoder + likelihood, 150 complete adjoints of 48 segments each (one launch), Adam."""
     import torch
     from easy_neural_ode_b200 import latent_step, latent
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    model = latent_step.LatentGen(LT["D"], LT["LAYERS"], LT["U"], LT["DATA"], reg="r3", lam=LT["LAM"], rtol=LT["TOL"], atol=LT["TOL"],
-                                  device=dev, seed=0)
+    strong = args.scaling == "strong" and world > 1
+    sl, parity = slice(0, LT["B"]), None
     ts = torch.linspace(0., 1., LT["T"], dtype=torch.float64, device=dev)
+
+    def make(w):
+        return latent_step.LatentGen(LT["D"], LT["LAYERS"], LT["U"], LT["DATA"], reg="r3", lam=LT["LAM"], rtol=LT["TOL"],
+                                     atol=LT["TOL"], device=dev, seed=0, world=w)
+
+    def cut(b, rows):                                         # z0 [S, B, D], data / mask [B, T, F]: rows of the batch axis
+        return b[0][:, rows].contiguous(), b[1][rows].contiguous(), b[2][rows].contiguous()
+    if world > 1:
+        import torch.distributed as dist
+        import easy_neural_ode_b200 as eno
+        dist.init_process_group("nccl", device_id=dev)
+        if strong:
+            sl = eno.shard_rows(LT["B"], world, rank)
+        # driver-visible parity: train step 0 sharded vs the same step on one GPU over the concatenated batch
+        parts = [lt_batch(0, rank=0 if strong else r) for r in range(1 if strong else world)]
+        full = tuple(t.to(dev) for t in (torch.cat([q[0] for q in parts], dim=1), torch.cat([q[1] for q in parts]),
+                                         torch.cat([q[2] for q in parts])))
+        want = make(1).loss_and_grads(full[0], ts, full[1], full[2])
+        rows = sl if strong else slice(rank * LT["B"], (rank + 1) * LT["B"])
+        got = make(world).loss_and_grads(*[x for x in (cut(full, rows)[0], ts) + cut(full, rows)[1:]])
+        parity = {"against": f"the same train step on one GPU over the concatenated batch ({full[1].shape[0]} series)",
+                  "loss_rel": abs(float(got["loss"]) - float(want["loss"])) / abs(float(want["loss"])),
+                  "grad_rel": max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(got["grads"], want["grads"])),
+                  "nfe_identical": bool(torch.equal(got["nfe"], want["nfe"][:, rows])) if want["nfe"].dim() == 2 else None}
+        del want, got, full
+    model = make(world)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    dev_b = [tuple(t.to(dev) for t in lt_batch(s)) for s in range(8)]
-    host_b = [lt_batch(s, pin=True) for s in range(8)]
+    src = 0 if strong else rank
+    dev_b = [tuple(t.to(dev) for t in cut(lt_batch(s, rank=src), sl)) for s in range(8)]
+    host_b = [tuple(t.pin_memory() for t in cut(lt_batch(s, rank=src), sl)) for s in range(8)]
     snap = model.snapshot()
     for s in range(max(args.warmup, 3)):
         out = model.update(dev_b[s % 8][0], ts, *dev_b[s % 8][1:])
@@ -707,6 +739,9 @@ def lt_main(args, result_out, local_rank):
     model.restore(snap)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     nfe_total, rhs_f, rhs_b, it_b = 0.0, 0, 0, 0
     for s in range(args.steps):
@@ -721,7 +756,13 @@ def lt_main(args, result_out, local_rank):
     torch.cuda.synchronize()
     clocks = sampler.stop()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    if world > 1:                                             # device time of the slowest rank
+        t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t)
     ms_per_step = dev_ms / args.steps
+    units = 1 if (strong or world == 1) else world            # 150-trajectory steps one step of the job advances
     loss_dev = float(out["loss"])
 
     model.restore(snap)
@@ -733,11 +774,20 @@ def lt_main(args, result_out, local_rank):
         step_e2e(s)
     model.restore(snap)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
         step_e2e(s)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t)
+        dist.destroy_process_group()
+        if rank != 0:
+            return
 
     # the dominant kernel (the adjoint of all trajectories, one launch) timed alone on the training state of step 0
     model.restore(snap)
@@ -787,12 +837,12 @@ def lt_main(args, result_out, local_rank):
                 "note": "float64 work on the non-tensor pipe (the script runs with jax_enable_x64); the tensor pipe is the contract's "
                         "denominator, 37 TFLOP/s is B200's nominal float64 vector peak (not in MEASURED_PEAKS.json).  150 sequential "
                         "per-trajectory solves of 2,500-FMA products are latency bound: one trajectory cannot fill an SM"}
-    line = {"metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": lt_config(),
-            "samples_per_s": LT["S"] * LT["B"] * 1e3 / ms_per_step, "clocks": clocks,
-            "e2e": {"value": args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host_b[0]),
-                    "d2h_bytes_per_step": 8},
+    line = {"metric": METRIC, "value": units * 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": lt_config(world, strong),
+            "samples_per_s": units * LT["S"] * LT["B"] * 1e3 / ms_per_step, "clocks": clocks,
+            "e2e": {"value": units * args.steps / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": world * sum(x.numel() * x.element_size() for x in host_b[0]), "d2h_bytes_per_step": 8 * world},
             "gpu_launches": 3 * args.steps, "nfe_per_s": nfe_total / (dev_ms * 1e-3),
             "adjoint_rhs_per_s": rhs_b / (dev_ms * 1e-3),
             "solver": {"mean_nfe_per_trajectory": nfe_total / args.steps / (LT["S"] * LT["B"]),
@@ -800,7 +850,9 @@ def lt_main(args, result_out, local_rank):
             "launch_mode": "two solver launches per step (all forward solves; all adjoints) + the per-trajectory sum; decoder, "
                            "likelihood and Adam are float64 torch ops",
             "roofline": roofline}
-    if not args.no_cpu_baseline:
+    if parity:
+        line["parity"] = parity
+    if not args.no_cpu_baseline and world == 1:
         threads = len(os.sched_getaffinity(0))
         n = 2
         sec, nfe, bwd = lt_cpu_sample(n, threads)
@@ -830,7 +882,7 @@ def main():
                          "over the GPUs in contiguous row blocks (100 rows on 8 GPUs = 13,13,13,13,12,12,12,12: uneven shards)")
     ap.add_argument("--workload", default="mnist", choices=["mnist", "ffjord_tabular", "latent_ode", "ffjord_mnist"],
                     help="mnist = BASELINE configs[0], the configuration the metric is quoted on (default); "
-                         "ffjord_tabular = configs[1] (--gpus N: batch rows sharded, collective solves); latent_ode = configs[2] (single GPU); ffjord_mnist = configs[3] "
+                         "ffjord_tabular = configs[1] (--gpus N: batch rows sharded, collective solves); latent_ode = configs[2] (--gpus N: series sharded, independent solves, gradients all-reduced); ffjord_mnist = configs[3] "
                          "(--gpus N: batch rows sharded, collective solves; --scaling strong splits the batch-200 step itself)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -863,7 +915,7 @@ def main():
     if args.workload == "latent_ode":
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
-        return lt_main(args, result_out, local_rank) if rank == 0 else None
+        return lt_main(args, result_out, local_rank, rank, world)
     if args.workload == "ffjord_mnist":
         if not torch.cuda.is_available():
             raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")

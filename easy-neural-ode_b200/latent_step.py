@@ -21,7 +21,11 @@ from . import ode, latent
 
 class LatentGen:
     def __init__(self, latent_dim=20, layers=3, units=50, data_dim=37, reg="r3", lam=1e-2, rtol=1.4e-8, atol=1.4e-8,
-                 device="cuda", dtype=torch.float64, seed=0, lr=1e-2, scale=1.0):
+                 device="cuda", dtype=torch.float64, seed=0, lr=1e-2, scale=1.0, world=1):
+        """world > 1 (torch.distributed initialised): the batch axis of z0 / data / mask is sharded over the ranks.  The
+        per-trajectory solves are independent (vmap), so there is no collective inside the ODE path: the per-sample
+        log-likelihood sums, the mask count and the regulariser mean are all-reduced (S + 2 scalars), every rank forms the
+        same loss, and the parameter gradients are all-reduced once per step."""
         self.spec = GenDynamics(latent_dim, layers, units, reg=reg)
         self.device = ode._norm_device(device)
         self.dtype, self.lam, self.rtol, self.atol, self.lr = dtype, lam, rtol, atol, lr
@@ -34,6 +38,16 @@ class LatentGen:
         self.m = [torch.zeros_like(t) for t in self.tensors]
         self.v = [torch.zeros_like(t) for t in self.tensors]
         self.itr = 0
+        self.world = world
+
+    def _global_sum(self, x):
+        """sum over ranks as a value, identity as a derivative (every rank differentiates the same global loss wrt its own rows)"""
+        if self.world == 1:
+            return x
+        import torch.distributed as dist
+        tot = x.detach().clone()
+        dist.all_reduce(tot)
+        return x + (tot - x.detach())
 
     def snapshot(self):
         return [t.clone() for t in self.tensors + self.m + self.v] + [self.itr]
@@ -52,9 +66,19 @@ class LatentGen:
         pred = zs @ w + b                                               # [S, B, T, data_dim]
         std = 0.01
         ll = (-((data[None] * mask - pred * mask) ** 2) / (2 * std ** 2) - math.log(std) - math.log(2 * math.pi) / 2)
-        ll = ll.sum(dim=(1, 2, 3)) / mask.sum()                          # _likelihood, latent_ode.py:404-413
-        loss = -torch.logsumexp(ll, dim=0) + self.lam * rs[..., -1].mean()
+        ll = self._global_sum(ll.sum(dim=(1, 2, 3))) / self._global_sum(mask.sum())   # _likelihood, latent_ode.py:404-413
+        n_traj = self._global_sum(torch.tensor(float(rs[..., -1].numel()), dtype=self.dtype, device=self.device))
+        loss = -torch.logsumexp(ll, dim=0) + self.lam * self._global_sum(rs[..., -1].sum()) / n_traj
         grads = torch.autograd.grad(loss, leaves)
+        if self.world > 1:
+            import torch.distributed as dist
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat)
+            out, o = [], 0
+            for g in grads:
+                out.append(flat[o:o + g.numel()].reshape(g.shape))
+                o += g.numel()
+            grads = tuple(out)
         return dict(loss=loss.detach(), nfe=nfe, grads=grads, fwd_iters=latent.last_stats["fwd"]["iters"],
                     bwd_iters=latent.last_stats["bwd"]["iters"])
 
