@@ -273,7 +273,10 @@ int32_t eno_read_stats(eno_ctx* ctx, const void* workspace, eno_stats* out, void
  * call it with their shard; the error norm (lib/ode.py:518-527), the initial-step norms (86-104) and,
  * in the adjoint, the batch-summed blocks params_bar / t0_bar are exchanged over NCCL every iteration so
  * that all ranks follow the step sequence of the single-device solve on the concatenated batch.
- * params_bar_out and ts_bar_out are then already global sums, identical on every rank.
+ * params_bar_out and ts_bar_out are then already global sums, identical on every rank.  This holds for every
+ * architecture: the ConcatSquash / ConcatConv2D engine all-reduces the stage combinations of its replicated
+ * [t0_bar | params_bar] block once per adjoint iteration and gathers the per-rank error-norm sums (NCCL, part of the
+ * captured iteration graph; the peer-memory exchange below serves the MLP dynamics).  eno_rhs stays local.
  * Rank 0 obtains `id` (128 bytes) from eno_comm_unique_id and ships it to the other ranks (e.g. with
  * torch.distributed); `nccl_path` may name libnccl.so.2 explicitly (NULL: the copy already loaded).
  */
