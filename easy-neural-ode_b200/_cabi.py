@@ -18,7 +18,7 @@ TABLEAUX = {"dopri5": 0, "heun": 1, "fehlberg": 2, "bosh": 3, "rk_fehlberg": 4, 
 
 # every symbol include/eno.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["eno_abi_version", "eno_last_error_string", "eno_create", "eno_destroy", "eno_param_count",
-           "eno_adjoint_state_size", "eno_workspace_bytes", "eno_odeint_fwd", "eno_odeint_fwd_vmap", "eno_odeint_bwd", "eno_odeint_bwd_sepaux", "eno_rhs",
+           "eno_adjoint_state_size", "eno_workspace_bytes", "eno_odeint_fwd", "eno_odeint_fwd_vmap", "eno_odeint_bwd", "eno_odeint_bwd_sepaux", "eno_odeint_grid_fwd", "eno_odeint_grid_bwd", "eno_rhs",
            "eno_mnist_head", "eno_momentum_update", "eno_profile_enable", "eno_profile_read", "eno_ffma_peak", "eno_comm_unique_id", "eno_comm_init",
            "eno_comm_destroy", "eno_comm_set_shards", "eno_set_deferred", "eno_read_stats", "eno_gemm_tf32x3", "eno_gemm_tf32x3_mn", "eno_adam_update", "eno_profile_read_gemm", "eno_peer_export", "eno_peer_attach",
            "eno_traj_param_count", "eno_traj_workspace_bytes", "eno_traj_fwd", "eno_traj_bwd", "eno_traj_rhs"]
@@ -80,6 +80,11 @@ def lib():
     L.eno_odeint_bwd_sepaux.restype = i32
     L.eno_odeint_bwd_sepaux.argtypes = [vp, C.POINTER(Desc), i32, vp, vp, i32, vp, vp, vp, vp, f32, f32, i32, vp, sz, vp, vp,
                                         vp, vp, vp, C.POINTER(Stats), vp, i32, vp]
+    L.eno_odeint_grid_fwd.restype = i32
+    L.eno_odeint_grid_fwd.argtypes = [vp, C.POINTER(Desc), i32, vp, vp, i32, vp, vp, f32, vp, sz, vp, vp, C.POINTER(Stats), vp]
+    L.eno_odeint_grid_bwd.restype = i32
+    L.eno_odeint_grid_bwd.argtypes = [vp, C.POINTER(Desc), i32, vp, vp, i32, vp, vp, vp, vp, f32, vp, sz, vp, vp, vp, vp, vp,
+                                      C.POINTER(Stats), vp]
     L.eno_rhs.restype = i32
     L.eno_rhs.argtypes = [vp, C.POINTER(Desc), i32, i32, vp, f32, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp, vp, vp, vp]
     L.eno_mnist_head.restype = i32

@@ -506,7 +506,7 @@ int css_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
 
 int css_prepare(eno_ctx* ctx, Plan& p, const float* params, const float* eps, cudaStream_t st) {
   const css::Net& n = p.net;
-  Tableau* tab = &ctx->tabs[ENO_TABLEAU_DOPRI5];
+  Tableau* tab = &ctx->tabs[p.flat.grid_step > 0.f ? ENO_NUM_TABLEAUX : ENO_TABLEAU_DOPRI5];
   CSS_CUDA(ctx, cudaMemcpyToSymbolAsync(css::c_tab, tab, sizeof(Tableau), 0, cudaMemcpyHostToDevice, st));
   CSS_CUDA(ctx, cudaMemcpyAsync(p.params, params, p.P * 4, cudaMemcpyDeviceToDevice, st));
   if (eps) CSS_CUDA(ctx, cudaMemcpyAsync(p.eps, eps, (size_t)n.B * n.D * 4, cudaMemcpyDeviceToDevice, st));
@@ -530,7 +530,7 @@ int css_prepare(eno_ctx* ctx, Plan& p, const float* params, const float* eps, cu
 
 // cached graph of one loop iteration, keyed by everything its kernel arguments depend on
 struct GraphKey {
-  void* ws; int B, D, H, L, aug, reg, mode, T, world, rank;
+  void* ws; int B, D, H, L, aug, reg, mode, T, world, rank, grid, spare;
   bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
 };
 struct CssState {
@@ -579,6 +579,7 @@ int allreduce_replicated(const Plan& p, const DistCtx* dc, float* vec, cudaStrea
 
 int enqueue_iteration(const Plan& p, const DistCtx* dc, int sms, cudaStream_t st, std::string* err) {
   for (int s = 1; s <= 6; ++s) {
+    if (p.flat.grid_step > 0.f && (s == 4 || s == 5)) continue;   // RK4 in the 7-stage frame (tableaux.cuh:fill_rk4_grid)
     int rc = css_rhs_launch(p, s, css::ST_STAGE, nullptr, sms, st, err);
     if (rc) return rc;
   }
@@ -607,7 +608,13 @@ int run_loop(eno_ctx* ctx, const Plan& p, const GraphKey& key, int which, eno_st
   // summed over the ranks (the controller ring is at slot 0 here: F[cur] = F), the norms gathered in rank order.
   if ((rc = css_rhs_launch(p, 0, css::ST_INIT0, nullptr, sms, st, &err))) return css_fail(ctx, rc, err);
   const int igrid = std::min<int>((int)((p.flat.N + 255) / 256), p.flat.n_part);
-  for (int phase = 0; phase < 2; ++phase) {
+  const bool grid = p.flat.grid_step > 0.f;
+  if (grid) {   // fixed grid: no initial step-size selection; stage buffers 4 and 5 are never written, clear all of them
+    if ((rc = allreduce_replicated(p, dc, p.flat.F, st, &err))) return css_fail(ctx, rc, err);
+    CSS_CUDA(ctx, cudaMemsetAsync(p.flat.KS, 0, 5 * p.flat.N * sizeof(float), st));
+    css::k_flat_grid_begin<<<1, 1, 0, st>>>(p.flat);
+  }
+  for (int phase = 0; phase < 2 && !grid; ++phase) {
     if (phase == 1 && (rc = css_rhs_launch(p, 0, css::ST_INIT1, nullptr, sms, st, &err))) return css_fail(ctx, rc, err);
     if ((rc = allreduce_replicated(p, dc, phase == 0 ? p.flat.F : p.flat.KS, st, &err))) return css_fail(ctx, rc, err);
     css::k_flat_init<<<igrid, 256, 0, st>>>(p.flat, phase);
@@ -634,7 +641,7 @@ int run_loop(eno_ctx* ctx, const Plan& p, const GraphKey& key, int which, eno_st
       } else cudaGetLastError();
     }
   }
-  int chunk = profiling ? 1 : S->hint[which];
+  int chunk = profiling ? 1 : (grid ? 8 : S->hint[which]);
   int n_launched_iters = 0;
   for (;;) {
     for (int k = 0; k < chunk; ++k) {
@@ -649,10 +656,10 @@ int run_loop(eno_ctx* ctx, const Plan& p, const GraphKey& key, int which, eno_st
   }
   if (profiling) { S->prof.resolve(); S->prof.on = false; }
   const Ctrl& c = *ctx->mailbox;
-  S->hint[which] = std::min(64, c.n_iters + 1);
+  if (!grid) S->hint[which] = std::min(64, c.n_iters + 1);
   if (stats) {
     stats->nfe = (float)c.nfe; stats->n_iters = c.n_iters; stats->n_accepted = c.n_accepted; stats->status = c.status;
-    stats->last_dt = c.dt; stats->last_t = c.t; stats->n_rhs = 2 + 6 * c.n_iters;
+    stats->last_dt = c.dt; stats->last_t = c.t; stats->n_rhs = grid ? 1 + 4 * c.n_iters : 2 + 6 * c.n_iters;
     stats->n_launches = n_launched_iters;   // iteration graphs (or direct iteration sequences) enqueued
   }
   if (launches) *launches += n_launched_iters;
@@ -705,8 +712,9 @@ size_t workspace_bytes(const eno_dynamics_desc* d, int B, int T, int mode) {
 
 int odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* y0, const float* ts, int T, const float* params,
                const float* eps, float rtol, float atol, int mxstep, void* ws, size_t ws_bytes, float* ys_out, float* aux_out,
-               eno_stats* stats, eno_trace_row* trace, int trace_cap, cudaStream_t st) {
+               eno_stats* stats, eno_trace_row* trace, int trace_cap, cudaStream_t st, float grid_step) {
   if (!desc_ok(desc)) return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_fwd: unsupported ConcatSquash descriptor");
+  if (grid_step > 0.f && T != 2) return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_grid_fwd: ts must be [t0, t1] (lib/ode.py:884)");
   if (B <= 0 || T < 1 || !y0 || !ts || !params || !ws || !ys_out) return css_fail(ctx, ENO_E_ARG, "eno_odeint_fwd: null pointer or empty batch");
   const int na = aux_count(desc->aug);
   if (na > 0 && !eps) return css_fail(ctx, ENO_E_ARG, "eno_odeint_fwd: the FFJORD closures read eps");
@@ -717,6 +725,7 @@ int odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* 
   CSS_CUDA(ctx, cudaSetDevice(ctx->device));
   p.flat.ts = ts;
   p.flat.trace = trace;
+  p.flat.grid_step = grid_step;
   int rc;
   if ((rc = css_prepare(ctx, p, params, eps, st))) return rc;
   const size_t N = p.flat.N, BD = (size_t)B * desc->D;
@@ -728,7 +737,7 @@ int odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* 
   int launches = 0;
   int status = ENO_OK;
   if (T > 1) {
-    GraphKey key{ws, B, desc->D, desc->H, desc->n_hidden, desc->aug, desc->reg_order, 0, T, p.flat.world, p.flat.rank};
+    GraphKey key{ws, B, desc->D, desc->H, desc->n_hidden, desc->aug, desc->reg_order, 0, T, p.flat.world, p.flat.rank, grid_step > 0.f ? 1 : 0, 0};
     status = run_loop(ctx, p, key, 0, stats, &launches, st);
     if (status < 0) return status;
   } else if (stats) memset(stats, 0, sizeof(*stats));
@@ -743,8 +752,9 @@ int odeint_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* 
 int odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* ys, const float* ts, int T, const float* params,
                const float* eps, const float* g_y, const float* g_aux, float rtol, float atol, int mxstep, void* ws,
                size_t ws_bytes, float* y0_bar_out, float* aux0_bar_out, float* eps_bar_out, float* ts_bar_out,
-               float* params_bar_out, eno_stats* stats, eno_trace_row* trace, int trace_cap, cudaStream_t st) {
+               float* params_bar_out, eno_stats* stats, eno_trace_row* trace, int trace_cap, cudaStream_t st, float grid_step) {
   if (!desc_ok(desc)) return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: unsupported ConcatSquash descriptor");
+  if (grid_step > 0.f && T != 2) return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_grid_bwd: ts must be [t0, t1] (lib/ode.py:884)");
   const int na = aux_count(desc->aug);
   if (desc->aug != ENO_AUG_REG && desc->aug != ENO_AUG_FIN)
     return css_fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_bwd: the FFJORD adjoint integrates aug_dynamics ('our' or 'fin')");
@@ -766,6 +776,7 @@ int odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* 
     return ENO_OK;
   }
   int rc;
+  p.flat.grid_step = grid_step;
   if ((rc = css_prepare(ctx, p, params, eps, st))) return rc;
   p.flat.ts = p.seg_ts;
   p.flat.trace = trace;
@@ -787,7 +798,7 @@ int odeint_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int B, const float* 
       if (dc->allreduce(p.flat.xbuf, 1, st) != 0) return css_fail(ctx, ENO_E_CUDA, "ncclAllReduce failed (t_bar)");
       css::k_css_tbar_apply<<<1, 1, 0, st>>>(p.flat, ts_bar_out + i);
     }
-    GraphKey key{ws, B, desc->D, desc->H, desc->n_hidden, desc->aug, desc->reg_order, 1, 2, p.flat.world, p.flat.rank};
+    GraphKey key{ws, B, desc->D, desc->H, desc->n_hidden, desc->aug, desc->reg_order, 1, 2, p.flat.world, p.flat.rank, grid_step > 0.f ? 1 : 0, 0};
     int status = run_loop(ctx, p, key, 1, stats ? stats + (T - 1 - i) : nullptr, &launches, st);
     if (status < 0) return status;
     if (status != ENO_OK && worst == ENO_OK) worst = status;

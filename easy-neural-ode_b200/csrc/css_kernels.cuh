@@ -28,6 +28,8 @@ struct Flat {
   double* gbuf;         // [world][2] per-rank sums of the sharded elements (all-gathered), then [2] replicated-block sums
   float* xbuf;          // [4][n_x] stage combinations (sol, err, mid, k6) of the replicated elements, all-reduced
   size_t n_x;           // 1 + P
+  // fixed grid (odeint_grid, lib/ode.py:561-577, 864-903): > 0 = the RK4 step size; no error control
+  float grid_step;
   float* out;           // [T][N]
   eno_trace_row* trace;
   float tsign;          // +1 forward, -1 adjoint (RHS time = tsign * solver time)
@@ -414,6 +416,50 @@ __global__ void k_flat_init_control(Flat a, int phase) {
 // (stages 1..6; the first stage is the global derivative the previous iteration left in the F ring), and everything
 // downstream of the batch sum is linear: k_flat_xcomb forms the three stage combinations + k6, ONE all-reduce sums
 // them, k_flat_finish completes the replicated elements from the sums and stores the global k6 into the F ring.
+// Fixed-grid controller (lib/ode.py:877-897): every step is taken; next_t = min(t + step_size, ts[-1]), dt = next_t - t,
+// nfe += 4.  Single thread.
+__device__ __forceinline__ void finish_grid_step(Ctrl* cp, const float* __restrict__ ts, float step, eno_trace_row* trace) {
+  Ctrl c = *cp;
+  const float t_end = ts[c.T - 1];
+  if (trace && c.n_iters < c.trace_cap) {
+    eno_trace_row r;
+    r.t = c.t; r.dt = c.dt; r.ratio = 0.f; r.accepted = 1.0f;
+    trace[c.n_iters] = r;
+  }
+  c.ratio = 0.f;
+  c.out_begin = c.out_end;
+  const int old_prev = c.prev;
+  c.prev = c.cur;
+  c.cur = c.cand;
+  c.cand = old_prev;
+  c.mid_acc ^= 1;
+  c.last_t = c.t;
+  c.step_dt = c.dt;
+  c.t = fminf(c.t + step, t_end);
+  c.dt = fminf(c.t + step, t_end) - c.t;
+  c.n_accepted += 1;
+  c.iters_tgt += 1;
+  c.n_iters += 1;
+  c.nfe += 4;
+  advance_targets_local(c, ts);
+  *cp = c;
+}
+
+// start of a fixed-grid solve: F[cur] = f(y0, t0) has been evaluated (the first stage of the first step)
+__global__ void k_flat_grid_begin(Flat a) {
+  Ctrl* c = a.ctrl;
+  const float t0 = a.ts[0], t_end = a.ts[c->T - 1];
+  c->t = t0;
+  c->last_t = t0;
+  c->step_dt = 0.f;
+  c->dt = fminf(t0 + a.grid_step, t_end) - t0;
+  c->iters_tgt = 0; c->tgt = 1;
+  c->n_iters = 0; c->n_accepted = 0; c->nfe = 0;
+  c->out_begin = 1; c->out_end = 1;
+  c->done = 0; c->status = ENO_OK;
+  advance_targets(c, a.ts);
+}
+
 __global__ void k_flat_xcomb(Flat a) {
   const Ctrl* c = a.ctrl;
   if (c->done) return;
@@ -504,7 +550,8 @@ __global__ void k_flat_finish(Flat a) {
   if (threadIdx.x == 0) {
     c->ticket = 0;
     const float ratio = (float)(sum / (double)c->n_state);
-    finish_iteration(c, a.ts, ratio, dt, c_tab, a.trace);
+    if (a.grid_step > 0.f) finish_grid_step(c, a.ts, a.grid_step, a.trace);
+    else finish_iteration(c, a.ts, ratio, dt, c_tab, a.trace);
   }
 }
 
@@ -512,7 +559,8 @@ __global__ void k_flat_control(Flat a) {
   Ctrl* c = a.ctrl;
   if (c->done) return;
   const float ratio = (float)(gathered_sum(a, 0) / (double)c->n_state);
-  finish_iteration(c, a.ts, ratio, c->dt, c_tab, a.trace);
+  if (a.grid_step > 0.f) finish_grid_step(c, a.ts, a.grid_step, a.trace);
+  else finish_iteration(c, a.ts, ratio, c->dt, c_tab, a.trace);
 }
 
 // ---- dense output for the targets the last iteration left behind (lib/ode.py:56-84, 849-850) -------------------
@@ -548,6 +596,7 @@ __global__ void k_flat_out(Flat a) {
       v = v * x + cc;
       v = v * x + cd;
       v = v * x + ce;
+      if (a.grid_step > 0.f && !degenerate) v = Yc[i];   // the last grid step lands on ts[-1]: the state itself
       a.out[(size_t)o * N + i] = v;
     }
   }

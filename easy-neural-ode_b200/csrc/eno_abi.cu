@@ -151,8 +151,9 @@ int32_t eno_create(eno_ctx** out, int32_t device) {
   c->device = device;
   ENO_CUDA(c, cudaSetDevice(device));
   ENO_CUDA(c, cudaMallocHost(&c->mailbox, sizeof(Ctrl)));
-  ENO_CUDA(c, cudaMallocHost(&c->tabs, sizeof(Tableau) * ENO_NUM_TABLEAUX));
+  ENO_CUDA(c, cudaMallocHost(&c->tabs, sizeof(Tableau) * (ENO_NUM_TABLEAUX + 1)));
   for (int i = 0; i < ENO_NUM_TABLEAUX; ++i) fill_tableau(i, &c->tabs[i]);
+  fill_rk4_grid(&c->tabs[ENO_NUM_TABLEAUX]);   // odeint_grid (css_engine.cu)
   cudaDeviceProp prop;
   ENO_CUDA(c, cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -425,6 +426,30 @@ int32_t eno_rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t mode, int32
   }
   return adj_rhs(ctx->path_mode, &ctx->err, ctx->sm_count, desc, mode, B, y, t, params, eps, y_bar, r_bar, workspace,
                  workspace_bytes, dy_out, aux_out, ybar_dot_out, tbar_out, params_bar_out, eps_bar_dot_out, stream);
+}
+
+int32_t eno_odeint_grid_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, const float* y0, const float* ts, int32_t T,
+                            const float* params, const float* eps, float step_size, void* workspace, size_t workspace_bytes,
+                            float* ys_out, float* aux_out, eno_stats* stats_host, void* stream_) {
+  if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_odeint_grid_fwd: ctx is null");
+  if (!desc || !(desc->arch == ENO_ARCH_CONCATSQUASH || desc->arch == ENO_ARCH_CONCATCONV))
+    return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_grid_fwd: the fixed-grid solver runs on the ConcatSquash / ConcatConv2D engine");
+  if (!(step_size > 0.f)) return fail(ctx, ENO_E_ARG, "eno_odeint_grid_fwd: step_size must be positive");
+  return css::odeint_fwd(ctx, desc, B, y0, ts, T, params, eps, 1.f, 1.f, 0, workspace, workspace_bytes, ys_out, aux_out, stats_host,
+                         nullptr, 0, static_cast<cudaStream_t>(stream_), step_size);
+}
+
+int32_t eno_odeint_grid_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, const float* ys, const float* ts, int32_t T,
+                            const float* params, const float* eps, const float* g_y, const float* g_aux, float step_size,
+                            void* workspace, size_t workspace_bytes, float* y0_bar_out, float* aux0_bar_out, float* eps_bar_out,
+                            float* ts_bar_out, float* params_bar_out, eno_stats* stats_host, void* stream_) {
+  if (!ctx) return fail(nullptr, ENO_E_ARG, "eno_odeint_grid_bwd: ctx is null");
+  if (!desc || !(desc->arch == ENO_ARCH_CONCATSQUASH || desc->arch == ENO_ARCH_CONCATCONV))
+    return fail(ctx, ENO_E_UNSUPPORTED, "eno_odeint_grid_bwd: the fixed-grid solver runs on the ConcatSquash / ConcatConv2D engine");
+  if (!(step_size > 0.f)) return fail(ctx, ENO_E_ARG, "eno_odeint_grid_bwd: step_size must be positive");
+  return css::odeint_bwd(ctx, desc, B, ys, ts, T, params, eps, g_y, g_aux, 1.f, 1.f, 0, workspace, workspace_bytes, y0_bar_out,
+                         aux0_bar_out, eps_bar_out, ts_bar_out, params_bar_out, stats_host, nullptr, 0,
+                         static_cast<cudaStream_t>(stream_), step_size);
 }
 
 int32_t eno_odeint_bwd_sepaux(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, const float* ys, const float* ts,

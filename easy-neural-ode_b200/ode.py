@@ -221,6 +221,26 @@ def _warn_status(what, status):
                       "(last interpolant extrapolated / NaNs)", RuntimeWarning, stacklevel=3)
 
 
+def _grid_fwd_call(spec, y0, ts, pflat, step_size):
+    """eno_odeint_grid_fwd (fixed-grid RK4, lib/ode.py:864-903) on device tensors. -> (ys [2,B,D], stats dict)."""
+    L = _cabi.lib()
+    device = y0.device
+    h = _cabi.ctx(device.index)
+    B, D = y0.shape
+    T = ts.numel()
+    desc = spec.desc(_cabi.AUG_NONE)
+    nbytes = L.eno_workspace_bytes(C.byref(desc), B, T, 0, 0)
+    ws = _workspace(device, nbytes)
+    ys = torch.empty((T, B, D), dtype=torch.float32, device=device)
+    st = _cabi.Stats()
+    stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    with torch.cuda.device(device):
+        rc = L.eno_odeint_grid_fwd(h, C.byref(desc), B, _ptr(y0), _ptr(ts), T, _ptr(pflat), None, float(step_size), _ptr(ws),
+                                   ws.numel(), _ptr(ys), None, C.byref(st), stream)
+    _cabi.check(rc, h, "eno_odeint_grid_fwd")
+    return ys, st.as_dict()
+
+
 def _fwd_call(spec, solver, y0, ts, pflat, rtol, atol, mxstep, trace_cap=0, owner=None):
     """eno_odeint_fwd on device tensors. -> (ys [T,B,D], stats dict, trace or None)."""
     L = _cabi.lib()
@@ -347,9 +367,9 @@ class _OdeintSepauxFn(torch.autograd.Function):
         return None, None, None, None, y0_bar, r0_bar[0], r0_bar[1], ts_bar, eps_bar, p_bar
 
 
-def _bwd_call_split(spec, aug, n_aux, ys, ts, pflat, eps, g_y, g_aux, rtol, atol, mxstep):
-    """eno_odeint_bwd_sepaux for a dynamics family whose rev_func carries ``n_aux`` auxiliary states (g_aux [T, n_aux, B]).
-    -> (y0_bar, aux0_bar [n_aux, B], ts_bar, params_bar, eps_bar, stats)."""
+def _bwd_call_split(spec, aug, n_aux, ys, ts, pflat, eps, g_y, g_aux, rtol, atol, mxstep, grid_step=None):
+    """eno_odeint_bwd_sepaux (or, with ``grid_step``, eno_odeint_grid_bwd) for a dynamics family whose rev_func carries
+    ``n_aux`` auxiliary states (g_aux [T, n_aux, B]).  -> (y0_bar, aux0_bar [n_aux, B], ts_bar, params_bar, eps_bar, stats)."""
     L = _cabi.lib()
     device = ys.device
     h = _cabi.ctx(device.index)
@@ -365,10 +385,15 @@ def _bwd_call_split(spec, aug, n_aux, ys, ts, pflat, eps, g_y, g_aux, rtol, atol
     st = (_cabi.Stats * max(T - 1, 1))()
     stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
     with torch.cuda.device(device):
-        rc = L.eno_odeint_bwd_sepaux(h, C.byref(desc), B, _ptr(ys), _ptr(ts), T, _ptr(pflat), _ptr(eps), _ptr(g_y),
-                                     _ptr(g_aux), float(rtol), float(atol), _mx(mxstep), _ptr(ws), ws.numel(),
-                                     _ptr(y0_bar), _ptr(a0_bar), _ptr(eps_bar), _ptr(ts_bar), _ptr(p_bar), st, None, 0, stream)
-    _cabi.check(rc, h, "eno_odeint_bwd_sepaux")
+        if grid_step is not None:
+            rc = L.eno_odeint_grid_bwd(h, C.byref(desc), B, _ptr(ys), _ptr(ts), T, _ptr(pflat), _ptr(eps), _ptr(g_y), _ptr(g_aux),
+                                       float(grid_step), _ptr(ws), ws.numel(), _ptr(y0_bar), _ptr(a0_bar), _ptr(eps_bar),
+                                       _ptr(ts_bar), _ptr(p_bar), st, stream)
+        else:
+            rc = L.eno_odeint_bwd_sepaux(h, C.byref(desc), B, _ptr(ys), _ptr(ts), T, _ptr(pflat), _ptr(eps), _ptr(g_y),
+                                         _ptr(g_aux), float(rtol), float(atol), _mx(mxstep), _ptr(ws), ws.numel(),
+                                         _ptr(y0_bar), _ptr(a0_bar), _ptr(eps_bar), _ptr(ts_bar), _ptr(p_bar), st, None, 0, stream)
+    _cabi.check(rc, h, "eno_odeint_grid_bwd" if grid_step is not None else "eno_odeint_bwd_sepaux")
     return y0_bar, a0_bar, ts_bar, p_bar, eps_bar, [s.as_dict() for s in st][:max(T - 1, 0)]
 
 
@@ -379,7 +404,10 @@ class _OdeintSplitFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, aug, n_aux, rtol, atol, mxstep, y0, ts, eps, pflat, *aux0):
-        ys, st, _ = _fwd_call(spec, "dopri5", y0, ts, pflat, rtol, atol, mxstep)
+        if rtol is None:      # fixed grid: atol carries step_size (odeint_grid_sepaux*, lib/ode.py:579-615)
+            ys, st = _grid_fwd_call(spec, y0, ts, pflat, atol)
+        else:
+            ys, st, _ = _fwd_call(spec, "dopri5", y0, ts, pflat, rtol, atol, mxstep)
         last_stats["fwd"] = st
         ctx.spec, ctx.aug, ctx.n_aux = spec, aug, n_aux
         ctx.tols = (rtol, atol, mxstep)
@@ -399,7 +427,7 @@ class _OdeintSplitFn(torch.autograd.Function):
         g_y = g_ys.contiguous().float()
         g_aux = torch.stack([g.reshape(T, B) for g in rest[:n_aux]], dim=1).contiguous().float()   # [T, n_aux, B]
         y0_bar, a0_bar, ts_bar, p_bar, eps_bar, st = _bwd_call_split(ctx.spec, ctx.aug, n_aux, ys, ts, pflat, eps, g_y, g_aux,
-                                                                      rtol, atol, mxstep)
+                                                                      rtol, atol, mxstep, grid_step=atol if rtol is None else None)
         last_stats["bwd"] = st
         return (None,) * 6 + (y0_bar, ts_bar, eps_bar, p_bar) + tuple(a0_bar[q] for q in range(n_aux))
 
@@ -581,6 +609,56 @@ def odeint_fin_sepaux(fwd_func, rev_func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8
             or fwd_func.spec is not rev_func.spec):
         raise TypeError("odeint_fin_sepaux expects (spec.fwd, spec.aug_dynamics) of one ConcatSquashDynamics built with reg_type='fin'")
     return _odeint_split("odeint_fin_sepaux", "fin", fwd_func, rev_func, y0, t, args, rtol, atol, mxstep)
+
+
+def _require_flat(func, what):
+    _require_spec(func, what)
+    if getattr(func.spec, "num_layers", None) is None:
+        raise NotImplementedError(f"{what}: the fixed-grid solver runs on the ConcatSquash / ConcatConv2D engine; MLPDynamics "
+                                  "solves are adaptive (odeint, odeint_aux_one, odeint_sepaux)")
+
+
+def odeint_grid(func, y0, t, *args, step_size):
+    """Fixed-grid RK4, lib/ode.py:561-577 -> _rk4_odeint (864-903): steps of ``step_size`` from t[0], the last one clipped to
+    land on t[-1]; returns the two rows (y0, y(t[-1])) and nfe = 4 per step.  Not differentiable through this wrapper
+    (the scripts differentiate the split variants below).  -> (ys [2, B, D], nfe)."""
+    _require_flat(func, "odeint_grid")
+    if func.kind != "plain":
+        raise NotImplementedError("odeint_grid: plain dynamics only (spec.fwd / spec.dynamics_wrap)")
+    spec = func.spec
+    _eps, params = _split_args(func, args)
+    out_dev = y0.device
+    dev = _dev(params if isinstance(params, torch.Tensor) else y0)
+    y = _f32c(y0.reshape(-1, spec.dim), dev)
+    ts = _f32c(torch.as_tensor(t), dev)
+    pflat = _f32c(spec.flatten_params(params), dev)
+    with torch.no_grad():
+        ys, st = _grid_fwd_call(spec, y, ts, pflat, step_size)
+    last_stats["fwd"] = st
+    nfe = torch.tensor(st["nfe"], dtype=torch.float32, device=dev)
+    ys = ys.reshape((2,) + tuple(y0.shape))
+    return (ys.to(out_dev), nfe.to(out_dev)) if out_dev != ys.device else (ys, nfe)
+
+
+def odeint_grid_sepaux_one(fwd_func, rev_func, y0, t, *args, step_size):
+    """Fixed-grid split solve with TWO auxiliary states, lib/ode.py:598-615 -> _rk4_odeint_sepaux_one (906-918), adjoint
+    _rk4_odeint_rev (1531-1566): what the FFJORD scripts use as ``_odeint_aux2`` with a fixed-grid method
+    (ffjord_tabular.py:77, ffjord_mnist.py:70).  -> ((ys [2,B,D], delta_logp [2,B,1], r [2,B,1]), nfe)."""
+    _require_flat(fwd_func, "odeint_grid_sepaux_one")
+    _require_spec(rev_func, "odeint_grid_sepaux_one")
+    if fwd_func.kind != "plain" or rev_func.kind != "aug" or fwd_func.spec is not rev_func.spec:
+        raise TypeError("odeint_grid_sepaux_one expects (spec.fwd, spec.aug_dynamics) of one spec built with reg_type='our'")
+    return _odeint_split("odeint_grid_sepaux_one", "aug", fwd_func, rev_func, y0, t, args, None, float(step_size), None)
+
+
+def odeint_grid_sepaux(fwd_func, rev_func, y0, t, *args, step_size):
+    """Fixed-grid split solve with THREE auxiliary states, lib/ode.py:579-596 -> _rk4_odeint_sepaux (934-946): ``_odeint_aux3``
+    of the FFJORD scripts (--reg_type fin).  -> ((ys, delta_logp, fro, kin), nfe)."""
+    _require_flat(fwd_func, "odeint_grid_sepaux")
+    _require_spec(rev_func, "odeint_grid_sepaux")
+    if fwd_func.kind != "plain" or rev_func.kind != "fin" or fwd_func.spec is not rev_func.spec:
+        raise TypeError("odeint_grid_sepaux expects (spec.fwd, spec.aug_dynamics) of one spec built with reg_type='fin'")
+    return _odeint_split("odeint_grid_sepaux", "fin", fwd_func, rev_func, y0, t, args, None, float(step_size), None)
 
 
 def odeint_vmap(func, y0, t, *args, rtol=1.4e-8, atol=1.4e-8, mxstep=math.inf):

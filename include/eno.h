@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ENO_ABI_VERSION 8
+#define ENO_ABI_VERSION 9
 
 /* status codes */
 #define ENO_OK 0
@@ -213,6 +213,24 @@ int32_t eno_odeint_bwd_sepaux(eno_ctx* ctx, const eno_dynamics_desc* desc, int32
                               float* y0_bar_out, float* aux0_bar_out, float* eps_bar_out, float* ts_bar_out,
                               float* params_bar_out, eno_stats* stats_host, eno_trace_row* trace_out, int32_t trace_cap,
                               void* stream);
+
+/*
+ * Fixed-grid RK4 solves.  Replace
+ *   odeint_grid(func, y0, t, *args, step_size)                                  lib/ode.py:561-577 -> _rk4_odeint 864-903
+ *   odeint_grid_sepaux_one / odeint_grid_sepaux(fwd_func, rev_func, ...)        lib/ode.py:579-615, 906-946
+ *   _rk4_odeint_rev (the adjoint: the same RK4 grid on the augmented system)    lib/ode.py:1531-1566
+ * as ffjord_tabular.py:75-78 / ffjord_mnist.py:68-71 select them: steps of step_size from ts[0], the last one clipped so
+ * that it lands on ts[-1]; the result has the two rows (y0, y(ts[-1])) - T must be 2, like the reference (lib/ode.py:884) -
+ * and nfe = 4 per step.  ENO_ARCH_CONCATSQUASH / ENO_ARCH_CONCATCONV only (ENO_E_UNSUPPORTED otherwise).  Arguments as in
+ * eno_odeint_fwd / eno_odeint_bwd_sepaux, step_size in place of (rtol, atol, mxstep); collective after eno_comm_init.
+ */
+int32_t eno_odeint_grid_fwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, const float* y0, const float* ts, int32_t T,
+                            const float* params, const float* eps, float step_size, void* workspace, size_t workspace_bytes,
+                            float* ys_out, float* aux_out, eno_stats* stats_host, void* stream);
+int32_t eno_odeint_grid_bwd(eno_ctx* ctx, const eno_dynamics_desc* desc, int32_t B, const float* ys, const float* ts, int32_t T,
+                            const float* params, const float* eps, const float* g_y, const float* g_aux, float step_size,
+                            void* workspace, size_t workspace_bytes, float* y0_bar_out, float* aux0_bar_out, float* eps_bar_out,
+                            float* ts_bar_out, float* params_bar_out, eno_stats* stats_host, void* stream);
 
 /*
  * One evaluation of the integrated function (unit-test hook), the closures of

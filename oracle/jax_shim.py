@@ -308,6 +308,7 @@ def install():
     np = _make_numpy()
     lax = types.ModuleType("jax.lax")
     lax.while_loop, lax.fori_loop, lax.scan, lax.cond = _while_loop, _fori_loop, _scan, _cond
+    lax.min = np.minimum        # lax.min(cur_t + step_size, ts[-1]) in the fixed-grid loop (lib/ode.py:891)
     ops = types.ModuleType("jax.ops")
     ops.index = _Index()
     ops.index_update = _index_update

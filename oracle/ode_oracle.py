@@ -304,3 +304,85 @@ def odeint_split_rev(rev_func, rtol, atol, mxstep, res_ys, ts, args, g, stats=No
 
     out = odeint_rev(flat_func, rtol, atol, mxstep, flat_res, ts, args, flat_g, stats)
     return (unravel(out[0]), *out[1:])
+
+
+# ----------------------------------------------------------------------------
+# fixed-grid RK4 family (lib/ode.py:561-634 wrappers, 864-946 primal, 1446-1460 fwd rules, 1531-1593 adjoint).
+# PINNED by tests/golden/css_grid.npz (tests/golden/make_grid.py runs the unmodified reference on the JAX stand-in).
+# ----------------------------------------------------------------------------
+def rk4_solve(fun, step_size, y0, ts):
+    """_rk4_odeint, lib/ode.py:864-903, on a flat state: steps of ``step_size`` from ts[0] while t < ts[-1], the last one
+    clipped (next_t = min(t + step_size, ts[-1])); returns (stack(y0, y(ts[-1])), nfe = 4 per step)."""
+    step_size = torch.as_tensor(step_size, dtype=y0.dtype)
+    cur_y, cur_t, nfe = y0, ts[0], 0
+    while bool(cur_t < ts[-1]):
+        next_t = torch.minimum(cur_t + step_size, ts[-1])
+        dt = next_t - cur_t
+        k1 = fun(cur_y, cur_t)
+        k2 = fun(cur_y + dt * k1 / 2, cur_t + dt / 2)
+        k3 = fun(cur_y + dt * k2 / 2, cur_t + dt / 2)
+        k4 = fun(cur_y + dt * k3, cur_t + dt)
+        cur_y = cur_y + (k1 + 2 * k2 + 2 * k3 + k4) * (dt / 6)
+        cur_t = next_t
+        nfe += 4
+    return torch.stack([y0, cur_y]), float(nfe)
+
+
+def odeint_grid(func, y0, t, *args, step_size):
+    """odeint_grid, lib/ode.py:561-577 / 750-754: ravel, _rk4_odeint, un-ravel with a leading time axis of 2."""
+    flat0, unravel = ravel(y0)
+
+    def fun(yflat, tt):
+        return ravel(func(unravel(yflat), tt, *args))[0]
+
+    ys, nfe = rk4_solve(fun, step_size, flat0, t)
+    leaves_t = [unravel(ys[i]) for i in range(2)]
+    l0, td = _flatten(leaves_t[0])
+    stacked = [torch.stack([_flatten(lt)[0][j] for lt in leaves_t]) for j in range(len(l0))]
+    return _unflatten(td, stacked), nfe
+
+
+def odeint_grid_split_fwd(fwd_func, y0, t, *args, n_aux, step_size):
+    """_rk4_odeint_aux / _sepaux_one / _sepaux (n_aux = 1 / 2 / 3), lib/ode.py:906-946: integrate y0[0] with fwd_func on
+    the grid, zeros of shape [2, B, 1] for every auxiliary output."""
+    out, nfe = odeint_grid(fwd_func, y0[0], t, *args, step_size=step_size)
+    B = out.shape[1]
+    return (out,) + tuple(torch.zeros((2, B, 1), dtype=out.dtype) for _ in range(n_aux)), nfe
+
+
+def rk4_odeint_rev(func, step_size, ys, ts, args, g):
+    """_rk4_odeint_rev, lib/ode.py:1531-1566, on a flat state: per segment t_bar = <func(ys[i]), g[i]>, then the same
+    fixed-grid RK4 on (y, y_bar, t0_bar, args_bar) over [-ts[i], -ts[i-1]]."""
+    def aug(state, tneg, *a):
+        y, y_bar = state[0], state[1]
+        y_dot, pull = torch.func.vjp(func, y, -tneg, *a)
+        return (-y_dot, *pull(y_bar))
+
+    y_bar = g[-1]
+    t0_bar = torch.zeros((), dtype=ys.dtype)
+    args_bar = tree_map(torch.zeros_like, tuple(args))
+    rev_ts_bar = []
+    for i in range(len(ts) - 1, 0, -1):
+        t_bar = torch.dot(func(ys[i], ts[i], *args), g[i])
+        t0_bar = t0_bar - t_bar
+        out, _ = odeint_grid(aug, (ys[i], y_bar, t0_bar, args_bar), torch.stack([-ts[i], -ts[i - 1]]), *args, step_size=step_size)
+        _, y_bar, t0_bar, args_bar = out
+        y_bar, t0_bar, args_bar = tree_map(lambda x: x[1], (y_bar, t0_bar, args_bar))
+        y_bar = y_bar + g[i - 1]
+        rev_ts_bar.append(t_bar)
+    ts_bar = torch.stack([t0_bar] + rev_ts_bar[::-1])
+    return (y_bar, ts_bar, *args_bar)
+
+
+def odeint_grid_split_rev(rev_func, step_size, res_ys, ts, args, g):
+    """_rk4_odeint_sepaux_rev and siblings, lib/ode.py:1568-1593: flatten per time, rk4_odeint_rev with rev_func."""
+    T = res_ys[0].shape[0]
+    flat_res = torch.stack([ravel(tuple(r[i] for r in res_ys))[0] for i in range(T)])
+    flat_g = torch.stack([ravel(tuple(x[i] for x in g))[0] for i in range(T)])
+    _, unravel = ravel(tuple(r[0] for r in res_ys))
+
+    def flat_func(yflat, tt, *a):
+        return ravel(rev_func(unravel(yflat), tt, *a))[0]
+
+    out = rk4_odeint_rev(flat_func, step_size, flat_res, ts, args, flat_g)
+    return (unravel(out[0]), *out[1:])
