@@ -33,6 +33,7 @@ int rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int mode, int B, const floa
         float* ybar_dot_out, float* tbar_out, float* params_bar_out, float* eps_bar_dot_out, cudaStream_t st);
 
 void destroy(eno_ctx* ctx);
+void drop_collective_graphs(eno_ctx* ctx);
 
 }  // namespace css
 }  // namespace eno

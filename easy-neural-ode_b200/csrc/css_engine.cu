@@ -857,6 +857,17 @@ int rhs(eno_ctx* ctx, const eno_dynamics_desc* desc, int mode, int B, const floa
   return ENO_OK;
 }
 
+// The iteration graphs of collective solves contain NCCL kernels bound to one communicator: they must not outlive it
+// (eno_comm_init / eno_comm_destroy call this).
+void drop_collective_graphs(eno_ctx* ctx) {
+  if (!ctx || !ctx->css) return;
+  CssState* s = static_cast<CssState*>(ctx->css);
+  for (auto it = s->graphs.begin(); it != s->graphs.end();) {
+    if (it->first.world > 1) { cudaGraphExecDestroy(it->second); it = s->graphs.erase(it); }
+    else ++it;
+  }
+}
+
 void destroy(eno_ctx* ctx) {
   if (!ctx || !ctx->css) return;
   CssState* s = static_cast<CssState*>(ctx->css);

@@ -565,6 +565,7 @@ int32_t eno_comm_init(eno_ctx* ctx, const uint8_t* id, int32_t rank, int32_t wor
   if (world == 1) { ctx->dist.world = 1; ctx->dist.rank = 0; return ENO_OK; }
   if (!ctx->dist.api.load(nccl_path, &ctx->err)) return ENO_E_UNSUPPORTED;
   ENO_CUDA(ctx, cudaSetDevice(ctx->device));
+  css::drop_collective_graphs(ctx);
   NcclUniqueId uid;
   memcpy(uid.internal, id, 128);
   if (int rc = ctx->dist.api.CommInitRank(&ctx->dist.comm, world, uid, rank))
@@ -628,6 +629,7 @@ int32_t eno_peer_attach(eno_ctx* ctx, const uint8_t* handles /*[world][64]*/) {
 
 int32_t eno_comm_destroy(eno_ctx* ctx) {
   if (!ctx) return ENO_E_ARG;
+  css::drop_collective_graphs(ctx);
   if (ctx->dist.comm) ctx->dist.api.CommDestroy(ctx->dist.comm);
   ctx->dist.comm = nullptr;
   for (int r = 0; r < ctx->dist.peer.world; ++r)

@@ -52,6 +52,9 @@ class ImageFfjord:
         """images in [0, 1], eps Rademacher, both [B, H, W, 1] on self.device.  Forward solve -> loss head -> adjoint."""
         B = images.shape[0]
         n = self.rows_global or B * self.world
+        if self.world > 1 and ode._dist["world"] != self.world:
+            raise RuntimeError(f"world = {self.world} needs collective solves: call easy_neural_ode_b200.init_distributed() first "
+                               "(otherwise every rank would return the gradient of its own rows only)")
         D = self.spec.dim
         fin = self.reg_type == "fin"
         aug, n_aux = self.spec.AUG_OF_KIND["fin" if fin else "aug"]

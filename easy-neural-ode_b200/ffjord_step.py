@@ -54,6 +54,9 @@ class TabularFfjord:
         """x, eps [B, dim] on self.device.  Forward solve -> loss head -> adjoint solve (no autograd graph)."""
         B = x.shape[0]
         n = B * self.world
+        if self.world > 1 and ode._dist["world"] != self.world:
+            raise RuntimeError(f"world = {self.world} needs collective solves: call easy_neural_ode_b200.init_distributed() first "
+                               "(otherwise every rank would return the gradient of its own rows only)")
         fin = self.reg_type == "fin"
         aug, n_aux = self.spec.AUG_OF_KIND["fin" if fin else "aug"]
         ys, st_f, _ = ode._fwd_call(self.spec, "dopri5", x, self.ts, self.params, self.rtol, self.atol, math.inf)
