@@ -81,6 +81,9 @@ __device__ __forceinline__ size_t replicated_at(const Flat& a, size_t j) { retur
 
 // ---- stage input + network input + gate vectors, one launch ---------------------------------------------------
 __global__ void k_css_stage(Flat a, Net n, int stage, int init_mode) {
+  // the GEMM that follows is a programmatic dependent launch (gemm_tc.cuh:launch_pdl): let its prologue start now; it waits
+  // for this grid to complete before it reads anything
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   Ctrl* c = a.ctrl;
   if (init_mode == ST_STAGE && c->done) return;
   const float dt = c->dt;
@@ -140,6 +143,7 @@ __global__ void k_css_eps(Net n) {
 // ---- after the forward passes: per-sample scalars, and (adjoint) the seeds of the reverse sweep ------------------
 // one warp per sample.  Cotangents: aux_bar rows of the stage input (constant blocks of the adjoint state).
 __global__ void k_css_seed(Flat a, Net n) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see k_css_stage
   if (a.ctrl->done) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n.B) return;
@@ -191,6 +195,7 @@ __global__ void k_css_seed(Flat a, Net n) {
 
 // seed of the primal reverse sweep: u_bar of the last layer = y_bar (+ cotangent of d_0 = f) (+ kin term)
 __global__ void k_css_seed2(Flat a, Net n) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see k_css_stage
   if (a.ctrl->done) return;
   const size_t BD = (size_t)n.B * n.D;
   const int Ll = n.L - 1, ldo = n.ldo[Ll];
