@@ -448,7 +448,7 @@ int css_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
   const int L = n.L, B = n.B, Bp = n.Bp;
   const int* done = (init_mode == css::ST_STAGE) ? &f.ctrl->done : nullptr;
   const int egrid = std::min<int>((int)((std::max(f.n_feed, (size_t)n.hmax) + 255) / 256), 4 * sms);
-  css::k_css_stage<<<egrid, 256, 0, st>>>(f, n, stage, init_mode);
+  CSS_G(tc::launch_pdl(css::k_css_stage, dim3(egrid), dim3(256), 0, st, f, n, stage, init_mode));
   // forward: primal stream, then the tangent streams stacked
   for (int l = 0; l < L; ++l) {
     tc::GemmOperand A{n.X2[l], 3 * Bp, n.din[l], n.ldi[l], n.xplane(l), 0};
@@ -462,7 +462,7 @@ int css_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
       CSS_G(gemm(A, W, n.nq * Bp, n.dout[l], 1, done, css::EpiTangent{n, l}, st, err));
     }
   }
-  if (n.mode != css::MODE_PLAIN) css::k_css_seed<<<(B * 32 + 255) / 256, 256, 0, st>>>(f, n);
+  if (n.mode != css::MODE_PLAIN) CSS_G(tc::launch_pdl(css::k_css_seed, dim3((B * 32 + 255) / 256), dim3(256), 0, st, f, n));
   if (n.mode == css::MODE_ADJ) {
     // reverse: tangent streams
     if (n.nq > 0) {
@@ -473,7 +473,7 @@ int css_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
         else CSS_G(gemm(A, W, n.nq * Bp, n.din[l], 1, done, css::EpiTanRev0{n}, st, err));
       }
     }
-    css::k_css_seed2<<<std::min((int)(((size_t)B * n.D + 255) / 256), 4 * sms), 256, 0, st>>>(f, n);
+    CSS_G(tc::launch_pdl(css::k_css_seed2, dim3(std::min((int)(((size_t)B * n.D + 255) / 256), 4 * sms)), dim3(256), 0, st, f, n));
     for (int l = L - 1; l >= 0; --l) {
       tc::GemmOperand A{n.AB2[l], 3 * Bp, n.dout[l], n.ldo[l], n.abplane(l), 0};
       tc::GemmOperand W{n.W2[l], n.din[l], n.dout[l], n.ldo[l], (size_t)n.din[l] * n.ldo[l], 0};
@@ -495,11 +495,13 @@ int css_rhs_launch(const Plan& p, int stage, int init_mode, float* k_override, i
       else CSS_G(tc::launch_gemm_mn<64>(txa, txb, n.din[l], n.dout[l], K, 1 + n.nq, 0, done, epi, st));
       if (prof) g_prof->end(st);
     }
-    css::k_css_colred<<<dim3((n.hmax + 31) / 32, n.cr_chunks, L), dim3(32, 8), 0, st>>>(f, n);
-    css::k_css_colfin<<<dim3((n.hmax + 63) / 64, L), 64, 0, st>>>(f, n, stage, init_mode, k_override ? k_override + f.oPR : nullptr);
+    CSS_G(tc::launch_pdl(css::k_css_colred, dim3((n.hmax + 31) / 32, n.cr_chunks, L), dim3(32, 8), 0, st, f, n));
+    CSS_G(tc::launch_pdl(css::k_css_colfin, dim3((n.hmax + 63) / 64, L), dim3(64), 0, st, f, n, stage, init_mode,
+                         k_override ? k_override + f.oPR : (float*)nullptr));
   }
   const size_t work = std::max((size_t)B * n.D, n.mode == css::MODE_ADJ ? (size_t)n.H * n.H : (size_t)1);
-  css::k_css_assemble<<<std::min((int)((work + 255) / 256), 8 * sms), 256, 0, st>>>(f, n, stage, init_mode, k_override);
+  CSS_G(tc::launch_pdl(css::k_css_assemble, dim3(std::min((int)((work + 255) / 256), 8 * sms)), dim3(256), 0, st, f, n, stage, init_mode,
+                       k_override));
   CSS_G(cudaGetLastError());
   return 0;
 }
@@ -588,12 +590,12 @@ int enqueue_iteration(const Plan& p, const DistCtx* dc, int sms, cudaStream_t st
     css::k_flat_xcomb<<<std::min<int>((int)((p.flat.n_x + 255) / 256), 4 * sms), 256, 0, st>>>(p.flat);
     CSS_NCCL(dc->allreduce(p.flat.xbuf, 4 * p.flat.n_x, st), "ncclAllReduce");
   }
-  css::k_flat_finish<<<fgrid, 256, 0, st>>>(p.flat);
+  CSS_G(tc::launch_pdl(css::k_flat_finish, dim3(fgrid), dim3(256), 0, st, p.flat));
   if (dc) {
     CSS_NCCL(dc->gather(p.flat.gbuf, 2, st), "ncclAllGather");
     css::k_flat_control<<<1, 1, 0, st>>>(p.flat);
   }
-  css::k_flat_out<<<std::min<int>((int)((p.flat.N + 255) / 256), 4 * sms), 256, 0, st>>>(p.flat);
+  CSS_G(tc::launch_pdl(css::k_flat_out, dim3(std::min<int>((int)((p.flat.N + 255) / 256), 4 * sms)), dim3(256), 0, st, p.flat));
   return 0;
 }
 

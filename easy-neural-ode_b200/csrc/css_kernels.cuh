@@ -79,11 +79,18 @@ __device__ __forceinline__ bool replicated(const Flat& a, size_t i, size_t* j) {
 }
 __device__ __forceinline__ size_t replicated_at(const Flat& a, size_t j) { return j == 0 ? a.oT0 : a.oPR + (j - 1); }
 
+// Programmatic dependent launch (gemm_tc.cuh:launch_pdl): every kernel of the iteration that is launched with the attribute
+// starts with this - wait until the kernel before it has completed (nothing is read earlier), then let the kernel after it
+// start its own prologue.  Both instructions are no-ops in a plain launch.
+#define CSS_PDL_ENTRY()                                            \
+  do {                                                             \
+    asm volatile("griddepcontrol.wait;" ::: "memory");             \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); \
+  } while (0)
+
 // ---- stage input + network input + gate vectors, one launch ---------------------------------------------------
 __global__ void k_css_stage(Flat a, Net n, int stage, int init_mode) {
-  // the GEMM that follows is a programmatic dependent launch (gemm_tc.cuh:launch_pdl): let its prologue start now; it waits
-  // for this grid to complete before it reads anything
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  CSS_PDL_ENTRY();
   Ctrl* c = a.ctrl;
   if (init_mode == ST_STAGE && c->done) return;
   const float dt = c->dt;
@@ -143,7 +150,7 @@ __global__ void k_css_eps(Net n) {
 // ---- after the forward passes: per-sample scalars, and (adjoint) the seeds of the reverse sweep ------------------
 // one warp per sample.  Cotangents: aux_bar rows of the stage input (constant blocks of the adjoint state).
 __global__ void k_css_seed(Flat a, Net n) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see k_css_stage
+  CSS_PDL_ENTRY();
   if (a.ctrl->done) return;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n.B) return;
@@ -195,7 +202,7 @@ __global__ void k_css_seed(Flat a, Net n) {
 
 // seed of the primal reverse sweep: u_bar of the last layer = y_bar (+ cotangent of d_0 = f) (+ kin term)
 __global__ void k_css_seed2(Flat a, Net n) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see k_css_stage
+  CSS_PDL_ENTRY();
   if (a.ctrl->done) return;
   const size_t BD = (size_t)n.B * n.D;
   const int Ll = n.L - 1, ldo = n.ldo[Ll];
@@ -220,6 +227,7 @@ __global__ void k_css_seed2(Flat a, Net n) {
 //   q 0: sum_b (w lin + v_e a1_e + v_d a1_d)   -> G_bar        q 1: sum_b v_d lin   -> G1_bar
 //   q 2: sum_b w                                               q 3: sum_b v_d
 __global__ void k_css_colred(Flat a, Net n) {
+  CSS_PDL_ENTRY();
   if (a.ctrl->done) return;
   const int l = blockIdx.z, dout = n.dout[l], ldo = n.ldo[l];
   const int col = blockIdx.x * 32 + threadIdx.x;
@@ -257,6 +265,7 @@ __global__ void k_css_colred(Flat a, Net n) {
 constexpr int kCrChunks = 16;   // row chunks of k_css_colred (Net::cr_chunks)
 
 __global__ void k_css_colfin(Flat a, Net n, int stage, int init_mode, float* pr_override) {
+  CSS_PDL_ENTRY();
   if (init_mode == ST_STAGE && a.ctrl->done) return;
   float* pr = pr_override ? pr_override : k_slot(a, stage, init_mode) + a.oPR;
   const float t = *n.tval;
@@ -288,6 +297,7 @@ __global__ void k_css_colfin(Flat a, Net n, int stage, int init_mode, float* pr_
 // ---- stage derivative of every block --------------------------------------------------------------------------
 // plain: k = f.   aug: k = (f, -div [, r, fro, kin]).   adjoint: (-f, +div, -r | vjp_y, 0 | vjp_t | vjp_eps | vjp_params)
 __global__ void k_css_assemble(Flat a, Net n, int stage, int init_mode, float* k_override) {
+  CSS_PDL_ENTRY();
   if (init_mode == ST_STAGE && a.ctrl->done) return;
   float* k = k_override ? k_override : k_slot(a, stage, init_mode);
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
@@ -491,6 +501,7 @@ __global__ void k_flat_xcomb(Flat a) {
 __global__ void k_flat_finish(Flat a) {
   __shared__ double sm[32];
   __shared__ double dred[512];
+  CSS_PDL_ENTRY();
   Ctrl* c = a.ctrl;
   if (c->done) return;
   const float dt = c->dt, rtol = c->rtol, atol = c->atol;
@@ -570,6 +581,7 @@ __global__ void k_flat_control(Flat a) {
 
 // ---- dense output for the targets the last iteration left behind (lib/ode.py:56-84, 849-850) -------------------
 __global__ void k_flat_out(Flat a) {
+  CSS_PDL_ENTRY();
   const Ctrl* c = a.ctrl;
   const int ob = c->out_begin, oe = c->out_end;
   if (oe <= ob) return;

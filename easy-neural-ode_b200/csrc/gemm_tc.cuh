@@ -438,20 +438,21 @@ struct GemmOperand {
 
 // Launches of the flat-state engine carry the programmatic-stream-serialization attribute, so that a GEMM's prologue (barrier
 // init, TMEM allocation, descriptor prefetch) overlaps the tail of the kernel before it: ffjord_tabular 45.1 -> 49.3 train
-// steps/s, ffjord_mnist 8.59 -> 8.66 (ENO_GEMM_PDL=0 restores plain launches for A/B runs).
+// steps/s, 51.1 with the element-wise kernels of the iteration launched the same way (css_kernels.cuh:CSS_PDL_ENTRY);
+// ffjord_mnist 8.59 -> 8.68 (ENO_GEMM_PDL=0 restores plain launches for A/B runs).
 inline bool gemm_pdl_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("ENO_GEMM_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }
   return on == 1;
 }
 template <class Kern, class... Args>
-inline cudaError_t launch_pdl(Kern kern, dim3 grid, int threads, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   if (!gemm_pdl_enabled()) {
-    kern<<<grid, threads, smem, st>>>(args...);
+    kern<<<grid, block, smem, st>>>(args...);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
