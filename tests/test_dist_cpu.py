@@ -49,6 +49,18 @@ WORKER = textwrap.dedent('''
     parts = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
     dist.all_gather(parts, part)
     assert float(sum(parts)) == float(x.sum())
+    # 2b. the loss terms of the sharded latent step (latent_step.LatentGen._global_sum): the VALUE is the sum over ranks,
+    #     the derivative wrt this rank's term is 1 - so every rank differentiates the same global loss wrt its own rows and
+    #     the all-reduced parameter gradient is the gradient of the concatenated batch
+    import types
+    from easy_neural_ode_b200 import latent_step
+    w = torch.tensor([1.0 + rank, 2.0], dtype=torch.float64, requires_grad=True)
+    local = (w * w).sum()
+    tot = latent_step.LatentGen._global_sum(types.SimpleNamespace(world=world), local)
+    assert float(tot) == sum((1.0 + r) ** 2 + 4.0 for r in range(world))
+    loss = torch.log(tot)
+    g, = torch.autograd.grad(loss, w)
+    assert torch.allclose(g, 2 * w.detach() / float(tot))
     # 3. without a GPU the collective set-up fails loudly (no CPU fallback)
     try:
         eno.init_distributed()
