@@ -617,7 +617,7 @@ def fm_main(args, result_out, rank, local_rank, world):
     print(json.dumps(line), file=result_out, flush=True)
 
 
-# ---- BASELINE configs[2]: latent_ode.py generative ODE, per-trajectory solves (development workload, single GPU) --------
+# ---- BASELINE configs[2]: latent_ode.py generative ODE, per-trajectory solves (development workload; --gpus N shards the series) --
 LT = dict(S=3, B=50, D=20, U=50, LAYERS=3, T=49, DATA=37, LAM=1e-2, TOL=1.4e-8)
 LT_WORKLOAD = ("latent_ode.py generative ODE, synthetic Physionet-shaped series (37 features, 49 time points on [0, 1]), "
                "GenDynamics 20-50x4-20 tanh, dopri5, --reg r3 --lam 1e-2, 3 samples x batch 50 = 150 per-trajectory solves "
