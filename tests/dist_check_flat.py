@@ -3,7 +3,7 @@ batch-sharded collective split solve (odeint_sepaux: forward + adjoint) must rep
 concatenated batch - same forward NFE and adjoint iteration count, every rank the same controller trajectory, y(t1) and
 the gradients (image / eps rows of the shard, GLOBAL parameter gradient on every rank) within 1e-5 (3e-5 where the
 error estimates are at fp32 round-off, see the comment in main).  Run under torchrun,
-one process per GPU; not collected by pytest directly (tests/test_gpu_dist.py launches it when 2 GPUs are visible):
+one process per GPU; not collected by pytest directly (tests/test_dist_cpu.py::test_two_gpu_collective_flat_engine_matches_single_device launches it when 2 GPUs are visible):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
         --master-port 29513 tests/dist_check_flat.py
